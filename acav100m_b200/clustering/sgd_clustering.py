@@ -1,0 +1,248 @@
+"""``KMeans`` -- mini-batch SGD k-means with the reference's operator API, computed on a B200.
+
+Mirror of ``clustering/code/sgd_clustering.py:10-129`` of the reference: same constructor, same
+attributes (``centers``, ``counts``, ``count``, ``lr``, ``initial_rounds``, ``reinit``, ``fallback``),
+same methods (``to``, ``initialize``, ``add``, ``calc_best``, ``get_attrs``, ``load``), same
+multi-GPU semantics (replicated centers, per-rank batch slice, sum of histograms and deltas).
+Every tensor operation of the reference is replaced by a call into ``libacav_b200.so``; there is
+no torch math and no CPU fallback on the compute path.
+
+Differences a user can observe (all documented in DESIGN.md):
+  * the per-step ``all_gather`` of the batch (reference :97, used only for ``len``) is dropped;
+  * ``fallback`` is kept on the device (no host sync per step, reference :116-119) and read lazily;
+  * ``add`` / ``calc_best`` take ``sync=False`` to return the mean distance as a 0-dim device tensor
+    instead of a python float (the reference's ``.item()`` at :79 stalls the stream every call).
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class KMeans:
+    def __init__(self, args=None, d=None, k=None, lr=1e-2,
+                 initial_rounds=10, reinit=(.7, 5.0), saved_dt=None,
+                 assign_mode="auto", warmup_rng="cpu"):
+        self._ws = None
+        self._ws_batch = 0
+        self._fallback_base = 0
+        self._fallback_dev = None
+        self.assign_mode = assign_mode
+        self.warmup_rng = warmup_rng
+        if saved_dt is not None:
+            self.load_from_saves(saved_dt)
+        else:
+            self.args = args
+            self.centers = torch.rand(k, d) * 1e-5          # reference :24 (global CPU generator)
+            self.counts = torch.zeros(k)
+            self.count = 0
+            self.lr = lr
+            self.initial_rounds = initial_rounds
+            self.reinit = reinit
+            self.fallback = 0
+            self.sequential = False
+
+    # -- state ---------------------------------------------------------------------------------
+
+    @property
+    def fallback(self):
+        """Number of lr fallbacks taken (reference :119); the device counter is read on access."""
+        extra = int(self._fallback_dev.item()) if self._fallback_dev is not None else 0
+        return self._fallback_base + extra
+
+    @fallback.setter
+    def fallback(self, value):
+        self._fallback_base = int(value)
+        if self._fallback_dev is not None:
+            self._fallback_dev.zero_()
+
+    def get_attrs(self):
+        """reference :34-46."""
+        return {
+            'args': self.args, 'count': self.count, 'lr': self.lr,
+            'initial_rounds': self.initial_rounds, 'reinit': self.reinit,
+            'fallback': self.fallback, 'sequential': self.sequential,
+            'centers': self.centers.cpu().numpy(), 'counts': self.counts.cpu().numpy(),
+        }
+
+    def load_from_saves(self, dt):
+        """reference :48-52."""
+        for key, val in dt.items():
+            setattr(self, key, val)
+        self.centers = torch.from_numpy(np.ascontiguousarray(self.centers, dtype=np.float32))
+        self.counts = torch.from_numpy(np.ascontiguousarray(self.counts, dtype=np.float32))
+
+    @classmethod
+    def load(cls, dt):
+        return cls(saved_dt=dt)
+
+    def to(self, device):
+        """reference :59-61."""
+        self.centers = self.centers.to(device).contiguous()
+        self.counts = self.counts.to(device).contiguous()
+        self._release()
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st['_fallback_base'] = self.fallback
+        st['_fallback_dev'] = None
+        st['_ws'] = None
+        st['_ws_batch'] = 0
+        st['centers'] = self.centers.cpu()
+        st['counts'] = self.counts.cpu()
+        return st
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    # -- workspace -----------------------------------------------------------------------------
+
+    def _release(self):
+        if self._ws is not None:
+            _lib.load().acav_kmeans_destroy(self._ws)
+            self._ws = None
+            self._ws_batch = 0
+
+    def _device(self):
+        if self.centers.device.type != 'cuda':
+            raise RuntimeError("KMeans is on %s: move it with .to('cuda') -- acav100m_b200 has no CPU path"
+                               % self.centers.device)
+        return self.centers.device
+
+    def _workspace(self, b):
+        dev = self._device()
+        if self._ws is None or b > self._ws_batch:
+            self._release()
+            k, d = self.centers.shape
+            cap = max(int(b), 1024)
+            handle = _lib.c_vp()
+            with torch.cuda.device(dev):
+                _lib.call("acav_kmeans_create", _lib.ctypes.byref(handle), k, d, cap)
+            self._ws, self._ws_batch = handle, cap
+        if self._fallback_dev is None or self._fallback_dev.device != dev:
+            self._fallback_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._ws
+
+    def _prep_batch(self, batch):
+        dev = self._device()
+        batch = batch.to(device=dev, dtype=torch.float32)
+        if batch.dim() != 2 or batch.shape[1] != self.centers.shape[1]:
+            raise ValueError("batch must be [b, %d], got %s" % (self.centers.shape[1], tuple(batch.shape)))
+        if batch.stride(1) != 1 or batch.stride(0) < batch.shape[1]:
+            batch = batch.contiguous()
+        return batch
+
+    def _mode(self):
+        if self.assign_mode in ("exact", _lib.ASSIGN_EXACT):
+            return _lib.ASSIGN_EXACT
+        if self.assign_mode in ("tensor", _lib.ASSIGN_TENSOR):
+            return _lib.ASSIGN_TENSOR
+        return _lib.ASSIGN_EXACT                   # "auto": exact until the tensor path is validated
+
+    def mode_name(self):
+        return "exact" if self._mode() == _lib.ASSIGN_EXACT else "tensor"
+
+    def launches_per_step(self):
+        """CUDA kernels of this library launched by one add() past warm-up (bench.py gpu_launches)."""
+        assign = 4 if self._mode() == _lib.ASSIGN_EXACT else 6
+        _, world = self._world()
+        return assign + 4 + 2 + (1 if world > 1 else 0)
+
+    # -- operator ------------------------------------------------------------------------------
+
+    @property
+    def in_warmup(self):
+        """reference :67."""
+        return self.count < self.initial_rounds * self.centers.shape[0]
+
+    def underused_threshold(self):
+        """Right-hand side of ``counts < (count / k) ** p`` (reference :77) as torch compares it:
+        the python scalar is cast to fp32 before the comparison."""
+        k = self.centers.shape[0]
+        return float(np.float32((self.count / k) ** self.reinit[0]))
+
+    def _assign(self, batch, want_mean):
+        """Device part of calc_best: returns (best int64[b], mean 0-dim tensor or None)."""
+        dev = self._device()
+        k, d = self.centers.shape
+        b = batch.shape[0]
+        ws = self._workspace(b)
+        best = torch.empty(b, dtype=torch.int64, device=dev)
+        mean = torch.empty(1, dtype=torch.float32, device=dev) if want_mean else None
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            if self.in_warmup:
+                if self.warmup_rng == "cpu":
+                    noise = torch.rand(k, b).to(dev, non_blocking=False)        # reference :68
+                else:
+                    noise = torch.rand(k, b, device=dev)
+                mind = torch.empty(b, dtype=torch.float32, device=dev) if want_mean else None
+                _lib.call("acav_kmeans_assign_noise", _lib.ptr(noise), k, b, _lib.ptr(best),
+                          _lib.ptr(mind), _lib.ptr(mean), st)
+            else:
+                _lib.call("acav_kmeans_assign", ws, _lib.ptr(batch), b, batch.stride(0),
+                          _lib.ptr(self.centers), _lib.ptr(self.counts),
+                          self.underused_threshold(), float(self.reinit[1]),
+                          _lib.ptr(best), None, _lib.ptr(mean), None, self._mode(), st)
+        return best, mean
+
+    def calc_best(self, batch, sync=True):
+        """reference :63-79 -> (best LongTensor[b] on the device, mean min-distance)."""
+        batch = self._prep_batch(batch)
+        best, mean = self._assign(batch, want_mean=True)
+        return best, (mean.item() if sync else mean[0])
+
+    @property
+    def is_distributed(self):
+        """reference :81-86."""
+        return (self.args is not None and self.args.computation.device == 'cuda'
+                and self.args.computation.num_gpus > 1)
+
+    def _world(self):
+        import torch.distributed as dist
+        if self.is_distributed and dist.is_available() and dist.is_initialized():
+            return dist, dist.get_world_size()
+        return None, 1
+
+    def initialize(self):
+        """reference :88-92 -- average the independently drawn inits over ranks."""
+        dist, world = self._world()
+        if dist is not None and world > 1:
+            for t in (self.centers, self.counts):
+                dist.all_reduce(t)
+                t.mul_(1.0 / world)
+
+    def add(self, batch, sync=True):
+        """reference :94-129 (fast parallel update) -> mean min-distance of the batch."""
+        if self.sequential:
+            raise NotImplementedError("sequential=True (reference :103-109, disabled by default) is not provided")
+        batch = self._prep_batch(batch)
+        dev = self._device()
+        k, d = self.centers.shape
+        b = batch.shape[0]
+        dist, world = self._world()
+        lr = self.lr(self.count) if callable(self.lr) else self.lr
+        best, mean = self._assign(batch, want_mean=True)
+        ws = self._workspace(b)
+        counts_b = torch.empty(k, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.call("acav_kmeans_histogram", ws, _lib.ptr(best), b, _lib.ptr(counts_b), st)       # :113
+            if world > 1:
+                dist.all_reduce(counts_b)                                                           # :114-115
+                deltas = torch.empty(k, d, dtype=torch.float32, device=dev)
+                _lib.call("acav_kmeans_update_local", ws, _lib.ptr(batch), b, batch.stride(0),
+                          _lib.ptr(counts_b), float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts),
+                          _lib.ptr(deltas), _lib.ptr(self._fallback_dev), st)                       # :116-123
+                dist.all_reduce(deltas)                                                             # :125-126
+                _lib.call("acav_kmeans_apply_deltas", _lib.ptr(self.centers), _lib.ptr(deltas), k * d, st)
+            else:
+                _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(batch), b, batch.stride(0),
+                          _lib.ptr(counts_b), float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts),
+                          _lib.ptr(self._fallback_dev), st)                                         # :116-127
+        self.count += b * world                                                                     # :128
+        self.last_best = best
+        return mean.item() if sync else mean[0]

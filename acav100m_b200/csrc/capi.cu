@@ -1,0 +1,298 @@
+// extern "C" surface of libacav_b200.so (declared in include/acav_b200.h).
+#include <new>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace acav;
+
+struct acav_kmeans {
+    int32_t k, d;
+    int64_t max_batch;
+    int32_t sm_count;
+    int64_t bytes;
+    // assignment scratch
+    float *xn, *cn, *mind;
+    // partition scratch
+    uint32_t *blockhist, *lrank, *total, *seg_start, *sorted_rows;
+    float *lr_eff;
+    bool partition_valid;
+    int64_t partition_rows;
+};
+
+struct acav_mi {
+    MiState s;
+    int64_t max_picks;
+    int32_t sm_count;
+    float *consts_dev;
+    bool loaded, tabled;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, size_t n, int64_t *bytes) {
+    *p = nullptr;
+    size_t sz = sizeof(T) * (n ? n : 1);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), sz);
+    if (e != cudaSuccess) return (int)e;
+    if (bytes) *bytes += (int64_t)sz;
+    return 0;
+}
+
+int query_sm_count(int32_t *out) {
+    int dev = 0;
+    ACAV_CUDA_TRY(cudaGetDevice(&dev));
+    int n = 0;
+    ACAV_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    *out = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int acav_abi_version(void) { return ACAV_B200_ABI_VERSION; }
+
+const char *acav_status_string(int status) {
+    switch (status) {
+        case ACAV_OK: return "ok";
+        case ACAV_E_INVALID: return "acav: invalid argument";
+        case ACAV_E_UNSUPPORTED: return "acav: unsupported shape or alignment";
+        case ACAV_E_STATE: return "acav: call order violated";
+        case ACAV_E_NO_DEVICE: return "acav: no sm_100 device";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "acav: unknown status";
+}
+
+int acav_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    ACAV_CUDA_TRY(cudaGetDevice(&dev));
+    int v = 0;
+    if (sm_count) { ACAV_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+    if (cc_major) { ACAV_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+    if (cc_minor) { ACAV_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- k-means ------------------- */
+
+int acav_kmeans_destroy(acav_kmeans_t *h) {
+    if (!h) return 0;
+    cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind);
+    cudaFree(h->blockhist); cudaFree(h->lrank); cudaFree(h->total); cudaFree(h->seg_start);
+    cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
+    delete h;
+    return 0;
+}
+
+int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_batch) {
+    if (!out || k <= 0 || d <= 0 || max_batch < 0) return ACAV_E_INVALID;
+    if (max_batch >= (int64_t)1 << 31) return ACAV_E_UNSUPPORTED;
+    *out = nullptr;
+    acav_kmeans *h = new (std::nothrow) acav_kmeans();
+    if (!h) return (int)cudaErrorMemoryAllocation;
+    h->k = k; h->d = d; h->max_batch = max_batch; h->bytes = 0;
+    h->partition_valid = false; h->partition_rows = 0;
+    int rc = query_sm_count(&h->sm_count);
+    const int64_t nblk = ceil_div(max_batch, 512);
+    if (!rc) rc = dev_alloc(&h->xn, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->cn, (size_t)k, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->mind, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->blockhist, (size_t)(nblk * k), &h->bytes);
+    if (!rc) rc = dev_alloc(&h->lrank, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->total, (size_t)k, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->seg_start, (size_t)k + 1, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->sorted_rows, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->lr_eff, 1, &h->bytes);
+    if (rc) { acav_kmeans_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int64_t acav_kmeans_workspace_bytes(const acav_kmeans_t *h) { return h ? h->bytes : 0; }
+
+int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                       const float *centers, const float *counts,
+                       float underused_threshold, float reinit_r,
+                       int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
+                       int32_t mode, void *stream) {
+    if (!h || !x || !centers || !counts || !best || b < 0 || ldx < h->d) return ACAV_E_INVALID;
+    if (b > h->max_batch) return ACAV_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == ACAV_ASSIGN_EXACT) {
+        int rc = launch_row_norm2(x, b, h->d, ldx, nullptr, h->xn, st);
+        if (!rc) rc = launch_row_norm2(centers, h->k, h->d, h->d, nullptr, h->cn, st);
+        float *mind = min_dist ? min_dist : h->mind;
+        if (!rc) rc = launch_assign_exact(x, ldx, nullptr, b, centers, h->k, h->d, h->xn, h->cn, counts,
+                                          underused_threshold, reinit_r, best, mind, st);
+        if (!rc && mean_dist) rc = launch_mean(mind, b, mean_dist, st);
+        if (!rc && n_refined) ACAV_CUDA_TRY(cudaMemsetAsync(n_refined, 0, sizeof(int32_t), st));
+        return rc;
+    }
+    return ACAV_E_UNSUPPORTED;
+}
+
+int acav_kmeans_assign_noise(const float *noise, int32_t k, int64_t b,
+                             int64_t *best, float *min_dist, float *mean_dist, void *stream) {
+    if (!noise || !best || k <= 0 || b < 0) return ACAV_E_INVALID;
+    if (mean_dist && !min_dist) return ACAV_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_assign_noise(noise, k, b, best, min_dist, st);
+    if (!rc && mean_dist) rc = launch_mean(min_dist, b, mean_dist, st);
+    return rc;
+}
+
+int acav_kmeans_histogram(acav_kmeans_t *h, const int64_t *best, int64_t b, float *counts_b, void *stream) {
+    if (!h || !best || !counts_b || b < 0 || b > h->max_batch) return ACAV_E_INVALID;
+    int rc = launch_partition(best, b, h->k, h->blockhist, h->lrank, h->total, h->seg_start, h->sorted_rows,
+                              counts_b, (cudaStream_t)stream);
+    h->partition_valid = (rc == 0);
+    h->partition_rows = b;
+    return rc;
+}
+
+static int update_common(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, const float *counts_b,
+                         double lr, float *centers, float *counts, float *deltas, int32_t *fallback,
+                         cudaStream_t st) {
+    if (!h || !x || !counts_b || !centers || !counts || ldx < h->d) return ACAV_E_INVALID;
+    if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
+    int rc = launch_effective_lr(counts_b, h->k, lr, h->lr_eff, fallback, st);
+    if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, counts_b, h->lr_eff, centers,
+                                counts, deltas, st);
+    h->partition_valid = false;
+    return rc;
+}
+
+int acav_kmeans_update_fused(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                             const float *counts_b, double lr,
+                             float *centers, float *counts, int32_t *fallback, void *stream) {
+    return update_common(h, x, b, ldx, counts_b, lr, centers, counts, nullptr, fallback, (cudaStream_t)stream);
+}
+
+int acav_kmeans_update_local(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                             const float *counts_b_global, double lr,
+                             float *centers, float *counts, float *deltas, int32_t *fallback, void *stream) {
+    if (!deltas) return ACAV_E_INVALID;
+    return update_common(h, x, b, ldx, counts_b_global, lr, centers, counts, deltas, fallback, (cudaStream_t)stream);
+}
+
+int acav_kmeans_apply_deltas(float *centers, const float *deltas, int64_t n, void *stream) {
+    if (!centers || !deltas || n < 0) return ACAV_E_INVALID;
+    return launch_apply_deltas(centers, deltas, n, (cudaStream_t)stream);
+}
+
+/* ---------------------------------------------------------------- greedy MI ----------------- */
+
+int acav_mi_destroy(acav_mi_t *h) {
+    if (!h) return 0;
+    MiState &s = h->s;
+    cudaFree(s.cells); cudaFree(s.n_cells); cudaFree(s.a_cols); cudaFree(s.b_rows); cudaFree(s.gain);
+    cudaFree(s.col_term); cudaFree(s.row_term); cudaFree(s.sums); cudaFree(s.key); cudaFree(h->consts_dev);
+    delete h;
+    return 0;
+}
+
+int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t max_picks, int64_t pos_base) {
+    if (!out || w < 0 || k_a <= 0 || k_v <= 0 || max_picks < 0 || pos_base < 0) return ACAV_E_INVALID;
+    if (k_a > 65535 || k_v > 65535) return ACAV_E_UNSUPPORTED;            // 2 x uint16 packing, 0xFFFF.. = tombstone
+    if (pos_base + w >= 0xFFFFFFFFll) return ACAV_E_UNSUPPORTED;          // positions live in 32 bits of the key
+    if (max_picks >= (1ll << 24)) return ACAV_E_UNSUPPORTED;              // fp32 counts must stay exact integers
+    *out = nullptr;
+    acav_mi *h = new (std::nothrow) acav_mi();
+    if (!h) return (int)cudaErrorMemoryAllocation;
+    MiState &s = h->s;
+    s = MiState();
+    s.w = w; s.k_a = k_a; s.k_v = k_v; s.pos_base = pos_base; s.logs = nullptr; s.n_logs = 0;
+    h->max_picks = max_picks; h->loaded = false; h->tabled = false; h->consts_dev = nullptr;
+    int rc = query_sm_count(&h->sm_count);
+    const size_t cells = (size_t)k_a * k_v;
+    if (!rc) rc = dev_alloc(&s.cells, (size_t)w + 4, nullptr);
+    if (!rc) rc = dev_alloc(&s.n_cells, cells, nullptr);
+    if (!rc) rc = dev_alloc(&s.a_cols, (size_t)k_v, nullptr);
+    if (!rc) rc = dev_alloc(&s.b_rows, (size_t)k_a, nullptr);
+    if (!rc) rc = dev_alloc(&s.gain, cells, nullptr);
+    if (!rc) rc = dev_alloc(&s.col_term, (size_t)k_v, nullptr);
+    if (!rc) rc = dev_alloc(&s.row_term, (size_t)k_a, nullptr);
+    if (!rc) rc = dev_alloc(&s.sums, 8, nullptr);
+    if (!rc) rc = dev_alloc(&s.key, 2, nullptr);
+    if (!rc) rc = dev_alloc(&h->consts_dev, 8, nullptr);
+    if (rc) { acav_mi_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int acav_mi_load_candidates(acav_mi_t *h, const int64_t *cells, void *stream) {
+    if (!h || (!cells && h->s.w > 0)) return ACAV_E_INVALID;
+    int rc = launch_mi_pack(cells, h->s.w, h->s.cells, (cudaStream_t)stream);
+    h->loaded = (rc == 0);
+    return rc;
+}
+
+int acav_mi_set_tables(acav_mi_t *h, const float *logs, int64_t n_logs, const float *consts, void *stream) {
+    if (!h || !logs || !consts || n_logs < h->max_picks + 3) return ACAV_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->s.logs = logs; h->s.n_logs = n_logs;
+    ACAV_CUDA_TRY(cudaMemcpyAsync(h->consts_dev, consts, 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+    ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `consts` is pageable host memory owned by the caller
+    int rc = launch_mi_reset(h->s, h->consts_dev, st);
+    h->tabled = (rc == 0);
+    return rc;
+}
+
+int acav_mi_add_sample(acav_mi_t *h, int32_t c1, int32_t c2, void *stream) {
+    if (!h || c1 < 0 || c2 < 0 || c1 >= h->s.k_a || c2 >= h->s.k_v) return ACAV_E_INVALID;
+    if (!h->tabled) return ACAV_E_STATE;
+    return launch_mi_add_sample(h->s, c1, c2, (cudaStream_t)stream);
+}
+
+int acav_mi_local_best(acav_mi_t *h, uint64_t *key_cell, void *stream) {
+    if (!h || !key_cell) return ACAV_E_INVALID;
+    if (!h->tabled || !h->loaded) return ACAV_E_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_mi_gain_table(h->s, st);
+    if (!rc) rc = launch_mi_scan(h->s, h->sm_count, st);
+    if (!rc) rc = launch_mi_emit(h->s, reinterpret_cast<unsigned long long *>(key_cell), st);
+    return rc;
+}
+
+int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n, int64_t *out_pos, float *out_gain,
+                  void *stream) {
+    if (!h || !key_cells || n <= 0) return ACAV_E_INVALID;
+    if (!h->tabled || !h->loaded) return ACAV_E_STATE;
+    return launch_mi_apply(h->s, reinterpret_cast<const unsigned long long *>(key_cells), n, out_pos, out_gain,
+                           (cudaStream_t)stream);
+}
+
+int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t mode, void *stream) {
+    if (!h || n_picks < 0 || (n_picks > 0 && (!out_pos || !out_gain))) return ACAV_E_INVALID;
+    if (!h->tabled || !h->loaded) return ACAV_E_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == ACAV_MI_LOOP_KERNELS) {
+        for (int64_t it = 0; it < n_picks; ++it) {
+            int rc = launch_mi_gain_table(h->s, st);
+            if (!rc) rc = launch_mi_scan(h->s, h->sm_count, st);
+            if (!rc) rc = launch_mi_apply(h->s, nullptr, 0, out_pos + it, out_gain + it, st);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    return ACAV_E_UNSUPPORTED;
+}
+
+int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows, float *sums,
+                       void *stream) {
+    if (!h) return ACAV_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const MiState &s = h->s;
+    if (n_cells) ACAV_CUDA_TRY(cudaMemcpyAsync(n_cells, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
+    if (a_cols) ACAV_CUDA_TRY(cudaMemcpyAsync(a_cols, s.a_cols, sizeof(uint32_t) * (size_t)s.k_v, cudaMemcpyDeviceToDevice, st));
+    if (b_rows) ACAV_CUDA_TRY(cudaMemcpyAsync(b_rows, s.b_rows, sizeof(uint32_t) * (size_t)s.k_a, cudaMemcpyDeviceToDevice, st));
+    if (sums) ACAV_CUDA_TRY(cudaMemcpyAsync(sums, s.sums, sizeof(float) * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// Shared device/host helpers for libacav_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/acav_b200.h"
+
+#define ACAV_CUDA_TRY(expr)                                  \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return (int)_e;               \
+    } while (0)
+
+#define ACAV_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        cudaError_t _e = cudaPeekAtLastError();              \
+        if (_e != cudaSuccess) return (int)_e;               \
+    } while (0)
+
+namespace acav {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// fp32 -> uint32 whose unsigned order equals the float order (-0 canonicalised to +0).
+__device__ __forceinline__ uint32_t orderable(float s) {
+    if (s == 0.0f) s = 0.0f;
+    uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// (score, position) -> key; larger key = larger score, then smaller position.  0 = "nothing".
+__device__ __forceinline__ unsigned long long make_key(float s, uint32_t pos) {
+    return ((unsigned long long)orderable(s) << 32) | (unsigned long long)(0xFFFFFFFFu - pos);
+}
+__device__ __forceinline__ uint32_t key_pos(unsigned long long key) {
+    return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+}
+__device__ __forceinline__ float key_score(unsigned long long key) {
+    return from_orderable((uint32_t)(key >> 32));
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace acav

@@ -1,0 +1,56 @@
+// Internal launch wrappers shared between the translation units of libacav_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acav {
+
+// kmeans_exact.cu
+int launch_row_norm2(const float *x, int64_t rows, int32_t d, int64_t ldx, const int32_t *rowlist,
+                     float *out, cudaStream_t st);
+int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int64_t nrows,
+                        const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
+                        const float *counts, float thr, float r, int64_t *best, float *mind,
+                        cudaStream_t st);
+int launch_assign_noise(const float *noise, int32_t k, int64_t b, int64_t *best, float *mind,
+                        cudaStream_t st);
+int launch_mean(const float *v, int64_t n, float *out, cudaStream_t st);
+
+// kmeans_update.cu
+int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockhist, uint32_t *lrank,
+                     uint32_t *total, uint32_t *seg_start, uint32_t *sorted_rows, float *counts_b,
+                     cudaStream_t st);
+int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_eff, int32_t *fallback,
+                        cudaStream_t st);
+int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
+                  const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
+                  float *centers, float *counts, float *deltas, cudaStream_t st);
+int launch_apply_deltas(float *centers, const float *deltas, int64_t n, cudaStream_t st);
+
+// mi_scan.cu
+struct MiState {                 // device-resident table + running sums of one clustering pair
+    uint32_t *cells;             // [w] packed (c1 << 16 | c2); 0xFFFFFFFF = removed
+    uint32_t *n_cells;           // [k_a * k_v] contingency counts  N   (mi.py cache['N'])
+    uint32_t *a_cols;            // [k_v] column marginals           a   (cache['a'], index c2)
+    uint32_t *b_rows;            // [k_a] row marginals              b   (cache['b'], index c1)
+    float *gain;                 // [k_a * k_v] per-iteration score of adding one sample to a cell
+    float *col_term;             // [k_v]
+    float *row_term;             // [k_a]
+    float *sums;                 // {NlogN, aloga, blogb, n, fN0, fa0}
+    const float *logs;           // torch-CPU log table
+    int64_t n_logs;
+    unsigned long long *key;     // [2] running argmax key + packed cell of the local winner
+    int64_t w;
+    int64_t pos_base;
+    int32_t k_a, k_v;
+};
+int launch_mi_pack(const int64_t *cells, int64_t w, uint32_t *packed, cudaStream_t st);
+int launch_mi_reset(const MiState &s, const float *consts_dev, cudaStream_t st);
+int launch_mi_add_sample(const MiState &s, int32_t c1, int32_t c2, cudaStream_t st);
+int launch_mi_gain_table(const MiState &s, cudaStream_t st);
+int launch_mi_scan(const MiState &s, int sm_count, cudaStream_t st);
+int launch_mi_emit(const MiState &s, unsigned long long *out, cudaStream_t st);
+int launch_mi_apply(const MiState &s, const unsigned long long *key_cells, int32_t n,
+                    int64_t *out_pos, float *out_gain, cudaStream_t st);
+
+}  // namespace acav

@@ -1,0 +1,264 @@
+// Centroid update of the mini-batch SGD k-means (the "fast parallel update" branch of KMeans.add,
+// clustering/code/sgd_clustering.py:113-127).
+//
+// The reference accumulates  deltas[best[j]] += fl32(x_j * lr)  with torch-scatter's scatter_add;
+// its CPU kernel walks the rows in order, so every centroid's sum is a strict row-order fp32 chain.
+// To be bit-identical we (1) partition the batch rows by centroid with a STABLE counting sort and
+// (2) let one thread own one (centroid, 4 columns) slot and add its member rows sequentially.  Reads
+// are coalesced across columns; the only serial dependence is the fp32 add chain itself.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace acav {
+
+constexpr int kRankRows = 512;   // rows per block in the rank / scatter kernels
+
+// Stable local rank of every row among the rows of the same centroid inside its 512-row block, and
+// the block's histogram.  Warps take turns in row order so ranks follow row order.
+__global__ void __launch_bounds__(kRankRows)
+km_block_rank_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
+                     uint32_t *__restrict__ blockhist, uint32_t *__restrict__ lrank) {
+    extern __shared__ uint32_t hist[];
+    for (int32_t i = threadIdx.x; i < k; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * kRankRows + threadIdx.x;
+    int64_t key = -1;
+    if (row < b) {
+        key = best[row];
+        if (key < 0 || key >= k) key = -1;          // out-of-range ids are ignored (never produced)
+    }
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    for (int w = 0; w < kRankRows / kWarp; ++w) {
+        if (warp == w) {
+            unsigned m = __match_any_sync(0xffffffffu, key);
+            int leader = __ffs(m) - 1;
+            uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            uint32_t base = 0;
+            if (key >= 0 && lane == leader) {
+                base = hist[key];
+                hist[key] = base + __popc(m);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (key >= 0) lrank[row] = base + rank;
+        }
+        __syncthreads();
+    }
+    uint32_t *dst = blockhist + (int64_t)blockIdx.x * k;
+    for (int32_t i = threadIdx.x; i < k; i += blockDim.x) dst[i] = hist[i];
+}
+
+// Per centroid: exclusive prefix over blocks (in place) and the batch histogram (fp32, :113).
+__global__ void km_block_prefix_kernel(uint32_t *__restrict__ blockhist, int32_t nblk, int32_t k,
+                                       uint32_t *__restrict__ total, float *__restrict__ counts_b) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    uint32_t run = 0;
+    for (int32_t blk = 0; blk < nblk; ++blk) {
+        uint32_t t = blockhist[(int64_t)blk * k + i];
+        blockhist[(int64_t)blk * k + i] = run;
+        run += t;
+    }
+    total[i] = run;
+    counts_b[i] = (float)run;
+}
+
+// seg_start[0..k] = exclusive scan of total[0..k) (single block, chunks of 1024 with carry).
+__global__ void __launch_bounds__(1024)
+km_segment_start_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t *__restrict__ seg_start) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+    for (int32_t base = 0; base < k; base += 1024) {
+        int32_t i = base + threadIdx.x;
+        uint32_t v = i < k ? total[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < kWarp; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == kWarp - 1) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sums[lane];
+            uint32_t winc = ws;
+#pragma unroll
+            for (int o = 1; o < kWarp; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sums[lane] = winc - ws;           // exclusive warp offsets
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[warp] + inc - v;
+        if (i < k) seg_start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg_start[k] = carry;
+}
+
+__global__ void __launch_bounds__(kRankRows)
+km_scatter_rows_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
+                       const uint32_t *__restrict__ blockhist, const uint32_t *__restrict__ lrank,
+                       const uint32_t *__restrict__ seg_start, uint32_t *__restrict__ sorted_rows) {
+    const int64_t row = (int64_t)blockIdx.x * kRankRows + threadIdx.x;
+    if (row >= b) return;
+    int64_t key = best[row];
+    if (key < 0 || key >= k) return;
+    uint32_t dst = seg_start[key] + blockhist[(int64_t)blockIdx.x * k + key] + lrank[row];
+    sorted_rows[dst] = (uint32_t)row;
+}
+
+// lr fallback of sgd_clustering.py:116-119 evaluated on the device in the same python-float (double)
+// arithmetic:  if max(counts_b) * lr >= 1.0: lr = 0.5 / max(counts_b); fallback += 1.
+// `lr * counts` in the reference is an fp32 tensor times a python scalar: torch casts the scalar to
+// fp32 first, so lr_eff is stored as float.
+__global__ void __launch_bounds__(1024)
+km_effective_lr_kernel(const float *__restrict__ counts_b, int32_t k, double lr,
+                       float *__restrict__ lr_eff, int32_t *__restrict__ fallback) {
+    __shared__ float wmax[32];
+    float m = 0.f;
+    for (int32_t i = threadIdx.x; i < k; i += blockDim.x) m = fmaxf(m, counts_b[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x % kWarp == 0) wmax[threadIdx.x / kWarp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.f;
+        for (int w = 0; w < (int)(blockDim.x / kWarp); ++w) mm = fmaxf(mm, wmax[w]);
+        double eff = lr;
+        if ((double)mm * lr >= 1.0) {
+            eff = 0.5 / (double)mm;
+            if (fallback) *fallback += 1;
+        }
+        *lr_eff = (float)eff;
+    }
+}
+
+// One thread = one centroid x VEC columns.  FUSED: centers = centers*decay + delta (:121,:127);
+// otherwise centers *= decay and the local delta is written out for the all-reduce (:125-126).
+template <int VEC, bool FUSED>
+__global__ void __launch_bounds__(128)
+km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
+                 const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
+                 const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
+                 float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas) {
+    const int32_t c = blockIdx.x;
+    const int32_t col = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+    const float lr = *lr_eff_p;
+    const float cb = counts_b[c];
+    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
+    if (col >= d) return;
+    const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    constexpr int kUnroll = 8;
+    uint32_t s = lo;
+    for (; s + kUnroll <= hi; s += kUnroll) {
+        float vals[kUnroll][VEC];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const float *p = x + (int64_t)sorted_rows[s + u] * ldx + col;
+            if constexpr (VEC == 4) {
+                float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+                vals[u][0] = t.x; vals[u][1] = t.y; vals[u][2] = t.z; vals[u][3] = t.w;
+            } else {
+                vals[u][0] = __ldg(p);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(vals[u][v], lr));   // :123
+    }
+    for (; s < hi; ++s) {
+        const float *p = x + (int64_t)sorted_rows[s] * ldx + col;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(__ldg(p + v), lr));
+    }
+    const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                    // :121
+    float *cp = centers + (int64_t)c * d + col;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        float scaled = __fmul_rn(cp[v], decay);
+        if (FUSED) {
+            cp[v] = __fadd_rn(scaled, acc[v]);                                                 // :127
+        } else {
+            cp[v] = scaled;
+            deltas[(int64_t)c * d + col + v] = acc[v];
+        }
+    }
+}
+
+__global__ void km_apply_deltas_kernel(float *__restrict__ centers, const float *__restrict__ deltas,
+                                       int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) centers[i] = __fadd_rn(centers[i], deltas[i]);
+}
+
+int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockhist, uint32_t *lrank,
+                     uint32_t *total, uint32_t *seg_start, uint32_t *sorted_rows, float *counts_b,
+                     cudaStream_t st) {
+    const int32_t nblk = (int32_t)ceil_div(b, kRankRows);
+    const size_t smem = (size_t)k * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return ACAV_E_UNSUPPORTED;
+        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_block_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    }
+    if (nblk > 0) {
+        km_block_rank_kernel<<<nblk, kRankRows, smem, st>>>(best, b, k, blockhist, lrank);
+        ACAV_LAUNCH_CHECK();
+    }
+    km_block_prefix_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(blockhist, nblk, k, total, counts_b);
+    ACAV_LAUNCH_CHECK();
+    km_segment_start_kernel<<<1, 1024, 0, st>>>(total, k, seg_start);
+    ACAV_LAUNCH_CHECK();
+    if (nblk > 0) {
+        km_scatter_rows_kernel<<<nblk, kRankRows, 0, st>>>(best, b, k, blockhist, lrank, seg_start, sorted_rows);
+        ACAV_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_eff, int32_t *fallback,
+                        cudaStream_t st) {
+    km_effective_lr_kernel<<<1, 1024, 0, st>>>(counts_b, k, lr, lr_eff, fallback);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
+                  const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
+                  float *centers, float *counts, float *deltas, cudaStream_t st) {
+    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int vec = vec4 ? 4 : 1;
+    dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128 * vec));
+    if (deltas) {
+        if (vec4)
+            km_update_kernel<4, false><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas);
+        else
+            km_update_kernel<1, false><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas);
+    } else {
+        if (vec4)
+            km_update_kernel<4, true><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr);
+        else
+            km_update_kernel<1, true><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr);
+    }
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_apply_deltas(float *centers, const float *deltas, int64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    km_apply_deltas_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(centers, deltas, n);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace acav

@@ -1,0 +1,212 @@
+"""``EfficientMemMI`` -- exact greedy mutual-information selection on a B200.
+
+Mirror of the reference's ``EfficientMemMI`` (``subset_selection/code/measures/mi.py:284-412``) with
+the greedy loop of ``EfficientMI.run_greedy`` (:150-192): same constructor keywords, ``init(pairs,
+candidates)``, ``add_samples(ids)``, ``run_greedy(...) -> (S, GAIN, timelapse, LOOKUPS)``, same
+selected indices and the same fp32 scores bit for bit.  All per-iteration work (score every
+remaining candidate, first arg-max, table update, removal) happens inside ``libacav_b200.so``.
+
+Scope: one clustering pair (P = 1, the K_a x K_v audio-visual table of BASELINE.json); P > 1 raises.
+New (not in the reference): ``shard=(rank, world)`` splits the candidate list into contiguous ranges
+across ranks with one 16-byte all-gather per iteration; every rank returns the same S and GAIN.
+"""
+import time
+
+import numpy as np
+import torch
+
+from ... import _lib
+from . import tables
+
+
+class EfficientMemMI:
+    def __init__(self, assignments, measure_type='mutual_info', average_method='arithmetic',
+                 ncentroids=20, device=None, shard=None, loop='auto', **kwargs):
+        self.average_method = average_method.lower()
+        self.ncentroids = int(ncentroids)
+        if torch.is_tensor(assignments):
+            self.assignments = assignments.to(torch.long)
+        else:
+            self.assignments = torch.from_numpy(np.asarray(assignments)).to(torch.long)   # V x D (:24)
+        self.eps = tables.EPS
+        dev = device if device not in (None, 'cpu', 'cuda') else None
+        self.device = _lib.require_cuda(dev)
+        self.shard = shard
+        self.loop = loop
+        self._engine = None
+        self._picked = 0
+
+    # -- setup -----------------------------------------------------------------------------------
+
+    def init(self, clustering_combinations, candidates):
+        """reference :27-30 -- empty table + candidate list."""
+        self.combinations = [tuple(p) for p in clustering_combinations]
+        if len(self.combinations) != 1 or len(self.combinations[0]) != 2:
+            raise NotImplementedError(
+                "the CUDA engine handles one clustering pair (P = 1); got pairs %r" % (self.combinations,))
+        self.init_candidates(candidates)
+        self.init_cache()
+
+    def init_candidates(self, candidates):
+        """``calc_N`` :285-295 -- (c1, c2) of every candidate, in list order."""
+        if torch.is_tensor(candidates):
+            self.candidate_ids = candidates.to(torch.long).cpu()
+        else:
+            self.candidate_ids = torch.as_tensor(np.asarray(candidates, dtype=np.int64))
+        W = self.candidate_ids.numel()
+        lo, hi = 0, W
+        self._dist = None
+        if self.shard is not None:
+            import torch.distributed as dist
+            rank, world = self.shard
+            lo, hi = (W * rank) // world, (W * (rank + 1)) // world
+            self._dist = dist
+        self._range = (lo, hi)
+        pair = self.combinations[0]
+        ids = self.candidate_ids[lo:hi]
+        a = self.assignments
+        if a.device.type == 'cuda':
+            cells = a.index_select(0, ids.to(a.device))[:, list(pair)].to(self.device).contiguous()
+        else:
+            cells = a.index_select(0, ids)[:, list(pair)].contiguous().to(self.device)
+        if cells.numel() and (int(cells.min()) < 0 or int(cells.max()) >= self.ncentroids):
+            raise ValueError("cluster ids must lie in [0, ncentroids)")
+        self._W = W
+        self._cells = cells
+
+    def init_from_cells(self, clustering_combinations, cells, w_global=None, lo=0, max_picks=None):
+        """Fast setup for big lists: `cells` is this rank's int64 [w, 2] tensor of (c1, c2) in list
+        order (pinned host or device memory), covering positions [lo, lo + w) of a candidate list of
+        `w_global` entries whose ids are their positions.  Skips the per-candidate python objects of
+        ``init`` (run_greedy.py:33 builds ``list(range(V))``)."""
+        self.combinations = [tuple(p) for p in clustering_combinations]
+        if len(self.combinations) != 1:
+            raise NotImplementedError("the CUDA engine handles one clustering pair (P = 1)")
+        w = cells.shape[0]
+        self._W = int(w_global) if w_global is not None else w
+        self._range = (int(lo), int(lo) + w)
+        self.candidate_ids = None
+        self._dist = None
+        if self.shard is not None:
+            import torch.distributed as dist
+            self._dist = dist
+        self._cells = cells.to(self.device, non_blocking=True).contiguous()
+        self.init_cache(max_picks=max_picks if max_picks is not None else min(self._W + 8, (1 << 24) - 8))
+
+    def launches_per_iteration(self):
+        if self._dist is not None:
+            return 4                                   # gain, scan, emit, apply (+ one NCCL all-gather)
+        return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0
+
+    def loop_name(self):
+        if self._dist is not None:
+            return "kernels+allgather"
+        return "kernels" if self._loop_mode() == _lib.MI_LOOP_KERNELS else "persistent"
+
+    def init_cache(self, max_picks=None):
+        """``init_cache`` :32-39, :297-308 on the device."""
+        self._release()
+        lo, hi = self._range
+        C = self.ncentroids
+        if max_picks is None:
+            max_picks = min(self._W + 8, (1 << 24) - 8)
+        self._max_picks = int(max_picks)
+        handle = _lib.c_vp()
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr(self.device)
+            _lib.call("acav_mi_create", _lib.ctypes.byref(handle), hi - lo, C, C, self._max_picks, lo)
+            self._engine = handle
+            _lib.call("acav_mi_load_candidates", handle, _lib.ptr(self._cells), st)
+            self._logs = tables.log_table(self._max_picks + 4).to(self.device)
+            consts = tables.empty_table_constants(C)
+            _lib.call("acav_mi_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
+                      consts.ctypes.data_as(_lib.c_vp), st)
+        self._picked = 0
+
+    def _release(self):
+        if self._engine is not None:
+            _lib.load().acav_mi_destroy(self._engine)
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    # -- operator ------------------------------------------------------------------------------
+
+    def add_samples(self, ids):
+        """reference :408-412 -- count samples into the table without selecting them."""
+        pair = self.combinations[0]
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr(self.device)
+            for idx in ids:
+                row = self.assignments[int(idx)]
+                _lib.call("acav_mi_add_sample", self._engine, int(row[pair[0]]), int(row[pair[1]]), st)
+        self._picked += len(ids)
+
+    def _loop_mode(self):
+        if self.loop in ('kernels', _lib.MI_LOOP_KERNELS):
+            return _lib.MI_LOOP_KERNELS
+        if self.loop in ('persistent', _lib.MI_LOOP_PERSISTENT):
+            return _lib.MI_LOOP_PERSISTENT
+        return _lib.MI_LOOP_KERNELS
+
+    def select(self, n_picks):
+        """Run `n_picks` greedy iterations; returns (positions int64[n] in the candidate list,
+        gains fp32[n]) as device tensors, without a host sync."""
+        if self._picked + n_picks + 2 > self._max_picks:
+            raise RuntimeError("engine was sized for %d picks" % self._max_picks)
+        pos = torch.empty(n_picks, dtype=torch.int64, device=self.device)
+        gain = torch.empty(n_picks, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr(self.device)
+            if self._dist is None:
+                _lib.call("acav_mi_run", self._engine, n_picks, _lib.ptr(pos), _lib.ptr(gain),
+                          self._loop_mode(), st)
+            else:
+                world = self.shard[1]
+                mine = torch.empty(2, dtype=torch.int64, device=self.device)
+                allp = torch.empty(world, 2, dtype=torch.int64, device=self.device)
+                for i in range(n_picks):
+                    _lib.call("acav_mi_local_best", self._engine, _lib.ptr(mine), st)
+                    self._dist.all_gather_into_tensor(allp, mine)
+                    _lib.call("acav_mi_apply", self._engine, _lib.ptr(allp), world,
+                              _lib.c_vp(pos.data_ptr() + 8 * i), _lib.c_vp(gain.data_ptr() + 4 * i), st)
+        self._picked += n_picks
+        return pos, gain
+
+    def run_greedy(self, subset_size, start_indices, intermediate_target=None,
+                   verbose=False, log_every=1, log_times=None,
+                   node_rank=None, pid=None):
+        """reference :150-192.  `start_indices` seed S but are NOT counted into the table, and the
+        loop runs ``range(len(start_indices), subset_size - 1)`` -- both kept as in the reference."""
+        S = start_indices
+        n_picks = max(subset_size - 1 - len(start_indices), 0)
+        if n_picks > self._W:
+            raise RuntimeError("cannot pick %d of %d candidates" % (n_picks, self._W))
+        t0 = time.time()
+        pos, gain = self.select(n_picks)
+        pos = pos.cpu()
+        gains = gain.cpu().tolist()
+        elapsed = time.time() - t0
+        S.extend((pos if self.candidate_ids is None else self.candidate_ids[pos]).tolist())
+        GAIN = [float(g) for g in gains]
+        timelapse = [elapsed / n_picks] * n_picks if n_picks else []
+        LOOKUPS = [0] * n_picks
+        if verbose:
+            print("Time Consumed: {} seconds".format(elapsed))
+        return (S, GAIN, timelapse, LOOKUPS)
+
+    def read_state(self):
+        """Table counts and running sums (N [C,C], a [C], b [C], {NlogN, aloga, blogb, n}) for tests."""
+        C = self.ncentroids
+        N = torch.empty(C * C, dtype=torch.int32, device=self.device)
+        a = torch.empty(C, dtype=torch.int32, device=self.device)
+        b = torch.empty(C, dtype=torch.int32, device=self.device)
+        sums = torch.empty(4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("acav_mi_read_state", self._engine, _lib.ptr(N), _lib.ptr(a), _lib.ptr(b),
+                      _lib.ptr(sums), _lib.stream_ptr(self.device))
+        return N.view(C, C).cpu(), a.cpu(), b.cpu(), sums.cpu()

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on B200: greedy-MI candidate-clips/s (+ k-means iter/s), K = 1024.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload, DESIGN.md "Measurement"):
+  * greedy MI: BASELINE config 4's candidate list -- 100 M (c_a, c_v) cluster-id pairs, K_a = K_v =
+    1024 -- PER GPU (weak scaling; larger than L2, so every iteration streams from HBM).  One step =
+    one exact greedy iteration: score every remaining candidate, first arg-max, table update, removal.
+    value = candidates scored per second over the K timed steps, summed over ranks.
+  * k-means (reported under "kmeans"): BASELINE config 3's per-GPU shard -- 1.25 M x 2048 fp32 rows
+    resident in HBM, K = 1024, per-GPU batch 8192 (global 65 536 at 8 GPUs) -- SGD steps/s via
+    KMeans.add and assignment rows/s via KMeans.calc_best.
+Inputs are synthetic (acav100m_b200.synth) and resident in HBM when the timed region starts; "e2e"
+repeats the measurement through the public API starting from pinned HOST buffers.
+`--impl reference` times the reference's CPU implementation (the oracle port; the reference is pure
+Python and does not travel to the GPU box) on the host cores for the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "greedy_mi_candidate_clips_per_sec"
+UNIT = "candidate-clips/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--k", type=int, default=1024)
+    p.add_argument("--mi-candidates", type=int, default=100_000_000, help="per GPU")
+    p.add_argument("--mi-loop", default="auto")
+    p.add_argument("--km-rows", type=int, default=1_250_000, help="per GPU, resident")
+    p.add_argument("--km-d", type=int, default=2048)
+    p.add_argument("--km-batch", type=int, default=8192, help="per GPU")
+    p.add_argument("--km-steps", type=int, default=0, help="0 = min(steps, rows/batch)")
+    p.add_argument("--km-mode", default="auto")
+    p.add_argument("--cpu-sample", type=int, default=10_000_000)
+    p.add_argument("--skip-cpu-baseline", action="store_true")
+    p.add_argument("--skip-kmeans", action="store_true")
+    p.add_argument("--skip-e2e", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist, rank, world, local
+    if n > 1:
+        raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % n)
+    torch.cuda.set_device(0)
+    return None, 0, 1, 0
+
+
+def timed(dist, fn_warm, fn_timed):
+    """barrier + sync, CUDA events around fn_timed on the current stream, max over ranks (ms)."""
+    fn_warm()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    out = fn_timed()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), out
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+
+def mi_engine(cells_src, k, rank, world, loop, w_global, lo):
+    from acav100m_b200.subset_selection import get_measure
+    shard = (rank, world) if world > 1 else None
+    m = get_measure("mem_mi")(cells_src, ncentroids=k, device="cuda", shard=shard, loop=loop)
+    m.init_from_cells([(0, 1)], cells_src, w_global=w_global, lo=lo)
+    return m
+
+
+def run_mi(args, dist, rank, world):
+    from acav100m_b200 import synth
+    W = args.mi_candidates
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cells = synth.zipf_pairs_torch(W, args.k, 1004 + rank, dev)
+    m = mi_engine(cells, args.k, rank, world, args.mi_loop, W * world, W * rank)
+    ms, _ = timed(dist, lambda: m.select(args.warmup), lambda: m.select(args.steps))
+    w_global = W * world
+    scored = sum(w_global - args.warmup - i for i in range(args.steps))
+    per_iter_bytes = 4.0 * (W - args.warmup - args.steps / 2.0) + 4.0 * args.k * args.k   # per GPU
+    res = {
+        "ms": ms, "scored": scored, "value": scored / (ms * 1e-3),
+        "us_per_iteration": ms * 1e3 / args.steps,
+        "algorithmic_bytes_per_launch": per_iter_bytes,
+        "achieved_gbs": per_iter_bytes / (ms * 1e-3 / args.steps) / 1e9,
+        "launches": m.launches_per_iteration() * args.steps,
+        "loop": m.loop_name(),
+    }
+    e2e = None
+    if not args.skip_e2e:
+        del m
+        host = torch.empty((W, 2), dtype=torch.int64, pin_memory=True)
+        host.copy_(cells)
+        del cells
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        m2 = mi_engine(host, args.k, rank, world, args.mi_loop, W * world, W * rank)
+        pos, gain = m2.select(args.steps)
+        pos_h, gain_h = pos.cpu(), gain.cpu()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        scored2 = sum(w_global - i for i in range(args.steps))
+        e2e = {"value": scored2 / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": host.numel() * 8 / args.steps,
+               "d2h_bytes_per_step": (pos_h.numel() * 8 + gain_h.numel() * 4) / args.steps,
+               "seconds": float(dt.item()),
+               "what": "EfficientMemMI built from a pinned host int64 [W,2] tensor + %d greedy iterations + "
+                       "D2H of (S, GAIN)" % args.steps}
+    return res, e2e
+
+
+def run_kmeans(args, dist, rank, world):
+    from acav100m_b200 import synth
+    from acav100m_b200.clustering import KMeans
+    import types
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n, d, k, b = args.km_rows, args.km_d, args.k, args.km_batch
+    x = synth.gaussian_mixture_torch(n, d, k, 1003 + rank, dev)
+    kargs = types.SimpleNamespace(computation=types.SimpleNamespace(device="cuda", num_gpus=world))
+    torch.manual_seed(1003)
+    km = KMeans(kargs, d, k, assign_mode=args.km_mode)
+    km.to(dev)
+    # start past warm-up from centroids near data rows (all ranks identical)
+    g = torch.Generator(device=dev).manual_seed(5)
+    seedrows = synth.gaussian_mixture_torch(k, d, k, 1003, dev)
+    km.centers.copy_(seedrows + 0.1 * torch.randn(k, d, generator=g, device=dev))
+    km.counts.fill_(float(b * world) / k)
+    km.count = 10 * k * 8
+    km.lr = 1e-2
+    nb = n // b
+    steps = args.km_steps or min(args.steps, nb)
+    warm = min(args.warmup, nb)
+
+    def run_steps(cnt, off=0):
+        for i in range(cnt):
+            j = (off + i) % nb
+            km.add(x[j * b:(j + 1) * b], sync=False)
+
+    ms_step, _ = timed(dist, lambda: run_steps(max(warm, 3)), lambda: run_steps(steps, warm))
+
+    def run_assign(cnt, off=0):
+        for i in range(cnt):
+            j = (off + i) % nb
+            km.calc_best(x[j * b:(j + 1) * b], sync=False)
+
+    ms_assign, _ = timed(dist, lambda: run_assign(3), lambda: run_assign(steps, 3))
+    pk = peaks()
+    flops = 2.0 * b * k * d
+    t_assign = ms_assign * 1e-3 / steps
+    out = {
+        "metric": "kmeans_iter_per_sec", "value": steps / (ms_step * 1e-3), "unit": "iter/s",
+        "global_batch": b * world, "k": k, "d": d, "rows_resident_per_gpu": n, "steps": steps,
+        "ms_per_step": ms_step / steps, "samples_per_sec": steps * b * world / (ms_step * 1e-3),
+        "assign_rows_per_sec": steps * b * world / (ms_assign * 1e-3),
+        "assign_ms_per_batch": ms_assign / steps, "assign_mode": km.mode_name(),
+        "gpu_launches": km.launches_per_step() * steps,
+        "roofline": {"bound": "tensor", "achieved": flops / t_assign / 1e12, "peak": pk["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": flops / t_assign / 1e12 / pk["bf16_tflops"], "traffic": None,
+                     "kernel": "k-means assign (KMeans.calc_best), 2*b*K*D flop per batch",
+                     "peak_source": pk["source"] + " bf16 burst"},
+    }
+    if not args.skip_e2e:
+        host = torch.empty((steps, b, d), dtype=torch.float32).pin_memory()
+        host.copy_(x[:steps * b].view(steps, b, d))
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        last = None
+        for i in range(steps):
+            last = km.add(host[i].to(dev, non_blocking=True), sync=False)
+        float(last)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": steps / float(dt.item()), "unit": "iter/s", "h2d_bytes_per_step": b * d * 4,
+                      "d2h_bytes_per_step": 4, "what": "KMeans.add on pinned host batches, mean distance read back"}
+    del x
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arms (oracle port of the reference; the only place bench.py touches oracle/)
+# -------------------------------------------------------------------------------------------------
+
+def cpu_mi(args, repeats, warm=1):
+    from acav100m_b200 import synth
+    from oracle import mi_oracle as mo
+    W = min(args.cpu_sample, args.mi_candidates)
+    a = synth.zipf_pairs(W, args.k, 1004)
+    threads = os.cpu_count() or 1
+    c1, c2 = a[:, 0].astype(np.int32), a[:, 1].astype(np.int32)
+    mo.scan_once_seconds(c1, c2, args.k, max(warm, 1), threads)      # warm-up scans
+    sec = mo.scan_once_seconds(c1, c2, args.k, repeats, threads)
+    return {"value": W * repeats / sec, "unit": UNIT, "cores": threads, "kind": "port", "seconds": sec,
+            "sample": "%d full scans of a %d-candidate sample (same Zipf pair distribution, K=%d) with "
+                      "oracle/mi_oracle.c, OpenMP over %d threads" % (repeats, W, args.k, threads)}
+
+
+def cpu_kmeans(args, steps):
+    from acav100m_b200 import synth
+    from oracle import kmeans_oracle as ko
+    torch.set_num_threads(os.cpu_count() or 1)
+    d, k, b = args.km_d, args.k, args.km_batch
+    x = torch.from_numpy(synth.gaussian_mixture(b * 2, d, k, 1003))
+    st = ko.new_state(d, k)
+    st.centers = x[:k].clone() if k <= len(x) else torch.from_numpy(synth.gaussian_mixture(k, d, k, 1))
+    st.count = 10 * k * 8
+    ko.sgd_step(st, x[:b])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ko.sgd_step(st, x[(i % 2) * b:(i % 2 + 1) * b])
+    sec = time.perf_counter() - t0
+    return {"value": steps / sec, "unit": "iter/s", "cores": torch.get_num_threads(), "kind": "port",
+            "samples_per_sec": steps * b / sec,
+            "sample": "%d KMeans.add steps, b=%d d=%d k=%d, torch CPU (oracle/kmeans_oracle.py)" % (steps, b, d, k)}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def config_dict(args, world):
+    return {"workload": "C4 candidate list (100M Zipf cluster-id pairs, K=1024) per GPU for greedy MI; "
+                        "C3 per-GPU shard (1.25M x 2048 fp32, K=1024, batch 8192/GPU) for k-means",
+            "mi_candidates_per_gpu": args.mi_candidates, "k": args.k, "km_rows_per_gpu": args.km_rows,
+            "km_d": args.km_d, "km_batch_per_gpu": args.km_batch, "parallelism": "shard%d" % world,
+            "l2": "candidate stream %.0f MB/GPU > 126 MB L2; k-means walks %.1f GB/GPU of resident rows"
+                  % (args.mi_candidates * 4 / 1e6, args.km_rows * args.km_d * 4 / 1e9)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    mi = cpu_mi(args, args.steps, args.warmup)        # one step = one full scan of the bounded sample
+    km = None if args.skip_kmeans else cpu_kmeans(args, max(min(args.steps, 20), 3))
+    W = min(args.cpu_sample, args.mi_candidates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mi["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * W / mi["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, args.gpus), "cpu_baseline": mi, "cpu_model": cpu_model(),
+        "e2e": {"value": mi["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "kmeans": km, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    from acav100m_b200 import _lib
+    _lib.load()
+    dist, rank, world, local = dist_setup(args.gpus)
+    sampler = ClockSampler(local)
+    sampler.start()
+    mi, e2e = run_mi(args, dist, rank, world)
+    km = None if args.skip_kmeans else run_kmeans(args, dist, rank, world)
+    clocks = sampler.stop()
+    if rank == 0:
+        pk = peaks()
+        cpu = None
+        if world == 1 and not args.skip_cpu_baseline:
+            cpu = cpu_mi(args, 200, 3)
+            if km is not None:
+                km["cpu_baseline"] = cpu_kmeans(args, 5)
+        line = {
+            "metric": METRIC, "value": mi["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": mi["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, world), "us_per_iteration": mi["us_per_iteration"],
+            "mi_loop": mi["loop"], "gpu_launches": mi["launches"] + (km["gpu_launches"] if km else 0),
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": mi["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": mi["achieved_gbs"] / pk["hbm_gbs"], "traffic": None,
+                         "kernel": "greedy-MI iteration (gain table + candidate scan + apply), per GPU",
+                         "algorithmic_bytes_per_launch": mi["algorithmic_bytes_per_launch"],
+                         "peak_source": pk["source"] + " copy bandwidth"},
+            "cpu_baseline": cpu, "cpu_model": cpu_model(), "kmeans": km, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/*
+ * acav_b200.h -- C ABI of libacav_b200.so: the sm_100a CUDA implementation of ACAV100M's two
+ * GPU-bound curation operators (mini-batch SGD k-means, exact greedy mutual-information selection).
+ *
+ * The reference (sangho-vision/acav100m) is pure Python: it has no FFI layer, its "plugin points"
+ * are the Python classes `KMeans` (clustering/code/sgd_clustering.py:10-129) and the measures
+ * returned by `get_measure` (subset_selection/code/measures/__init__.py:5-14).  Every entry point
+ * below names the reference lines it replaces; INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless marked "host";
+ *   - the caller owns every buffer; the library allocates only inside *_create handles
+ *     (freed by *_destroy);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless stated;
+ *   - return value: 0 = success, > 0 = cudaError_t, < 0 = ACAV_E_* below; functions never throw;
+ *   - one host thread per device at a time per handle.
+ */
+#ifndef ACAV_B200_H
+#define ACAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACAV_B200_ABI_VERSION 1
+
+#define ACAV_OK              0
+#define ACAV_E_INVALID      (-1)   /* bad argument (null pointer, negative size, shape mismatch)   */
+#define ACAV_E_UNSUPPORTED  (-2)   /* shape/alignment outside what the kernel was built for         */
+#define ACAV_E_STATE        (-3)   /* call order violated (e.g. run before load)                    */
+#define ACAV_E_NO_DEVICE    (-4)   /* no sm_100 device / driver entry point missing                 */
+
+int         acav_abi_version(void);
+const char *acav_status_string(int status);                 /* static string, never NULL            */
+int         acav_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * k-means (clustering/code/sgd_clustering.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct acav_kmeans acav_kmeans_t;                    /* per-(k,d) workspace, no model state  */
+
+/* Workspace for batches of up to `max_batch` rows against `k` centroids of dimension `d`.
+ * Model state (centers[k,d], counts[k]) stays in caller-owned tensors, exactly like the attributes
+ * of the reference object (sgd_clustering.py:24-26). */
+int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_batch);
+int acav_kmeans_destroy(acav_kmeans_t *h);
+int64_t acav_kmeans_workspace_bytes(const acav_kmeans_t *h);
+
+/* Assignment modes */
+#define ACAV_ASSIGN_EXACT   0      /* fp32 inputs, fp64-accumulated dot products on CUDA cores     */
+#define ACAV_ASSIGN_TENSOR  1      /* tcgen05 bf16 distance GEMM + top-2 screening + exact refine  */
+
+/* Replaces the distance branch of KMeans.calc_best (sgd_clustering.py:70-79):
+ *   dist[i,j] = (-2<c_i,x_j> + |x_j|^2) + |c_i|^2 ; rows i with counts[i] < underused_threshold
+ *   divided by reinit_r (:76-77) ; best[j] = first argmin_i ; *mean_dist = mean_j min_i dist.
+ * x: [b, d] fp32 row-major with row stride ldx (elements).  best: int64[b] (torch.long, :78).
+ * min_dist: fp32[b] or NULL.  mean_dist: fp32[1] on the device or NULL (no host sync here; the
+ * reference's .item() at :79 is the caller's choice).  n_refined: int32[1] device or NULL -- rows
+ * that went through the exact re-check in ACAV_ASSIGN_TENSOR mode. */
+int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                       const float *centers, const float *counts,
+                       float underused_threshold, float reinit_r,
+                       int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
+                       int32_t mode, void *stream);
+
+/* Replaces the warm-up branch of calc_best (sgd_clustering.py:67-68,78-79): `noise` is the [k, b]
+ * fp32 tensor the caller drew with torch.rand; best[j] = first argmin over rows. */
+int acav_kmeans_assign_noise(const float *noise, int32_t k, int64_t b,
+                             int64_t *best, float *min_dist, float *mean_dist, void *stream);
+
+/* Step 1 of the "fast parallel update" (sgd_clustering.py:113): counts_b[i] = #{j : best[j] = i}
+ * as fp32, and -- inside the workspace -- the rows of the batch partitioned by centroid in stable
+ * (row) order, which acav_kmeans_update_* consume.  In a multi-GPU run the caller all-reduces
+ * counts_b (sgd_clustering.py:114-115) before the next call. */
+int acav_kmeans_histogram(acav_kmeans_t *h, const int64_t *best, int64_t b,
+                          float *counts_b, void *stream);
+
+/* Steps 2-4 (sgd_clustering.py:116-127), single process:
+ *   lr_eff = lr, or 0.5/max(counts_b) when max(counts_b)*lr >= 1 (then ++*fallback)   [:116-119]
+ *   counts += counts_b ; centers *= (1 - counts_b*lr_eff)                              [:120-121]
+ *   centers += sum_{j: best[j]=i} fl32(x_j*lr_eff), summed in row order j             [:122-127]
+ * The row-ordered fp32 sum is what torch-scatter's CPU kernel computes, so the result is
+ * bit-identical to the reference's CPU path.  fallback: int32[1] device counter or NULL. */
+int acav_kmeans_update_fused(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                             const float *counts_b, double lr,
+                             float *centers, float *counts, int32_t *fallback, void *stream);
+
+/* Multi-GPU split of the same step: `update_local` applies the decay with the GLOBAL counts_b and
+ * writes this rank's deltas[k,d] (to be all-reduced, sgd_clustering.py:125-126);
+ * `apply_deltas` is centers += deltas (:127). */
+int acav_kmeans_update_local(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                             const float *counts_b_global, double lr,
+                             float *centers, float *counts, float *deltas, int32_t *fallback,
+                             void *stream);
+int acav_kmeans_apply_deltas(float *centers, const float *deltas, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * greedy mutual-information selection (subset_selection/code/measures/mi.py, EfficientMemMI)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct acav_mi acav_mi_t;
+
+/* Engine for one clustering pair (P = 1): a K_a x K_v contingency table and `w` candidates.
+ * `pos_base` is the global position of this engine's first candidate (multi-GPU: each rank holds a
+ * contiguous range of the candidate list, so "first index wins ties" stays global). */
+int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t max_picks,
+                   int64_t pos_base);
+int acav_mi_destroy(acav_mi_t *h);
+
+/* Candidate cells as the reference holds them (EfficientMemMI.calc_N, mi.py:285-295): int64 [w, 2]
+ * of (c1, c2), row-major, on the device.  Packed to 2 x uint16 per candidate inside the engine. */
+int acav_mi_load_candidates(acav_mi_t *h, const int64_t *cells, void *stream);
+
+/* Tables that make the fp32 arithmetic bit-identical to torch's CPU kernels:
+ *   logs[k] = log(float(k)) for k in [0, n_logs) exactly as torch.log returns it (device pointer);
+ *   consts (HOST pointer, 6 floats) = { x*log(x) of an empty table cell, of an empty marginal,
+ *   n0, NlogN0, aloga0, blogb0 } from init_cache (mi.py:32-39, 297-308).
+ * Resets the table to the empty state. */
+int acav_mi_set_tables(acav_mi_t *h, const float *logs, int64_t n_logs, const float *consts,
+                       void *stream);
+
+/* Adds one sample to the table without selecting it (EfficientMemMI.add_samples, mi.py:408-412). */
+int acav_mi_add_sample(acav_mi_t *h, int32_t c1, int32_t c2, void *stream);
+
+/* One greedy iteration split for multi-GPU use (calc_measure, mi.py:108-114):
+ *   local_best: scores every remaining local candidate (get_last :322-333, calc_MI :368-381) and
+ *               writes key_cell[0] = (orderable(score) << 32) | (0xFFFFFFFF - global_position)
+ *               (0 when no candidate remains) and key_cell[1] = (c1 << 16) | c2 of that candidate;
+ *   apply:      given the `n` (key, cell) pairs of all ranks (all-gathered by the caller; n = 1 on
+ *               one GPU) adopts the pair with the largest key -- highest score, earliest position --
+ *               (update_cache :383-389, update_mats :401-406, remove_idx_all :104-106).  Every rank
+ *               applies the same pairs; the rank owning the position tombstones the candidate.
+ *               out_pos / out_gain: one element each (device) or NULL. */
+int acav_mi_local_best(acav_mi_t *h, uint64_t *key_cell, void *stream);
+int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n,
+                  int64_t *out_pos, float *out_gain, void *stream);
+
+/* Single-GPU greedy loop (EfficientMI.run_greedy, mi.py:150-192, body of the for loop x n_picks):
+ * out_pos[i] = position in the candidate list of the i-th pick, out_gain[i] = its score.
+ * mode 0: three kernels per iteration (reference-shaped); mode 1: persistent cooperative kernel.
+ * Continues from the engine's current state. */
+#define ACAV_MI_LOOP_KERNELS     0
+#define ACAV_MI_LOOP_PERSISTENT  1
+int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain,
+                int32_t mode, void *stream);
+
+/* Introspection for tests: copies table counts (uint32 [k_a*k_v], [k_v], [k_a]) and the four running
+ * sums {NlogN, aloga, blogb, n} to device buffers (any may be NULL). */
+int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows,
+                       float *sums, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACAV_B200_H */

@@ -1,0 +1,201 @@
+"""GPU parity: CUDA k-means operator (through the C ABI) vs the oracle / reference goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from acav100m_b200 import synth
+from oracle import gen_golden, kmeans_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+KM = sorted(gen_golden.KMEANS_CASES)
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz")))
+
+
+def make_gpu_kmeans(d, k, **kw):
+    from acav100m_b200.clustering import KMeans
+    km = KMeans(None, d, k, **kw)
+    km.to("cuda")
+    return km
+
+
+def state_to_gpu(st, **kw):
+    from acav100m_b200.clustering import KMeans
+    km = KMeans(None, st.centers.shape[1], st.centers.shape[0], **kw)
+    km.centers, km.counts, km.count, km.lr = st.centers.clone(), st.counts.clone(), st.count, st.lr
+    km.reinit, km.initial_rounds = st.reinit, st.initial_rounds
+    km.to("cuda")
+    return km
+
+
+def assert_ids_match_up_to_fp32_ties(got, want, centers, x, underused=None):
+    got, want = np.asarray(got), np.asarray(want)
+    differ = got != want
+    if differ.any():
+        _, d1, d2 = ko.assign_truth_f64(centers, x, underused)
+        band = ko.fp32_ambiguity_band(centers, x)
+        assert np.all((d2 - d1)[differ] <= band[differ]), "id mismatch outside the fp32 near-tie band"
+    return int(differ.sum())
+
+
+@pytest.mark.parametrize("name", KM)
+def test_assign_exact_matches_reference_ids(golden_dir, name):
+    case, g = gen_golden.KMEANS_CASES[name], load(golden_dir, name)
+    x = synth.gaussian_mixture(case["n"], case["d"], case["k_true"], case["seed"])
+    st = ko.SgdKMeansState(centers=torch.from_numpy(g["centers"]), counts=torch.from_numpy(g["counts"]),
+                           count=int(g["count"]))
+    km = state_to_gpu(st, assign_mode="exact")
+    best, mean_d = km.calc_best(torch.from_numpy(x))
+    assert best.dtype == torch.int64 and best.is_cuda
+    n_diff = assert_ids_match_up_to_fp32_ties(best.cpu().numpy(), g["assign_best"], g["centers"], x,
+                                              ko.underused_mask(st).numpy())
+    assert n_diff <= 2
+    assert mean_d == pytest.approx(float(g["assign_mean_dist"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("name", KM)
+def test_training_trajectory_matches_reference(golden_dir, name):
+    """Whole train loop (warm-up noise from the same seeded CPU generator, lr schedule, fallback,
+    re-init scaling) through KMeans.add: centers/counts vs the reference's CPU run."""
+    case, g = gen_golden.KMEANS_CASES[name], load(golden_dir, name)
+    x = torch.from_numpy(synth.gaussian_mixture(case["n"], case["d"], case["k_true"], case["seed"]))
+    gen_golden.seed_all(case["seed"])
+    km = make_gpu_kmeans(case["d"], case["k"], assign_mode="exact", warmup_rng="cpu")
+    assert np.array_equal(km.centers.cpu().numpy(), g["init_centers"])
+    dists = []
+    for epoch in range(case["epochs"]):
+        km.lr = ko.epoch_lr(epoch)
+        for xb in gen_golden.kmeans_batches(x, case["batch"]):
+            dists.append(km.add(xb))
+    assert km.count == int(g["count"])
+    assert km.fallback == int(g["fallback"])
+    assert np.array_equal(km.counts.cpu().numpy(), g["counts"])
+    centers = km.centers.cpu().numpy()
+    if not np.array_equal(centers, g["centers"]):          # bit-exact unless an fp32 near-tie flipped
+        np.testing.assert_allclose(centers, g["centers"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(np.array(dists), g["step_mean_dist"], rtol=1e-5)
+    best, _ = km.calc_best(x)
+    assert (best.cpu().numpy() == g["assign_best"]).mean() > 0.998
+
+
+@pytest.mark.parametrize("b,d,k", [(1, 8, 1), (63, 13, 5), (64, 64, 64), (65, 88, 17), (1000, 352, 33),
+                                   (4096, 128, 300)])
+def test_update_is_bit_exact_given_assignments(b, d, k):
+    rng = np.random.RandomState(b + d + k)
+    x = torch.from_numpy((rng.standard_normal((b, d)) * 10 ** rng.uniform(-2, 2, (b, 1))).astype(np.float32))
+    best = torch.from_numpy(rng.randint(0, k, size=b).astype(np.int64))
+    if k > 2:
+        best[best == 1] = 0                                 # an empty centroid and a heavy one
+    for lr in (1e-2, 1e-3):
+        st = ko.SgdKMeansState(centers=torch.from_numpy(rng.standard_normal((k, d)).astype(np.float32)),
+                               counts=torch.from_numpy(rng.randint(0, 50, k).astype(np.float32)),
+                               count=12345, lr=lr)
+        km = state_to_gpu(st, assign_mode="exact")
+        ko.sgd_step(st, x, best=best)
+        from acav100m_b200 import _lib
+        xg, bg = x.cuda(), best.cuda()
+        counts_b = torch.empty(k, dtype=torch.float32, device="cuda")
+        ws = km._workspace(b)
+        s = _lib.stream_ptr()
+        _lib.call("acav_kmeans_histogram", ws, _lib.ptr(bg), b, _lib.ptr(counts_b), s)
+        _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(xg), b, xg.stride(0), _lib.ptr(counts_b), float(lr),
+                  _lib.ptr(km.centers), _lib.ptr(km.counts), _lib.ptr(km._fallback_dev), s)
+        assert np.array_equal(counts_b.cpu().numpy(), np.bincount(best.numpy(), minlength=k).astype(np.float32))
+        assert np.array_equal(km.counts.cpu().numpy(), st.counts.numpy())
+        assert np.array_equal(km.centers.cpu().numpy(), st.centers.numpy()), "row-order fp32 sum must be bit-exact"
+        assert km.fallback == st.fallback
+
+
+def test_split_update_equals_fused():
+    """update_local + apply_deltas (the multi-GPU split) reproduces update_fused bit for bit."""
+    from acav100m_b200 import _lib
+    rng = np.random.RandomState(3)
+    b, d, k = 3000, 96, 40
+    x = torch.from_numpy(rng.standard_normal((b, d)).astype(np.float32)).cuda()
+    best = torch.from_numpy(rng.randint(0, k, size=b).astype(np.int64)).cuda()
+    c0 = torch.from_numpy(rng.standard_normal((k, d)).astype(np.float32))
+    outs = []
+    for split in (False, True):
+        st = ko.SgdKMeansState(centers=c0.clone(), counts=torch.zeros(k), count=999)
+        km = state_to_gpu(st)
+        ws = km._workspace(b)
+        s = _lib.stream_ptr()
+        counts_b = torch.empty(k, dtype=torch.float32, device="cuda")
+        _lib.call("acav_kmeans_histogram", ws, _lib.ptr(best), b, _lib.ptr(counts_b), s)
+        if split:
+            deltas = torch.empty(k, d, dtype=torch.float32, device="cuda")
+            _lib.call("acav_kmeans_update_local", ws, _lib.ptr(x), b, d, _lib.ptr(counts_b), 0.01,
+                      _lib.ptr(km.centers), _lib.ptr(km.counts), _lib.ptr(deltas), None, s)
+            _lib.call("acav_kmeans_apply_deltas", _lib.ptr(km.centers), _lib.ptr(deltas), k * d, s)
+        else:
+            _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(x), b, d, _lib.ptr(counts_b), 0.01,
+                      _lib.ptr(km.centers), _lib.ptr(km.counts), None, s)
+        outs.append(km.centers.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_update_requires_histogram_first():
+    from acav100m_b200 import _lib
+    km = make_gpu_kmeans(8, 4)
+    ws = km._workspace(16)
+    x = torch.zeros(16, 8, device="cuda")
+    cb = torch.zeros(4, device="cuda")
+    with pytest.raises(_lib.AcavError) as e:
+        _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(x), 16, 8, _lib.ptr(cb), 0.01, _lib.ptr(km.centers),
+                  _lib.ptr(km.counts), None, _lib.stream_ptr())
+    assert e.value.status == -3
+
+
+@pytest.mark.parametrize("k,b", [(1, 1), (16, 32), (37, 1000), (256, 4097)])
+def test_warmup_noise_assign_is_first_argmin(k, b):
+    from acav100m_b200 import _lib
+    g = torch.Generator().manual_seed(k * b)
+    noise = torch.rand(k, b, generator=g)
+    noise[:, ::7] = noise[0, ::7]                           # whole-column ties -> index 0 must win
+    want_d, want_i = noise.min(axis=0)
+    ng = noise.cuda()
+    best = torch.empty(b, dtype=torch.int64, device="cuda")
+    mind = torch.empty(b, dtype=torch.float32, device="cuda")
+    mean = torch.empty(1, dtype=torch.float32, device="cuda")
+    _lib.call("acav_kmeans_assign_noise", _lib.ptr(ng), k, b, _lib.ptr(best), _lib.ptr(mind), _lib.ptr(mean),
+              _lib.stream_ptr())
+    assert torch.equal(best.cpu(), want_i)
+    assert torch.equal(mind.cpu(), want_d)
+    assert mean.item() == pytest.approx(want_d.mean().item(), rel=1e-6)
+
+
+@pytest.mark.parametrize("b,d,k", [(1, 3, 2), (5, 7, 3), (130, 70, 129), (513, 2304, 20)])
+def test_assign_exact_ragged_shapes_and_ties(b, d, k):
+    rng = np.random.RandomState(b * 31 + d)
+    c = rng.standard_normal((k, d)).astype(np.float32)
+    c[k - 1] = c[0]                                          # duplicate centroid: lower index wins
+    x = (c[rng.randint(0, k, size=b)] + 0.01 * rng.standard_normal((b, d))).astype(np.float32)
+    counts = rng.randint(0, 100, k).astype(np.float32)
+    st = ko.SgdKMeansState(centers=torch.from_numpy(c), counts=torch.from_numpy(counts), count=40 * k)
+    km = state_to_gpu(st, assign_mode="exact")
+    best, mean_d = km.calc_best(torch.from_numpy(x))
+    under = ko.underused_mask(st).numpy()
+    want, d1, _ = ko.assign_truth_f64(c, x, under)
+    assert_ids_match_up_to_fp32_ties(best.cpu().numpy(), want, c, x, under)
+    assert (best.cpu().numpy() != k - 1).all() or under[k - 1] != under[0]
+    scale = np.abs(d1).mean() + (x.astype(np.float64) ** 2).sum(1).mean()
+    assert abs(mean_d - d1.mean()) <= 1e-5 * scale
+
+
+def test_assign_strided_batch_and_empty_batch():
+    rng = np.random.RandomState(9)
+    big = torch.from_numpy(rng.standard_normal((200, 96)).astype(np.float32)).cuda()
+    view = big[:, :64]                                       # row stride 96, d = 64
+    km = make_gpu_kmeans(64, 8, assign_mode="exact")
+    km.count = 10_000
+    km.centers = torch.from_numpy(rng.standard_normal((8, 64)).astype(np.float32)).cuda()
+    b1, _ = km.calc_best(view)
+    b2, _ = km.calc_best(view.contiguous())
+    assert torch.equal(b1, b2)
+    best, mean = km.calc_best(torch.zeros(0, 64))
+    assert best.numel() == 0 and np.isnan(mean)

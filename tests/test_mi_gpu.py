@@ -1,0 +1,140 @@
+"""GPU parity: CUDA greedy-MI engine (through the C ABI) vs reference goldens and the C oracle."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from acav100m_b200 import synth
+from oracle import gen_golden, mi_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+P1 = [m for m in sorted(gen_golden.MI_CASES) if gen_golden.MI_CASES[m]["dcols"] == 2]
+LOOPS = ["kernels"]
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name + ".npz")))
+
+
+def gpu_measure(assignments, C, **kw):
+    from acav100m_b200.subset_selection import get_measure
+    return get_measure("mem_mi")(assignments, ncentroids=C, batch_size=20, selection_size=4, device="cuda",
+                                 keep_unselected=True, **kw)
+
+
+@pytest.mark.parametrize("loop", LOOPS)
+@pytest.mark.parametrize("name", P1)
+def test_selection_matches_reference_bits(golden_dir, name, loop):
+    g = load(golden_dir, name + "_mem_mi")
+    a = g["assignments"].astype(np.int64)
+    order = g["candidate_order"].tolist()
+    m = gpu_measure(a, int(g["c"]), loop=loop)
+    m.init([tuple(p) for p in g["pairs"].tolist()], order[1:])
+    S, GAIN, timelapse, LOOKUPS = m.run_greedy(int(g["subset"]), [order[0]])
+    assert S == g["S"].tolist()
+    assert np.array_equal(np.array(GAIN), g["GAIN"]), "fp32 scores must be bit-identical"
+    assert len(timelapse) == len(GAIN) == len(LOOKUPS) == int(g["subset"]) - 2
+
+
+@pytest.mark.parametrize("loop", LOOPS)
+@pytest.mark.parametrize("W,C,picks,seed", [(20_000, 64, 3000, 1), (100_003, 256, 1500, 2), (5000, 1024, 800, 3),
+                                            (257, 3, 256, 4)])
+def test_selection_matches_c_oracle(W, C, picks, seed, loop):
+    a = synth.zipf_pairs(W, C, seed)
+    a[0] = C - 1
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C, loop=loop)
+    m.init([(0, 1)], list(range(W)))
+    pos, gain = m.select(picks)
+    assert np.array_equal(pos.cpu().numpy(), pos_want)
+    assert np.array_equal(gain.cpu().numpy(), gain_want)
+    N, ca, rb, sums = m.read_state()
+    assert int(N.sum()) == picks and int(ca.sum()) == picks and int(rb.sum()) == picks
+    want_N = np.zeros((C, C), dtype=np.int64)
+    np.add.at(want_N, (a[pos_want, 0], a[pos_want, 1]), 1)
+    assert np.array_equal(N.numpy(), want_N)
+    assert float(sums[3]) == float(picks)
+
+
+def test_driver_matches_oracle_driver_with_shuffle():
+    import types
+    from acav100m_b200.subset_selection.run_greedy import _run_greedy
+    a = synth.zipf_pairs(3000, 32, 77)
+    a[5] = 31
+    args = types.SimpleNamespace(batch=types.SimpleNamespace(batch_size=20, selection_size=4, keep_unselected=True),
+                                 computation=types.SimpleNamespace(device="cuda"), log_every=1, log_times=None,
+                                 node_rank=None, parent_pid=None)
+    keys = [("audio", "layer_4"), ("video", "layer_4")]
+    random.seed(5)
+    S, GAIN, _ = _run_greedy(args, a, keys, None, 0.1, measure_name="mem_mi", shuffle_candidates=True)
+    S2, GAIN2 = mo.run_greedy_driver(a, subset_ratio=0.1, shuffle_candidates=True, rng=random.Random(5))
+    assert S == S2 and GAIN == GAIN2 and len(S) == 299
+
+
+def test_add_samples_counts_into_table():
+    a = synth.zipf_pairs(500, 8, 3)
+    m = gpu_measure(a, 8)
+    m.init([(0, 1)], list(range(10, 500)))
+    m.add_samples(list(range(10)))
+    N, ca, rb, sums = m.read_state()
+    want = np.zeros((8, 8), dtype=np.int64)
+    np.add.at(want, (a[:10, 0], a[:10, 1]), 1)
+    assert np.array_equal(N.numpy(), want) and float(sums[3]) == 10.0
+
+
+def test_two_engines_sharded_equal_one_engine():
+    """The multi-GPU protocol (contiguous shards, pos_base, key max, broadcast apply) driven by hand
+    on one device: two engines holding halves of the list pick exactly what one engine picks."""
+    from acav100m_b200 import _lib
+    from acav100m_b200.subset_selection.measures import tables
+    W, C, picks = 7001, 16, 600
+    a = torch.from_numpy(synth.zipf_pairs(W, C, 11))
+    single = gpu_measure(a.numpy(), C)
+    single.init([(0, 1)], list(range(W)))
+    pos_want, gain_want = single.select(picks)
+    logs = tables.log_table(W + 16).cuda()
+    consts = tables.empty_table_constants(C)
+    st = _lib.stream_ptr()
+    engines, bounds = [], [(0, 3333), (3333, W)]
+    cells = a.cuda()
+    for lo, hi in bounds:
+        h = _lib.c_vp()
+        _lib.call("acav_mi_create", _lib.ctypes.byref(h), hi - lo, C, C, W + 8, lo)
+        part = cells[lo:hi].contiguous()
+        _lib.call("acav_mi_load_candidates", h, _lib.ptr(part), st)
+        _lib.call("acav_mi_set_tables", h, _lib.ptr(logs), logs.numel(), consts.ctypes.data_as(_lib.c_vp), st)
+        engines.append(h)
+    pairs = torch.zeros(2, 2, dtype=torch.int64, device="cuda")
+    pos = torch.empty(2, picks, dtype=torch.int64, device="cuda")
+    gain = torch.empty(2, picks, dtype=torch.float32, device="cuda")
+    for i in range(picks):
+        for r, h in enumerate(engines):
+            _lib.call("acav_mi_local_best", h, _lib.c_vp(pairs.data_ptr() + 16 * r), st)
+        for r, h in enumerate(engines):
+            _lib.call("acav_mi_apply", h, _lib.ptr(pairs), 2, _lib.c_vp(pos.data_ptr() + 8 * (r * picks + i)),
+                      _lib.c_vp(gain.data_ptr() + 4 * (r * picks + i)), st)
+    for h in engines:
+        _lib.call("acav_mi_destroy", h)
+    assert torch.equal(pos[0], pos_want) and torch.equal(pos[1], pos_want)
+    assert torch.equal(gain[0], gain_want) and torch.equal(gain[1], gain_want)
+
+
+def test_errors():
+    a = synth.zipf_pairs(50, 4, 1)
+    m = gpu_measure(a, 4)
+    with pytest.raises(NotImplementedError):
+        m.init([(0, 1), (0, 1)], list(range(50)))
+    m.init([(0, 1)], list(range(1, 50)))
+    with pytest.raises(RuntimeError):
+        m.run_greedy(80, [0])
+    bad = gpu_measure(a, 3)
+    with pytest.raises(ValueError):
+        bad.init([(0, 1)], list(range(50)))
+    from acav100m_b200.subset_selection import get_measure
+    with pytest.raises(NotImplementedError):
+        get_measure("batch_mi")
+    with pytest.raises(AssertionError):
+        get_measure("nope")
