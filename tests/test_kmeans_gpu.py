@@ -156,7 +156,7 @@ def test_warmup_noise_assign_is_first_argmin(k, b):
     from acav100m_b200 import _lib
     g = torch.Generator().manual_seed(k * b)
     noise = torch.rand(k, b, generator=g)
-    noise[:, ::7] = noise[0, ::7]                           # whole-column ties -> index 0 must win
+    noise[:, ::7] = noise[0, ::7].clone()                   # whole-column ties -> index 0 must win
     want_d, want_i = noise.min(axis=0)
     ng = noise.cuda()
     best = torch.empty(b, dtype=torch.int64, device="cuda")
