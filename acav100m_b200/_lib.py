@@ -94,9 +94,13 @@ def stream_ptr(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def ptr(t):
-    """Device/host pointer of a contiguous torch tensor (or None)."""
+def ptr(t, row_strided=False):
+    """Device/host pointer of a contiguous torch tensor (or None).  `row_strided` admits a 2-D
+    tensor whose rows are dense but separated by a larger stride (the ABI takes `ldx`)."""
     if t is None:
         return None
-    assert t.is_contiguous(), "non-contiguous tensor passed to the C ABI"
+    if row_strided:
+        assert t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]
+    else:
+        assert t.is_contiguous(), "non-contiguous tensor passed to the C ABI"
     return ctypes.c_void_p(t.data_ptr())

@@ -183,7 +183,7 @@ class KMeans:
                 _lib.call("acav_kmeans_assign_noise", _lib.ptr(noise), k, b, _lib.ptr(best),
                           _lib.ptr(mind), _lib.ptr(mean), st)
             else:
-                _lib.call("acav_kmeans_assign", ws, _lib.ptr(batch), b, batch.stride(0),
+                _lib.call("acav_kmeans_assign", ws, _lib.ptr(batch, row_strided=True), b, batch.stride(0),
                           _lib.ptr(self.centers), _lib.ptr(self.counts),
                           self.underused_threshold(), float(self.reinit[1]),
                           _lib.ptr(best), None, _lib.ptr(mean), None, self._mode(), st)
@@ -234,13 +234,13 @@ class KMeans:
             if world > 1:
                 dist.all_reduce(counts_b)                                                           # :114-115
                 deltas = torch.empty(k, d, dtype=torch.float32, device=dev)
-                _lib.call("acav_kmeans_update_local", ws, _lib.ptr(batch), b, batch.stride(0),
+                _lib.call("acav_kmeans_update_local", ws, _lib.ptr(batch, row_strided=True), b, batch.stride(0),
                           _lib.ptr(counts_b), float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts),
                           _lib.ptr(deltas), _lib.ptr(self._fallback_dev), st)                       # :116-123
                 dist.all_reduce(deltas)                                                             # :125-126
                 _lib.call("acav_kmeans_apply_deltas", _lib.ptr(self.centers), _lib.ptr(deltas), k * d, st)
             else:
-                _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(batch), b, batch.stride(0),
+                _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(batch, row_strided=True), b, batch.stride(0),
                           _lib.ptr(counts_b), float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts),
                           _lib.ptr(self._fallback_dev), st)                                         # :116-127
         self.count += b * world                                                                     # :128

@@ -13,6 +13,14 @@ struct acav_kmeans {
     int64_t bytes;
     // assignment scratch
     float *xn, *cn, *mind;
+    // tensor-core path: bf16 copies, epilogue parameters, screening results, TMA descriptors
+    int32_t dp;
+    void *xb, *cb, *cparams, *partial;
+    float *cmax;
+    int32_t *amb_rows, *n_amb;
+    alignas(64) unsigned char tmap_x[128];
+    alignas(64) unsigned char tmap_c[128];
+    bool tensor_ready;
     // partition scratch
     uint32_t *blockhist, *lrank, *total, *seg_start, *sorted_rows;
     float *lr_eff;
@@ -85,6 +93,8 @@ int acav_kmeans_destroy(acav_kmeans_t *h) {
     cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind);
     cudaFree(h->blockhist); cudaFree(h->lrank); cudaFree(h->total); cudaFree(h->seg_start);
     cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
+    cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial); cudaFree(h->cmax);
+    cudaFree(h->amb_rows); cudaFree(h->n_amb);
     delete h;
     return 0;
 }
@@ -108,7 +118,22 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) rc = dev_alloc(&h->seg_start, (size_t)k + 1, &h->bytes);
     if (!rc) rc = dev_alloc(&h->sorted_rows, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->lr_eff, 1, &h->bytes);
+    // tensor-core path (bf16 operands padded to a multiple of 64 columns)
+    h->dp = (int32_t)ceil_div(d, 64) * 64;
+    h->tensor_ready = false;
+    unsigned char *raw = nullptr;
+    if (!rc) { rc = dev_alloc(&raw, (size_t)(max_batch ? max_batch : 1) * h->dp * 2, &h->bytes); h->xb = raw; }
+    if (!rc) { rc = dev_alloc(&raw, (size_t)k * h->dp * 2, &h->bytes); h->cb = raw; }
+    if (!rc) { rc = dev_alloc(&raw, (size_t)umma_param_bytes(k), &h->bytes); h->cparams = raw; }
+    if (!rc) { rc = dev_alloc(&raw, (size_t)umma_partial_bytes(max_batch ? max_batch : 1), &h->bytes); h->partial = raw; }
+    if (!rc) rc = dev_alloc(&h->cmax, 1, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->amb_rows, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->n_amb, 1, &h->bytes);
     if (rc) { acav_kmeans_destroy(h); return rc; }
+    if (max_batch > 0 &&
+        make_bf16_tensor_map(h->tmap_x, h->xb, max_batch, h->dp, 128) == 0 &&
+        make_bf16_tensor_map(h->tmap_c, h->cb, k, h->dp, umma_tile_n(k)) == 0)
+        h->tensor_ready = true;
     *out = h;
     return 0;
 }
@@ -127,13 +152,35 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
         int rc = launch_row_norm2(x, b, h->d, ldx, nullptr, h->xn, st);
         if (!rc) rc = launch_row_norm2(centers, h->k, h->d, h->d, nullptr, h->cn, st);
         float *mind = min_dist ? min_dist : h->mind;
-        if (!rc) rc = launch_assign_exact(x, ldx, nullptr, b, centers, h->k, h->d, h->xn, h->cn, counts,
+        if (!rc) rc = launch_assign_exact(x, ldx, nullptr, b, nullptr, centers, h->k, h->d, h->xn, h->cn, counts,
                                           underused_threshold, reinit_r, best, mind, st);
         if (!rc && mean_dist) rc = launch_mean(mind, b, mean_dist, st);
         if (!rc && n_refined) ACAV_CUDA_TRY(cudaMemsetAsync(n_refined, 0, sizeof(int32_t), st));
         return rc;
     }
-    return ACAV_E_UNSUPPORTED;
+    if (mode != ACAV_ASSIGN_TENSOR) return ACAV_E_INVALID;
+    if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
+    // 1. bf16 operands + reference-style norms; 2. per-centroid epilogue parameters
+    int rc = launch_prep_rows(x, b, h->d, ldx, h->dp, h->xb, h->xn, st);
+    if (!rc) rc = launch_prep_rows(centers, h->k, h->d, h->d, h->dp, h->cb, h->cn, st);
+    if (!rc) rc = launch_centroid_params(h->cn, counts, h->k, underused_threshold, reinit_r, h->cparams, h->cmax, st);
+    // 3. tcgen05 distance GEMM + top-2 screen; 4. merge / classify; 5. exact re-check of near-ties
+    int32_t n_split = 1;
+    if (!rc) rc = launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
+                                     h->partial, &n_split, st);
+    float *mind = min_dist ? min_dist : h->mind;
+    if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cmax, best, mind, h->amb_rows,
+                                        h->n_amb, st);
+    if (!rc) rc = launch_assign_exact(x, ldx, h->amb_rows, b, h->n_amb, centers, h->k, h->d, h->xn, h->cn, counts,
+                                      underused_threshold, reinit_r, best, mind, st);
+    // 6. exact distance to the assigned centroid, only when the caller wants distances back
+    if (!rc && (min_dist || mean_dist))
+        rc = launch_exact_min_dist(x, b, h->d, ldx, centers, best, h->xn, h->cn, counts, underused_threshold,
+                                   reinit_r, mind, st);
+    if (!rc && mean_dist) rc = launch_mean(mind, b, mean_dist, st);
+    if (!rc && n_refined)
+        ACAV_CUDA_TRY(cudaMemcpyAsync(n_refined, h->n_amb, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return rc;
 }
 
 int acav_kmeans_assign_noise(const float *noise, int32_t k, int64_t b,

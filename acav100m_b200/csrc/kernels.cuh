@@ -9,12 +9,30 @@ namespace acav {
 int launch_row_norm2(const float *x, int64_t rows, int32_t d, int64_t ldx, const int32_t *rowlist,
                      float *out, cudaStream_t st);
 int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int64_t nrows,
-                        const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
+                        const int32_t *nrows_dev, const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
                         const float *counts, float thr, float r, int64_t *best, float *mind,
                         cudaStream_t st);
 int launch_assign_noise(const float *noise, int32_t k, int64_t b, int64_t *best, float *mind,
                         cudaStream_t st);
 int launch_mean(const float *v, int64_t n, float *out, cudaStream_t st);
+
+// kmeans_umma.cu
+constexpr int kMaxSplit = 8;
+int make_bf16_tensor_map(void *out_map, const void *base, int64_t rows, int32_t dp, int32_t box_rows);
+int umma_tile_n(int32_t k);
+int64_t umma_partial_bytes(int64_t max_batch);
+int64_t umma_param_bytes(int32_t k);
+int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
+                     cudaStream_t st);
+int launch_centroid_params(const float *cn, const float *counts, int32_t k, float thr, float r, void *params,
+                           float *cmax, cudaStream_t st);
+int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, const void *cparams, int32_t b,
+                       int32_t k, int32_t dp, int32_t sm_count, void *partial, int32_t *n_split_out, cudaStream_t st);
+int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const float *cmax,
+                          int64_t *best, float *mind, int32_t *amb_rows, int32_t *n_amb, cudaStream_t st);
+int launch_exact_min_dist(const float *x, int64_t b, int32_t d, int64_t ldx, const float *centers,
+                          const int64_t *best, const float *xn, const float *cn, const float *counts, float thr,
+                          float r, float *mind, cudaStream_t st);
 
 // kmeans_update.cu
 int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockhist, uint32_t *lrank,

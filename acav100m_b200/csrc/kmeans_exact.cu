@@ -50,7 +50,8 @@ __device__ __forceinline__ bool better(float d, int32_t i, float bd, int32_t bi)
 // One block = 64 rows (optionally gathered through rowlist) against all k centroids.
 __global__ void __launch_bounds__(256)
 assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__restrict__ rowlist,
-                    int64_t nrows, const float *__restrict__ centers, int32_t k, int32_t d,
+                    int64_t nrows, const int32_t *__restrict__ nrows_dev,
+                    const float *__restrict__ centers, int32_t k, int32_t d,
                     const float *__restrict__ xn, const float *__restrict__ cn,
                     const float *__restrict__ counts, float thr, float r,
                     int64_t *__restrict__ best, float *__restrict__ mind) {
@@ -59,6 +60,8 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int64_t row0 = (int64_t)blockIdx.x * kTR;
+    if (nrows_dev) nrows = min(nrows, (int64_t)*nrows_dev);      // list length lives on the device
+    if (row0 >= nrows) return;
 
     // loader mapping: 64 rows x 16 k per tile, 4 scalars per thread
     const int lrow = tid / 4, lk = (tid % 4) * 4;
@@ -74,7 +77,7 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int64_t rr = row0 + ty * 4 + i;
-        xnr[i] = rr < nrows ? xn[rr] : 0.f;
+        xnr[i] = rr < nrows ? xn[rowlist ? (int64_t)rowlist[rr] : rr] : 0.f;     // xn is per source row
     }
 
     for (int32_t c0 = 0; c0 < k; c0 += kTC) {
@@ -184,12 +187,13 @@ int launch_row_norm2(const float *x, int64_t rows, int32_t d, int64_t ldx, const
 }
 
 int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int64_t nrows,
+                        const int32_t *nrows_dev,
                         const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
                         const float *counts, float thr, float r, int64_t *best, float *mind,
                         cudaStream_t st) {
     if (nrows == 0) return 0;
     assign_exact_kernel<<<(unsigned)ceil_div(nrows, kTR), 256, 0, st>>>(
-        x, ldx, rowlist, nrows, centers, k, d, xn, cn, counts, thr, r, best, mind);
+        x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, best, mind);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

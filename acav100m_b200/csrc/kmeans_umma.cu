@@ -1,0 +1,405 @@
+// k-means assignment as a tcgen05 distance-GEMM fused with a per-row top-2 (arg)min.
+//
+// Replaces the hot part of KMeans.calc_best (clustering/code/sgd_clustering.py:72-78): the reference
+// materialises dist[k, b] = -2 * centers @ batch.T + |x|^2 + |c|^2 (cuBLAS SGEMM + three elementwise
+// passes + a min reduction).  Here one persistent, warp-specialised kernel per SM does
+//     TMA (bf16 tiles of X and C, 128B-swizzled)  ->  tcgen05.mma (fp32 accumulators in TMEM)
+//     ->  epilogue straight out of TMEM: dist = s_c*|x|^2 + (a_c*acc + b_c), running (d1, i1, d2)
+// and never writes the distance matrix.  bf16 operands make the distances approximate, so the kernel
+// is a SCREEN: rows whose best/second-best margin is inside the worst-case bf16 error bound are
+// re-evaluated by the exact fp32/fp64 kernel (kmeans_exact.cu); all other rows provably have the same
+// arg-min as an exact evaluation (DESIGN.md "assignment exactness").
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected
+// lane), warps 2-5 = epilogue (TMEM lane quarter = warp_idx % 4).  Pipelines: smem full/empty ring
+// (kStages), TMEM full/empty (2 accumulator stages of 256 columns).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "sm100_ptx.cuh"
+
+namespace acav {
+
+constexpr int kBM = 128;                 // rows of X per tile (UMMA M)
+constexpr int kBK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kBNMax = 256;              // centroids per accumulator stage (UMMA N <= 256)
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;           // 16 KiB
+constexpr int kBBytesMax = kBNMax * kBK * 2;     // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kTmemCols = 512;
+constexpr int kUmmaThreads = 192;
+constexpr int kEpiThreads = 128;
+
+struct UmmaSmem {
+    // dynamic smem, 1024-byte aligned base:
+    //   [kStages][A 16K | B 32K] | cparams[2][256] float4 | barriers
+    static constexpr int kParamsOff = kStages * kStageBytes;
+    static constexpr int kBarOff = kParamsOff + 2 * kBNMax * 16;
+    static constexpr int kBytes = kBarOff + 256;
+};
+
+struct __align__(16) CentroidParam {     // dist = s*|x|^2 + (a*dot + b)
+    float a, b, s, pad;
+};
+
+struct Top2 {
+    float d1;
+    int32_t i1;
+    float d2;
+};
+
+__device__ __forceinline__ void top2_update(float dist, int32_t idx, float &d1, int32_t &i1, float &d2) {
+    d2 = fminf(d2, fmaxf(dist, d1));
+    i1 = dist < d1 ? idx : i1;
+    d1 = fminf(d1, dist);
+}
+
+// fp32 [rows, d] -> bf16 [rows, dp] (zero padded) + |row|^2 as the reference computes it (norm ** 2).
+__global__ void km_prep_rows_kernel(const float *__restrict__ x, int64_t rows, int32_t d, int64_t ldx,
+                                    int32_t dp, __nv_bfloat16 *__restrict__ xb, float *__restrict__ xn) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
+    const int lane = threadIdx.x % kWarp;
+    if (r >= rows) return;
+    const float *p = x + r * ldx;
+    __nv_bfloat16 *q = xb + r * dp;
+    double s = 0.0;
+    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec) {
+        for (int32_t i = lane * 4; i < dp; i += kWarp * 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < d) v = __ldg(reinterpret_cast<const float4 *>(p + i));
+            s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(q + i) = pk;
+        }
+    } else {
+        for (int32_t i = lane; i < dp; i += kWarp) {
+            float v = i < d ? __ldg(p + i) : 0.f;
+            s += (double)v * v;
+            q[i] = __float2bfloat16_rn(v);
+        }
+    }
+    s = warp_sum_f64(s);
+    if (lane == 0) {
+        float nrm = sqrtf((float)s);
+        xn[r] = __fmul_rn(nrm, nrm);
+    }
+}
+
+// Per-centroid epilogue parameters and max |c| (for the error bound).  scale s = 1/r for under-used
+// centroids (sgd_clustering.py:76-77), else 1.
+__global__ void __launch_bounds__(1024)
+km_centroid_params_kernel(const float *__restrict__ cn, const float *__restrict__ counts, int32_t k,
+                          float thr, float r, CentroidParam *__restrict__ params, float *__restrict__ cmax) {
+    __shared__ float wmax[32];
+    float m = 0.f;
+    for (int32_t i = threadIdx.x; i < k; i += blockDim.x) {
+        const float s = counts[i] < thr ? 1.0f / r : 1.0f;
+        CentroidParam p;
+        p.a = -2.0f * s; p.b = cn[i] * s; p.s = s; p.pad = 0.f;
+        params[i] = p;
+        m = fmaxf(m, cn[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x % kWarp == 0) wmax[threadIdx.x / kWarp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.f;
+        for (int w = 0; w < 32; ++w) mm = fmaxf(mm, wmax[w]);
+        *cmax = sqrtf(mm);
+    }
+}
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
+                      const float *__restrict__ xn, const CentroidParam *__restrict__ cparams,
+                      int32_t b, int32_t k, int32_t num_kb, int32_t bn, int32_t n_tiles, int32_t n_split,
+                      Top2 *__restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    CentroidParam *sparams = reinterpret_cast<CentroidParam *>(smem + UmmaSmem::kParamsOff);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + UmmaSmem::kBarOff);
+    uint64_t *full_bar = bars;                       // [kStages]
+    uint64_t *empty_bar = bars + kStages;            // [kStages]
+    uint64_t *tfull_bar = bars + 2 * kStages;        // [2]
+    uint64_t *tempty_bar = bars + 2 * kStages + 2;   // [2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int32_t num_m = (b + kBM - 1) / kBM;
+    const int32_t tpg = (n_tiles + n_split - 1) / n_split;        // n-tiles per group
+    const int32_t num_units = num_m * n_split;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_x);
+        ptx::prefetch_tensormap(&tmap_c);
+        for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], kEpiThreads); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t tx_bytes = (uint32_t)kABytes + (uint32_t)bn * kBK * 2;
+            for (int32_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+                const int32_t mb = u / n_split, g = u % n_split;
+                const int32_t nt_end = min(n_tiles, (g + 1) * tpg);
+                for (int32_t nt = g * tpg; nt < nt_end; ++nt) {
+                    for (int32_t kb = 0; kb < num_kb; ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                        uint8_t *sa = smem + stage * kStageBytes;
+                        ptx::tma_load_2d(sa, &tmap_x, kb * kBK, mb * kBM, &full_bar[stage]);
+                        ptx::tma_load_2d(sa + kABytes, &tmap_c, kb * kBK, nt * kBNMax, &full_bar[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(kBM, (uint32_t)bn);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int32_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+                const int32_t g = u % n_split;
+                const int32_t nt_end = min(n_tiles, (g + 1) * tpg);
+                for (int32_t nt = g * tpg; nt < nt_end; ++nt) {
+                    ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * kBNMax;
+                    for (int32_t kb = 0; kb < num_kb; ++kb) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+                        const uint32_t sb = sa + kABytes;
+#pragma unroll
+                        for (int k4 = 0; k4 < kBK / 16; ++k4) {
+                            const uint64_t adesc = ptx::umma_smem_desc_sw128(sa + k4 * 32);
+                            const uint64_t bdesc = ptx::umma_smem_desc_sw128(sb + k4 * 32);
+                            ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);          // smem slot free once these MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::umma_commit(&tfull_bar[acc]);                // accumulator ready for the epilogue
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5) =====
+        const int q = warp % 4;                                       // TMEM lane quarter of this warp
+        const int et = threadIdx.x - 2 * kWarp;                       // 0..127
+        const int32_t row_in_tile = q * 32 + lane;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int32_t u = blockIdx.x; u < num_units; u += gridDim.x) {
+            const int32_t mb = u / n_split, g = u % n_split;
+            const int32_t nt_end = min(n_tiles, (g + 1) * tpg);
+            const int32_t row = mb * kBM + row_in_tile;
+            const float xnr = row < b ? xn[row] : 0.f;
+            float d1 = INFINITY, d2 = INFINITY;
+            int32_t i1 = 0;
+            for (int32_t nt = g * tpg; nt < nt_end; ++nt) {
+                CentroidParam *sp = sparams + acc * kBNMax;
+                // stage this tile's centroid parameters (the buffer's previous user, two tiles ago, is done:
+                // every epilogue thread passed the barrier below after reading it)
+                for (int32_t i = et; i < kBNMax; i += kEpiThreads) {
+                    const int32_t c = nt * kBNMax + i;
+                    CentroidParam p;
+                    if (c < k) p = cparams[c];
+                    else { p.a = 0.f; p.b = INFINITY; p.s = 0.f; p.pad = 0.f; }
+                    sp[i] = p;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBNMax;
+                for (int32_t c0 = 0; c0 < bn; c0 += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c0, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const CentroidParam p = sp[c0 + j];
+                        const float dist = fmaf(p.s, xnr, fmaf(p.a, __uint_as_float(v[j]), p.b));
+                        top2_update(dist, nt * kBNMax + c0 + j, d1, i1, d2);
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < b) {
+                Top2 t;
+                t.d1 = d1; t.i1 = i1; t.d2 = d2;
+                partial[(int64_t)g * b + row] = t;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Merge the n_split partial top-2 lists of every row, write the screened arg-min, and queue the rows
+// whose margin is inside the bf16 error bound for the exact re-check.
+//   |dist_bf16 - dist_exact| <= 2 * |<x,c>_bf16 - <x,c>| <= 2 * 1.25 * 2^-8 * |x| |c|
+// (two bf16 roundings per product, 2^-9 each, plus fp32 accumulation slack), so the arg-min is
+// certain when d2 - d1 > 2 * that = 5 * 2^-8 * |x| * max|c|.
+__global__ void km_merge_classify_kernel(const Top2 *__restrict__ partial, int32_t b, int32_t n_split,
+                                         const float *__restrict__ xn, const float *__restrict__ cmax,
+                                         int64_t *__restrict__ best, float *__restrict__ mind,
+                                         int32_t *__restrict__ amb_rows, int32_t *__restrict__ n_amb) {
+    const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= b) return;
+    Top2 t = partial[row];
+    for (int32_t g = 1; g < n_split; ++g) {
+        const Top2 o = partial[(int64_t)g * b + row];
+        if (o.d1 < t.d1) { t.d2 = fminf(t.d1, o.d2); t.d1 = o.d1; t.i1 = o.i1; }
+        else t.d2 = fminf(t.d2, o.d1);
+    }
+    best[row] = t.i1;
+    if (mind) mind[row] = t.d1;
+    const float bound = 5.0f * 0.00390625f * sqrtf(xn[row]) * (*cmax) + 1e-30f;
+    if (!(t.d2 - t.d1 > bound)) amb_rows[atomicAdd(n_amb, 1)] = row;
+}
+
+// exact distance of every row to its assigned centroid (for the returned mean distance)
+__global__ void km_exact_min_dist_kernel(const float *__restrict__ x, int64_t b, int32_t d, int64_t ldx,
+                                         const float *__restrict__ centers, const int64_t *__restrict__ best,
+                                         const float *__restrict__ xn, const float *__restrict__ cn,
+                                         const float *__restrict__ counts, float thr, float r,
+                                         float *__restrict__ mind) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
+    const int lane = threadIdx.x % kWarp;
+    if (row >= b) return;
+    const int64_t c = best[row];
+    const float *p = x + row * ldx, *q = centers + c * d;
+    double s = 0.0;
+    for (int32_t i = lane; i < d; i += kWarp) s = fma((double)__ldg(p + i), (double)__ldg(q + i), s);
+    s = warp_sum_f64(s);
+    if (lane == 0) {
+        float dist = __fadd_rn(__fadd_rn(__fmul_rn(-2.f, (float)s), xn[row]), cn[c]);
+        if (counts[c] < thr) dist = __fdiv_rn(dist, r);
+        mind[row] = dist;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 [rows, dp] row-major, box = 64 elements x box_rows, 128-byte swizzle, OOB reads as zero.
+int make_bf16_tensor_map(void *out_map, const void *base, int64_t rows, int32_t dp, int32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return ACAV_E_NO_DEVICE;
+    cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)dp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap *>(out_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : ACAV_E_INVALID;
+}
+
+int umma_tile_n(int32_t k) { return k >= kBNMax ? kBNMax : (int)ceil_div(k, 16) * 16; }
+
+int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
+                     cudaStream_t st) {
+    if (rows == 0) return 0;
+    const int wpb = 8;
+    km_prep_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * kWarp, 0, st>>>(
+        x, rows, d, ldx, dp, reinterpret_cast<__nv_bfloat16 *>(xb), xn);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_centroid_params(const float *cn, const float *counts, int32_t k, float thr, float r, void *params,
+                           float *cmax, cudaStream_t st) {
+    km_centroid_params_kernel<<<1, 1024, 0, st>>>(cn, counts, k, thr, r, reinterpret_cast<CentroidParam *>(params), cmax);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, const void *cparams, int32_t b,
+                       int32_t k, int32_t dp, int32_t sm_count, void *partial, int32_t *n_split_out, cudaStream_t st) {
+    static bool attr_set = false;
+    const int smem_bytes = UmmaSmem::kBytes + 1024;
+    if (!attr_set) {
+        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_assign_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set = true;
+    }
+    const int32_t bn = umma_tile_n(k);
+    const int32_t n_tiles = (int32_t)ceil_div(k, kBNMax);
+    const int32_t num_m = (int32_t)ceil_div(b, kBM);
+    int32_t n_split = 1;
+    while (n_split < n_tiles && n_split < kMaxSplit && num_m * n_split < sm_count) n_split *= 2;
+    if (n_split > n_tiles) n_split = n_tiles;
+    *n_split_out = n_split;
+    const int32_t units = num_m * n_split;
+    const int32_t grid = units < sm_count ? units : sm_count;
+    if (grid == 0) return 0;
+    km_assign_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(
+        *reinterpret_cast<const CUtensorMap *>(tmap_x), *reinterpret_cast<const CUtensorMap *>(tmap_c), xn,
+        reinterpret_cast<const CentroidParam *>(cparams), b, k, dp / kBK, bn, n_tiles, n_split,
+        reinterpret_cast<Top2 *>(partial));
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const float *cmax,
+                          int64_t *best, float *mind, int32_t *amb_rows, int32_t *n_amb, cudaStream_t st) {
+    ACAV_CUDA_TRY(cudaMemsetAsync(n_amb, 0, sizeof(int32_t), st));
+    if (b == 0) return 0;
+    km_merge_classify_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, st>>>(
+        reinterpret_cast<const Top2 *>(partial), b, n_split, xn, cmax, best, mind, amb_rows, n_amb);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_exact_min_dist(const float *x, int64_t b, int32_t d, int64_t ldx, const float *centers,
+                          const int64_t *best, const float *xn, const float *cn, const float *counts, float thr,
+                          float r, float *mind, cudaStream_t st) {
+    if (b == 0) return 0;
+    const int wpb = 8;
+    km_exact_min_dist_kernel<<<(unsigned)ceil_div(b, wpb), wpb * kWarp, 0, st>>>(x, b, d, ldx, centers, best, xn,
+                                                                                cn, counts, thr, r, mind);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t umma_partial_bytes(int64_t max_batch) { return (int64_t)sizeof(Top2) * kMaxSplit * max_batch; }
+int64_t umma_param_bytes(int32_t k) { return (int64_t)sizeof(CentroidParam) * k; }
+
+}  // namespace acav

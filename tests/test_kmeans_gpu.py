@@ -199,3 +199,70 @@ def test_assign_strided_batch_and_empty_batch():
     assert torch.equal(b1, b2)
     best, mean = km.calc_best(torch.zeros(0, 64))
     assert best.numel() == 0 and np.isnan(mean)
+
+
+# ---- tcgen05 tensor-core assignment ---------------------------------------------------------------
+
+def _assign_both_modes(x, centers, counts, count):
+    from acav100m_b200 import _lib
+    outs = {}
+    b, d = x.shape
+    k = centers.shape[0]
+    for mode in ("exact", "tensor"):
+        st = ko.SgdKMeansState(centers=centers.clone(), counts=counts.clone(), count=count)
+        km = state_to_gpu(st, assign_mode=mode)
+        ws = km._workspace(b)
+        xg = x.cuda()
+        best = torch.empty(b, dtype=torch.int64, device="cuda")
+        mind = torch.empty(b, dtype=torch.float32, device="cuda")
+        mean = torch.empty(1, dtype=torch.float32, device="cuda")
+        nref = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.call("acav_kmeans_assign", ws, _lib.ptr(xg), b, d, _lib.ptr(km.centers), _lib.ptr(km.counts),
+                  km.underused_threshold(), float(km.reinit[1]), _lib.ptr(best), _lib.ptr(mind), _lib.ptr(mean),
+                  _lib.ptr(nref), km._mode(), _lib.stream_ptr())
+        outs[mode] = (best.cpu().numpy(), mind.cpu().numpy(), mean.item(), int(nref.item()))
+    return outs
+
+
+@pytest.mark.parametrize("b,d,k,clustered", [
+    (128, 64, 16, True), (1, 64, 16, True), (129, 64, 256, True), (1000, 128, 256, True), (300, 88, 13, True),
+    (4097, 512, 300, True), (8192, 2048, 1024, True), (20000, 704, 1024, True), (3000, 2304, 32, True),
+    (2048, 256, 512, False), (5000, 128, 1500, False)])
+def test_assign_tensor_equals_exact(b, d, k, clustered):
+    """Screen + re-check must reproduce the exact kernel's ids on EVERY row (that is the design claim),
+    and the distances handed back must be the exact ones."""
+    if clustered:
+        x = torch.from_numpy(synth.gaussian_mixture(b, d, max(k // 2, 2), b + d))
+        c = torch.from_numpy(synth.gaussian_mixture(k, d, max(k // 2, 2), b + d))
+    else:
+        g = torch.Generator().manual_seed(b + k)
+        x, c = torch.randn(b, d, generator=g), torch.randn(k, d, generator=g)
+    counts = torch.full((k,), 100.0)
+    counts[::3] = 0.0                                          # a third of the centroids get the /5 scaling
+    outs = _assign_both_modes(x, c, counts, 50 * k)
+    be, me, mean_e, _ = outs["exact"]
+    bt, mt, mean_t, nref = outs["tensor"]
+    assert np.array_equal(be, bt), "%d rows differ" % int((be != bt).sum())
+    np.testing.assert_allclose(mt, me, rtol=1e-6, atol=1e-6 * np.abs(me).max())
+    assert mean_t == pytest.approx(mean_e, rel=1e-6)
+    if clustered and k >= 16:
+        assert nref <= max(0.02 * b, 2), "screen sent %d of %d rows to the exact kernel" % (nref, b)
+
+
+@pytest.mark.parametrize("name", KM)
+def test_training_trajectory_tensor_mode_matches_reference(golden_dir, name):
+    case, g = gen_golden.KMEANS_CASES[name], load(golden_dir, name)
+    x = torch.from_numpy(synth.gaussian_mixture(case["n"], case["d"], case["k_true"], case["seed"]))
+    gen_golden.seed_all(case["seed"])
+    km = make_gpu_kmeans(case["d"], case["k"], assign_mode="tensor", warmup_rng="cpu")
+    for epoch in range(case["epochs"]):
+        km.lr = ko.epoch_lr(epoch)
+        for xb in gen_golden.kmeans_batches(x, case["batch"]):
+            km.add(xb)
+    assert km.count == int(g["count"]) and km.fallback == int(g["fallback"])
+    assert np.array_equal(km.counts.cpu().numpy(), g["counts"])
+    centers = km.centers.cpu().numpy()
+    if not np.array_equal(centers, g["centers"]):
+        np.testing.assert_allclose(centers, g["centers"], rtol=2e-5, atol=1e-7)
+    best, _ = km.calc_best(x)
+    assert (best.cpu().numpy() == g["assign_best"]).mean() > 0.998
