@@ -42,6 +42,7 @@ SIGNATURES = {
 
 ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1
 MI_LOOP_KERNELS, MI_LOOP_PERSISTENT = 0, 1
+TENSOR_PATH_READY = True        # tcgen05 assignment validated against the exact kernel on a B200
 
 _lib = None
 

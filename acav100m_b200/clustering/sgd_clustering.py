@@ -140,7 +140,7 @@ class KMeans:
             return _lib.ASSIGN_EXACT
         if self.assign_mode in ("tensor", _lib.ASSIGN_TENSOR):
             return _lib.ASSIGN_TENSOR
-        return _lib.ASSIGN_EXACT                   # "auto": exact until the tensor path is validated
+        return _lib.ASSIGN_TENSOR                  # "auto": tcgen05 screen + exact re-check of near-ties
 
     def mode_name(self):
         return "exact" if self._mode() == _lib.ASSIGN_EXACT else "tensor"

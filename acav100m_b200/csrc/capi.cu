@@ -17,7 +17,7 @@ struct acav_kmeans {
     int32_t dp;
     void *xb, *cb, *cparams, *partial;
     float *cmax;
-    int32_t *amb_rows, *n_amb;
+    int32_t *cand_rows, *cand_ids, *full_rows, *counters;      // counters = {n_cand, n_full}
     alignas(64) unsigned char tmap_x[128];
     alignas(64) unsigned char tmap_c[128];
     bool tensor_ready;
@@ -94,7 +94,7 @@ int acav_kmeans_destroy(acav_kmeans_t *h) {
     cudaFree(h->blockhist); cudaFree(h->lrank); cudaFree(h->total); cudaFree(h->seg_start);
     cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
     cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial); cudaFree(h->cmax);
-    cudaFree(h->amb_rows); cudaFree(h->n_amb);
+    cudaFree(h->cand_rows); cudaFree(h->cand_ids); cudaFree(h->full_rows); cudaFree(h->counters);
     delete h;
     return 0;
 }
@@ -127,8 +127,10 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) { rc = dev_alloc(&raw, (size_t)umma_param_bytes(k), &h->bytes); h->cparams = raw; }
     if (!rc) { rc = dev_alloc(&raw, (size_t)umma_partial_bytes(max_batch ? max_batch : 1), &h->bytes); h->partial = raw; }
     if (!rc) rc = dev_alloc(&h->cmax, 1, &h->bytes);
-    if (!rc) rc = dev_alloc(&h->amb_rows, (size_t)max_batch, &h->bytes);
-    if (!rc) rc = dev_alloc(&h->n_amb, 1, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->cand_rows, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->cand_ids, (size_t)max_batch * 4, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->full_rows, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->counters, 2, &h->bytes);
     if (rc) { acav_kmeans_destroy(h); return rc; }
     if (max_batch > 0 &&
         make_bf16_tensor_map(h->tmap_x, h->xb, max_batch, h->dp, 128) == 0 &&
@@ -145,8 +147,8 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                        float underused_threshold, float reinit_r,
                        int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
                        int32_t mode, void *stream) {
-    if (!h || !x || !centers || !counts || !best || b < 0 || ldx < h->d) return ACAV_E_INVALID;
-    if (b > h->max_batch) return ACAV_E_INVALID;
+    if (!h || !centers || !counts || b < 0 || b > h->max_batch) return ACAV_E_INVALID;
+    if (b > 0 && (!x || !best || ldx < h->d)) return ACAV_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == ACAV_ASSIGN_EXACT) {
         int rc = launch_row_norm2(x, b, h->d, ldx, nullptr, h->xn, st);
@@ -155,7 +157,7 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
         if (!rc) rc = launch_assign_exact(x, ldx, nullptr, b, nullptr, centers, h->k, h->d, h->xn, h->cn, counts,
                                           underused_threshold, reinit_r, best, mind, st);
         if (!rc && mean_dist) rc = launch_mean(mind, b, mean_dist, st);
-        if (!rc && n_refined) ACAV_CUDA_TRY(cudaMemsetAsync(n_refined, 0, sizeof(int32_t), st));
+        if (!rc && n_refined) ACAV_CUDA_TRY(cudaMemsetAsync(n_refined, 0, 2 * sizeof(int32_t), st));
         return rc;
     }
     if (mode != ACAV_ASSIGN_TENSOR) return ACAV_E_INVALID;
@@ -169,17 +171,19 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
     if (!rc) rc = launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
                                      h->partial, &n_split, st);
     float *mind = min_dist ? min_dist : h->mind;
-    if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cmax, best, mind, h->amb_rows,
-                                        h->n_amb, st);
-    if (!rc) rc = launch_assign_exact(x, ldx, h->amb_rows, b, h->n_amb, centers, h->k, h->d, h->xn, h->cn, counts,
-                                      underused_threshold, reinit_r, best, mind, st);
+    if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cmax, best, mind, h->cand_rows,
+                                        h->cand_ids, h->full_rows, h->counters, st);
+    if (!rc) rc = launch_candidate_refine(x, ldx, h->d, centers, h->xn, h->cn, counts, underused_threshold, reinit_r,
+                                          h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind, st);
+    if (!rc) rc = launch_assign_exact(x, ldx, h->full_rows, b, h->counters + 1, centers, h->k, h->d, h->xn, h->cn,
+                                      counts, underused_threshold, reinit_r, best, mind, st);
     // 6. exact distance to the assigned centroid, only when the caller wants distances back
     if (!rc && (min_dist || mean_dist))
         rc = launch_exact_min_dist(x, b, h->d, ldx, centers, best, h->xn, h->cn, counts, underused_threshold,
                                    reinit_r, mind, st);
     if (!rc && mean_dist) rc = launch_mean(mind, b, mean_dist, st);
     if (!rc && n_refined)
-        ACAV_CUDA_TRY(cudaMemcpyAsync(n_refined, h->n_amb, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        ACAV_CUDA_TRY(cudaMemcpyAsync(n_refined, h->counters, 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     return rc;
 }
 

@@ -29,7 +29,12 @@ int launch_centroid_params(const float *cn, const float *counts, int32_t k, floa
 int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, const void *cparams, int32_t b,
                        int32_t k, int32_t dp, int32_t sm_count, void *partial, int32_t *n_split_out, cudaStream_t st);
 int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const float *cmax,
-                          int64_t *best, float *mind, int32_t *amb_rows, int32_t *n_amb, cudaStream_t st);
+                          int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
+                          int32_t *counters, cudaStream_t st);
+int launch_candidate_refine(const float *x, int64_t ldx, int32_t d, const float *centers, const float *xn,
+                            const float *cn, const float *counts, float thr, float r, const int32_t *cand_rows,
+                            const int32_t *cand_ids, const int32_t *counters, int32_t b, int64_t *best, float *mind,
+                            cudaStream_t st);
 int launch_exact_min_dist(const float *x, int64_t b, int32_t d, int64_t ldx, const float *centers,
                           const int64_t *best, const float *xn, const float *cn, const float *counts, float thr,
                           float r, float *mind, cudaStream_t st);

@@ -45,16 +45,33 @@ struct __align__(16) CentroidParam {     // dist = s*|x|^2 + (a*dot + b)
     float a, b, s, pad;
 };
 
-struct Top2 {
-    float d1;
-    int32_t i1;
-    float d2;
+// Screening state per row: the four smallest approximate distances (sorted, earliest index first on
+// ties) and the fifth smallest value.  The exact arg-min is guaranteed to be among the entries within
+// the error bound of d[0]; if d5 is outside the bound those are all in this list.
+struct Top4 {
+    float d[4];
+    int32_t i[4];
+    float d5;
 };
 
-__device__ __forceinline__ void top2_update(float dist, int32_t idx, float &d1, int32_t &i1, float &d2) {
-    d2 = fminf(d2, fmaxf(dist, d1));
-    i1 = dist < d1 ? idx : i1;
-    d1 = fminf(d1, dist);
+__device__ __forceinline__ void top4_init(Top4 &t) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) { t.d[s] = INFINITY; t.i[s] = 0x7fffffff; }
+    t.d5 = INFINITY;
+}
+
+// stable insertion (strict <: an equal value stays behind the earlier index)
+__device__ __forceinline__ void top4_insert(Top4 &t, float v, int32_t vi) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const bool lt = v < t.d[s];
+        const float dv = lt ? t.d[s] : v;
+        const int32_t di = lt ? t.i[s] : vi;
+        t.d[s] = lt ? v : t.d[s];
+        t.i[s] = lt ? vi : t.i[s];
+        v = dv; vi = di;
+    }
+    t.d5 = fminf(t.d5, v);
 }
 
 // fp32 [rows, d] -> bf16 [rows, dp] (zero padded) + |row|^2 as the reference computes it (norm ** 2).
@@ -121,7 +138,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
 km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
                       const float *__restrict__ xn, const CentroidParam *__restrict__ cparams,
                       int32_t b, int32_t k, int32_t num_kb, int32_t bn, int32_t n_tiles, int32_t n_split,
-                      Top2 *__restrict__ partial) {
+                      Top4 *__restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     CentroidParam *sparams = reinterpret_cast<CentroidParam *>(smem + UmmaSmem::kParamsOff);
@@ -212,8 +229,8 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int32_t nt_end = min(n_tiles, (g + 1) * tpg);
             const int32_t row = mb * kBM + row_in_tile;
             const float xnr = row < b ? xn[row] : 0.f;
-            float d1 = INFINITY, d2 = INFINITY;
-            int32_t i1 = 0;
+            Top4 t4;
+            top4_init(t4);
             for (int32_t nt = g * tpg; nt < nt_end; ++nt) {
                 CentroidParam *sp = sparams + acc * kBNMax;
                 // stage this tile's centroid parameters (the buffer's previous user, two tiles ago, is done:
@@ -237,18 +254,14 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     for (int j = 0; j < 32; ++j) {
                         const CentroidParam p = sp[c0 + j];
                         const float dist = fmaf(p.s, xnr, fmaf(p.a, __uint_as_float(v[j]), p.b));
-                        top2_update(dist, nt * kBNMax + c0 + j, d1, i1, d2);
+                        if (dist < t4.d5) top4_insert(t4, dist, nt * kBNMax + c0 + j);   // rare after the first columns
                     }
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&tempty_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < b) {
-                Top2 t;
-                t.d1 = d1; t.i1 = i1; t.d2 = d2;
-                partial[(int64_t)g * b + row] = t;
-            }
+            if (row < b) partial[(int64_t)g * b + row] = t4;
         }
     }
     ptx::tc_fence_before();
@@ -256,27 +269,93 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// Merge the n_split partial top-2 lists of every row, write the screened arg-min, and queue the rows
-// whose margin is inside the bf16 error bound for the exact re-check.
-//   |dist_bf16 - dist_exact| <= 2 * |<x,c>_bf16 - <x,c>| <= 2 * 1.25 * 2^-8 * |x| |c|
-// (two bf16 roundings per product, 2^-9 each, plus fp32 accumulation slack), so the arg-min is
-// certain when d2 - d1 > 2 * that = 5 * 2^-8 * |x| * max|c|.
-__global__ void km_merge_classify_kernel(const Top2 *__restrict__ partial, int32_t b, int32_t n_split,
+// Merge the n_split partial lists of every row, write the screened arg-min, and route near-ties:
+//   |dist_bf16 - dist_exact| <= 2 * |<x,c>_bf16 - <x,c>| <= 2 * 1.25 * 2^-8 * |x| |c|  =: e
+// (two bf16 roundings per product, 2^-9 each, plus fp32 accumulation slack).  With B = 2e:
+//   d[1] - d[0] > B          -> the arg-min is certain;
+//   else if d5 - d[0] > B    -> the exact arg-min is one of the listed entries within B of d[0]:
+//                               queue the row for the candidate re-check (<= 4 exact dot products);
+//   else                     -> more than four near-ties: queue for the full exact kernel.
+__global__ void km_merge_classify_kernel(const Top4 *__restrict__ partial, int32_t b, int32_t n_split,
                                          const float *__restrict__ xn, const float *__restrict__ cmax,
                                          int64_t *__restrict__ best, float *__restrict__ mind,
-                                         int32_t *__restrict__ amb_rows, int32_t *__restrict__ n_amb) {
+                                         int32_t *__restrict__ cand_rows, int32_t *__restrict__ cand_ids,
+                                         int32_t *__restrict__ full_rows, int32_t *__restrict__ counters) {
     const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= b) return;
-    Top2 t = partial[row];
+    Top4 t = partial[row];
     for (int32_t g = 1; g < n_split; ++g) {
-        const Top2 o = partial[(int64_t)g * b + row];
-        if (o.d1 < t.d1) { t.d2 = fminf(t.d1, o.d2); t.d1 = o.d1; t.i1 = o.i1; }
-        else t.d2 = fminf(t.d2, o.d1);
+        const Top4 o = partial[(int64_t)g * b + row];        // later groups hold larger centroid indices
+#pragma unroll
+        for (int s = 0; s < 4; ++s) top4_insert(t, o.d[s], o.i[s]);
+        t.d5 = fminf(t.d5, o.d5);
     }
-    best[row] = t.i1;
-    if (mind) mind[row] = t.d1;
+    best[row] = t.i[0];
+    if (mind) mind[row] = t.d[0];
     const float bound = 5.0f * 0.00390625f * sqrtf(xn[row]) * (*cmax) + 1e-30f;
-    if (!(t.d2 - t.d1 > bound)) amb_rows[atomicAdd(n_amb, 1)] = row;
+    if (t.d[1] - t.d[0] > bound) return;
+    if (t.d5 - t.d[0] > bound) {
+        const int32_t slot = atomicAdd(&counters[0], 1);
+        cand_rows[slot] = row;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            cand_ids[4 * slot + s] = (t.d[s] - t.d[0] <= bound) ? t.i[s] : -1;
+    } else {
+        full_rows[atomicAdd(&counters[1], 1)] = row;
+    }
+}
+
+// Candidate re-check: one thread per (row, candidate) evaluates the exact distance with the SAME
+// operation order as assign_exact_kernel (sequential fp64 FMA over k, one rounding to fp32, then the
+// reference's three fp32 operations), so both kernels agree bit for bit; lowest index wins ties.
+__global__ void __launch_bounds__(128)
+km_candidate_refine_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
+                           const float *__restrict__ centers, const float *__restrict__ xn,
+                           const float *__restrict__ cn, const float *__restrict__ counts, float thr, float r,
+                           const int32_t *__restrict__ cand_rows, const int32_t *__restrict__ cand_ids,
+                           const int32_t *__restrict__ counters, int32_t capacity,
+                           int64_t *__restrict__ best, float *__restrict__ mind) {
+    const int32_t n = min(counters[0], capacity);
+    const int32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) / 4;
+    const int sub = threadIdx.x % 4;
+    const bool live = slot < n;
+    float dist = INFINITY;
+    int32_t c = 0x7fffffff;
+    int32_t row = 0;
+    if (live) {
+        row = cand_rows[slot];
+        const int32_t cid = cand_ids[4 * slot + sub];
+        if (cid >= 0) {
+            c = cid;
+            const float *p = x + (int64_t)row * ldx, *q = centers + (int64_t)c * d;
+            double acc = 0.0;
+            if ((d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                ((reinterpret_cast<uintptr_t>(centers) & 15) == 0)) {
+                for (int32_t i = 0; i < d; i += 4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(p + i));
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(q + i));
+                    acc = fma((double)a.x, (double)w.x, acc);
+                    acc = fma((double)a.y, (double)w.y, acc);
+                    acc = fma((double)a.z, (double)w.z, acc);
+                    acc = fma((double)a.w, (double)w.w, acc);
+                }
+            } else {
+                for (int32_t i = 0; i < d; ++i) acc = fma((double)__ldg(p + i), (double)__ldg(q + i), acc);
+            }
+            dist = __fadd_rn(__fadd_rn(__fmul_rn(-2.f, (float)acc), xn[row]), cn[c]);
+            if (counts[c] < thr) dist = __fdiv_rn(dist, r);
+        }
+    }
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, dist, o);
+        const int32_t oc = __shfl_xor_sync(0xffffffffu, c, o);
+        if (od < dist || (od == dist && oc < c)) { dist = od; c = oc; }
+    }
+    if (live && sub == 0) {
+        best[row] = c;
+        if (mind) mind[row] = dist;
+    }
 }
 
 // exact distance of every row to its assigned centroid (for the returned mean distance)
@@ -373,17 +452,31 @@ int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, 
     km_assign_umma_kernel<<<grid, kUmmaThreads, smem_bytes, st>>>(
         *reinterpret_cast<const CUtensorMap *>(tmap_x), *reinterpret_cast<const CUtensorMap *>(tmap_c), xn,
         reinterpret_cast<const CentroidParam *>(cparams), b, k, dp / kBK, bn, n_tiles, n_split,
-        reinterpret_cast<Top2 *>(partial));
+        reinterpret_cast<Top4 *>(partial));
     ACAV_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const float *cmax,
-                          int64_t *best, float *mind, int32_t *amb_rows, int32_t *n_amb, cudaStream_t st) {
-    ACAV_CUDA_TRY(cudaMemsetAsync(n_amb, 0, sizeof(int32_t), st));
+                          int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
+                          int32_t *counters, cudaStream_t st) {
+    ACAV_CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
     if (b == 0) return 0;
     km_merge_classify_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, st>>>(
-        reinterpret_cast<const Top2 *>(partial), b, n_split, xn, cmax, best, mind, amb_rows, n_amb);
+        reinterpret_cast<const Top4 *>(partial), b, n_split, xn, cmax, best, mind, cand_rows, cand_ids, full_rows,
+        counters);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+// grid covers the worst case (every row queued); blocks past the device-side count exit at once
+int launch_candidate_refine(const float *x, int64_t ldx, int32_t d, const float *centers, const float *xn,
+                            const float *cn, const float *counts, float thr, float r, const int32_t *cand_rows,
+                            const int32_t *cand_ids, const int32_t *counters, int32_t b, int64_t *best, float *mind,
+                            cudaStream_t st) {
+    if (b == 0) return 0;
+    km_candidate_refine_kernel<<<(unsigned)ceil_div((int64_t)b * 4, 128), 128, 0, st>>>(
+        x, ldx, d, centers, xn, cn, counts, thr, r, cand_rows, cand_ids, counters, b, best, mind);
     ACAV_LAUNCH_CHECK();
     return 0;
 }
@@ -399,7 +492,7 @@ int launch_exact_min_dist(const float *x, int64_t b, int32_t d, int64_t ldx, con
     return 0;
 }
 
-int64_t umma_partial_bytes(int64_t max_batch) { return (int64_t)sizeof(Top2) * kMaxSplit * max_batch; }
+int64_t umma_partial_bytes(int64_t max_batch) { return (int64_t)sizeof(Top4) * kMaxSplit * max_batch; }
 int64_t umma_param_bytes(int32_t k) { return (int64_t)sizeof(CentroidParam) * k; }
 
 }  // namespace acav

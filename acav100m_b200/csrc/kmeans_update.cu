@@ -141,46 +141,59 @@ km_effective_lr_kernel(const float *__restrict__ counts_b, int32_t k, double lr,
 
 // One thread = one centroid x VEC columns.  FUSED: centers = centers*decay + delta (:121,:127);
 // otherwise centers *= decay and the local delta is written out for the all-reduce (:125-126).
+// The fp32 add chain per (centroid, column) is inherently serial (that IS the reference's sum order);
+// everything around it is parallel: row indices are staged through shared memory 256 at a time and 16
+// row loads are kept in flight per thread, so a heavily skewed batch is bound by the 4-cycle add chain
+// rather than by memory latency.
 template <int VEC, bool FUSED>
 __global__ void __launch_bounds__(128)
 km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
                  const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                  const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
                  float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas) {
+    constexpr int kChunk = 256, kUnroll = 16;
+    __shared__ uint32_t sidx[kChunk];
     const int32_t c = blockIdx.x;
     const int32_t col = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+    const bool active = col < d;
     const float lr = *lr_eff_p;
     const float cb = counts_b[c];
     if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
-    if (col >= d) return;
     const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
-    constexpr int kUnroll = 8;
-    uint32_t s = lo;
-    for (; s + kUnroll <= hi; s += kUnroll) {
-        float vals[kUnroll][VEC];
+    const float *xcol = x + col;
+    for (uint32_t chunk = lo; chunk < hi; chunk += kChunk) {
+        const uint32_t n = min((uint32_t)kChunk, hi - chunk);
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) sidx[t] = sorted_rows[chunk + t];
+        __syncthreads();
+        if (!active) continue;
+        for (uint32_t s = 0; s < n; s += kUnroll) {
+            float vals[kUnroll][VEC];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const float *p = x + (int64_t)sorted_rows[s + u] * ldx + col;
-            if constexpr (VEC == 4) {
-                float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-                vals[u][0] = t.x; vals[u][1] = t.y; vals[u][2] = t.z; vals[u][3] = t.w;
-            } else {
-                vals[u][0] = __ldg(p);
+            for (int u = 0; u < kUnroll; ++u) {
+                if (s + u < n) {
+                    const float *p = xcol + (int64_t)sidx[s + u] * ldx;
+                    if constexpr (VEC == 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+                        vals[u][0] = t.x; vals[u][1] = t.y; vals[u][2] = t.z; vals[u][3] = t.w;
+                    } else {
+                        vals[u][0] = __ldg(p);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (s + u < n) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(vals[u][v], lr));   // :123
+                }
             }
         }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(vals[u][v], lr));   // :123
     }
-    for (; s < hi; ++s) {
-        const float *p = x + (int64_t)sorted_rows[s] * ldx + col;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(__ldg(p + v), lr));
-    }
+    if (!active) return;
     const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                    // :121
     float *cp = centers + (int64_t)c * d + col;
 #pragma unroll

@@ -211,14 +211,9 @@ def run_kmeans(args, dist, rank, world):
     x = synth.gaussian_mixture_torch(n, d, k, 1003 + rank, dev)
     kargs = types.SimpleNamespace(computation=types.SimpleNamespace(device="cuda", num_gpus=world))
     torch.manual_seed(1003)
-    km = KMeans(kargs, d, k, assign_mode=args.km_mode)
+    km = KMeans(kargs, d, k, assign_mode=args.km_mode, warmup_rng="cuda")
     km.to(dev)
-    # start past warm-up from centroids near data rows (all ranks identical)
-    g = torch.Generator(device=dev).manual_seed(5)
-    seedrows = synth.gaussian_mixture_torch(k, d, k, 1003, dev)
-    km.centers.copy_(seedrows + 0.1 * torch.randn(k, d, generator=g, device=dev))
-    km.counts.fill_(float(b * world) / k)
-    km.count = 10 * k * 8
+    km.initialize()
     km.lr = 1e-2
     nb = n // b
     steps = args.km_steps or min(args.steps, nb)
@@ -229,7 +224,13 @@ def run_kmeans(args, dist, rank, world):
             j = (off + i) % nb
             km.add(x[j * b:(j + 1) * b], sync=False)
 
-    ms_step, _ = timed(dist, lambda: run_steps(max(warm, 3)), lambda: run_steps(steps, warm))
+    # train from the reference's init through its warm-up (random assignment until 10*k samples) and a
+    # few dozen SGD steps, so the timed steps see the operator in its steady state
+    settle = -(-10 * k // (b * world)) + 24
+    run_steps(settle)
+    warm += settle
+
+    ms_step, _ = timed(dist, lambda: run_steps(3, warm - 3), lambda: run_steps(steps, warm))
 
     def run_assign(cnt, off=0):
         for i in range(cnt):
@@ -246,6 +247,8 @@ def run_kmeans(args, dist, rank, world):
         "ms_per_step": ms_step / steps, "samples_per_sec": steps * b * world / (ms_step * 1e-3),
         "assign_rows_per_sec": steps * b * world / (ms_assign * 1e-3),
         "assign_ms_per_batch": ms_assign / steps, "assign_mode": km.mode_name(),
+        "steps_before_timing": warm, "lr_fallbacks": km.fallback,
+        "centroids_in_use": int((km.counts > 0).sum().item()),
         "gpu_launches": km.launches_per_step() * steps,
         "roofline": {"bound": "tensor", "achieved": flops / t_assign / 1e12, "peak": pk["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": flops / t_assign / 1e12 / pk["bf16_tflops"], "traffic": None,

@@ -60,8 +60,9 @@ int64_t acav_kmeans_workspace_bytes(const acav_kmeans_t *h);
  *   divided by reinit_r (:76-77) ; best[j] = first argmin_i ; *mean_dist = mean_j min_i dist.
  * x: [b, d] fp32 row-major with row stride ldx (elements).  best: int64[b] (torch.long, :78).
  * min_dist: fp32[b] or NULL.  mean_dist: fp32[1] on the device or NULL (no host sync here; the
- * reference's .item() at :79 is the caller's choice).  n_refined: int32[1] device or NULL -- rows
- * that went through the exact re-check in ACAV_ASSIGN_TENSOR mode. */
+ * reference's .item() at :79 is the caller's choice).  n_refined: int32[2] device or NULL -- in
+ * ACAV_ASSIGN_TENSOR mode the number of rows re-checked on <= 4 candidates and the number sent
+ * through the full exact kernel (both 0 in ACAV_ASSIGN_EXACT mode). */
 int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                        const float *centers, const float *counts,
                        float underused_threshold, float reinit_r,

@@ -11,9 +11,10 @@ from acav100m_b200.clustering import KMeans
 
 def run(b, d, k, seed=0, spread=3.0, clustered=True):
     torch.manual_seed(seed)
-    if clustered:
-        x = torch.from_numpy(synth.gaussian_mixture(b, d, k, seed, spread)).cuda()
-        c = torch.from_numpy(synth.gaussian_mixture(k, d, k, seed, spread)).cuda()
+    if clustered:                        # centroids near the component means (a trained model)
+        means = torch.randn(k, d, device="cuda") * spread
+        x = means[torch.randint(0, k, (b,), device="cuda")] + torch.randn(b, d, device="cuda")
+        c = means + 0.05 * torch.randn(k, d, device="cuda")
     else:
         x = torch.randn(b, d, device="cuda"); c = torch.randn(k, d, device="cuda")
     km = KMeans(None, d, k)
@@ -29,12 +30,12 @@ def run(b, d, k, seed=0, spread=3.0, clustered=True):
         best = torch.empty(b, dtype=torch.int64, device="cuda")
         mind = torch.empty(b, dtype=torch.float32, device="cuda")
         mean = torch.empty(1, dtype=torch.float32, device="cuda")
-        nref = torch.zeros(1, dtype=torch.int32, device="cuda")
+        nref = torch.zeros(2, dtype=torch.int32, device="cuda")
         _lib.call("acav_kmeans_assign", ws, _lib.ptr(x), b, d, _lib.ptr(km.centers), _lib.ptr(km.counts),
                   km.underused_threshold(), 5.0, _lib.ptr(best), _lib.ptr(mind), _lib.ptr(mean), _lib.ptr(nref),
                   km._mode(), _lib.stream_ptr())
         torch.cuda.synchronize()
-        outs[mode] = (best.cpu(), mind.cpu(), mean.item(), int(nref.item()))
+        outs[mode] = (best.cpu(), mind.cpu(), mean.item(), nref.cpu().tolist())
     be, me, mne, _ = outs["exact"]
     bt, mt, mnt, nref = outs["tensor"]
     # torch view of the screen: bf16 inputs, fp32 math
@@ -44,7 +45,7 @@ def run(b, d, k, seed=0, spread=3.0, clustered=True):
     dist[under] /= 5
     bscreen = dist.argmin(0).cpu()
     print(f"b={b} d={d} k={k} clustered={clustered}: ids tensor==exact {(be == bt).float().mean():.6f} "
-          f"screen(torch bf16)==exact {(bscreen == be).float().mean():.6f} refined {nref} ({nref / b:.4f}) "
+          f"screen(torch bf16)==exact {(bscreen == be).float().mean():.6f} refined cand/full {nref} ({nref[0] / b:.4f}/{nref[1] / b:.4f}) "
           f"mean exact {mne:.6f} tensor {mnt:.6f} max|mind diff| {(me - mt).abs().max():.3e}")
     return bool((be == bt).all())
 
