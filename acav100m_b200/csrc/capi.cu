@@ -1,5 +1,6 @@
 // extern "C" surface of libacav_b200.so (declared in include/acav_b200.h).
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -34,6 +35,14 @@ struct acav_mi {
     int32_t sm_count;
     float *consts_dev;
     bool loaded, tabled;
+    // persistent-loop resources (row-partitioned stream), built on first use
+    uint16_t *c2s;
+    uint32_t *pos_s, *row_start, *row_total, *tilehist, *chunk_start;
+    unsigned long long *slots;
+    unsigned int *bar;
+    int32_t grid, rows_smem;
+    int64_t w_sorted;
+    bool sorted_valid;
 };
 
 namespace {
@@ -54,6 +63,71 @@ int query_sm_count(int32_t *out) {
     int n = 0;
     ACAV_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     *out = n;
+    return 0;
+}
+
+// Build (or rebuild) the row-partitioned candidate stream and the per-CTA chunk table.
+int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
+    if (h->sorted_valid) return 0;
+    MiState &s = h->s;
+    h->rows_smem = mi_persistent_rows_that_fit(s.k_v);
+    if (h->rows_smem < 1 || s.k_a > 16384) return ACAV_E_UNSUPPORTED;
+    const int ntiles = mi_partition_scratch_tiles(s.w);
+    int rc = 0;
+    if (!h->c2s) {
+        if (!rc) rc = dev_alloc(&h->c2s, (size_t)s.w + 32, nullptr);
+        if (!rc) rc = dev_alloc(&h->pos_s, (size_t)s.w + 8, nullptr);
+        if (!rc) rc = dev_alloc(&h->row_start, (size_t)s.k_a + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->row_total, (size_t)s.k_a, nullptr);
+        if (!rc) rc = dev_alloc(&h->tilehist, (size_t)ntiles * s.k_a, nullptr);
+        if (!rc) rc = dev_alloc(&h->chunk_start, (size_t)h->sm_count + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->slots, 2, nullptr);
+        if (!rc) rc = dev_alloc(&h->bar, 2, nullptr);
+        if (rc) return rc;
+    }
+    rc = launch_mi_partition(s.cells, s.w, s.k_a, h->tilehist, h->row_total, h->row_start, h->c2s, h->pos_s,
+                             s.w + 32, st);
+    if (rc) return rc;
+    std::vector<uint32_t> rs((size_t)s.k_a + 1);
+    ACAV_CUDA_TRY(cudaMemcpyAsync(rs.data(), h->row_start, sizeof(uint32_t) * rs.size(), cudaMemcpyDeviceToHost, st));
+    ACAV_CUDA_TRY(cudaStreamSynchronize(st));
+    h->w_sorted = rs[s.k_a];
+    // balanced cut: cost(e) = e + row_cost * (#non-empty rows that start before e)
+    const int32_t grid = h->sm_count;
+    const double row_cost = 3.0 * s.k_v;
+    std::vector<double> cum((size_t)s.k_a + 1);
+    double run = 0.0;
+    for (int32_t r = 0; r < s.k_a; ++r) {
+        cum[r] = run;
+        const uint32_t n = rs[r + 1] - rs[r];
+        if (n) run += row_cost + (double)n;
+    }
+    cum[s.k_a] = run;
+    std::vector<uint32_t> chunks((size_t)grid + 1);
+    int32_t r = 0;
+    for (int32_t g = 0; g <= grid; ++g) {
+        const double t = run * (double)g / (double)grid;
+        while (r < s.k_a && cum[r + 1] <= t) ++r;
+        uint32_t e;
+        if (r >= s.k_a) e = rs[s.k_a];
+        else {
+            const uint32_t n = rs[r + 1] - rs[r];
+            double off = t - cum[r] - row_cost;
+            if (off < 0) off = 0;
+            if (off > (double)n) off = (double)n;
+            e = rs[r] + (uint32_t)off;
+        }
+        chunks[g] = e;
+    }
+    chunks[0] = 0;
+    chunks[grid] = rs[s.k_a];
+    for (int32_t g = 1; g <= grid; ++g)
+        if (chunks[g] < chunks[g - 1]) chunks[g] = chunks[g - 1];
+    ACAV_CUDA_TRY(cudaMemcpyAsync(h->chunk_start, chunks.data(), sizeof(uint32_t) * chunks.size(),
+                                  cudaMemcpyHostToDevice, st));
+    ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `chunks` is a host temporary
+    h->grid = grid;
+    h->sorted_valid = true;
     return 0;
 }
 
@@ -243,6 +317,8 @@ int acav_mi_destroy(acav_mi_t *h) {
     MiState &s = h->s;
     cudaFree(s.cells); cudaFree(s.n_cells); cudaFree(s.a_cols); cudaFree(s.b_rows); cudaFree(s.gain);
     cudaFree(s.col_term); cudaFree(s.row_term); cudaFree(s.sums); cudaFree(s.key); cudaFree(h->consts_dev);
+    cudaFree(h->c2s); cudaFree(h->pos_s); cudaFree(h->row_start); cudaFree(h->row_total); cudaFree(h->tilehist);
+    cudaFree(h->chunk_start); cudaFree(h->slots); cudaFree(h->bar);
     delete h;
     return 0;
 }
@@ -259,6 +335,9 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     s = MiState();
     s.w = w; s.k_a = k_a; s.k_v = k_v; s.pos_base = pos_base; s.logs = nullptr; s.n_logs = 0;
     h->max_picks = max_picks; h->loaded = false; h->tabled = false; h->consts_dev = nullptr;
+    h->c2s = nullptr; h->pos_s = nullptr; h->row_start = nullptr; h->row_total = nullptr; h->tilehist = nullptr;
+    h->chunk_start = nullptr; h->slots = nullptr; h->bar = nullptr; h->grid = 0; h->rows_smem = 0; h->w_sorted = 0;
+    h->sorted_valid = false;
     int rc = query_sm_count(&h->sm_count);
     const size_t cells = (size_t)k_a * k_v;
     if (!rc) rc = dev_alloc(&s.cells, (size_t)w + 4, nullptr);
@@ -280,6 +359,7 @@ int acav_mi_load_candidates(acav_mi_t *h, const int64_t *cells, void *stream) {
     if (!h || (!cells && h->s.w > 0)) return ACAV_E_INVALID;
     int rc = launch_mi_pack(cells, h->s.w, h->s.cells, (cudaStream_t)stream);
     h->loaded = (rc == 0);
+    h->sorted_valid = false;
     return rc;
 }
 
@@ -314,6 +394,7 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n, int64_t *o
                   void *stream) {
     if (!h || !key_cells || n <= 0) return ACAV_E_INVALID;
     if (!h->tabled || !h->loaded) return ACAV_E_STATE;
+    h->sorted_valid = false;                 // the row-partitioned stream does not see this removal
     return launch_mi_apply(h->s, reinterpret_cast<const unsigned long long *>(key_cells), n, out_pos, out_gain,
                            (cudaStream_t)stream);
 }
@@ -323,6 +404,7 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
     if (!h->tabled || !h->loaded) return ACAV_E_STATE;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == ACAV_MI_LOOP_KERNELS) {
+        if (n_picks > 0) h->sorted_valid = false;
         for (int64_t it = 0; it < n_picks; ++it) {
             int rc = launch_mi_gain_table(h->s, st);
             if (!rc) rc = launch_mi_scan(h->s, h->sm_count, st);
@@ -331,7 +413,12 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         }
         return 0;
     }
-    return ACAV_E_UNSUPPORTED;
+    if (mode != ACAV_MI_LOOP_PERSISTENT) return ACAV_E_INVALID;
+    if (n_picks == 0) return 0;
+    int rc = mi_prepare_persistent(h, st);
+    if (rc) return rc;
+    return launch_mi_persistent(h->s, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->slots, h->bar,
+                                h->w_sorted, n_picks, out_pos, out_gain, h->rows_smem, st);
 }
 
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows, float *sums,

@@ -76,4 +76,15 @@ int launch_mi_emit(const MiState &s, unsigned long long *out, cudaStream_t st);
 int launch_mi_apply(const MiState &s, const unsigned long long *key_cells, int32_t n,
                     int64_t *out_pos, float *out_gain, cudaStream_t st);
 
+// mi_persistent.cu
+int mi_partition_scratch_tiles(int64_t w);
+int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t *tilehist, uint32_t *row_total,
+                        uint32_t *row_start, uint16_t *c2s, uint32_t *pos_s, int64_t stream_capacity,
+                        cudaStream_t st);
+int mi_persistent_rows_that_fit(int32_t k_v);
+int launch_mi_persistent(const MiState &s, uint16_t *c2s, const uint32_t *pos_s, const uint32_t *row_start,
+                         const uint32_t *chunk_start, int32_t grid, unsigned long long *slots, unsigned int *bar,
+                         int64_t w_sorted, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
+                         cudaStream_t st);
+
 }  // namespace acav

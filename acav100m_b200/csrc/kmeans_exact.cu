@@ -36,7 +36,7 @@ __global__ void row_norm2_kernel(const float *__restrict__ x, int64_t rows, int3
 constexpr int kTR = 64;      // rows per block tile
 constexpr int kTC = 64;      // centroids per inner tile
 constexpr int kKC = 16;      // reduction chunk
-constexpr int kPad = 68;     // smem row stride (floats), keeps float4 reads aligned
+constexpr int kPad = 66;     // smem row stride (doubles), keeps double2 reads aligned
 
 struct BestPair {
     float d;
@@ -55,8 +55,10 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
                     const float *__restrict__ xn, const float *__restrict__ cn,
                     const float *__restrict__ counts, float thr, float r,
                     int64_t *__restrict__ best, float *__restrict__ mind) {
-    __shared__ __align__(16) float Xs[kKC][kPad];
-    __shared__ __align__(16) float Cs[kKC][kPad];
+    // tiles are widened to fp64 once, on the way into shared memory (F2F.F64 is a slow pipe: doing it
+    // per FMA operand made the kernel conversion-bound)
+    __shared__ __align__(16) double Xs[kKC][kPad];
+    __shared__ __align__(16) double Cs[kKC][kPad];
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int64_t row0 = (int64_t)blockIdx.x * kTR;
@@ -96,16 +98,18 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
                     if (xsrc >= 0) xv = __ldg(x + xsrc * ldx + kk);
                     if (csrc < k) cv = __ldg(centers + (int64_t)csrc * d + kk);
                 }
-                Xs[lk + q][lrow] = xv;
-                Cs[lk + q][lrow] = cv;
+                Xs[lk + q][lrow] = (double)xv;
+                Cs[lk + q][lrow] = (double)cv;
             }
             __syncthreads();
 #pragma unroll
             for (int kk = 0; kk < kKC; ++kk) {
-                float4 xa = *reinterpret_cast<const float4 *>(&Xs[kk][ty * 4]);
-                float4 cb = *reinterpret_cast<const float4 *>(&Cs[kk][tx * 4]);
-                double xd[4] = {(double)xa.x, (double)xa.y, (double)xa.z, (double)xa.w};
-                double cd[4] = {(double)cb.x, (double)cb.y, (double)cb.z, (double)cb.w};
+                const double2 xa = *reinterpret_cast<const double2 *>(&Xs[kk][ty * 4]);
+                const double2 xb = *reinterpret_cast<const double2 *>(&Xs[kk][ty * 4 + 2]);
+                const double2 ca = *reinterpret_cast<const double2 *>(&Cs[kk][tx * 4]);
+                const double2 cb = *reinterpret_cast<const double2 *>(&Cs[kk][tx * 4 + 2]);
+                const double xd[4] = {xa.x, xa.y, xb.x, xb.y};
+                const double cd[4] = {ca.x, ca.y, cb.x, cb.y};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll

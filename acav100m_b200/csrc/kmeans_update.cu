@@ -151,7 +151,7 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
                  const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                  const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
                  float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas) {
-    constexpr int kChunk = 256, kUnroll = 16;
+    constexpr int kChunk = 256, kGroup = 32 / VEC;          // rows per register buffer
     __shared__ uint32_t sidx[kChunk];
     const int32_t c = blockIdx.x;
     const int32_t col = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
@@ -164,33 +164,42 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     const float *xcol = x + col;
+    float buf[2][kGroup][VEC];                              // double buffer: loads of group g+1 fly during adds of g
+    auto load_group = [&](float (&dst)[kGroup][VEC], uint32_t s, uint32_t n) {
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            if (s + u < n) {
+                const float *p = xcol + (int64_t)sidx[s + u] * ldx;
+                if constexpr (VEC == 4) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+                    dst[u][0] = t.x; dst[u][1] = t.y; dst[u][2] = t.z; dst[u][3] = t.w;
+                } else {
+                    dst[u][0] = __ldg(p);
+                }
+            }
+        }
+    };
+    auto add_group = [&](const float (&src)[kGroup][VEC], uint32_t s, uint32_t n) {
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            if (s + u < n) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(src[u][v], lr));     // :123
+            }
+        }
+    };
     for (uint32_t chunk = lo; chunk < hi; chunk += kChunk) {
         const uint32_t n = min((uint32_t)kChunk, hi - chunk);
         __syncthreads();
         for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) sidx[t] = sorted_rows[chunk + t];
         __syncthreads();
         if (!active) continue;
-        for (uint32_t s = 0; s < n; s += kUnroll) {
-            float vals[kUnroll][VEC];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (s + u < n) {
-                    const float *p = xcol + (int64_t)sidx[s + u] * ldx;
-                    if constexpr (VEC == 4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-                        vals[u][0] = t.x; vals[u][1] = t.y; vals[u][2] = t.z; vals[u][3] = t.w;
-                    } else {
-                        vals[u][0] = __ldg(p);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                if (s + u < n) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(vals[u][v], lr));   // :123
-                }
-            }
+        load_group(buf[0], 0, n);
+        for (uint32_t s = 0; s < n; s += 2 * kGroup) {
+            if (s + kGroup < n) load_group(buf[1], s + kGroup, n);
+            add_group(buf[0], s, n);
+            if (s + 2 * kGroup < n) load_group(buf[0], s + 2 * kGroup, n);
+            if (s + kGroup < n) add_group(buf[1], s + kGroup, n);
         }
     }
     if (!active) return;

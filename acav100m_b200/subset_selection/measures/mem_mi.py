@@ -96,7 +96,7 @@ class EfficientMemMI:
     def launches_per_iteration(self):
         if self._dist is not None:
             return 4                                   # gain, scan, emit, apply (+ one NCCL all-gather)
-        return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0
+        return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0      # persistent: one launch per select()
 
     def loop_name(self):
         if self._dist is not None:
@@ -151,7 +151,8 @@ class EfficientMemMI:
             return _lib.MI_LOOP_KERNELS
         if self.loop in ('persistent', _lib.MI_LOOP_PERSISTENT):
             return _lib.MI_LOOP_PERSISTENT
-        return _lib.MI_LOOP_KERNELS
+        # "auto": the persistent row-partitioned kernel whenever its gain rows fit in shared memory
+        return _lib.MI_LOOP_PERSISTENT if self.ncentroids <= 16384 else _lib.MI_LOOP_KERNELS
 
     def select(self, n_picks):
         """Run `n_picks` greedy iterations; returns (positions int64[n] in the candidate list,

@@ -12,7 +12,7 @@ from oracle import gen_golden, mi_oracle as mo
 pytestmark = pytest.mark.gpu
 
 P1 = [m for m in sorted(gen_golden.MI_CASES) if gen_golden.MI_CASES[m]["dcols"] == 2]
-LOOPS = ["kernels"]
+LOOPS = ["kernels", "persistent"]
 
 
 def load(golden_dir, name):
@@ -138,3 +138,50 @@ def test_errors():
         get_measure("batch_mi")
     with pytest.raises(AssertionError):
         get_measure("nope")
+
+
+@pytest.mark.parametrize("W,C,picks,seed", [(50_000, 16, 4000, 21), (300_000, 1024, 600, 22), (40, 4, 39, 23),
+                                            (1_000_003, 256, 300, 24), (9000, 2048, 500, 25)])
+def test_persistent_loop_matches_c_oracle(W, C, picks, seed):
+    """Row-partitioned persistent kernel: massive early ties (every cell scores the same at first),
+    rows split across CTAs, more rows per CTA than fit in shared memory, resumed runs."""
+    a = synth.zipf_pairs(W, C, seed)
+    a[0] = C - 1
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C, loop="persistent")
+    m.init([(0, 1)], list(range(W)))
+    first = picks // 3
+    p1, g1 = m.select(first)
+    p2, g2 = m.select(picks - first)                       # resumes from the engine's state
+    pos = torch.cat([p1, p2]).cpu().numpy()
+    gain = torch.cat([g1, g2]).cpu().numpy()
+    assert np.array_equal(pos, pos_want)
+    assert np.array_equal(gain, gain_want)
+
+
+def test_loops_can_be_mixed():
+    W, C, picks = 30_000, 32, 900
+    a = synth.zipf_pairs(W, C, 31)
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C, loop="persistent")
+    m.init([(0, 1)], list(range(W)))
+    out = []
+    for loop, n in (("persistent", 300), ("kernels", 300), ("persistent", 300)):
+        m.loop = loop
+        out.append(m.select(n))
+    pos = torch.cat([o[0] for o in out]).cpu().numpy()
+    gain = torch.cat([o[1] for o in out]).cpu().numpy()
+    assert np.array_equal(pos, pos_want) and np.array_equal(gain, gain_want)
+
+
+def test_persistent_loop_uniform_ids_all_ties():
+    """Every candidate in one cell: all scores tie on every iteration, list order must be kept."""
+    W = 5000
+    a = np.zeros((W, 2), dtype=np.int64)
+    a[:, 1] = 3
+    a[0] = (7, 7)
+    m = gpu_measure(a, 8, loop="persistent")
+    m.init([(0, 1)], list(range(W)))
+    pos, _ = m.select(200)
+    want, _ = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], 8, 200, bucketed=False)
+    assert np.array_equal(pos.cpu().numpy(), want)
