@@ -16,7 +16,7 @@ Differences a user can observe (all documented in DESIGN.md):
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, parallel
 
 
 class KMeans:
@@ -215,6 +215,40 @@ class KMeans:
                 dist.all_reduce(t)
                 t.mul_(1.0 / world)
 
+    # device hooks of add(): each is one or two C-ABI calls (overridden by the CPU protocol tests)
+
+    def _histogram(self, batch, best):
+        k = self.centers.shape[0]
+        b = batch.shape[0]
+        counts_b = torch.empty(k, dtype=torch.float32, device=self.centers.device)
+        with torch.cuda.device(self.centers.device):
+            _lib.call("acav_kmeans_histogram", self._workspace(b), _lib.ptr(best), b, _lib.ptr(counts_b),
+                      _lib.stream_ptr(self.centers.device))
+        return counts_b
+
+    def _update_fused(self, batch, counts_b, lr):
+        b = batch.shape[0]
+        with torch.cuda.device(self.centers.device):
+            _lib.call("acav_kmeans_update_fused", self._workspace(b), _lib.ptr(batch, row_strided=True), b,
+                      batch.stride(0), _lib.ptr(counts_b), lr, _lib.ptr(self.centers), _lib.ptr(self.counts),
+                      _lib.ptr(self._fallback_dev), _lib.stream_ptr(self.centers.device))
+
+    def _update_local(self, batch, counts_b_global, lr):
+        k, d = self.centers.shape
+        b = batch.shape[0]
+        deltas = torch.empty(k, d, dtype=torch.float32, device=self.centers.device)
+        with torch.cuda.device(self.centers.device):
+            _lib.call("acav_kmeans_update_local", self._workspace(b), _lib.ptr(batch, row_strided=True), b,
+                      batch.stride(0), _lib.ptr(counts_b_global), lr, _lib.ptr(self.centers),
+                      _lib.ptr(self.counts), _lib.ptr(deltas), _lib.ptr(self._fallback_dev),
+                      _lib.stream_ptr(self.centers.device))
+        return deltas
+
+    def _apply_deltas(self, deltas):
+        with torch.cuda.device(self.centers.device):
+            _lib.call("acav_kmeans_apply_deltas", _lib.ptr(self.centers), _lib.ptr(deltas), deltas.numel(),
+                      _lib.stream_ptr(self.centers.device))
+
     def add(self, batch, sync=True):
         """reference :94-129 (fast parallel update) -> mean min-distance of the batch."""
         if self.sequential:
@@ -226,23 +260,14 @@ class KMeans:
         dist, world = self._world()
         lr = self.lr(self.count) if callable(self.lr) else self.lr
         best, mean = self._assign(batch, want_mean=True)
-        ws = self._workspace(b)
-        counts_b = torch.empty(k, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            st = _lib.stream_ptr(dev)
-            _lib.call("acav_kmeans_histogram", ws, _lib.ptr(best), b, _lib.ptr(counts_b), st)       # :113
-            if world > 1:
-                dist.all_reduce(counts_b)                                                           # :114-115
-                deltas = torch.empty(k, d, dtype=torch.float32, device=dev)
-                _lib.call("acav_kmeans_update_local", ws, _lib.ptr(batch, row_strided=True), b, batch.stride(0),
-                          _lib.ptr(counts_b), float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts),
-                          _lib.ptr(deltas), _lib.ptr(self._fallback_dev), st)                       # :116-123
-                dist.all_reduce(deltas)                                                             # :125-126
-                _lib.call("acav_kmeans_apply_deltas", _lib.ptr(self.centers), _lib.ptr(deltas), k * d, st)
-            else:
-                _lib.call("acav_kmeans_update_fused", ws, _lib.ptr(batch, row_strided=True), b, batch.stride(0),
-                          _lib.ptr(counts_b), float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts),
-                          _lib.ptr(self._fallback_dev), st)                                         # :116-127
-        self.count += b * world                                                                     # :128
+        counts_b = self._histogram(batch, best)                                                     # :113
+        if world > 1:
+            dist.all_reduce(counts_b)                                                               # :114-115
+            deltas = self._update_local(batch, counts_b, float(lr))                                 # :116-123
+            dist.all_reduce(deltas)                                                                 # :125-126
+            self._apply_deltas(deltas)                                                              # :127
+        else:
+            self._update_fused(batch, counts_b, float(lr))                                          # :116-127
+        self.count += parallel.kmeans_global_batch(b, world)                                                                   # :128
         self.last_best = best
         return mean.item() if sync else mean[0]

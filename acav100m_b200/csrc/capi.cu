@@ -71,7 +71,7 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     if (h->sorted_valid) return 0;
     MiState &s = h->s;
     h->rows_smem = mi_persistent_rows_that_fit(s.k_v);
-    if (h->rows_smem < 1 || s.k_a > 16384) return ACAV_E_UNSUPPORTED;
+    if (h->rows_smem < 1 || s.k_a > 16384 || s.k_v >= 65535) return ACAV_E_UNSUPPORTED;
     const int ntiles = mi_partition_scratch_tiles(s.w);
     int rc = 0;
     if (!h->c2s) {

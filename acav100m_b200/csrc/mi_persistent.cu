@@ -3,8 +3,8 @@
 //
 // Data layout (built once per engine by the partition kernels below, DESIGN.md "MI layout"):
 //   * candidates are STABLY partitioned by table row c1; the stream holds only c2 as uint16
-//     (2 bytes per candidate per iteration instead of the reference's 16-byte int64 pair), 0xFFFF =
-//     removed.  Inside a row the stream keeps list order, so "first maximum wins" (mi.py:79) is
+//     (2 bytes per candidate per iteration instead of the reference's 16-byte int64 pair), value K_v =
+//     removed (its gain slot holds -inf, so the hot loop has no branch for it).  Inside a row the stream keeps list order, so "first maximum wins" (mi.py:79) is
 //     "first in stream" within a row and "smallest original position" (pos[] side array, read only on
 //     ties and for the per-thread winner) across rows.
 //   * the stream is cut into one contiguous chunk per CTA, balanced by (candidates + 3 * K_v per row
@@ -22,11 +22,11 @@
 
 namespace acav {
 
-constexpr uint16_t kGone = 0xFFFFu;
 constexpr int kPersistThreads = 1024;
 constexpr int kTileElems = 32768;            // elements per partition tile
 constexpr int kPartThreads = 512;
 constexpr int kSmallCounts = 256;            // per-iteration table of tN(x) for counts below this
+constexpr int kRing = 4;                     // 16-byte stream loads in flight per thread (cp.async ring)
 
 __device__ __forceinline__ float xlogx_cnt(uint32_t k, float f0, const float *__restrict__ logs) {
     return k == 0 ? f0 : __fmul_rn((float)k, __ldg(logs + k));
@@ -168,6 +168,7 @@ struct MiPersist {
     int64_t *out_pos;
     float *out_gain;
     int32_t rows_smem;               // gain rows that fit in shared memory
+    int32_t ring_offset;             // byte offset of the cp.async ring in dynamic shared memory
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks) {
@@ -190,6 +191,67 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nbl
 
 __device__ __forceinline__ uint4 ldcg_u4(const uint4 *p) { return __ldcg(p); }
 
+// 16-byte asynchronous global->shared copy that bypasses L1 (coherent at L2: removals written by
+// another SM before the grid barrier are seen), used to keep kRing loads per thread in flight while
+// the previous vectors are being scored.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Per-thread running arg-max.  `bi` is the stream index of the first candidate (of its row segment)
+// holding the best gain `bs`; equal-gain candidates of LATER row segments are parked in tie[] and only
+// compared by original position if this thread ends up holding the block maximum.
+struct ScanBest {
+    float bs;
+    uint32_t bi, bend;
+    uint32_t tie[3];
+    int ntie;
+};
+
+__device__ __forceinline__ void scan_tie(ScanBest &b, uint32_t e, uint32_t rend, const uint32_t *__restrict__ pos_s) {
+    if (b.ntie < 3) {
+        b.tie[b.ntie++] = e;
+    } else {                                   // list full: settle by original position now
+        uint32_t bp = __ldg(pos_s + b.bi);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const uint32_t pt = __ldg(pos_s + b.tie[t]);
+            if (pt < bp) { bp = pt; b.bi = b.tie[t]; }
+        }
+        if (__ldg(pos_s + e) < bp) b.bi = e;
+        b.ntie = 0;
+    }
+    b.bend = rend;
+}
+
+__device__ __forceinline__ void scan_consider(ScanBest &b, float g, uint32_t e, uint32_t rend,
+                                              const uint32_t *__restrict__ pos_s) {
+    if (g > b.bs) { b.bs = g; b.bi = e; b.bend = rend; b.ntie = 0; }
+    else if (g == b.bs && b.bi != 0xFFFFFFFFu && e >= b.bend) scan_tie(b, e, rend, pos_s);
+}
+
+// generic path for the few vectors that straddle a row boundary or a chunk edge
+__device__ __forceinline__ void scan_vector_slow(ScanBest &b, const uint4 q, uint32_t e0, uint32_t s_lo,
+                                                 uint32_t s_hi, int32_t &crow, const uint32_t *__restrict__ rs_local,
+                                                 const float *__restrict__ gain, int32_t gstride,
+                                                 const uint32_t *__restrict__ pos_s) {
+    uint32_t rend = rs_local[crow + 1];
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t e = e0 + j;
+        if (e < s_lo || e >= s_hi) continue;
+        while (e >= rend) { ++crow; rend = rs_local[crow + 1]; }
+        const uint32_t word = j < 4 ? (j < 2 ? q.x : q.y) : (j < 6 ? q.z : q.w);
+        const uint32_t c2 = (word >> ((j & 1) * 16)) & 0xFFFFu;
+        scan_consider(b, gain[crow * gstride + c2], e, rend, pos_s);      // removed entries read -inf
+    }
+}
+
 __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPersist P) {
     extern __shared__ __align__(16) unsigned char psmem[];
     const MiState &s = P.s;
@@ -197,7 +259,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
     float *col_term = reinterpret_cast<float *>(psmem);                 // [k_v]
     float *tn_small = col_term + k_v;                                   // [kSmallCounts]
     uint32_t *rs_local = reinterpret_cast<uint32_t *>(tn_small + kSmallCounts);   // [rows_smem + 1]
-    float *gain = reinterpret_cast<float *>(rs_local + P.rows_smem + 1 + ((P.rows_smem + 1) & 1));  // [rows_smem][k_v]
+    float *rt_local = reinterpret_cast<float *>(rs_local + P.rows_smem + 1);       // [rows_smem]
+    float *gain = rt_local + P.rows_smem;                                          // [rows_smem][k_v + 1]
+    uint4 *ring = reinterpret_cast<uint4 *>(psmem + P.ring_offset) + threadIdx.x;   // [kRing][1024] uint4, slot stride 1024
+    const int32_t gstride = k_v + 1;                                               // slot k_v holds -inf
     __shared__ unsigned long long wkey[32];
     __shared__ uint32_t widx[32];
     __shared__ unsigned long long sh_best_key;
@@ -224,61 +289,121 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         for (int32_t i = threadIdx.x; i < k_v; i += blockDim.x) col_term[i] = __ldcg(s.col_term + i);
         for (int32_t i = threadIdx.x; i < kSmallCounts; i += blockDim.x)
             tn_small[i] = __fdiv_rn(bump_sum(NlogN, (uint32_t)i, fN0, s.logs), np);
-        float bs = 0.f;                 // best gain of this thread
-        uint32_t bi = 0xFFFFFFFFu;      // its stream index
-        uint32_t bend = 0;              // end of the row segment that holds it (ties inside are never earlier)
-        uint32_t bp = 0;                // its original position (valid when bpv)
-        bool bpv = false;
+        ScanBest B;
+        B.bs = -INFINITY; B.bi = 0xFFFFFFFFu; B.bend = 0; B.ntie = 0;
+        B.tie[0] = B.tie[1] = B.tie[2] = 0;
         for (int32_t rb = r_lo; rb <= r_hi; rb += P.rows_smem) {
             const int32_t nr = min(P.rows_smem, r_hi - rb + 1);
             __syncthreads();            // previous sub-batch finished reading gain rows / first use of col_term
             for (int32_t i = threadIdx.x; i <= nr; i += blockDim.x) rs_local[i] = P.row_start[rb + i];
-            for (int32_t i = threadIdx.x; i < nr * k_v; i += blockDim.x) {
-                const int32_t rr = i / k_v, c2 = i - rr * k_v;
-                const uint32_t x = __ldcg(s.n_cells + (int64_t)(rb + rr) * k_v + c2);
-                const float tN = x < (uint32_t)kSmallCounts ? tn_small[x]
-                                                           : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
-                const float rt = __ldcg(s.row_term + rb + rr);
-                gain[i] = __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt), lognp);
+            for (int32_t i = threadIdx.x; i < nr; i += blockDim.x) {
+                rt_local[i] = __ldcg(s.row_term + rb + i);
+                gain[i * gstride + k_v] = -INFINITY;           // slot read by removed entries (c2 == k_v)
+            }
+            __syncthreads();
+            {   // gain rows: table counts of rows rb..rb+nr are contiguous; 8 loads in flight per thread
+                const int32_t ncell = nr * k_v;
+                const uint32_t *nbase = s.n_cells + (int64_t)rb * k_v;
+                for (int32_t base = 0; base < ncell; base += 8 * kPersistThreads) {
+                    uint32_t xs[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int32_t i = base + u * kPersistThreads + (int32_t)threadIdx.x;
+                        xs[u] = i < ncell ? __ldcg(nbase + i) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int32_t i = base + u * kPersistThreads + (int32_t)threadIdx.x;
+                        if (i < ncell) {
+                            const int32_t rr = i / k_v, c2 = i - rr * k_v;
+                            const uint32_t x = xs[u];
+                            const float tN = x < (uint32_t)kSmallCounts
+                                                 ? tn_small[x]
+                                                 : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
+                            gain[rr * gstride + c2] =
+                                __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt_local[rr]), lognp);
+                        }
+                    }
+                }
             }
             __syncthreads();
             const uint32_t s_lo = max(e_lo, rs_local[0]), s_hi = min(e_hi, rs_local[nr]);
             if (s_hi <= s_lo) continue;
             const uint32_t v_lo = s_lo >> 3, v_hi = (s_hi + 7) >> 3;
+            const uint4 *vec = reinterpret_cast<const uint4 *>(P.c2s_ro);
             int32_t crow = 0;                                  // cached local row of this thread
-            for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += blockDim.x) {
-                const uint4 q = ldcg_u4(reinterpret_cast<const uint4 *>(P.c2s_ro) + v);
+            // software pipeline: vector r of this thread is v_lo + tid + r * 1024
+            const uint32_t vfirst = v_lo + threadIdx.x;
+#pragma unroll
+            for (int r = 0; r < kRing - 1; ++r) {
+                const uint32_t v = vfirst + (uint32_t)r * kPersistThreads;
+                if (v < v_hi) cp_async16(ring + r * kPersistThreads, vec + v);
+                cp_async_commit();
+            }
+            int slot = 0;
+            for (uint32_t v = vfirst; v < v_hi; v += kPersistThreads) {
+                {
+                    const uint32_t vn = v + (kRing - 1) * kPersistThreads;
+                    int sn = slot + kRing - 1;
+                    if (sn >= kRing) sn -= kRing;
+                    if (vn < v_hi) cp_async16(ring + sn * kPersistThreads, vec + vn);
+                    cp_async_commit();
+                }
+                cp_async_wait<kRing - 1>();
+                const uint4 q = ring[slot * kPersistThreads];
+                if (++slot == kRing) slot = 0;
                 const uint32_t words[4] = {q.x, q.y, q.z, q.w};
                 const uint32_t e0 = v << 3;
-                uint32_t ef = max(e0, s_lo);
-                if (!(ef >= rs_local[crow] && ef < rs_local[crow + 1])) {
-                    int32_t a = 0, b = nr;                     // row with rs_local[row] <= ef < rs_local[row+1]
+                uint32_t rlo = rs_local[crow], rend = rs_local[crow + 1];
+                const uint32_t ef = max(e0, s_lo);
+                if (ef < rlo || ef >= rend) {              // row with rs_local[row] <= ef < rs_local[row+1]
+                    int32_t a = 0, b = nr;
                     while (a < b) { const int32_t m = (a + b) >> 1; if (rs_local[m + 1] > ef) b = m; else a = m + 1; }
-                    crow = a;
+                    crow = a; rlo = rs_local[crow]; rend = rs_local[crow + 1];
                 }
-                uint32_t rend = rs_local[crow + 1];
+                if (e0 >= max(s_lo, rlo) && e0 + 8 <= min(s_hi, rend)) {
+                    // fast path: all 8 candidates in one row segment; removed entries gather -inf
+                    const float *grow = gain + crow * gstride;
+                    float g[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t e = e0 + j;
-                    const uint32_t c2 = (words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                    if (e < s_lo || e >= s_hi) continue;
-                    while (e >= rend) { ++crow; rend = rs_local[crow + 1]; }
-                    if (c2 == kGone) continue;
-                    const float g = gain[crow * k_v + c2];
-                    if (bi == 0xFFFFFFFFu || g > bs) {
-                        bs = g; bi = e; bend = rend; bpv = false;
-                    } else if (g == bs && e >= bend) {           // tie with a candidate of a later row segment
-                        if (!bpv) { bp = __ldg(P.pos_s + bi); bpv = true; }
-                        const uint32_t pe = __ldg(P.pos_s + e);
-                        if (pe < bp) { bi = e; bp = pe; bend = rend; }
+                    for (int j = 0; j < 8; ++j) g[j] = grow[(words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu];
+                    const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
+                                          fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                    if (m > B.bs || (m == B.bs && B.bi != 0xFFFFFFFFu && e0 >= B.bend)) {
+                        int j = 0;
+#pragma unroll
+                        for (int t = 7; t >= 0; --t) j = g[t] == m ? t : j;       // first of the maxima
+                        scan_consider(B, m, e0 + j, rend, P.pos_s);
                     }
+                } else {
+                    scan_vector_slow(B, q, e0, s_lo, s_hi, crow, rs_local, gain, gstride, P.pos_s);
                 }
             }
+            cp_async_wait<0>();
         }
+        float bs = B.bs;
+        uint32_t bi = B.bi;
+        const int ntie = B.ntie;
+        uint32_t tie[3] = {B.tie[0], B.tie[1], B.tie[2]};
+        // block maximum of the gain, then only the threads holding it settle their ties by position
+        const uint32_t my32 = bi == 0xFFFFFFFFu ? 0u : orderable(bs);
+        uint32_t m32 = my32;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
+        if (threadIdx.x % kWarp == 0) widx[threadIdx.x / kWarp] = m32;
+        __syncthreads();
+        m32 = widx[threadIdx.x % kWarp];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
+        __syncthreads();                                       // widx is reused below
         unsigned long long key = 0ull;
-        if (bi != 0xFFFFFFFFu) {
-            if (!bpv) bp = __ldg(P.pos_s + bi);
-            key = make_key(bs, base_pos + bp);
+        if (my32 != 0u && my32 == m32) {
+            uint32_t bp = __ldg(P.pos_s + bi);
+            for (int t = 0; t < ntie; ++t) {
+                const uint32_t pt = __ldg(P.pos_s + tie[t]);
+                if (pt < bp) { bp = pt; bi = tie[t]; }
+            }
+            key = ((unsigned long long)m32 << 32) | (unsigned long long)(0xFFFFFFFFu - (base_pos + bp));
         }
         // block arg-max of (key, stream index)
         {
@@ -330,7 +455,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                 s.sums[2] = bump_sum(__ldcg(s.sums + 2), z, fa0w, s.logs);
                 s.sums[3] = __fadd_rn(__ldcg(s.sums + 3), 1.0f);                  // update_mats :401-406
                 s.n_cells[(int64_t)c1 * k_v + c2] = x + 1; s.a_cols[c2] = y + 1; s.b_rows[c1] = z + 1;
-                P.c2s[widx_s] = kGone;                                            // remove_idx_all :104-106
+                P.c2s[widx_s] = (uint16_t)k_v;                                    // remove_idx_all :104-106 (k_v = removed)
                 const int64_t pos = (int64_t)key_pos(win);
                 s.cells[pos - s.pos_base] = 0xFFFFFFFFu;                          // keep the list-order view in sync
                 P.out_pos[it] = pos;
@@ -382,23 +507,18 @@ int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t 
     return 0;
 }
 
-int launch_mi_fill_gone(uint16_t *c2s, int64_t lo, int64_t hi, cudaStream_t st) {
-    if (hi <= lo) return 0;
-    mi_fill_u16_kernel<<<(unsigned)ceil_div(hi - lo, 256), 256, 0, st>>>(c2s, lo, hi, kGone);
-    ACAV_LAUNCH_CHECK();
-    return 0;
-}
 
-// shared memory needed for `rows` gain rows
-static size_t persist_smem_bytes(int32_t k_v, int32_t rows) {
-    size_t words = (size_t)k_v + kSmallCounts + (size_t)rows + 1 + ((rows + 1) & 1) + (size_t)rows * k_v;
-    return words * 4 + 16;
+// dynamic shared memory: [col_term k_v | tn_small | rs_local rows+1 | rt_local rows | gain rows*(k_v+1)] | ring
+static size_t persist_table_bytes(int32_t k_v, int32_t rows) {
+    size_t words = (size_t)k_v + kSmallCounts + 2 * (size_t)rows + 1 + (size_t)rows * (k_v + 1);
+    return (words * 4 + 15) & ~(size_t)15;
 }
+static size_t persist_ring_bytes() { return (size_t)kRing * kPersistThreads * 16; }
 
 int mi_persistent_rows_that_fit(int32_t k_v) {
-    const size_t budget = 200 * 1024;
+    const size_t budget = 224 * 1024 - persist_ring_bytes();
     int32_t rows = 0;
-    while (persist_smem_bytes(k_v, rows + 1) <= budget && rows < 4096) ++rows;
+    while (persist_table_bytes(k_v, rows + 1) <= budget && rows < 4096) ++rows;
     return rows;
 }
 
@@ -410,7 +530,8 @@ int launch_mi_persistent(const MiState &s, uint16_t *c2s, const uint32_t *pos_s,
     P.s = s; P.c2s_ro = c2s; P.c2s = c2s; P.pos_s = pos_s; P.row_start = row_start; P.chunk_start = chunk_start;
     P.slots = slots; P.bar = bar; P.w_sorted = w_sorted; P.n_picks = n_picks; P.out_pos = out_pos;
     P.out_gain = out_gain; P.rows_smem = rows_smem;
-    const size_t smem = persist_smem_bytes(s.k_v, rows_smem);
+    P.ring_offset = (int32_t)persist_table_bytes(s.k_v, rows_smem);
+    const size_t smem = persist_table_bytes(s.k_v, rows_smem) + persist_ring_bytes();
     static size_t attr_set = 0;
     if (smem > attr_set) {
         ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -15,7 +15,7 @@ import time
 import numpy as np
 import torch
 
-from ... import _lib
+from ... import _lib, parallel
 from . import tables
 
 
@@ -59,7 +59,7 @@ class EfficientMemMI:
         if self.shard is not None:
             import torch.distributed as dist
             rank, world = self.shard
-            lo, hi = (W * rank) // world, (W * (rank + 1)) // world
+            lo, hi = parallel.shard_bounds(W, rank, world)
             self._dist = dist
         self._range = (lo, hi)
         pair = self.combinations[0]
@@ -167,14 +167,20 @@ class EfficientMemMI:
                 _lib.call("acav_mi_run", self._engine, n_picks, _lib.ptr(pos), _lib.ptr(gain),
                           self._loop_mode(), st)
             else:
-                world = self.shard[1]
-                mine = torch.empty(2, dtype=torch.int64, device=self.device)
-                allp = torch.empty(world, 2, dtype=torch.int64, device=self.device)
-                for i in range(n_picks):
-                    _lib.call("acav_mi_local_best", self._engine, _lib.ptr(mine), st)
-                    self._dist.all_gather_into_tensor(allp, mine)
-                    _lib.call("acav_mi_apply", self._engine, _lib.ptr(allp), world,
-                              _lib.c_vp(pos.data_ptr() + 8 * i), _lib.c_vp(gain.data_ptr() + 4 * i), st)
+                dev, eng = self.device, self._engine
+
+                class _Engine:
+                    def local_best(self, out_pair):
+                        _lib.call("acav_mi_local_best", eng, _lib.ptr(out_pair), st)
+
+                    def apply(self, all_pairs, world, i):
+                        _lib.call("acav_mi_apply", eng, _lib.ptr(all_pairs), world,
+                                  _lib.c_vp(pos.data_ptr() + 8 * i), _lib.c_vp(gain.data_ptr() + 4 * i), st)
+
+                parallel.sharded_greedy(
+                    _Engine(), self._dist, self.shard[1], n_picks,
+                    lambda: torch.empty(2, dtype=torch.int64, device=dev),
+                    lambda world: torch.empty(2 * world, dtype=torch.int64, device=dev))
         self._picked += n_picks
         return pos, gain
 

@@ -1,0 +1,81 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py
+
+k-means: N-rank KMeans.add (NCCL all-reduce of histogram and deltas) vs the oracle's world step.
+greedy MI: candidate list sharded over the ranks vs the C oracle on the whole list.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from acav100m_b200 import synth                                  # noqa: E402
+from acav100m_b200.clustering import KMeans                      # noqa: E402
+from acav100m_b200.subset_selection import get_measure           # noqa: E402
+from oracle import kmeans_oracle as ko, mi_oracle as mo          # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+# ---- k-means ----
+k, d, b, seed = 32, 256, 512, 9
+x = torch.from_numpy(synth.gaussian_mixture(b * world * 12, d, 20, 17))
+args = types.SimpleNamespace(computation=types.SimpleNamespace(device="cuda", num_gpus=world))
+for mode in ("exact", "tensor"):
+    torch.manual_seed(seed + rank)
+    km = KMeans(args, d, k, assign_mode=mode, warmup_rng="cpu")
+    km.to("cuda")
+    km.initialize()
+    for g0 in range(0, len(x), world * b):
+        km.add(x[g0 + rank * b: g0 + (rank + 1) * b])
+    # oracle replay of all ranks' RNG streams
+    inits, gens = [], []
+    for r in range(world):
+        torch.manual_seed(seed + r)
+        inits.append(torch.rand(k, d) * 1e-5)
+        gens.append(torch.get_rng_state())
+    c0 = inits[0].clone()
+    for t in inits[1:]:
+        c0 += t
+    st = ko.SgdKMeansState(centers=c0 * (1.0 / world), counts=torch.zeros(k))
+    for g0 in range(0, len(x), world * b):
+        noises = None
+        if ko.in_warmup(st):
+            noises = []
+            for r in range(world):
+                torch.set_rng_state(gens[r])
+                noises.append(torch.rand(k, b))
+                gens[r] = torch.get_rng_state()
+        ko.sgd_step_world(st, [x[g0 + r * b: g0 + (r + 1) * b] for r in range(world)], noises)
+    centers = km.centers.cpu()
+    rel = ((centers - st.centers).abs().max() / st.centers.abs().max()).item()
+    ok = (torch.equal(km.counts.cpu(), st.counts) and km.count == st.count and km.fallback == st.fallback
+          and rel < 1e-5)
+    best, _ = km.calc_best(x[:2048])
+    want, _ = ko.assign(st, x[:2048])
+    agree = (best.cpu() == want).float().mean().item()
+    print(f"[rank {rank}] kmeans {mode}: counts/count/fallback ok={ok} max rel |dcenter| {rel:.2e} ids agree {agree:.4f}",
+          flush=True)
+    assert ok and agree > 0.999
+
+# ---- greedy MI ----
+W, C, picks = 200_003, 64, 700
+a = synth.zipf_pairs(W, C, 23)
+pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks)
+m = get_measure("mem_mi")(a, ncentroids=C, device="cuda", shard=(rank, world))
+m.init([(0, 1)], list(range(W)))
+pos, gain = m.select(picks)
+ok = np.array_equal(pos.cpu().numpy(), pos_want) and np.array_equal(gain.cpu().numpy(), gain_want)
+print(f"[rank {rank}] greedy MI sharded over {world} ranks: bit-exact={ok}", flush=True)
+assert ok
+dist.barrier()
+dist.destroy_process_group()
+if rank == 0:
+    print("MULTIGPU OK")
