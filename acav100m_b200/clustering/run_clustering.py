@@ -1,0 +1,182 @@
+"""Host loops of the clustering stage (reference clustering/code/run_clustering.py:25-272 and
+process_batch.py:6-69): train the per-(model, layer) ``KMeans`` objects over the feature shards, then
+assign every clip and write cluster shards.  All tensor work happens inside ``KMeans`` (CUDA)."""
+import copy
+import math
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import hostio
+from . import data as D
+from .config import MODELS
+from .save import save_assignments
+from .sgd_clustering import KMeans
+
+
+def filter_models(args):
+    """utils.py:17-23."""
+    names = list(args.models)
+    data_name = Path(args.data.media.path).stem
+    if data_name in args.data.types and args.data.types[data_name] == 'audio_only':
+        names = [n for n in names if n in args.model_types.audio]
+    return names
+
+
+def model_key_map(model_names):
+    """run_clustering.py:119-129 -- model name -> 'EXTRACTOR/dataset' key of the collated batch."""
+    return {n: '/'.join((MODELS[n]['tag']['name'], MODELS[n]['tag']['dataset'])) for n in model_names}
+
+
+def _world(args):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_clusterings(args, model_names):
+    """run_clustering.py:32-52."""
+    clusterings = {}
+    for name in model_names:
+        dims = MODELS[name]['output_dims']
+        if isinstance(dims, int):
+            clusterings[name] = {'model': KMeans(args, dims, args.clustering.ncentroids)}
+        else:
+            clusterings[name] = {'layer_{}'.format(i): KMeans(args, d, args.clustering.ncentroids)
+                                 for i, d in enumerate(dims)}
+    return _place(args, clusterings)
+
+
+def _place(args, clusterings):
+    for per_model in clusterings.values():
+        for km in per_model.values():
+            km.to(args.computation.device)
+            km.initialize()
+    return clusterings
+
+
+def cache_path(args, epoch):
+    """utils.py:30-32 + run_clustering.py:110-116 -- ``cache_epoch_{e}_{basename(feature_path)}``."""
+    return args.data.output.path / "cache_epoch_{}_{}".format(epoch, Path(args.data.path).name)
+
+
+def save_clusterings(args, epoch, clusterings):
+    """Checkpoint after every epoch.  Written in the reference's ``save_scheme_ver2`` layout (a tree of
+    ``get_attrs()`` dicts with numpy arrays), which does not pickle any class."""
+    tree = {m: {k: km.get_attrs() for k, km in per.items()} for m, per in clusterings.items()}
+    for per in tree.values():
+        for attrs in per.values():
+            attrs['args'] = None
+    path = cache_path(args, epoch)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    torch.save(tree, str(path))
+    return path
+
+
+def load_clusterings(args, model_names):
+    """run_clustering.py:55-107 -- resume from ``--clustering.cached_epoch``."""
+    epoch = args.clustering.cached_epoch
+    if isinstance(epoch, int):
+        path = cache_path(args, epoch)
+        if path.is_file():
+            tree = torch.load(str(path), weights_only=False)
+            if set(model_names) <= set(tree.keys()):
+                clusterings = {}
+                for m in model_names:
+                    clusterings[m] = {}
+                    for k, v in tree[m].items():
+                        attrs = v if isinstance(v, dict) else v.get_attrs()
+                        km = KMeans.load(dict(attrs))
+                        km.args = args
+                        clusterings[m][k] = km
+                print("loading from clustering cache: {}".format(path))
+                return _place(args, clusterings), True
+            print("clustering cache features does not match with the given models")
+        else:
+            print("no clustering cache found.")
+    return init_clusterings(args, model_names), False
+
+
+def _train_batch(args, features, clusterings):
+    """process_batch.py:6-17."""
+    if isinstance(features, dict):
+        return float(np.mean([km.add(features[key]) for key, km in clusterings.items()]))
+    return clusterings['model'].add(features)
+
+
+def train_clusters(args, model_names):
+    """run_clustering.py:132-177."""
+    clusterings, loaded = load_clusterings(args, model_names)
+    if loaded and not args.clustering.resume_training:
+        return clusterings
+    rank, world = _world(args)
+    keys = model_key_map(model_names)
+    shard_paths = D.expand_shards(args.data.path)
+    pre_epochs = copy.deepcopy(args.clustering.cached_epoch) if loaded else 0
+    epochs = math.ceil(args.clustering.epochs / max(args.computation.num_gpus or 1, 1))      # :146
+    print("training sgd kmeans for models: {}".format(model_names))
+    for epoch in range(pre_epochs, epochs + pre_epochs):
+        for per_model in clusterings.values():
+            for km in per_model.values():
+                km.lr = 0.1 ** (2 + epoch // 5)                                              # :168
+        for batch in D.batches(shard_paths, args.data.batch_size, drop_last=True):
+            batch = D.rank_slice(batch, rank, world)
+            for name in model_names:
+                _train_batch(args, batch[keys[name]], clusterings[name])
+        if rank == 0:
+            save_clusterings(args, epoch, clusterings)
+    return clusterings
+
+
+def _extract_batch(features, clusterings):
+    """process_batch.py:37-56 -- ids per layer as np.int64."""
+    if isinstance(features, dict):
+        ids = {key: km.calc_best(features[key], sync=False)[0] for key, km in clusterings.items()}
+        ids = {key: v.cpu().numpy() for key, v in ids.items()}
+        keys = sorted(ids.keys())
+        return [dict(zip(keys, vals)) for vals in zip(*[ids[k] for k in keys])]
+    return list(clusterings['model'].calc_best(features, sync=False)[0].cpu().numpy())
+
+
+def assign_clusters(args, model_names, clusterings):
+    """run_clustering.py:180-272 -- rank r labels shards r::world, one output shard per input shard."""
+    rank, world = _world(args)
+    keys = model_key_map(model_names)
+    shard_paths = D.expand_shards(args.data.path)[rank::world]
+    prefix = '' if args.clustering.cached_epoch is None else 'epoch_{}_'.format(args.clustering.cached_epoch)
+    batch_size = max(int(args.data.batch_size), 1024)
+    saved_paths = []
+    print("extracting clustering for models: {}".format(model_names))
+    for shard_path in shard_paths:
+        out_path = args.data.output.path / (prefix + shard_path.stem + '.pkl')
+        if out_path.is_file():                                                               # :248-250
+            continue
+        ids = defaultdict(list)
+        shards = {name: defaultdict(dict) for name in model_names}
+        for batch in D.batches([shard_path], batch_size, drop_last=False):
+            per_model = {name: _extract_batch(batch[keys[name]], clusterings[name]) for name in model_names}
+            for j, idx in enumerate(batch['idx']):
+                shard_name = batch['shard_name'][j]
+                if idx in shards[model_names[0]][shard_name]:                                # dedupe :236
+                    continue
+                ids[shard_name].append(idx)
+                for name in model_names:
+                    shards[name][shard_name][idx] = {
+                        'assignments': per_model[name][j], 'filename': batch['filename'][j],
+                        'shard_name': shard_name, 'shard_size': batch['shard_size'][j], 'idx': idx}
+        for shard_name, id_list in ids.items():
+            data = [{'model_key': name, 'data': shards[name][shard_name], **MODELS[name]['tag']}
+                    for name in model_names]
+            saved_paths.append(save_assignments(args, shard_name, id_list, data, prefix=prefix))
+    return saved_paths
+
+
+def run_clustering(args):
+    """run_clustering.py:25-29."""
+    model_names = filter_models(args)
+    with torch.no_grad():
+        clusterings = train_clusters(args, model_names)
+        return assign_clusters(args, model_names, clusterings)

@@ -1,0 +1,144 @@
+"""Host-side I/O of the two CLI shims: reference on-disk formats in, reference formats out (CPU only)."""
+import csv
+import json
+import os
+import pickle
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from acav100m_b200 import hostio
+from acav100m_b200.clustering import args as cargs, data as cdata, save as csave
+from acav100m_b200.clustering.config import MODELS, defaults as cdefaults
+from acav100m_b200.subset_selection import cli as scli, dataloader as sdata, save as ssave
+from acav100m_b200.subset_selection.config import defaults as sdefaults
+from oracle import ref_shims
+from tests.shard_fixtures import write_feature_shards
+
+
+def test_cli_parsing_and_dotted_overrides():
+    cmd, kw = hostio.parse_cli(["cluster", "--feature_path=d/shard-{000000..000002}.pkl", "--out_path=o",
+                                "--clustering.ncentroids=8", "--data.batch_size", "64", "--debug"])
+    assert cmd == "cluster" and kw["clustering.ncentroids"] == 8 and kw["data.batch_size"] == 64 and kw["debug"] is True
+    args = cargs.get_args(**cargs.cli_aliases(kw))
+    assert args.clustering.ncentroids == 8 and args.data.batch_size == 64
+    assert str(args.data.path).endswith("d/shard-{000000..000002}.pkl")
+    assert args.data.output.path == Path("o").resolve()
+    assert args.clustering.save_scheme_ver2 is None and args.node_rank is None      # DefaultMunch(None) semantics
+    assert hostio.braceexpand("a/shard-{000008..000011}.pkl") == ["a/shard-0000%02d.pkl" % i for i in (8, 9, 10, 11)]
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not mounted")
+def test_default_flag_trees_equal_the_reference():
+    for sub, ours in (("clustering", cdefaults), ("subset_selection", sdefaults)):
+        spec = {}
+        exec(open(os.path.join(ref_shims.REFERENCE_ROOT, sub, "code", "config.py")).read(), spec)
+        ref = spec["defaults"]
+        mine = {k: v for k, v in ours.items()}
+        if sub == "subset_selection":
+            mine = json.loads(json.dumps(mine))
+            mine["clustering"].pop("columns")                  # our one documented extension
+            ref = json.loads(json.dumps(ref))
+        assert mine == ref
+
+
+def test_feature_shards_collate_like_the_reference(tmp_path):
+    feat_dir, _ = write_feature_shards(tmp_path, n_shards=2, clips_per_shard=10)
+    paths = cdata.expand_shards(feat_dir / "shard-{000000..000001}.pkl")
+    assert len(paths) == 2
+    got = list(cdata.batches(paths, 8, drop_last=True))
+    assert len(got) == 2                                        # 20 rows -> 2 full batches, batches span shards
+    b = got[1]
+    assert set(b.keys()) == {"VGGish/YouTube-8M", "SLOWFAST_8x8_R50/kinetics-400", "filename", "shard_name",
+                             "shard_size", "idx"}
+    assert b["shard_name"][:2] == ["shard-000000"] * 2 and b["shard_name"][2:] == ["shard-000001"] * 6
+    for key, model in (("VGGish/YouTube-8M", "layer_vggish"), ("SLOWFAST_8x8_R50/kinetics-400", "layer_slow_fast")):
+        for i, d in enumerate(MODELS[model]["output_dims"]):
+            t = b[key]["layer_%d" % i]
+            assert t.dtype == torch.float32 and tuple(t.shape) == (8, d)
+    assert b["idx"][0] == Path(b["filename"][0]).stem
+    half = cdata.rank_slice(b, 1, 2)
+    assert half["idx"] == b["idx"][4:] and torch.equal(half["VGGish/YouTube-8M"]["layer_0"],
+                                                       b["VGGish/YouTube-8M"]["layer_0"][4:])
+    assert len(list(cdata.batches(paths, 8, drop_last=False))) == 3
+
+
+def _fake_cluster_shard(args, name, n, rng):
+    ids = ["clip_%s_%04d" % (name[-6:], c) for c in range(n)]
+    data = []
+    for m in ("layer_vggish", "layer_slow_fast"):
+        per = {idx: {"assignments": {"layer_%d" % i: np.int64(rng.randint(8)) for i in range(5)},
+                     "filename": idx + ".mp4", "shard_name": name, "shard_size": n} for idx in ids}
+        data.append({"model_key": m, "data": per, **MODELS[m]["tag"]})
+    return csave.save_assignments(args, name, ids, data)
+
+
+def test_cluster_shards_round_trip_into_selection_inputs(tmp_path):
+    rng = np.random.RandomState(0)
+    args = cargs.get_args(**{"data.output.path": str(tmp_path / "clusters")})
+    p0 = _fake_cluster_shard(args, "shard-000000", 6, rng)
+    p1 = _fake_cluster_shard(args, "shard-000001", 5, rng)
+    log = csave.store_shards_set(args, [p0, p1])
+    assert log.name.startswith("log_") and json.load(open(log))["shards"] == ["shard-000000", "shard-000001"]
+    row = pickle.load(open(p0, "rb"))[0]
+    assert set(row) == {"video_assignments", "audio_assignments", "filename", "shard_size", "shard_name"}
+    feat = row["audio_assignments"][0]
+    assert feat["model_key"] == "layer_vggish" and feat["extractor_name"] == "VGGish"
+    assert isinstance(feat["array"]["layer_3"], np.int64)
+    parts, metas = sdata.load_data(str(tmp_path / "clusters" / "shard-{000000..000001}.pkl"), tmp_path)
+    assert list(parts.keys()) == [0] and len(parts[0]) == 11 and metas == {}
+    a, shard_names, filenames, ctypes_ = sdata.preprocess(parts[0])
+    assert a.shape == (11, 10) and a.dtype == np.int64
+    assert ctypes_ == sorted(ctypes_) and ctypes_[0] == ("layer_slow_fast", "layer_0") and ctypes_[-1] == ("layer_vggish", "layer_4")
+    a2, _, _, t2 = sdata.preprocess(parts[0], columns=[("layer_vggish", "layer_4"), ("layer_slow_fast", "layer_4")])
+    assert a2.shape == (11, 2) and np.array_equal(a2[:, 0], a[:, 9]) and np.array_equal(a2[:, 1], a[:, 4])
+    if ref_shims.reference_available():                        # the reference's own reader agrees
+        sys.modules.setdefault("braceexpand", types.SimpleNamespace(braceexpand=hostio.braceexpand))
+        code = os.path.join(ref_shims.REFERENCE_ROOT, "subset_selection", "code")
+        sys.path.insert(0, code)
+        try:
+            for stale in ("dataloader", "utils", "multiprocess"):
+                sys.modules.pop(stale, None)
+            import dataloader as ref_loader
+            ra, rs, rf, rt = ref_loader.preprocess(parts[0], num_workers=1)
+            assert np.array_equal(ra, a) and list(rs) == list(shard_names) and list(rf) == list(filenames) and rt == ctypes_
+        finally:
+            sys.path.remove(code)
+            for stale in ("dataloader", "utils", "multiprocess"):
+                sys.modules.pop(stale, None)
+
+
+def test_partitions_follow_newest_log(tmp_path):
+    d = tmp_path / "c"
+    d.mkdir()
+    json.dump({"shards": ["shard-000000", "shard-000001"]}, open(d / "log_host_1_100.json", "w"))
+    json.dump({"shards": ["shard-000001"]}, open(d / "log_host_2_200.json", "w"))
+    assert sdata.load_partitions(d) == {"shard-000000": 0, "shard-000001": 1}
+
+
+def test_output_csv_matches_reference_example(tmp_path):
+    metas = {"shard-000000": {"a": {"filename": "a.mp4", "id": "qZ1", "segment": [0.0, 10.0]}}}
+    data = [{"filename": "a.mp4", "shard_name": "shard-000000"}, {"filename": "b.mp4", "shard_name": "shard-000000"}]
+    out, n = ssave.save_output(data, metas, tmp_path / "output.csv")
+    out, n2 = ssave.save_output(data[:1], metas, tmp_path / "output.csv")            # append mode
+    rows = list(csv.reader(open(out)))
+    assert n == 2 and n2 == 1 and len(rows) == 3
+    assert rows[0] == ["shard-000000", "a.mp4", "qZ1", "[0.0, 10.0]"]
+    assert rows[1] == ["shard-000000", "b.mp4", "-1", "[-1.0, -1.0]"]
+    if ref_shims.reference_available():
+        ex = list(csv.reader(open(os.path.join(ref_shims.REFERENCE_ROOT, "examples", "output.csv"))))
+        assert len(ex[0]) == 4 and ex[0][3].startswith("[") and ex[0][0].startswith("shard-")
+
+
+def test_selection_cli_path_handling(tmp_path):
+    (tmp_path / "clusters").mkdir()
+    args = scli.prepare(out_path=str(tmp_path / "out"), shards_path=str(tmp_path / "clusters" / "shard-{0..1}.pkl"),
+                        **{"measure_name": "mem_mi", "subset.ratio": 0.1})
+    assert args.data.output.path == tmp_path / "out" / "output.csv"      # bare dir -> /output.csv
+    assert args.data.meta.path == tmp_path / "clusters"                  # meta defaults to the shard dir
+    assert args.measure_name == "mem_mi" and args.subset.ratio == 0.1 and args.computation.device == "cuda"
+    assert args.batch.batch_size == 20 and args.log_times == 10
