@@ -38,11 +38,18 @@ struct acav_mi {
     // persistent-loop resources (row-partitioned stream), built on first use
     uint16_t *c2s;
     uint32_t *pos_s, *row_start, *row_total, *tilehist, *chunk_start;
-    unsigned long long *slots;
+    uint32_t *n_alt;
+    unsigned char *pub;
     unsigned int *bar;
     int32_t grid, rows_smem;
     int64_t w_sorted;
     bool sorted_valid;
+    // multi-GPU mailbox (persistent loop, world > 1)
+    int32_t world, rank;
+    unsigned int seq_base;
+    unsigned char *mail_local;
+    void *mail_peer[kMiMaxWorld];
+    bool comm_connected;
 };
 
 namespace {
@@ -70,8 +77,8 @@ int query_sm_count(int32_t *out) {
 int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     if (h->sorted_valid) return 0;
     MiState &s = h->s;
-    h->rows_smem = mi_persistent_rows_that_fit(s.k_v);
-    if (h->rows_smem < 1 || s.k_a > 16384 || s.k_v >= 65535) return ACAV_E_UNSUPPORTED;
+    h->rows_smem = mi_persistent_rows_that_fit(s.k_a, s.k_v);
+    if (h->rows_smem < 1 || s.k_v >= 65535 || (int64_t)s.k_a * s.k_v >= (1ll << 31)) return ACAV_E_UNSUPPORTED;
     const int ntiles = mi_partition_scratch_tiles(s.w);
     int rc = 0;
     if (!h->c2s) {
@@ -81,7 +88,8 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
         if (!rc) rc = dev_alloc(&h->row_total, (size_t)s.k_a, nullptr);
         if (!rc) rc = dev_alloc(&h->tilehist, (size_t)ntiles * s.k_a, nullptr);
         if (!rc) rc = dev_alloc(&h->chunk_start, (size_t)h->sm_count + 1, nullptr);
-        if (!rc) rc = dev_alloc(&h->slots, 2, nullptr);
+        if (!rc) rc = dev_alloc(&h->n_alt, (size_t)s.k_a * s.k_v, nullptr);
+        if (!rc) rc = dev_alloc(&h->pub, mi_pub_bytes(h->sm_count), nullptr);
         if (!rc) rc = dev_alloc(&h->bar, 2, nullptr);
         if (rc) return rc;
     }
@@ -318,7 +326,11 @@ int acav_mi_destroy(acav_mi_t *h) {
     cudaFree(s.cells); cudaFree(s.n_cells); cudaFree(s.a_cols); cudaFree(s.b_rows); cudaFree(s.gain);
     cudaFree(s.col_term); cudaFree(s.row_term); cudaFree(s.sums); cudaFree(s.key); cudaFree(h->consts_dev);
     cudaFree(h->c2s); cudaFree(h->pos_s); cudaFree(h->row_start); cudaFree(h->row_total); cudaFree(h->tilehist);
-    cudaFree(h->chunk_start); cudaFree(h->slots); cudaFree(h->bar);
+    cudaFree(h->chunk_start); cudaFree(h->n_alt); cudaFree(h->pub); cudaFree(h->bar);
+    if (h->comm_connected)
+        for (int r = 0; r < h->world; ++r)
+            if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
+    cudaFree(h->mail_local);
     delete h;
     return 0;
 }
@@ -336,7 +348,9 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     s.w = w; s.k_a = k_a; s.k_v = k_v; s.pos_base = pos_base; s.logs = nullptr; s.n_logs = 0;
     h->max_picks = max_picks; h->loaded = false; h->tabled = false; h->consts_dev = nullptr;
     h->c2s = nullptr; h->pos_s = nullptr; h->row_start = nullptr; h->row_total = nullptr; h->tilehist = nullptr;
-    h->chunk_start = nullptr; h->slots = nullptr; h->bar = nullptr; h->grid = 0; h->rows_smem = 0; h->w_sorted = 0;
+    h->chunk_start = nullptr; h->n_alt = nullptr; h->pub = nullptr; h->bar = nullptr; h->grid = 0; h->rows_smem = 0;
+    h->w_sorted = 0; h->world = 1; h->rank = 0; h->seq_base = 0; h->mail_local = nullptr; h->comm_connected = false;
+    for (int r = 0; r < kMiMaxWorld; ++r) h->mail_peer[r] = nullptr;
     h->sorted_valid = false;
     int rc = query_sm_count(&h->sm_count);
     const size_t cells = (size_t)k_a * k_v;
@@ -415,10 +429,42 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
     }
     if (mode != ACAV_MI_LOOP_PERSISTENT) return ACAV_E_INVALID;
     if (n_picks == 0) return 0;
+    if (h->world > 1 && !h->comm_connected) return ACAV_E_STATE;
     int rc = mi_prepare_persistent(h, st);
     if (rc) return rc;
-    return launch_mi_persistent(h->s, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->slots, h->bar,
-                                h->w_sorted, n_picks, out_pos, out_gain, h->rows_smem, st);
+    rc = launch_mi_persistent(h->s, h->n_alt, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->pub, h->bar,
+                              n_picks, out_pos, out_gain, h->rows_smem, h->world, h->rank, h->seq_base, h->mail_local,
+                              h->mail_peer, st);
+    h->seq_base += (unsigned int)n_picks + 1u;          // mailbox tags never repeat across runs
+    if (!rc) rc = launch_mi_refresh_terms(h->s, st);
+    return rc;
+}
+
+int acav_mi_comm_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int acav_mi_comm_export(acav_mi_t *h, int32_t world, int32_t rank, void *handle_out) {
+    if (!h || !handle_out || world < 1 || world > kMiMaxWorld || rank < 0 || rank >= world) return ACAV_E_INVALID;
+    if (h->mail_local) return ACAV_E_STATE;
+    int rc = dev_alloc(&h->mail_local, mi_mail_bytes(world), nullptr);
+    if (rc) return rc;
+    ACAV_CUDA_TRY(cudaMemset(h->mail_local, 0, mi_mail_bytes(world)));
+    h->world = world; h->rank = rank;
+    ACAV_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle_out), h->mail_local));
+    return 0;
+}
+
+int acav_mi_comm_connect(acav_mi_t *h, const void *handles) {
+    if (!h || !handles) return ACAV_E_INVALID;
+    if (!h->mail_local || h->comm_connected) return ACAV_E_STATE;
+    const cudaIpcMemHandle_t *hs = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) { h->mail_peer[r] = h->mail_local; continue; }
+        void *p = nullptr;
+        ACAV_CUDA_TRY(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
+        h->mail_peer[r] = p;
+    }
+    h->comm_connected = true;
+    return 0;
 }
 
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows, float *sums,

@@ -70,6 +70,7 @@ struct MiState {                 // device-resident table + running sums of one 
 int launch_mi_pack(const int64_t *cells, int64_t w, uint32_t *packed, cudaStream_t st);
 int launch_mi_reset(const MiState &s, const float *consts_dev, cudaStream_t st);
 int launch_mi_add_sample(const MiState &s, int32_t c1, int32_t c2, cudaStream_t st);
+int launch_mi_refresh_terms(const MiState &s, cudaStream_t st);
 int launch_mi_gain_table(const MiState &s, cudaStream_t st);
 int launch_mi_scan(const MiState &s, int sm_count, cudaStream_t st);
 int launch_mi_emit(const MiState &s, unsigned long long *out, cudaStream_t st);
@@ -81,10 +82,14 @@ int mi_partition_scratch_tiles(int64_t w);
 int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t *tilehist, uint32_t *row_total,
                         uint32_t *row_start, uint16_t *c2s, uint32_t *pos_s, int64_t stream_capacity,
                         cudaStream_t st);
-int mi_persistent_rows_that_fit(int32_t k_v);
-int launch_mi_persistent(const MiState &s, uint16_t *c2s, const uint32_t *pos_s, const uint32_t *row_start,
-                         const uint32_t *chunk_start, int32_t grid, unsigned long long *slots, unsigned int *bar,
-                         int64_t w_sorted, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
+int mi_persistent_rows_that_fit(int32_t k_a, int32_t k_v);
+size_t mi_pub_bytes(int32_t grid);
+size_t mi_mail_bytes(int32_t world);
+constexpr int kMiMaxWorld = 16;
+int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const uint32_t *pos_s,
+                         const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
+                         unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
+                         int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
                          cudaStream_t st);
 
 }  // namespace acav

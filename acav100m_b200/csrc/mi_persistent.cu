@@ -154,21 +154,40 @@ __global__ void mi_fill_u16_kernel(uint16_t *p, int64_t lo, int64_t hi, uint16_t
 
 // ---- the persistent kernel -----------------------------------------------------------------------
 
+struct MiPub {                       // one per CTA and iteration parity: the CTA's best candidate
+    unsigned long long key;          // (orderable gain << 32) | (0xFFFFFFFF - global position), 0 = none
+    unsigned long long payload;      // (c1 << 48) | (c2 << 32) | table count x of that cell
+};
+
+struct MiMail {                      // one per (parity, source rank), written by peers over NVLink
+    unsigned long long key;
+    unsigned long long payload;
+    unsigned int seq;                // iteration tag, stored last with release semantics
+    unsigned int pad[3];
+};
+
+constexpr int kMaxWorld = 16;
+
 struct MiPersist {
-    MiState s;
+    MiState s;                       // canonical state in global memory (read at entry, written back at exit)
+    uint32_t *n_alt;                 // second copy of the table counts (double buffering, see kernel)
     const uint16_t *c2s_ro;          // same memory as c2s (loads bypass L1)
     uint16_t *c2s;
     const uint32_t *pos_s;
     const uint32_t *row_start;       // [k_a + 1]
-    const uint32_t *chunk_start;     // [grid + 1] element offsets, multiples of 8
-    unsigned long long *slots;       // [2] winner key per iteration parity
+    const uint32_t *chunk_start;     // [grid + 1] element offsets
+    MiPub *pub;                      // [2][grid]
     unsigned int *bar;               // [2] {count, generation}
-    int64_t w_sorted;                // live candidates in the stream
     int64_t n_picks;
     int64_t *out_pos;
     float *out_gain;
     int32_t rows_smem;               // gain rows that fit in shared memory
     int32_t ring_offset;             // byte offset of the cp.async ring in dynamic shared memory
+    // multi-GPU (world > 1): every rank's winner is pushed into every peer's mailbox
+    int32_t world, rank;
+    unsigned int seq_base;
+    MiMail *mail_local;              // [2][world] in this GPU's memory
+    MiMail *mail_peer[kMaxWorld];    // the same array on every rank (peer-mapped pointers)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks) {
@@ -252,41 +271,79 @@ __device__ __forceinline__ void scan_vector_slow(ScanBest &b, const uint4 q, uin
     }
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One cooperative launch = n_picks greedy iterations with ONE grid barrier each.
+//
+// State placement: the marginals a[], b[] and the running sums are replicated in every CTA's shared
+// memory (every CTA sees every winner and applies it itself, same fp32 ops => identical copies).  The
+// K_a x K_v table counts stay in global memory in TWO copies: iteration `it` reads copy it&1, which
+// holds all picks up to it-2, and patches the one cell of pick it-1 locally; CTA 0 meanwhile brings the
+// other copy up to date (picks it-2, it-1), which nobody reads until the barrier has passed.  So no
+// second barrier is needed to order the table update against the next iteration's reads.
 __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPersist P) {
     extern __shared__ __align__(16) unsigned char psmem[];
     const MiState &s = P.s;
-    const int32_t k_v = s.k_v;
-    float *col_term = reinterpret_cast<float *>(psmem);                 // [k_v]
-    float *tn_small = col_term + k_v;                                   // [kSmallCounts]
-    uint32_t *rs_local = reinterpret_cast<uint32_t *>(tn_small + kSmallCounts);   // [rows_smem + 1]
-    float *rt_local = reinterpret_cast<float *>(rs_local + P.rows_smem + 1);       // [rows_smem]
-    float *gain = rt_local + P.rows_smem;                                          // [rows_smem][k_v + 1]
-    uint4 *ring = reinterpret_cast<uint4 *>(psmem + P.ring_offset) + threadIdx.x;   // [kRing][1024] uint4, slot stride 1024
-    const int32_t gstride = k_v + 1;                                               // slot k_v holds -inf
+    const int32_t k_v = s.k_v, k_a = s.k_a;
+    float *col_term = reinterpret_cast<float *>(psmem);                             // [k_v]
+    float *tn_small = col_term + k_v;                                               // [kSmallCounts]
+    uint32_t *a_cnt = reinterpret_cast<uint32_t *>(tn_small + kSmallCounts);        // [k_v] column marginals
+    uint32_t *b_cnt = a_cnt + k_v;                                                  // [k_a] row marginals
+    uint32_t *rs_all = b_cnt + k_a;                                                 // [k_a + 1] row offsets
+    float *rt_local = reinterpret_cast<float *>(rs_all + k_a + 1);                  // [rows_smem]
+    float *gain = rt_local + P.rows_smem;                                           // [rows_smem][k_v + 1]
+    uint4 *ring = reinterpret_cast<uint4 *>(psmem + P.ring_offset) + threadIdx.x;   // [kRing][threads] uint4
+    const int32_t gstride = k_v + 1;                                                // slot k_v holds -inf
     __shared__ unsigned long long wkey[32];
+    __shared__ unsigned long long wpay[32];
     __shared__ uint32_t widx[32];
-    __shared__ unsigned long long sh_best_key;
+    __shared__ unsigned long long sh_best_key, sh_win_key, sh_win_pay;
     __shared__ uint32_t sh_best_idx;
+    __shared__ float ps[6];                                   // {NlogN, aloga, blogb, n, fN0, fa0}
+
+    for (int32_t i = threadIdx.x; i < k_v; i += blockDim.x) a_cnt[i] = __ldcg(s.a_cols + i);
+    for (int32_t i = threadIdx.x; i < k_a; i += blockDim.x) b_cnt[i] = __ldcg(s.b_rows + i);
+    for (int32_t i = threadIdx.x; i <= k_a; i += blockDim.x) rs_all[i] = P.row_start[i];
+    if (threadIdx.x < 6) ps[threadIdx.x] = __ldcg(s.sums + threadIdx.x);
+    __syncthreads();
 
     const uint32_t e_lo = P.chunk_start[blockIdx.x], e_hi = P.chunk_start[blockIdx.x + 1];
-    // rows touched by this chunk: first row with row_start[r+1] > e_lo ... last row with row_start[r] < e_hi
-    int32_t r_lo = 0, r_hi = -1;
+    int32_t r_lo = 0, r_hi = -1;                               // rows touched by this chunk
     if (e_hi > e_lo) {
-        int32_t a = 0, b = s.k_a;                                        // upper_bound(row_start, e_lo) - 1
-        while (a < b) { const int32_t m = (a + b) >> 1; if (P.row_start[m + 1] > e_lo) b = m; else a = m + 1; }
+        int32_t a = 0, b = k_a;
+        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_all[m + 1] > e_lo) b = m; else a = m + 1; }
         r_lo = a;
-        a = r_lo; b = s.k_a;
-        while (a < b) { const int32_t m = (a + b) >> 1; if (P.row_start[m] < e_hi) a = m + 1; else b = m; }
+        a = r_lo; b = k_a;
+        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_all[m] < e_hi) a = m + 1; else b = m; }
         r_hi = a - 1;
     }
     const uint32_t base_pos = (uint32_t)s.pos_base;
+    const uint32_t grid = gridDim.x;
+    int32_t prev1 = -1, prev2 = -1;                            // table cell of picks it-1, it-2
+    int64_t done = 0;
+    bool broke = false;
 
     for (int64_t it = 0; it < P.n_picks; ++it) {
-        // ---------------- phase A: score my chunk ----------------
-        const float NlogN = __ldcg(s.sums + 0), nn = __ldcg(s.sums + 3), fN0 = __ldcg(s.sums + 4);
-        const float np = __fadd_rn(nn, 1.0f);
+        const int cur = (int)(it & 1);
+        const uint32_t *Tcur = cur ? P.n_alt : s.n_cells;
+        uint32_t *Toth = cur ? s.n_cells : P.n_alt;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {             // lagged writer of the other table copy
+            if (prev2 >= 0) Toth[prev2] += 1;
+            if (prev1 >= 0) Toth[prev1] += 1;
+        }
+        // ---------------- score my chunk ----------------
+        const float NlogN = ps[0], aloga = ps[1], blogb = ps[2], fN0 = ps[4], fa0 = ps[5];
+        const float np = __fadd_rn(ps[3], 1.0f);
         const float lognp = __ldg(s.logs + (int64_t)np);
-        for (int32_t i = threadIdx.x; i < k_v; i += blockDim.x) col_term[i] = __ldcg(s.col_term + i);
+        for (int32_t i = threadIdx.x; i < k_v; i += blockDim.x)
+            col_term[i] = __fdiv_rn(-bump_sum(aloga, a_cnt[i], fa0, s.logs), np);
         for (int32_t i = threadIdx.x; i < kSmallCounts; i += blockDim.x)
             tn_small[i] = __fdiv_rn(bump_sum(NlogN, (uint32_t)i, fN0, s.logs), np);
         ScanBest B;
@@ -294,16 +351,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         B.tie[0] = B.tie[1] = B.tie[2] = 0;
         for (int32_t rb = r_lo; rb <= r_hi; rb += P.rows_smem) {
             const int32_t nr = min(P.rows_smem, r_hi - rb + 1);
-            __syncthreads();            // previous sub-batch finished reading gain rows / first use of col_term
-            for (int32_t i = threadIdx.x; i <= nr; i += blockDim.x) rs_local[i] = P.row_start[rb + i];
+            const uint32_t *rs_local = rs_all + rb;
+            __syncthreads();            // previous sub-batch finished reading gain rows; col_term/tn_small ready
             for (int32_t i = threadIdx.x; i < nr; i += blockDim.x) {
-                rt_local[i] = __ldcg(s.row_term + rb + i);
+                rt_local[i] = __fdiv_rn(-bump_sum(blogb, b_cnt[rb + i], fa0, s.logs), np);
                 gain[i * gstride + k_v] = -INFINITY;           // slot read by removed entries (c2 == k_v)
             }
             __syncthreads();
             {   // gain rows: table counts of rows rb..rb+nr are contiguous; 8 loads in flight per thread
                 const int32_t ncell = nr * k_v;
-                const uint32_t *nbase = s.n_cells + (int64_t)rb * k_v;
+                const int64_t cell0 = (int64_t)rb * k_v;                  // < 2^31 (checked on the host)
+                const uint32_t *nbase = Tcur + cell0;
                 for (int32_t base = 0; base < ncell; base += 8 * kPersistThreads) {
                     uint32_t xs[8];
 #pragma unroll
@@ -316,7 +374,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                         const int32_t i = base + u * kPersistThreads + (int32_t)threadIdx.x;
                         if (i < ncell) {
                             const int32_t rr = i / k_v, c2 = i - rr * k_v;
-                            const uint32_t x = xs[u];
+                            const uint32_t x = xs[u] + ((int32_t)cell0 + i == prev1 ? 1u : 0u);   // pick it-1 patched in
                             const float tN = x < (uint32_t)kSmallCounts
                                                  ? tn_small[x]
                                                  : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
@@ -332,7 +390,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             const uint32_t v_lo = s_lo >> 3, v_hi = (s_hi + 7) >> 3;
             const uint4 *vec = reinterpret_cast<const uint4 *>(P.c2s_ro);
             int32_t crow = 0;                                  // cached local row of this thread
-            // software pipeline: vector r of this thread is v_lo + tid + r * 1024
+            // software pipeline: vector r of this thread is v_lo + tid + r * threads
             const uint32_t vfirst = v_lo + threadIdx.x;
 #pragma unroll
             for (int r = 0; r < kRing - 1; ++r) {
@@ -405,8 +463,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             }
             key = ((unsigned long long)m32 << 32) | (unsigned long long)(0xFFFFFFFFu - (base_pos + bp));
         }
-        // block arg-max of (key, stream index)
-        {
+        {   // block arg-max of (key, stream index); thread 0 publishes the CTA's candidate
             unsigned long long k2 = key;
             uint32_t i2 = bi;
 #pragma unroll
@@ -426,56 +483,112 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                     if (ok > k2) { k2 = ok; i2 = oi; }
                 }
                 if (threadIdx.x == 0) {
+                    unsigned long long pay = 0ull;
+                    if (k2) {
+                        int32_t a = 0, b = k_a;                // row of the stream index
+                        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_all[m + 1] > i2) b = m; else a = m + 1; }
+                        const uint32_t c2 = __ldcg(reinterpret_cast<const unsigned short *>(P.c2s) + i2);
+                        const int32_t cell = a * k_v + (int32_t)c2;
+                        const uint32_t x = __ldcg(Tcur + cell) + (cell == prev1 ? 1u : 0u);
+                        pay = ((unsigned long long)a << 48) | ((unsigned long long)c2 << 32) | x;
+                    }
                     sh_best_key = k2; sh_best_idx = i2;
-                    if (k2) atomicMax(P.slots + (it & 1), k2);
+                    MiPub *pb = P.pub + (size_t)cur * grid + blockIdx.x;
+                    pb->key = k2; pb->payload = pay;
                 }
             }
         }
-        grid_barrier(P.bar, gridDim.x);
-        // ---------------- phase B: the owner applies the winner ----------------
-        const unsigned long long win = __ldcg(P.slots + (it & 1));
-        if (win == 0ull) {                                     // nothing left anywhere: record and stop
-            if (blockIdx.x == 0 && threadIdx.x == 0)
-                for (int64_t j = it; j < P.n_picks; ++j) { P.out_pos[j] = -1; P.out_gain[j] = nanf(""); }
-            break;
-        }
-        if (sh_best_key == win) {                              // keys are unique: exactly one owner
-            const uint32_t widx_s = sh_best_idx;
-            // locate the winner's row (c1) from the stream index
-            if (threadIdx.x == 0) {
-                int32_t a = 0, b = s.k_a;
-                while (a < b) { const int32_t m = (a + b) >> 1; if (P.row_start[m + 1] > widx_s) b = m; else a = m + 1; }
-                const int32_t c1 = a;
-                const int32_t c2 = (int32_t)__ldcg(reinterpret_cast<const unsigned short *>(P.c2s) + widx_s);
-                const uint32_t x = __ldcg(s.n_cells + (int64_t)c1 * k_v + c2), y = __ldcg(s.a_cols + c2),
-                               z = __ldcg(s.b_rows + c1);
-                const float fN0w = __ldcg(s.sums + 4), fa0w = __ldcg(s.sums + 5);
-                s.sums[0] = bump_sum(__ldcg(s.sums + 0), x, fN0w, s.logs);        // update_cache mi.py:383-389
-                s.sums[1] = bump_sum(__ldcg(s.sums + 1), y, fa0w, s.logs);
-                s.sums[2] = bump_sum(__ldcg(s.sums + 2), z, fa0w, s.logs);
-                s.sums[3] = __fadd_rn(__ldcg(s.sums + 3), 1.0f);                  // update_mats :401-406
-                s.n_cells[(int64_t)c1 * k_v + c2] = x + 1; s.a_cols[c2] = y + 1; s.b_rows[c1] = z + 1;
-                P.c2s[widx_s] = (uint16_t)k_v;                                    // remove_idx_all :104-106 (k_v = removed)
-                const int64_t pos = (int64_t)key_pos(win);
-                s.cells[pos - s.pos_base] = 0xFFFFFFFFu;                          // keep the list-order view in sync
-                P.out_pos[it] = pos;
-                P.out_gain[it] = key_score(win);
-                P.slots[(it + 1) & 1] = 0ull;
-                __threadfence();
+        grid_barrier(P.bar, grid);
+        // ---------------- everyone learns the winner ----------------
+        {
+            unsigned long long k2 = 0ull, p2 = 0ull;
+            for (uint32_t t = threadIdx.x; t < grid; t += blockDim.x) {
+                const MiPub *pb = P.pub + (size_t)cur * grid + t;
+                const unsigned long long kk = __ldcg(&pb->key);
+                if (kk > k2) { k2 = kk; p2 = __ldcg(&pb->payload); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k2, o);
+                const unsigned long long op = __shfl_xor_sync(0xffffffffu, p2, o);
+                if (ok > k2) { k2 = ok; p2 = op; }
+            }
+            if (threadIdx.x % kWarp == 0) { wkey[threadIdx.x / kWarp] = k2; wpay[threadIdx.x / kWarp] = p2; }
+            __syncthreads();
+            if (threadIdx.x < kWarp) {
+                k2 = wkey[threadIdx.x]; p2 = wpay[threadIdx.x];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k2, o);
+                    const unsigned long long op = __shfl_xor_sync(0xffffffffu, p2, o);
+                    if (ok > k2) { k2 = ok; p2 = op; }
+                }
+                if (threadIdx.x == 0) {
+                    if (P.world > 1) {
+                        // push this GPU's winner into every rank's mailbox (NVLink stores), then wait for
+                        // all ranks' entries of this iteration in the local mailbox
+                        const unsigned int tag = P.seq_base + (unsigned int)it + 1u;
+                        if (blockIdx.x == 0) {
+                            for (int r = 0; r < P.world; ++r) {
+                                MiMail *m = P.mail_peer[r] + (size_t)cur * P.world + P.rank;
+                                m->key = k2; m->payload = p2;
+                                st_release_sys(&m->seq, tag);
+                            }
+                        }
+                        for (int r = 0; r < P.world; ++r) {
+                            const MiMail *m = P.mail_local + (size_t)cur * P.world + r;
+                            while (ld_acquire_sys(&m->seq) != tag) { }
+                            const unsigned long long kk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
+                            if (r == 0 || kk > k2) {
+                                k2 = kk;
+                                p2 = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
+                            }
+                        }
+                    }
+                    sh_win_key = k2; sh_win_pay = p2;
+                }
             }
             __syncthreads();
-            // next iteration's per-row / per-column terms (same code path as mi_scan.cu: mi_terms)
-            {
-                const float npn = __fadd_rn(__ldcg(s.sums + 3), 1.0f);
-                const float aloga = __ldcg(s.sums + 1), blogb = __ldcg(s.sums + 2), fa0 = __ldcg(s.sums + 5);
-                for (int32_t i = threadIdx.x; i < s.k_v; i += blockDim.x)
-                    s.col_term[i] = __fdiv_rn(-bump_sum(aloga, __ldcg(s.a_cols + i), fa0, s.logs), npn);
-                for (int32_t i = threadIdx.x; i < s.k_a; i += blockDim.x)
-                    s.row_term[i] = __fdiv_rn(-bump_sum(blogb, __ldcg(s.b_rows + i), fa0, s.logs), npn);
-            }
-            __threadfence();
         }
-        grid_barrier(P.bar, gridDim.x);
+        const unsigned long long win = sh_win_key, wpayload = sh_win_pay;
+        if (win == 0ull) { broke = true; break; }              // nothing left on any rank
+        const int32_t c1 = (int32_t)(wpayload >> 48), c2w = (int32_t)((wpayload >> 32) & 0xFFFFu);
+        if (threadIdx.x == 0) {
+            if (sh_best_key == win) {                          // keys are unique: exactly one owner CTA
+                P.c2s[sh_best_idx] = (uint16_t)k_v;            // remove_idx_all mi.py:104-106 (k_v = removed)
+                s.cells[(int64_t)key_pos(win) - s.pos_base] = 0xFFFFFFFFu;     // list-order view stays in sync
+            }
+            const uint32_t x = (uint32_t)(wpayload & 0xFFFFFFFFull), y = a_cnt[c2w], z = b_cnt[c1];
+            ps[0] = bump_sum(ps[0], x, ps[4], s.logs);         // update_cache mi.py:383-389
+            ps[1] = bump_sum(ps[1], y, ps[5], s.logs);
+            ps[2] = bump_sum(ps[2], z, ps[5], s.logs);
+            ps[3] = __fadd_rn(ps[3], 1.0f);                    // update_mats :401-406
+            a_cnt[c2w] = y + 1; b_cnt[c1] = z + 1;
+            if (blockIdx.x == 0) {
+                P.out_pos[it] = (int64_t)key_pos(win);
+                P.out_gain[it] = key_score(win);
+            }
+        }
+        prev2 = prev1;
+        prev1 = c1 * k_v + c2w;
+        done = it + 1;
+        __syncthreads();
+    }
+    // ---------------- write the replicated state back (CTA 0) ----------------
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            for (int64_t j = done; j < P.n_picks; ++j) { P.out_pos[j] = -1; P.out_gain[j] = nanf(""); }
+            // canonical copy 0 holds picks <= done-2 if `done` is even (it was the read copy of
+            // iteration `done`), <= done-3 if odd
+            // (an early exit at an odd `done` happened after CTA 0 had already completed copy 0)
+            if (!(broke && (done & 1))) {
+                if (prev1 >= 0) s.n_cells[prev1] += 1;
+                if ((done & 1) && prev2 >= 0) s.n_cells[prev2] += 1;
+            }
+            for (int i = 0; i < 4; ++i) s.sums[i] = ps[i];
+        }
+        for (int32_t i = threadIdx.x; i < k_v; i += blockDim.x) s.a_cols[i] = a_cnt[i];
+        for (int32_t i = threadIdx.x; i < k_a; i += blockDim.x) s.b_rows[i] = b_cnt[i];
     }
 }
 
@@ -508,36 +621,47 @@ int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t 
 }
 
 
-// dynamic shared memory: [col_term k_v | tn_small | rs_local rows+1 | rt_local rows | gain rows*(k_v+1)] | ring
-static size_t persist_table_bytes(int32_t k_v, int32_t rows) {
-    size_t words = (size_t)k_v + kSmallCounts + 2 * (size_t)rows + 1 + (size_t)rows * (k_v + 1);
+// dynamic shared memory: [col_term k_v | tn_small | a_cnt k_v | b_cnt k_a | rs_all k_a+1 | rt_local rows |
+// gain rows*(k_v+1)] | cp.async ring
+static size_t persist_table_bytes(int32_t k_a, int32_t k_v, int32_t rows) {
+    size_t words = 2 * (size_t)k_v + kSmallCounts + 2 * (size_t)k_a + 1 + (size_t)rows + (size_t)rows * (k_v + 1);
     return (words * 4 + 15) & ~(size_t)15;
 }
 static size_t persist_ring_bytes() { return (size_t)kRing * kPersistThreads * 16; }
 
-int mi_persistent_rows_that_fit(int32_t k_v) {
+int mi_persistent_rows_that_fit(int32_t k_a, int32_t k_v) {
     const size_t budget = 224 * 1024 - persist_ring_bytes();
     int32_t rows = 0;
-    while (persist_table_bytes(k_v, rows + 1) <= budget && rows < 4096) ++rows;
+    while (persist_table_bytes(k_a, k_v, rows + 1) <= budget && rows < 4096) ++rows;
     return rows;
 }
 
-int launch_mi_persistent(const MiState &s, uint16_t *c2s, const uint32_t *pos_s, const uint32_t *row_start,
-                         const uint32_t *chunk_start, int32_t grid, unsigned long long *slots, unsigned int *bar,
-                         int64_t w_sorted, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
+size_t mi_pub_bytes(int32_t grid) { return sizeof(MiPub) * 2 * (size_t)grid; }
+size_t mi_mail_bytes(int32_t world) { return sizeof(MiMail) * 2 * (size_t)world; }
+
+int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const uint32_t *pos_s,
+                         const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
+                         unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
+                         int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
                          cudaStream_t st) {
     MiPersist P;
-    P.s = s; P.c2s_ro = c2s; P.c2s = c2s; P.pos_s = pos_s; P.row_start = row_start; P.chunk_start = chunk_start;
-    P.slots = slots; P.bar = bar; P.w_sorted = w_sorted; P.n_picks = n_picks; P.out_pos = out_pos;
-    P.out_gain = out_gain; P.rows_smem = rows_smem;
-    P.ring_offset = (int32_t)persist_table_bytes(s.k_v, rows_smem);
-    const size_t smem = persist_table_bytes(s.k_v, rows_smem) + persist_ring_bytes();
+    P.s = s; P.n_alt = n_alt; P.c2s_ro = c2s; P.c2s = c2s; P.pos_s = pos_s; P.row_start = row_start;
+    P.chunk_start = chunk_start; P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks;
+    P.out_pos = out_pos; P.out_gain = out_gain; P.rows_smem = rows_smem;
+    P.world = world; P.rank = rank; P.seq_base = seq_base;
+    P.mail_local = reinterpret_cast<MiMail *>(mail_local);
+    for (int r = 0; r < kMaxWorld; ++r)
+        P.mail_peer[r] = (world > 1 && r < world) ? reinterpret_cast<MiMail *>(mail_peer[r]) : nullptr;
+    P.ring_offset = (int32_t)persist_table_bytes(s.k_a, s.k_v, rows_smem);
+    const size_t smem = persist_table_bytes(s.k_a, s.k_v, rows_smem) + persist_ring_bytes();
     static size_t attr_set = 0;
     if (smem > attr_set) {
         ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    ACAV_CUDA_TRY(cudaMemsetAsync(slots, 0, 2 * sizeof(unsigned long long), st));
+    // both table copies start equal; the barrier words start at zero
+    ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
+    ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
     void *args[] = {&P};
     ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_persistent_kernel, dim3(grid), dim3(kPersistThreads), args,

@@ -71,6 +71,13 @@ __global__ void __launch_bounds__(1024) mi_add_sample_kernel(MiState s, int32_t 
     mi_terms(s);
 }
 
+// recompute the row / column terms from the current marginals and sums (after the persistent kernel
+// wrote its replicated state back)
+__global__ void __launch_bounds__(1024) mi_refresh_kernel(MiState s) {
+    if (threadIdx.x == 0) { s.key[0] = 0ull; s.key[1] = 0ull; }
+    mi_terms(s);
+}
+
 __global__ void mi_gain_kernel(MiState s) {
     const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= (int64_t)s.k_a * s.k_v) return;
@@ -181,6 +188,12 @@ int launch_mi_reset(const MiState &s, const float *consts_dev, cudaStream_t st) 
 
 int launch_mi_add_sample(const MiState &s, int32_t c1, int32_t c2, cudaStream_t st) {
     mi_add_sample_kernel<<<1, 1024, 0, st>>>(s, c1, c2);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_mi_refresh_terms(const MiState &s, cudaStream_t st) {
+    mi_refresh_kernel<<<1, 1024, 0, st>>>(s);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

@@ -94,13 +94,13 @@ class EfficientMemMI:
         self.init_cache(max_picks=max_picks if max_picks is not None else min(self._W + 8, (1 << 24) - 8))
 
     def launches_per_iteration(self):
-        if self._dist is not None:
+        if self._dist is not None and not self._nvlink:
             return 4                                   # gain, scan, emit, apply (+ one NCCL all-gather)
         return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0      # persistent: one launch per select()
 
     def loop_name(self):
         if self._dist is not None:
-            return "kernels+allgather"
+            return "persistent+nvlink-mailbox" if self._nvlink else "kernels+allgather"
         return "kernels" if self._loop_mode() == _lib.MI_LOOP_KERNELS else "persistent"
 
     def init_cache(self, max_picks=None):
@@ -122,6 +122,26 @@ class EfficientMemMI:
             _lib.call("acav_mi_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
                       consts.ctypes.data_as(_lib.c_vp), st)
         self._picked = 0
+        self._nvlink = False
+        if self._dist is not None and self._loop_mode() == _lib.MI_LOOP_PERSISTENT:
+            self._connect_ranks()
+
+    def _connect_ranks(self):
+        """Exchange the mailbox IPC handles so the persistent kernel can push each iteration's winner
+        straight into the peers' memory over NVLink (include/acav_b200.h, acav_mi_comm_*)."""
+        rank, world = self.shard
+        n = _lib.load().acav_mi_comm_handle_bytes()
+        mine = (_lib.ctypes.c_ubyte * n)()
+        with torch.cuda.device(self.device):
+            _lib.call("acav_mi_comm_export", self._engine, world, rank, mine)
+            local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device)
+            gathered = torch.empty(world * n, dtype=torch.uint8, device=self.device)
+            self._dist.all_gather_into_tensor(gathered, local)
+            blob = bytes(gathered.cpu().numpy().tobytes())
+            handles = (_lib.ctypes.c_ubyte * (world * n)).from_buffer_copy(blob)
+            _lib.call("acav_mi_comm_connect", self._engine, handles)
+            self._dist.barrier()
+        self._nvlink = True
 
     def _release(self):
         if self._engine is not None:
@@ -163,7 +183,7 @@ class EfficientMemMI:
         gain = torch.empty(n_picks, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)
-            if self._dist is None:
+            if self._dist is None or self._nvlink:
                 _lib.call("acav_mi_run", self._engine, n_picks, _lib.ptr(pos), _lib.ptr(gain),
                           self._loop_mode(), st)
             else:

@@ -150,6 +150,17 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n,
 int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain,
                 int32_t mode, void *stream);
 
+/* Multi-GPU persistent loop (one process per GPU on one node).  Every rank holds a contiguous range of
+ * the candidate list (pos_base); inside ACAV_MI_LOOP_PERSISTENT each rank's per-iteration winner is
+ * written straight into every peer's mailbox over NVLink (peer stores + release/acquire flags) -- no
+ * host round trip, no NCCL launch per iteration.  Setup: every rank calls comm_export (allocates its
+ * mailbox, returns a cudaIpcMemHandle_t, `acav_mi_comm_handle_bytes()` bytes, HOST pointer), the
+ * host language all-gathers the handles, every rank calls comm_connect with the world x handle
+ * array.  All ranks must then call acav_mi_run with the same n_picks. */
+int acav_mi_comm_handle_bytes(void);
+int acav_mi_comm_export(acav_mi_t *h, int32_t world, int32_t rank, void *handle_out);
+int acav_mi_comm_connect(acav_mi_t *h, const void *handles);
+
 /* Introspection for tests: copies table counts (uint32 [k_a*k_v], [k_v], [k_a]) and the four running
  * sums {NlogN, aloga, blogb, n} to device buffers (any may be NULL). */
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows,

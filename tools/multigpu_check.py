@@ -69,12 +69,16 @@ for mode in ("exact", "tensor"):
 W, C, picks = 200_003, 64, 700
 a = synth.zipf_pairs(W, C, 23)
 pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks)
-m = get_measure("mem_mi")(a, ncentroids=C, device="cuda", shard=(rank, world))
-m.init([(0, 1)], list(range(W)))
-pos, gain = m.select(picks)
-ok = np.array_equal(pos.cpu().numpy(), pos_want) and np.array_equal(gain.cpu().numpy(), gain_want)
-print(f"[rank {rank}] greedy MI sharded over {world} ranks: bit-exact={ok}", flush=True)
-assert ok
+for loop in ("kernels", "persistent"):
+    m = get_measure("mem_mi")(a, ncentroids=C, device="cuda", shard=(rank, world), loop=loop)
+    m.init([(0, 1)], list(range(W)))
+    p1, g1 = m.select(picks // 2)
+    p2, g2 = m.select(picks - picks // 2)
+    pos, gain = torch.cat([p1, p2]), torch.cat([g1, g2])
+    ok = np.array_equal(pos.cpu().numpy(), pos_want) and np.array_equal(gain.cpu().numpy(), gain_want)
+    print(f"[rank {rank}] greedy MI sharded over {world} ranks, loop={m.loop_name()}: bit-exact={ok}", flush=True)
+    assert ok
+    del m
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
