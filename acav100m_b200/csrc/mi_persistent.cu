@@ -188,6 +188,7 @@ struct MiPersist {
     unsigned int seq_base;
     MiMail *mail_local;              // [2][world] in this GPU's memory
     MiMail *mail_peer[kMaxWorld];    // the same array on every rank (peer-mapped pointers)
+    long long *dbg;                  // optional [grid][4] cycle counters of the LAST iteration (nullptr = off)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks) {
@@ -233,8 +234,11 @@ struct ScanBest {
 };
 
 __device__ __forceinline__ void scan_tie(ScanBest &b, uint32_t e, uint32_t rend, const uint32_t *__restrict__ pos_s) {
-    if (b.ntie < 3) {
-        b.tie[b.ntie++] = e;
+    if (b.ntie < 3) {                          // predicated stores: no dynamically indexed local array
+        if (b.ntie == 0) b.tie[0] = e;
+        else if (b.ntie == 1) b.tie[1] = e;
+        else b.tie[2] = e;
+        ++b.ntie;
     } else {                                   // list full: settle by original position now
         uint32_t bp = __ldg(pos_s + b.bi);
 #pragma unroll
@@ -332,6 +336,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
 
     for (int64_t it = 0; it < P.n_picks; ++it) {
         const int cur = (int)(it & 1);
+        const long long t0 = P.dbg ? clock64() : 0;
+        long long t_gain = 0;
         const uint32_t *Tcur = cur ? P.n_alt : s.n_cells;
         uint32_t *Toth = cur ? s.n_cells : P.n_alt;
         if (blockIdx.x == 0 && threadIdx.x == 0) {             // lagged writer of the other table copy
@@ -358,53 +364,60 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                 gain[i * gstride + k_v] = -INFINITY;           // slot read by removed entries (c2 == k_v)
             }
             __syncthreads();
-            {   // gain rows: table counts of rows rb..rb+nr are contiguous; 8 loads in flight per thread
-                const int32_t ncell = nr * k_v;
-                const int64_t cell0 = (int64_t)rb * k_v;                  // < 2^31 (checked on the host)
+            const long long tg0 = P.dbg ? clock64() : 0;
+            {   // gain rows: thread owns columns c2 = tid, tid + T, ...; 8 rows' counts in flight per thread
+                const int32_t cell0 = rb * k_v;                            // < 2^31 (checked on the host)
                 const uint32_t *nbase = Tcur + cell0;
-                for (int32_t base = 0; base < ncell; base += 8 * kPersistThreads) {
-                    uint32_t xs[8];
+                for (int32_t c2 = threadIdx.x; c2 < k_v; c2 += kPersistThreads) {
+                    const float ct = col_term[c2];
+                    for (int32_t r0 = 0; r0 < nr; r0 += 8) {
+                        uint32_t xs[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int32_t i = base + u * kPersistThreads + (int32_t)threadIdx.x;
-                        xs[u] = i < ncell ? __ldcg(nbase + i) : 0u;
-                    }
+                        for (int u = 0; u < 8; ++u)
+                            xs[u] = r0 + u < nr ? __ldcg(nbase + (r0 + u) * k_v + c2) : 0u;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int32_t i = base + u * kPersistThreads + (int32_t)threadIdx.x;
-                        if (i < ncell) {
-                            const int32_t rr = i / k_v, c2 = i - rr * k_v;
-                            const uint32_t x = xs[u] + ((int32_t)cell0 + i == prev1 ? 1u : 0u);   // pick it-1 patched in
-                            const float tN = x < (uint32_t)kSmallCounts
-                                                 ? tn_small[x]
-                                                 : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
-                            gain[rr * gstride + c2] =
-                                __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt_local[rr]), lognp);
+                        for (int u = 0; u < 8; ++u) {
+                            if (r0 + u < nr) {
+                                const int32_t rr = r0 + u;
+                                const uint32_t x = xs[u] + (cell0 + rr * k_v + c2 == prev1 ? 1u : 0u);   // pick it-1
+                                const float tN = x < (uint32_t)kSmallCounts
+                                                     ? tn_small[x]
+                                                     : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
+                                gain[rr * gstride + c2] = __fadd_rn(__fadd_rn(__fadd_rn(tN, ct), rt_local[rr]), lognp);
+                            }
                         }
                     }
                 }
             }
             __syncthreads();
+            if (P.dbg) t_gain += clock64() - tg0;
             const uint32_t s_lo = max(e_lo, rs_local[0]), s_hi = min(e_hi, rs_local[nr]);
             if (s_hi <= s_lo) continue;
             const uint32_t v_lo = s_lo >> 3, v_hi = (s_hi + 7) >> 3;
             const uint4 *vec = reinterpret_cast<const uint4 *>(P.c2s_ro);
             int32_t crow = 0;                                  // cached local row of this thread
-            // software pipeline: vector r of this thread is v_lo + tid + r * threads
-            const uint32_t vfirst = v_lo + threadIdx.x;
+            // each WARP walks its own contiguous span of vectors, 32 at a time (coalesced 512-byte
+            // loads), so consecutive vectors of a thread are 256 candidates apart and usually stay in
+            // the same table row: the cached row hits and the binary search below stays rare even
+            // where rows are short.  Per thread the elements are still visited in increasing order.
+            const uint32_t nwarps = kPersistThreads / kWarp;
+            const uint32_t span = (((v_hi - v_lo) + nwarps - 1) / nwarps + kWarp - 1) & ~(uint32_t)(kWarp - 1);
+            const uint32_t wv_lo = v_lo + (threadIdx.x / kWarp) * span;
+            const uint32_t wv_hi = min(v_hi, wv_lo + span);
+            const uint32_t vfirst = wv_lo + (threadIdx.x % kWarp);
 #pragma unroll
             for (int r = 0; r < kRing - 1; ++r) {
-                const uint32_t v = vfirst + (uint32_t)r * kPersistThreads;
-                if (v < v_hi) cp_async16(ring + r * kPersistThreads, vec + v);
+                const uint32_t v = vfirst + (uint32_t)r * kWarp;
+                if (v < wv_hi) cp_async16(ring + r * kPersistThreads, vec + v);
                 cp_async_commit();
             }
             int slot = 0;
-            for (uint32_t v = vfirst; v < v_hi; v += kPersistThreads) {
+            for (uint32_t v = vfirst; v < wv_hi; v += kWarp) {
                 {
-                    const uint32_t vn = v + (kRing - 1) * kPersistThreads;
+                    const uint32_t vn = v + (kRing - 1) * kWarp;
                     int sn = slot + kRing - 1;
                     if (sn >= kRing) sn -= kRing;
-                    if (vn < v_hi) cp_async16(ring + sn * kPersistThreads, vec + vn);
+                    if (vn < wv_hi) cp_async16(ring + sn * kPersistThreads, vec + vn);
                     cp_async_commit();
                 }
                 cp_async_wait<kRing - 1>();
@@ -439,6 +452,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             }
             cp_async_wait<0>();
         }
+        const long long t1 = P.dbg ? clock64() : 0;
         float bs = B.bs;
         uint32_t bi = B.bi;
         const int ntie = B.ntie;
@@ -457,9 +471,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         unsigned long long key = 0ull;
         if (my32 != 0u && my32 == m32) {
             uint32_t bp = __ldg(P.pos_s + bi);
-            for (int t = 0; t < ntie; ++t) {
-                const uint32_t pt = __ldg(P.pos_s + tie[t]);
-                if (pt < bp) { bp = pt; bi = tie[t]; }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (t < ntie) {
+                    const uint32_t pt = __ldg(P.pos_s + tie[t]);
+                    if (pt < bp) { bp = pt; bi = tie[t]; }
+                }
             }
             key = ((unsigned long long)m32 << 32) | (unsigned long long)(0xFFFFFFFFu - (base_pos + bp));
         }
@@ -498,7 +515,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                 }
             }
         }
+        const long long t2 = P.dbg ? clock64() : 0;
         grid_barrier(P.bar, grid);
+        if (P.dbg && threadIdx.x == 0) {
+            long long *d = P.dbg + 4 * blockIdx.x;
+            d[0] = t_gain; d[1] = t1 - t0 - t_gain; d[2] = t2 - t1; d[3] = clock64() - t2;
+        }
         // ---------------- everyone learns the winner ----------------
         {
             unsigned long long k2 = 0ull, p2 = 0ull;
@@ -643,8 +665,9 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
                          unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
-                         cudaStream_t st) {
+                         long long *dbg, cudaStream_t st) {
     MiPersist P;
+    P.dbg = dbg;
     P.s = s; P.n_alt = n_alt; P.c2s_ro = c2s; P.c2s = c2s; P.pos_s = pos_s; P.row_start = row_start;
     P.chunk_start = chunk_start; P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks;
     P.out_pos = out_pos; P.out_gain = out_gain; P.rows_smem = rows_smem;

@@ -238,9 +238,32 @@ def run_kmeans(args, dist, rank, world):
             km.calc_best(x[j * b:(j + 1) * b], sync=False)
 
     ms_assign, _ = timed(dist, lambda: run_assign(3), lambda: run_assign(steps, 3))
+    # the same operator on a converged model: centroids at the mixture's component means (every row has one
+    # clear nearest centroid, so the tensor-core screen decides it without the exact re-check)
+    km_sep = KMeans(kargs, d, k, assign_mode=args.km_mode, warmup_rng="cuda")
+    km_sep.to(dev)
+    gm = torch.Generator(device=dev).manual_seed(1003 + rank)
+    means = torch.randn(k, d, generator=gm, device=dev) * 3.0          # the means gaussian_mixture_torch drew
+    km_sep.centers.copy_(means)
+    km_sep.counts.fill_(1000.0)
+    km_sep.count = 1000 * k
+    km_sep.lr = 1e-3
+
+    def sep_steps(cnt, off=0):
+        for i in range(cnt):
+            j = (off + i) % nb
+            km_sep.add(x[j * b:(j + 1) * b], sync=False)
+
+    def sep_assign(cnt, off=0):
+        for i in range(cnt):
+            j = (off + i) % nb
+            km_sep.calc_best(x[j * b:(j + 1) * b], sync=False)
+
+    ms_sep_step, _ = timed(dist, lambda: sep_steps(3), lambda: sep_steps(steps, 3))
+    ms_sep_assign, _ = timed(dist, lambda: sep_assign(3), lambda: sep_assign(steps, 3))
     pk = peaks()
     flops = 2.0 * b * k * d
-    t_assign = ms_assign * 1e-3 / steps
+    t_assign = ms_sep_assign * 1e-3 / steps
     out = {
         "metric": "kmeans_iter_per_sec", "value": steps / (ms_step * 1e-3), "unit": "iter/s",
         "global_batch": b * world, "k": k, "d": d, "rows_resident_per_gpu": n, "steps": steps,
@@ -248,11 +271,19 @@ def run_kmeans(args, dist, rank, world):
         "assign_rows_per_sec": steps * b * world / (ms_assign * 1e-3),
         "assign_ms_per_batch": ms_assign / steps, "assign_mode": km.mode_name(),
         "steps_before_timing": warm, "lr_fallbacks": km.fallback,
-        "centroids_in_use": int((km.counts > 0).sum().item()),
+        "state": "trained from the reference init (torch.rand*1e-5, random-assignment warm-up); in this early, "
+                 "collapsed state ~K centroids are fp32-near-tied per row and rows take the exact re-check",
+        "converged": {
+            "state": "centroids at the mixture means (one clear nearest centroid per row)",
+            "value": steps / (ms_sep_step * 1e-3), "unit": "iter/s", "ms_per_step": ms_sep_step / steps,
+            "samples_per_sec": steps * b * world / (ms_sep_step * 1e-3),
+            "assign_rows_per_sec": steps * b * world / (ms_sep_assign * 1e-3),
+            "assign_ms_per_batch": ms_sep_assign / steps},
         "gpu_launches": km.launches_per_step() * steps,
         "roofline": {"bound": "tensor", "achieved": flops / t_assign / 1e12, "peak": pk["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": flops / t_assign / 1e12 / pk["bf16_tflops"], "traffic": None,
-                     "kernel": "k-means assign (KMeans.calc_best), 2*b*K*D flop per batch",
+                     "kernel": "k-means assign (KMeans.calc_best: prep + tcgen05 distance GEMM + classify + exact "
+                               "distance of the winner), converged state, 2*b*K*D flop per batch",
                      "peak_source": pk["source"] + " bf16 burst"},
     }
     if not args.skip_e2e:
@@ -378,7 +409,11 @@ def main():
             "mi_loop": mi["loop"], "gpu_launches": mi["launches"] + (km["gpu_launches"] if km else 0),
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": mi["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": mi["achieved_gbs"] / pk["hbm_gbs"], "traffic": None,
+                         "frac": mi["achieved_gbs"] / pk["hbm_gbs"],
+                         "traffic": 2.44 * args.mi_candidates if mi["loop"].startswith("persistent") else None,
+                         "traffic_source": "ncu dram__bytes_read+write per iteration, profiles/r01_mi_persist_v2.ncu.txt "
+                                           "(2-byte row-partitioned stream + table)",
+                         "bytes_per_candidate_accounted": 4,
                          "kernel": "greedy-MI iteration (gain table + candidate scan + apply), per GPU",
                          "algorithmic_bytes_per_launch": mi["algorithmic_bytes_per_launch"],
                          "peak_source": pk["source"] + " copy bandwidth"},

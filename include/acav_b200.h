@@ -161,6 +161,11 @@ int acav_mi_comm_handle_bytes(void);
 int acav_mi_comm_export(acav_mi_t *h, int32_t world, int32_t rank, void *handle_out);
 int acav_mi_comm_connect(acav_mi_t *h, const void *handles);
 
+/* Profiling aid: when `cycles` (device int64 [4 * #SMs]) is non-NULL the persistent loop records, per
+ * CTA and for the last iteration it ran, SM cycles spent in {gain rows, candidate scan, block reduce +
+ * publish, grid-barrier wait}.  NULL switches it off (default). */
+int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles);
+
 /* Introspection for tests: copies table counts (uint32 [k_a*k_v], [k_v], [k_a]) and the four running
  * sums {NlogN, aloga, blogb, n} to device buffers (any may be NULL). */
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows,
