@@ -166,14 +166,17 @@ def run_mi(args, dist, rank, world):
     ms, _ = timed(dist, lambda: m.select(args.warmup), lambda: m.select(args.steps))
     w_global = W * world
     scored = sum(w_global - args.warmup - i for i in range(args.steps))
-    per_iter_bytes = 4.0 * (W - args.warmup - args.steps / 2.0) + 4.0 * args.k * args.k   # per GPU
+    # algorithmic bytes per iteration and GPU in the layout the loop actually streams:
+    # persistent = 2-byte c2 stream + 4*K^2 table counts; list order = 4-byte packed pairs + 4*K^2 gains
+    bytes_per_cand = 2.0 if m.loop_name().startswith("persistent") else 4.0
+    per_iter_bytes = bytes_per_cand * (W - args.warmup - args.steps / 2.0) + 4.0 * args.k * args.k
     res = {
         "ms": ms, "scored": scored, "value": scored / (ms * 1e-3),
         "us_per_iteration": ms * 1e3 / args.steps,
         "algorithmic_bytes_per_launch": per_iter_bytes,
         "achieved_gbs": per_iter_bytes / (ms * 1e-3 / args.steps) / 1e9,
-        "launches": m.launches_per_iteration() * args.steps,
-        "loop": m.loop_name(),
+        "launches": max(m.launches_per_iteration() * args.steps, 2),     # persistent: one launch per select()
+        "loop": m.loop_name(), "bytes_per_candidate": bytes_per_cand,
     }
     e2e = None
     if not args.skip_e2e:
@@ -413,7 +416,8 @@ def main():
                          "traffic": 2.44 * args.mi_candidates if mi["loop"].startswith("persistent") else None,
                          "traffic_source": "ncu dram__bytes_read+write per iteration, profiles/r01_mi_persist_v2.ncu.txt "
                                            "(2-byte row-partitioned stream + table)",
-                         "bytes_per_candidate_accounted": 4,
+                         "bytes_per_candidate_accounted": mi["bytes_per_candidate"],
+                         "list_order_equivalent_gbs": mi["achieved_gbs"] * 4.0 / mi["bytes_per_candidate"],
                          "kernel": "greedy-MI iteration (gain table + candidate scan + apply), per GPU",
                          "algorithmic_bytes_per_launch": mi["algorithmic_bytes_per_launch"],
                          "peak_source": pk["source"] + " copy bandwidth"},
