@@ -102,9 +102,14 @@ def load_clusterings(args, model_names):
 
 def _train_batch(args, features, clusterings):
     """process_batch.py:6-17."""
+    # the reference collects the mean distances and drops them (:171-175); skipping them saves a pass
+    # over the batch and the host sync of `.item()`
     if isinstance(features, dict):
-        return float(np.mean([km.add(features[key]) for key, km in clusterings.items()]))
-    return clusterings['model'].add(features)
+        for key, km in clusterings.items():
+            km.add(features[key], sync=False, distance=False)
+    else:
+        clusterings['model'].add(features, sync=False, distance=False)
+    return None
 
 
 def train_clusters(args, model_names):
@@ -134,11 +139,11 @@ def train_clusters(args, model_names):
 def _extract_batch(features, clusterings):
     """process_batch.py:37-56 -- ids per layer as np.int64."""
     if isinstance(features, dict):
-        ids = {key: km.calc_best(features[key], sync=False)[0] for key, km in clusterings.items()}
+        ids = {key: km.calc_best(features[key], sync=False, distance=False)[0] for key, km in clusterings.items()}
         ids = {key: v.cpu().numpy() for key, v in ids.items()}
         keys = sorted(ids.keys())
         return [dict(zip(keys, vals)) for vals in zip(*[ids[k] for k in keys])]
-    return list(clusterings['model'].calc_best(features, sync=False)[0].cpu().numpy())
+    return list(clusterings['model'].calc_best(features, sync=False, distance=False)[0].cpu().numpy())
 
 
 def assign_clusters(args, model_names, clusterings):

@@ -87,6 +87,7 @@ class KMeans:
         st['_fallback_base'] = self.fallback
         st['_fallback_dev'] = None
         st['_ws'] = None
+        st['_ws_pair'] = None
         st['_ws_batch'] = 0
         st['centers'] = self.centers.cpu()
         st['counts'] = self.counts.cpu()
@@ -101,6 +102,7 @@ class KMeans:
     # -- workspace -----------------------------------------------------------------------------
 
     def _release(self):
+        self._release_pair()
         if self._ws is not None:
             _lib.load().acav_kmeans_destroy(self._ws)
             self._ws = None
@@ -189,11 +191,75 @@ class KMeans:
                           _lib.ptr(best), None, _lib.ptr(mean), None, self._mode(), st)
         return best, mean
 
-    def calc_best(self, batch, sync=True):
-        """reference :63-79 -> (best LongTensor[b] on the device, mean min-distance)."""
+    def calc_best(self, batch, sync=True, distance=True):
+        """reference :63-79 -> (best LongTensor[b] on the device, mean min-distance).
+        `distance=False` skips the exact-distance pass over the batch and returns None for the mean
+        (the reference's callers that only label clips discard it, process_batch.py:43-48)."""
         batch = self._prep_batch(batch)
-        best, mean = self._assign(batch, want_mean=True)
+        best, mean = self._assign(batch, want_mean=distance)
+        if not distance:
+            return best, None
         return best, (mean.item() if sync else mean[0])
+
+    def assign_all(self, x, chunk=131072):
+        """Labels for a whole resident feature matrix (the assignment pass, run_clustering.py:225-229),
+        walked in chunks with the fp32->bf16 preparation of chunk i+1 running on a second stream and
+        workspace while the tensor-core kernel works on chunk i.  Returns LongTensor[n] on the device."""
+        x = self._prep_batch(x)
+        dev = self._device()
+        n = x.shape[0]
+        best = torch.empty(n, dtype=torch.int64, device=dev)
+        if n == 0:
+            return best
+        if self.in_warmup or self._mode() != _lib.ASSIGN_TENSOR:
+            for lo in range(0, n, chunk):
+                best[lo:lo + chunk] = self._assign(x[lo:lo + chunk], want_mean=False)[0]
+            return best
+        k, d = self.centers.shape
+        chunk = int(min(chunk, n))
+        if getattr(self, "_ws_pair", None) is None or self._ws_pair[2] < chunk:
+            self._release_pair()
+            hs = []
+            with torch.cuda.device(dev):
+                for _ in range(2):
+                    h = _lib.c_vp()
+                    _lib.call("acav_kmeans_create", _lib.ctypes.byref(h), k, d, chunk)
+                    hs.append(h)
+            self._ws_pair = (hs[0], hs[1], chunk, torch.cuda.Stream(device=dev))
+        ws, side = self._ws_pair[:2], self._ws_pair[3]
+        thr, r = self.underused_threshold(), float(self.reinit[1])
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            mp = _lib.ctypes.c_void_p(main.cuda_stream)
+            sp = _lib.ctypes.c_void_p(side.cuda_stream)
+            for h in ws:
+                _lib.call("acav_kmeans_prepare_centers", h, _lib.ptr(self.centers), _lib.ptr(self.counts), thr, r, mp)
+            side.wait_stream(main)
+            done = [None, None]
+            for i, lo in enumerate(range(0, n, chunk)):
+                xb = x[lo:lo + chunk]
+                h = ws[i % 2]
+                if done[i % 2] is not None:
+                    side.wait_event(done[i % 2])                   # workspace free again
+                _lib.call("acav_kmeans_prepare_batch", h, _lib.ptr(xb, row_strided=True), xb.shape[0],
+                          xb.stride(0), sp)
+                ready = torch.cuda.Event()
+                ready.record(side)
+                main.wait_event(ready)
+                _lib.call("acav_kmeans_assign_prepared", h, _lib.ptr(xb, row_strided=True), xb.shape[0],
+                          xb.stride(0), _lib.ptr(self.centers), _lib.ptr(self.counts), thr, r,
+                          _lib.c_vp(best.data_ptr() + 8 * lo), None, None, None, mp)
+                done[i % 2] = torch.cuda.Event()
+                done[i % 2].record(main)
+        return best
+
+    def _release_pair(self):
+        pair = getattr(self, "_ws_pair", None)
+        if pair is not None:
+            torch.cuda.synchronize(self.centers.device)
+            for h in pair[:2]:
+                _lib.load().acav_kmeans_destroy(h)
+            self._ws_pair = None
 
     @property
     def is_distributed(self):
@@ -249,8 +315,9 @@ class KMeans:
             _lib.call("acav_kmeans_apply_deltas", _lib.ptr(self.centers), _lib.ptr(deltas), deltas.numel(),
                       _lib.stream_ptr(self.centers.device))
 
-    def add(self, batch, sync=True):
-        """reference :94-129 (fast parallel update) -> mean min-distance of the batch."""
+    def add(self, batch, sync=True, distance=True):
+        """reference :94-129 (fast parallel update) -> mean min-distance of the batch
+        (None with `distance=False`: the training driver discards it, run_clustering.py:171-175)."""
         if self.sequential:
             raise NotImplementedError("sequential=True (reference :103-109, disabled by default) is not provided")
         batch = self._prep_batch(batch)
@@ -259,7 +326,7 @@ class KMeans:
         b = batch.shape[0]
         dist, world = self._world()
         lr = self.lr(self.count) if callable(self.lr) else self.lr
-        best, mean = self._assign(batch, want_mean=True)
+        best, mean = self._assign(batch, want_mean=distance)
         counts_b = self._histogram(batch, best)                                                     # :113
         if world > 1:
             dist.all_reduce(counts_b)                                                               # :114-115
@@ -270,4 +337,6 @@ class KMeans:
             self._update_fused(batch, counts_b, float(lr))                                          # :116-127
         self.count += parallel.kmeans_global_batch(b, world)                                                                   # :128
         self.last_best = best
+        if not distance:
+            return None
         return mean.item() if sync else mean[0]

@@ -244,15 +244,42 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
         return rc;
     }
     if (mode != ACAV_ASSIGN_TENSOR) return ACAV_E_INVALID;
+    int rc = acav_kmeans_prepare_centers(h, centers, counts, underused_threshold, reinit_r, stream);
+    if (!rc) rc = acav_kmeans_prepare_batch(h, x, b, ldx, stream);
+    if (!rc) rc = acav_kmeans_assign_prepared(h, x, b, ldx, centers, counts, underused_threshold, reinit_r, best,
+                                              min_dist, mean_dist, n_refined, stream);
+    return rc;
+}
+
+int acav_kmeans_prepare_centers(acav_kmeans_t *h, const float *centers, const float *counts,
+                                float underused_threshold, float reinit_r, void *stream) {
+    if (!h || !centers || !counts) return ACAV_E_INVALID;
     if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
-    // 1. bf16 operands + reference-style norms; 2. per-centroid epilogue parameters
-    int rc = launch_prep_rows(x, b, h->d, ldx, h->dp, h->xb, h->xn, st);
-    if (!rc) rc = launch_prep_rows(centers, h->k, h->d, h->d, h->dp, h->cb, h->cn, st);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_prep_rows(centers, h->k, h->d, h->d, h->dp, h->cb, h->cn, st);
     if (!rc) rc = launch_centroid_params(h->cn, counts, h->k, underused_threshold, reinit_r, h->cparams, h->cmax, st);
-    // 3. tcgen05 distance GEMM + top-2 screen; 4. merge / classify; 5. exact re-check of near-ties
+    return rc;
+}
+
+int acav_kmeans_prepare_batch(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream) {
+    if (!h || b < 0 || b > h->max_batch || (b > 0 && (!x || ldx < h->d))) return ACAV_E_INVALID;
+    if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
+    return launch_prep_rows(x, b, h->d, ldx, h->dp, h->xb, h->xn, (cudaStream_t)stream);
+}
+
+int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                                const float *centers, const float *counts,
+                                float underused_threshold, float reinit_r,
+                                int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
+                                void *stream) {
+    if (!h || !centers || !counts || b < 0 || b > h->max_batch) return ACAV_E_INVALID;
+    if (b > 0 && (!x || !best || ldx < h->d)) return ACAV_E_INVALID;
+    if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // tcgen05 distance GEMM + top-4 screen; merge / classify; exact re-check of near-ties
     int32_t n_split = 1;
-    if (!rc) rc = launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
-                                     h->partial, &n_split, st);
+    int rc = launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
+                                h->partial, &n_split, st);
     float *mind = min_dist ? min_dist : h->mind;
     if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cmax, best, mind, h->cand_rows,
                                         h->cand_ids, h->full_rows, h->counters, st);
@@ -260,7 +287,7 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                                           h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind, st);
     if (!rc) rc = launch_assign_exact(x, ldx, h->full_rows, b, h->counters + 1, centers, h->k, h->d, h->xn, h->cn,
                                       counts, underused_threshold, reinit_r, best, mind, st);
-    // 6. exact distance to the assigned centroid, only when the caller wants distances back
+    // exact distance to the assigned centroid, only when the caller wants distances back
     if (!rc && (min_dist || mean_dist))
         rc = launch_exact_min_dist(x, b, h->d, ldx, centers, best, h->xn, h->cn, counts, underused_threshold,
                                    reinit_r, mind, st);

@@ -69,6 +69,23 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                        int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
                        int32_t mode, void *stream);
 
+/* The three stages of acav_kmeans_assign(ACAV_ASSIGN_TENSOR), exposed so that a caller walking a
+ * resident data set can (a) prepare the centroids once per pass and (b) run the memory-bound
+ * preparation of chunk i+1 (fp32 -> bf16 copy + row norms) on a second stream and workspace while
+ * the tensor-core kernel of chunk i is busy:
+ *   prepare_centers : bf16 centroids, |c|^2, per-centroid epilogue parameters (re-init scaling)
+ *   prepare_batch   : bf16 rows + |x|^2 into the workspace
+ *   assign_prepared : tcgen05 distance GEMM + top-4 screen + exact re-check (+ exact distances if
+ *                     min_dist / mean_dist are non-NULL); x must be the batch given to prepare_batch. */
+int acav_kmeans_prepare_centers(acav_kmeans_t *h, const float *centers, const float *counts,
+                                float underused_threshold, float reinit_r, void *stream);
+int acav_kmeans_prepare_batch(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream);
+int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
+                                const float *centers, const float *counts,
+                                float underused_threshold, float reinit_r,
+                                int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
+                                void *stream);
+
 /* Replaces the warm-up branch of calc_best (sgd_clustering.py:67-68,78-79): `noise` is the [k, b]
  * fp32 tensor the caller drew with torch.rand; best[j] = first argmin over rows. */
 int acav_kmeans_assign_noise(const float *noise, int32_t k, int64_t b,

@@ -265,3 +265,23 @@ def test_training_trajectory_tensor_mode_matches_reference(golden_dir, name):
         np.testing.assert_allclose(centers, g["centers"], rtol=2e-5, atol=1e-7)
     best, _ = km.calc_best(x)
     assert (best.cpu().numpy() == g["assign_best"]).mean() > 0.998
+
+
+def test_assign_all_overlapped_pass_equals_chunked_calc_best():
+    n, d, k = 40_000, 256, 300
+    g = torch.Generator().manual_seed(4)
+    means = torch.randn(k, d, generator=g) * 3
+    x = means[torch.randint(0, k, (n,), generator=g)] + torch.randn(n, d, generator=g)
+    st = ko.SgdKMeansState(centers=means + 0.05 * torch.randn(k, d, generator=g), counts=torch.full((k,), 50.0),
+                           count=20 * k)
+    st.counts[::4] = 0.0
+    km = state_to_gpu(st, assign_mode="tensor")
+    xg = x.cuda()
+    want = torch.cat([km.calc_best(xg[lo:lo + 7000])[0] for lo in range(0, n, 7000)])
+    got = km.assign_all(xg, chunk=6000)                      # ragged last chunk, 7 chunks over 2 workspaces
+    assert torch.equal(got, want)
+    best, mean = km.calc_best(xg[:5000], distance=False)
+    assert mean is None and torch.equal(best, want[:5000])
+    assert km.add(xg[:4096], distance=False) is None
+    km_exact = state_to_gpu(st, assign_mode="exact")
+    assert torch.equal(km_exact.assign_all(xg, chunk=9000), want)
