@@ -1,0 +1,91 @@
+"""CPU restatement of the reference's default CLI measure ``batch_mi`` (stochastic batch greedy).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows ``subset_selection/code/measures/batch.py`` (``EfficientBatchMI`` :10-260) on top of the dense
+measure of ``measures/mi.py`` (``init_cache`` :32-39, ``one_hot``/``gather_pairs`` :61-74, ``calc_MI``
+:85-91, ``get_last`` :93-98, ``_add_samples`` :127-148).  Every iteration the reference (1) reshuffles ALL
+remaining candidates with ``torch.randperm`` on the global CPU generator, (2) scores the first B of them
+with the dense fp32 MI of (table + one-hot), (3) keeps the top k, (4) adds them to the table and
+(5) re-appends the B-k losers in ascending id order.  Pinned by ``tests/golden/bmi_*.npz``.
+"""
+import math
+
+import numpy as np
+import torch
+
+EPS = np.finfo('float64').eps
+
+
+def one_hot(x, C):
+    """mi.py:68-74."""
+    out = torch.zeros((*x.shape, C), dtype=torch.float)
+    out.scatter_(-1, x.unsqueeze(-1), torch.ones((*x.shape, 1), dtype=torch.float))
+    return out
+
+
+def sample_tables(assignments, pairs, ids, C):
+    """``sample_batch`` batch.py:34-54 / ``_add_samples`` mi.py:127-143 -> dense one-hot tables
+    N [m,P,C,C], a [m,P,C] (index c2), b [m,P,C] (index c1), n [m,P]."""
+    rows = assignments.index_select(0, ids)                       # [m, D]
+    oh = one_hot(rows, C)                                         # [m, D, C]
+    pair_ids = torch.as_tensor(pairs, dtype=torch.long)           # [P, 2]
+    p1, p2 = oh[:, pair_ids[:, 0]], oh[:, pair_ids[:, 1]]         # [m, P, C]
+    N = torch.einsum('wpa,wpb->wpab', p1, p2)
+    a, b = N.sum(2), N.sum(3)
+    return {'N': N, 'a': a, 'b': b, 'n': b.sum(-1)}
+
+
+def dense_mi(last):
+    """``calc_MI`` mi.py:85-91 -> [m, P]."""
+    N = last['N']
+    a = last['a'].unsqueeze(2)
+    b = last['b'].unsqueeze(3)
+    n = last['n'].unsqueeze(-1).unsqueeze(-1)
+    return (N / n * (N.log() + n.log() - (a.log() + b.log()))).sum([2, 3])
+
+
+def modify_k(k, B, subset_size, dataset_size, keep_unselected):
+    """batch.py:173-188."""
+    term = B * subset_size / dataset_size
+    if k < term and not keep_unselected:
+        k = math.ceil(term)
+    return k
+
+
+def greedy_batch_mi(assignments, ncentroids, pairs, candidates, subset_size, start_indices,
+                    batch_size=20, selection_size=4, keep_unselected=True):
+    """``EfficientBatchMI._run_greedy`` batch.py:202-260 -> (S, GAIN).  The start indices are counted
+    into the table but never into S; |S| == subset_size exactly."""
+    a = torch.from_numpy(np.asarray(assignments)).to(torch.long)
+    C, P = ncentroids, len(pairs)
+    N = torch.full((P, C, C), EPS)                                # init_cache mi.py:32-39
+    cache = {'N': N, 'a': N.sum(dim=1), 'b': N.sum(dim=2)}
+    cache['n'] = cache['a'].sum(dim=-1)
+    cand = torch.as_tensor(list(candidates), dtype=torch.long)
+    B = batch_size
+    k = modify_k(selection_size, B, subset_size, a.shape[0], keep_unselected)
+    add = sample_tables(a, pairs, torch.as_tensor(list(start_indices), dtype=torch.long), C)
+    for key in cache:                                             # add_samples batch.py:190-193
+        cache[key] = cache[key] + add[key].sum(0)
+    S, GAIN = [], []
+    while len(S) < subset_size:
+        cand = cand.index_select(0, torch.randperm(cand.shape[0]))          # shuffle_candidate_ids :29-32
+        batch = cand[:B]
+        tabs = sample_tables(a, pairs, batch, C)
+        last = {key: cache[key].unsqueeze(0) + tabs[key] for key in tabs}   # get_last mi.py:93-98
+        scores = dense_mi(last).mean(dim=-1)                                # calc_ids :143-150
+        kk = k if scores.shape[0] >= B else math.floor(B / k * scores.shape[0])
+        top, ids = scores.topk(k=kk, dim=0)
+        win = sample_tables(a, pairs, batch.index_select(0, ids), C)
+        for key in cache:                                                   # update_cache :152-154
+            cache[key] = cache[key] + win[key].sum(0)
+        chosen = batch.index_select(0, ids)
+        cand = cand[B:]                                                     # update_candidates :156-165
+        if keep_unselected:
+            comb = torch.cat((batch, chosen), dim=0)
+            uniq, counts = comb.unique(return_counts=True)
+            cand = torch.cat((cand, uniq[counts == 1]), dim=0)
+        S += chosen.tolist()
+        GAIN += top.tolist()
+    return S[:subset_size], GAIN

@@ -40,6 +40,14 @@ MI_CASES = {
 }
 
 
+BATCH_MI_CASES = {
+    # the reference CLI's default measure (config.py:45): B = 20 candidates per iteration, keep top k = 4
+    "bmi_p3": dict(v=400, c=8, dcols=3, subset=80, seed=1005, keep_unselected=True),
+    "bmi_p1_c20": dict(v=600, c=20, dcols=2, subset=120, seed=1004, keep_unselected=True),
+    "bmi_drop_unselected": dict(v=500, c=6, dcols=2, subset=60, seed=1007, keep_unselected=False),
+}
+
+
 def seed_all(seed):
     random.seed(seed)
     np.random.seed(seed)
@@ -109,6 +117,28 @@ def run_reference_mi(case, measure_name):
                 GAIN=np.array(GAIN, dtype=np.float64), subset=case["subset"], c=case["c"])
 
 
+def run_reference_batch_mi(case):
+    import contextlib
+    import io
+    get_measure, get_pairing = ref_shims.load_reference_measures()
+    a = mi_assignments(case)
+    keys = [("m%d" % i, "layer") for i in range(case["dcols"])]
+    pairs = get_pairing(keys, "combination")
+    v = a.shape[0]
+    seed_all(case["seed"])
+    measure = get_measure("batch_mi")(a, ncentroids=case["c"], batch_size=min(20, v - 1), selection_size=4,
+                                      device="cpu", keep_unselected=case["keep_unselected"])
+    candidates = list(range(v))
+    start, candidates = [candidates[0]], candidates[1:]
+    measure.init(pairs, candidates)
+    with contextlib.redirect_stdout(io.StringIO()):
+        S, GAIN, _, _ = measure.run_greedy(case["subset"], start, None, verbose=False, log_every=1,
+                                           log_times=None, node_rank=None, pid=None)
+    return dict(seed=case["seed"], assignments=a.astype(np.int16), pairs=np.array(pairs, dtype=np.int64),
+                S=np.array(S, dtype=np.int64), GAIN=np.array(GAIN, dtype=np.float64), subset=case["subset"],
+                c=case["c"], keep_unselected=case["keep_unselected"])
+
+
 def main():
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -122,6 +152,10 @@ def main():
             out = run_reference_mi(case, measure)
             np.savez_compressed(os.path.join(GOLDEN, f"{name}_{measure}.npz"), **out)
             print(name, measure, "|S|", len(out["S"]), out["S"][:8].tolist(), out["GAIN"][:3].tolist())
+    for name, case in BATCH_MI_CASES.items():
+        out = run_reference_batch_mi(case)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, "batch_mi |S|", len(out["S"]), out["S"][:8].tolist(), out["GAIN"][:3].tolist())
 
 
 if __name__ == "__main__":
