@@ -42,6 +42,10 @@ SIGNATURES = {
     "acav_mi_apply": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "acav_mi_run": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp]),
     "acav_mi_read_state": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "acav_mi_dense_create": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp]),
+    "acav_mi_dense_destroy": (ctypes.c_int, [c_vp]),
+    "acav_mi_dense_add": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "acav_mi_dense_score": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "acav_mi_debug_timers": (ctypes.c_int, [c_vp, c_vp]),
     "acav_mi_comm_handle_bytes": (ctypes.c_int, []),
     "acav_mi_comm_export": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp]),

@@ -502,6 +502,62 @@ int acav_mi_comm_connect(acav_mi_t *h, const void *handles) {
     return 0;
 }
 
+/* ---------------------------------------------------------------- batch_mi scoring -------- */
+
+struct acav_mi_dense {
+    MiDense s;
+    float *per_pair;
+    int64_t per_pair_cap;
+};
+
+int acav_mi_dense_destroy(acav_mi_dense_t *h) {
+    if (!h) return 0;
+    cudaFree(h->s.n_cells); cudaFree(h->s.a_cols); cudaFree(h->s.b_rows); cudaFree(h->s.n); cudaFree(h->s.sums);
+    cudaFree(h->per_pair);
+    delete h;
+    return 0;
+}
+
+int acav_mi_dense_create(acav_mi_dense_t **out, int32_t p, int32_t c, void *stream) {
+    if (!out || p <= 0 || c <= 0) return ACAV_E_INVALID;
+    *out = nullptr;
+    acav_mi_dense *h = new (std::nothrow) acav_mi_dense();
+    if (!h) return (int)cudaErrorMemoryAllocation;
+    h->s = MiDense(); h->s.p = p; h->s.c = c; h->per_pair = nullptr; h->per_pair_cap = 0;
+    int rc = dev_alloc(&h->s.n_cells, (size_t)p * c * c, nullptr);
+    if (!rc) rc = dev_alloc(&h->s.a_cols, (size_t)p * c, nullptr);
+    if (!rc) rc = dev_alloc(&h->s.b_rows, (size_t)p * c, nullptr);
+    if (!rc) rc = dev_alloc(&h->s.n, (size_t)p, nullptr);
+    if (!rc) rc = dev_alloc(&h->s.sums, (size_t)p * 3, nullptr);
+    if (!rc) rc = launch_mi_dense_reset(h->s, (cudaStream_t)stream);
+    if (rc) { acav_mi_dense_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int acav_mi_dense_add(acav_mi_dense_t *h, const int64_t *cells, int64_t m, void *stream) {
+    if (!h || m < 0 || (m > 0 && !cells)) return ACAV_E_INVALID;
+    return launch_mi_dense_add(h->s, cells, m, (cudaStream_t)stream);
+}
+
+int acav_mi_dense_score(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, float *scores, float *per_pair,
+                        void *stream) {
+    if (!h || nb < 0 || (nb > 0 && (!cells || !scores))) return ACAV_E_INVALID;
+    float *pp = per_pair;
+    if (!pp) {
+        if (h->per_pair_cap < nb * h->s.p) {
+            ACAV_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(h->per_pair);
+            h->per_pair = nullptr;
+            int rc = dev_alloc(&h->per_pair, (size_t)(nb * h->s.p), nullptr);
+            if (rc) return rc;
+            h->per_pair_cap = nb * h->s.p;
+        }
+        pp = h->per_pair;
+    }
+    return launch_mi_dense_score(h->s, cells, nb, pp, scores, (cudaStream_t)stream);
+}
+
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows, float *sums,
                        void *stream) {
     if (!h) return ACAV_E_INVALID;

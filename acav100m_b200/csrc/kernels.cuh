@@ -92,4 +92,18 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
                          long long *dbg, cudaStream_t st);
 
+// mi_dense.cu
+struct MiDense {
+    uint32_t *n_cells;     // [P, C, C]
+    uint32_t *a_cols;      // [P, C]  (index c2)
+    uint32_t *b_rows;      // [P, C]  (index c1)
+    uint32_t *n;           // [P]
+    double *sums;          // [P, 3]  NlogN, aloga, blogb
+    int32_t p, c;
+};
+int launch_mi_dense_reset(const MiDense &s, cudaStream_t st);
+int launch_mi_dense_add(const MiDense &s, const int64_t *cells, int64_t m, cudaStream_t st);
+int launch_mi_dense_score(const MiDense &s, const int64_t *cells, int64_t nb, float *per_pair, float *scores,
+                          cudaStream_t st);
+
 }  // namespace acav

@@ -545,30 +545,33 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                     const unsigned long long op = __shfl_xor_sync(0xffffffffu, p2, o);
                     if (ok > k2) { k2 = ok; p2 = op; }
                 }
-                if (threadIdx.x == 0) {
-                    if (P.world > 1) {
-                        // push this GPU's winner into every rank's mailbox (NVLink stores), then wait for
-                        // all ranks' entries of this iteration in the local mailbox
-                        const unsigned int tag = P.seq_base + (unsigned int)it + 1u;
-                        if (blockIdx.x == 0) {
-                            for (int r = 0; r < P.world; ++r) {
-                                MiMail *m = P.mail_peer[r] + (size_t)cur * P.world + P.rank;
-                                m->key = k2; m->payload = p2;
-                                st_release_sys(&m->seq, tag);
-                            }
-                        }
-                        for (int r = 0; r < P.world; ++r) {
-                            const MiMail *m = P.mail_local + (size_t)cur * P.world + r;
-                            while (ld_acquire_sys(&m->seq) != tag) { }
-                            const unsigned long long kk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
-                            if (r == 0 || kk > k2) {
-                                k2 = kk;
-                                p2 = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
-                            }
-                        }
+                if (P.world > 1) {
+                    // push this GPU's winner into every rank's mailbox (NVLink stores), then lanes 0..world-1
+                    // each wait for one rank's entry of this iteration in the local mailbox
+                    const unsigned int tag = P.seq_base + (unsigned int)it + 1u;
+                    k2 = __shfl_sync(0xffffffffu, k2, 0);
+                    p2 = __shfl_sync(0xffffffffu, p2, 0);
+                    if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
+                        MiMail *m = P.mail_peer[threadIdx.x] + (size_t)cur * P.world + P.rank;
+                        m->key = k2; m->payload = p2;
+                        st_release_sys(&m->seq, tag);
                     }
-                    sh_win_key = k2; sh_win_pay = p2;
+                    unsigned long long gk = 0ull, gp = 0ull;
+                    if ((int)threadIdx.x < P.world) {
+                        const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
+                        while (ld_acquire_sys(&m->seq) != tag) { }
+                        gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
+                        gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, gk, o);
+                        const unsigned long long op = __shfl_xor_sync(0xffffffffu, gp, o);
+                        if (ok > gk) { gk = ok; gp = op; }
+                    }
+                    k2 = gk; p2 = gp;
                 }
+                if (threadIdx.x == 0) { sh_win_key = k2; sh_win_pay = p2; }
             }
             __syncthreads();
         }

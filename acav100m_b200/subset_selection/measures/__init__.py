@@ -1,10 +1,10 @@
 """Measure registry with the reference's plugin point (``measures/__init__.py:5-14``)."""
+from .batch_mi import EfficientBatchMI
 from .mem_mi import EfficientMemMI
 
 _PENDING = {
     'mi': "dense W x P x C x C measure (reference measures/mi.py:14-209)",
     'ami': "adjusted MI (reference measures/mi.py:212-260)",
-    'batch_mi': "stochastic batch greedy (reference measures/batch.py)",
 }
 
 
@@ -12,6 +12,8 @@ def get_measure(measure_name):
     name = measure_name.lower()
     if name == 'mem_mi':
         return EfficientMemMI
+    if name == 'batch_mi':
+        return EfficientBatchMI
     assert name in _PENDING, "no measure named {}".format(measure_name)
     raise NotImplementedError(
         "measure '{}' -- {} -- is outside the CUDA hot path built so far (DESIGN.md, scope table); "

@@ -188,6 +188,26 @@ int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles);
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows,
                        float *sums, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * batch_mi, the reference CLI's default measure (subset_selection/code/measures/batch.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct acav_mi_dense acav_mi_dense_t;
+
+/* Running contingency tables of P clustering pairs with C centroids each (init_cache, mi.py:32-39). */
+int acav_mi_dense_create(acav_mi_dense_t **out, int32_t p, int32_t c, void *stream);
+int acav_mi_dense_destroy(acav_mi_dense_t *h);
+
+/* Counts m samples into the tables (add_samples batch.py:190-193, update_cache :152-154).
+ * cells: int64 [m, P, 2] of (c1, c2) per pair, device. */
+int acav_mi_dense_add(acav_mi_dense_t *h, const int64_t *cells, int64_t m, void *stream);
+
+/* scores[i] = mean over pairs of MI(table_p + one-hot(candidate i)) -- what sample_batch + get_last +
+ * calc_MI + mean(dim=-1) compute (batch.py:34-54,143-144; mi.py:85-98) -- for nb candidates given as
+ * int64 [nb, P, 2] device cells.  per_pair: fp32 [nb, P] device or NULL. */
+int acav_mi_dense_score(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, float *scores, float *per_pair,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif
