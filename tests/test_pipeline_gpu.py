@@ -90,3 +90,22 @@ def test_cli_pipeline_end_to_end(tmp_path):
                "--verbose=False"])
     S2, _ = mo.run_greedy_driver(a, subset_size=40, shuffle_candidates=True, rng=random.Random(5))
     assert [l[1] for l in csv.reader(open(out2))] == [filenames[s] for s in sorted(S2)]
+
+
+def test_cli_default_measure_runs_on_all_pairs(tmp_path):
+    """`cli run` with the reference's defaults: measure batch_mi, pairing 'combination' over all ten layer
+    clusterings (45 contingency tables), ratio 0.2, shuffled candidates."""
+    feat_dir, meta_dir = write_feature_shards(tmp_path / "data", n_shards=2, clips_per_shard=60, seed=4)
+    clusters, out_csv = tmp_path / "data" / "clusters", tmp_path / "data" / "output.csv"
+    torch.manual_seed(3)
+    ccli.main(["cluster", "--feature_path=" + str(feat_dir / "shard-{000000..000001}.pkl"),
+               "--out_path=" + str(clusters), "--meta_path=" + str(meta_dir), "--clustering.ncentroids=6",
+               "--data.batch_size=32", "--computation.num_gpus=1"])
+    random.seed(1)
+    scli.main(["run", "--shards_path=" + str(clusters / "shard-{000000..000001}.pkl"),
+               "--meta_path=" + str(meta_dir), "--out_path=" + str(out_csv), "--verbose=False"])
+    lines = list(csv.reader(open(out_csv)))
+    assert len(lines) == round(0.2 * 120)
+    names = [l[1] for l in lines]
+    assert len(set(names)) == len(names) and all(n.endswith(".mp4") for n in names)
+    assert all(l[2].startswith("yt") for l in lines)
