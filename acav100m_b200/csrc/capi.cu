@@ -14,6 +14,7 @@ struct acav_kmeans {
     int64_t bytes;
     // assignment scratch
     float *xn, *cn, *mind;
+    unsigned long long *packed;      // exact kernel: per-row (distance, index) keys merged across centroid groups
     // tensor-core path: bf16 copies, epilogue parameters, screening results, TMA descriptors
     int32_t dp;
     void *xb, *cb, *cparams, *partial;
@@ -79,7 +80,7 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     if (h->sorted_valid) return 0;
     MiState &s = h->s;
     h->rows_smem = mi_persistent_rows_that_fit(s.k_a, s.k_v);
-    if (h->rows_smem < 1 || s.k_v >= 65535 || (int64_t)s.k_a * s.k_v >= (1ll << 31)) return ACAV_E_UNSUPPORTED;
+    if (h->rows_smem < 1 || s.k_v > 16383 || (int64_t)s.k_a * s.k_v >= (1ll << 31)) return ACAV_E_UNSUPPORTED;   // stream holds 4*c2 in 16 bits
     const int ntiles = mi_partition_scratch_tiles(s.w);
     int rc = 0;
     if (!h->c2s) {
@@ -173,7 +174,7 @@ int acav_device_info(int *sm_count, int *cc_major, int *cc_minor) {
 
 int acav_kmeans_destroy(acav_kmeans_t *h) {
     if (!h) return 0;
-    cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind);
+    cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind); cudaFree(h->packed);
     cudaFree(h->blockhist); cudaFree(h->lrank); cudaFree(h->total); cudaFree(h->seg_start);
     cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
     cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial); cudaFree(h->cmax);
@@ -195,6 +196,7 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) rc = dev_alloc(&h->xn, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->cn, (size_t)k, &h->bytes);
     if (!rc) rc = dev_alloc(&h->mind, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->packed, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->blockhist, (size_t)(nblk * k), &h->bytes);
     if (!rc) rc = dev_alloc(&h->lrank, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->total, (size_t)k, &h->bytes);
@@ -238,7 +240,7 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
         if (!rc) rc = launch_row_norm2(centers, h->k, h->d, h->d, nullptr, h->cn, st);
         float *mind = min_dist ? min_dist : h->mind;
         if (!rc) rc = launch_assign_exact(x, ldx, nullptr, b, nullptr, centers, h->k, h->d, h->xn, h->cn, counts,
-                                          underused_threshold, reinit_r, best, mind, st);
+                                          underused_threshold, reinit_r, best, mind, h->packed, h->sm_count, st);
         if (!rc && mean_dist) rc = launch_mean(mind, b, mean_dist, st);
         if (!rc && n_refined) ACAV_CUDA_TRY(cudaMemsetAsync(n_refined, 0, 2 * sizeof(int32_t), st));
         return rc;
@@ -286,7 +288,7 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
     if (!rc) rc = launch_candidate_refine(x, ldx, h->d, centers, h->xn, h->cn, counts, underused_threshold, reinit_r,
                                           h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind, st);
     if (!rc) rc = launch_assign_exact(x, ldx, h->full_rows, b, h->counters + 1, centers, h->k, h->d, h->xn, h->cn,
-                                      counts, underused_threshold, reinit_r, best, mind, st);
+                                      counts, underused_threshold, reinit_r, best, mind, h->packed, h->sm_count, st);
     // exact distance to the assigned centroid, only when the caller wants distances back
     if (!rc && (min_dist || mean_dist))
         rc = launch_exact_min_dist(x, b, h->d, ldx, centers, best, h->xn, h->cn, counts, underused_threshold,

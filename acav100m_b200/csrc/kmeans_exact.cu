@@ -54,7 +54,7 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
                     const float *__restrict__ centers, int32_t k, int32_t d,
                     const float *__restrict__ xn, const float *__restrict__ cn,
                     const float *__restrict__ counts, float thr, float r,
-                    int64_t *__restrict__ best, float *__restrict__ mind) {
+                    unsigned long long *__restrict__ packed) {
     // tiles are widened to fp64 once, on the way into shared memory (F2F.F64 is a slow pipe: doing it
     // per FMA operand made the kernel conversion-bound)
     __shared__ __align__(16) double Xs[kKC][kPad];
@@ -82,7 +82,11 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
         xnr[i] = rr < nrows ? xn[rowlist ? (int64_t)rowlist[rr] : rr] : 0.f;     // xn is per source row
     }
 
-    for (int32_t c0 = 0; c0 < k; c0 += kTC) {
+    // blockIdx.y selects a contiguous group of centroid tiles (more CTAs in flight than row blocks alone)
+    const int32_t tiles = (k + kTC - 1) / kTC;
+    const int32_t per = (tiles + (int32_t)gridDim.y - 1) / (int32_t)gridDim.y;
+    const int32_t c_begin = (int32_t)blockIdx.y * per * kTC, c_end = min(k, c_begin + per * kTC);
+    for (int32_t c0 = c_begin; c0 < c_end; c0 += kTC) {
         double acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -142,12 +146,30 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
             if (better(od, oi, bd[i], bi[i])) { bd[i] = od; bi[i] = oi; }
         }
         int64_t rr = row0 + ty * 4 + i;
-        if (tx == 0 && rr < nrows) {
-            int64_t dst = rowlist ? (int64_t)rowlist[rr] : rr;
-            best[dst] = (int64_t)bi[i];
-            if (mind) mind[dst] = bd[i];
+        if (tx == 0 && rr < nrows && bi[i] != 0x7fffffff) {
+            // smallest distance, then smallest index: unsigned order of (orderable(dist) << 32 | index)
+            const unsigned long long key = ((unsigned long long)orderable(bd[i]) << 32) | (uint32_t)bi[i];
+            atomicMin(packed + rr, key);
         }
     }
+}
+
+__global__ void assign_exact_init_kernel(unsigned long long *__restrict__ packed, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) packed[i] = ~0ull;
+}
+
+__global__ void assign_exact_finish_kernel(const unsigned long long *__restrict__ packed,
+                                           const int32_t *__restrict__ rowlist, int64_t nrows,
+                                           const int32_t *__restrict__ nrows_dev,
+                                           int64_t *__restrict__ best, float *__restrict__ mind) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (nrows_dev) nrows = min(nrows, (int64_t)*nrows_dev);
+    if (i >= nrows) return;
+    const unsigned long long key = packed[i];
+    const int64_t dst = rowlist ? (int64_t)rowlist[i] : i;
+    best[dst] = (int64_t)(key & 0xFFFFFFFFull);
+    if (mind) mind[dst] = from_orderable((uint32_t)(key >> 32));
 }
 
 // Warm-up branch (:67-68,78): column-wise first argmin of noise[k, b].
@@ -194,10 +216,20 @@ int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int
                         const int32_t *nrows_dev,
                         const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
                         const float *counts, float thr, float r, int64_t *best, float *mind,
-                        cudaStream_t st) {
+                        unsigned long long *packed, int32_t sm_count, cudaStream_t st) {
     if (nrows == 0) return 0;
-    assign_exact_kernel<<<(unsigned)ceil_div(nrows, kTR), 256, 0, st>>>(
-        x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, best, mind);
+    const unsigned row_blocks = (unsigned)ceil_div(nrows, kTR);
+    const int32_t tiles = (int32_t)ceil_div(k, kTC);
+    int32_t split = 1;                                   // aim for >= 4 CTAs per SM
+    while (split < tiles && (int64_t)row_blocks * split < 4ll * sm_count) split *= 2;
+    if (split > tiles) split = tiles;
+    assign_exact_init_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(packed, nrows);
+    ACAV_LAUNCH_CHECK();
+    assign_exact_kernel<<<dim3(row_blocks, (unsigned)split), 256, 0, st>>>(
+        x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, packed);
+    ACAV_LAUNCH_CHECK();
+    assign_exact_finish_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(packed, rowlist, nrows, nrows_dev,
+                                                                              best, mind);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

@@ -3,8 +3,8 @@
 //
 // Data layout (built once per engine by the partition kernels below, DESIGN.md "MI layout"):
 //   * candidates are STABLY partitioned by table row c1; the stream holds only c2 as uint16
-//     (2 bytes per candidate per iteration instead of the reference's 16-byte int64 pair), value K_v =
-//     removed (its gain slot holds -inf, so the hot loop has no branch for it).  Inside a row the stream keeps list order, so "first maximum wins" (mi.py:79) is
+//     (2 bytes per candidate per iteration instead of the reference's 16-byte int64 pair), stored as the
+//     byte offset 4*c2 into a gain row; 4*K_v = removed (that slot holds -inf: no branch in the hot loop).  Inside a row the stream keeps list order, so "first maximum wins" (mi.py:79) is
 //     "first in stream" within a row and "smallest original position" (pos[] side array, read only on
 //     ties and for the per-thread winner) across rows.
 //   * the stream is cut into one contiguous chunk per CTA, balanced by (candidates + 3 * K_v per row
@@ -138,7 +138,7 @@ mi_part_scatter_kernel(const uint32_t *__restrict__ cells, int64_t w, int32_t k_
                 }
                 basev = __shfl_sync(0xffffffffu, basev, leader);
                 if (live) {
-                    c2s[basev + rank] = (uint16_t)(cell & 0xFFFFu);
+                    c2s[basev + rank] = (uint16_t)((cell & 0xFFFFu) << 2);      // byte offset into a gain row
                     pos_s[basev + rank] = (uint32_t)e;
                 }
             }
@@ -270,7 +270,7 @@ __device__ __forceinline__ void scan_vector_slow(ScanBest &b, const uint4 q, uin
         if (e < s_lo || e >= s_hi) continue;
         while (e >= rend) { ++crow; rend = rs_local[crow + 1]; }
         const uint32_t word = j < 4 ? (j < 2 ? q.x : q.y) : (j < 6 ? q.z : q.w);
-        const uint32_t c2 = (word >> ((j & 1) * 16)) & 0xFFFFu;
+        const uint32_t c2 = ((word >> ((j & 1) * 16)) & 0xFFFFu) >> 2;             // stream holds c2 * 4
         scan_consider(b, gain[crow * gstride + c2], e, rend, pos_s);      // removed entries read -inf
     }
 }
@@ -395,7 +395,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             if (s_hi <= s_lo) continue;
             const uint32_t v_lo = s_lo >> 3, v_hi = (s_hi + 7) >> 3;
             const uint4 *vec = reinterpret_cast<const uint4 *>(P.c2s_ro);
-            int32_t crow = 0;                                  // cached local row of this thread
+            // cached row of this thread: index, element range clipped to my chunk, byte address of its gain row
+            int32_t crow = 0;
+            uint32_t rend = rs_local[1];
+            uint32_t lim_lo = max(s_lo, rs_local[0]), lim_hi = min(s_hi, rend);
+            const uint32_t gain_b = (uint32_t)__cvta_generic_to_shared(gain);
+            uint32_t grow_b = gain_b;
             // each WARP walks its own contiguous span of vectors, 32 at a time (coalesced 512-byte
             // loads), so consecutive vectors of a thread are 256 candidates apart and usually stay in
             // the same table row: the cached row hits and the binary search below stays rare even
@@ -423,21 +428,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                 cp_async_wait<kRing - 1>();
                 const uint4 q = ring[slot * kPersistThreads];
                 if (++slot == kRing) slot = 0;
-                const uint32_t words[4] = {q.x, q.y, q.z, q.w};
                 const uint32_t e0 = v << 3;
-                uint32_t rlo = rs_local[crow], rend = rs_local[crow + 1];
-                const uint32_t ef = max(e0, s_lo);
-                if (ef < rlo || ef >= rend) {              // row with rs_local[row] <= ef < rs_local[row+1]
-                    int32_t a = 0, b = nr;
-                    while (a < b) { const int32_t m = (a + b) >> 1; if (rs_local[m + 1] > ef) b = m; else a = m + 1; }
-                    crow = a; rlo = rs_local[crow]; rend = rs_local[crow + 1];
-                }
-                if (e0 >= max(s_lo, rlo) && e0 + 8 <= min(s_hi, rend)) {
-                    // fast path: all 8 candidates in one row segment; removed entries gather -inf
-                    const float *grow = gain + crow * gstride;
+                if (e0 >= lim_lo && e0 + 8 <= lim_hi) {
+                    // fast path: all 8 candidates in the cached row segment; the stream holds byte offsets
+                    // into a gain row and removed entries point at its -inf slot: 2 instructions + 1 LDS each
                     float g[8];
+                    const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = grow[(words[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu];
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t off = (j & 1) ? (words[j >> 1] >> 16) : (words[j >> 1] & 0xFFFFu);
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[j]) : "r"(grow_b + off));
+                    }
                     const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
                                           fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
                     if (m > B.bs || (m == B.bs && B.bi != 0xFFFFFFFFu && e0 >= B.bend)) {
@@ -447,7 +448,18 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                         scan_consider(B, m, e0 + j, rend, P.pos_s);
                     }
                 } else {
+                    // vector leaves the cached row (or straddles a boundary / chunk edge): generic path, then
+                    // re-cache the row the walk ended in
+                    const uint32_t ef = max(e0, s_lo);
+                    if (ef < rs_local[crow] || ef >= rs_local[crow + 1]) {
+                        int32_t a = 0, b = nr;             // row with rs_local[row] <= ef < rs_local[row+1]
+                        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_local[m + 1] > ef) b = m; else a = m + 1; }
+                        crow = a;
+                    }
                     scan_vector_slow(B, q, e0, s_lo, s_hi, crow, rs_local, gain, gstride, P.pos_s);
+                    rend = rs_local[crow + 1];
+                    lim_lo = max(s_lo, rs_local[crow]); lim_hi = min(s_hi, rend);
+                    grow_b = gain_b + (uint32_t)(crow * gstride) * 4u;
                 }
             }
             cp_async_wait<0>();
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                     if (k2) {
                         int32_t a = 0, b = k_a;                // row of the stream index
                         while (a < b) { const int32_t m = (a + b) >> 1; if (rs_all[m + 1] > i2) b = m; else a = m + 1; }
-                        const uint32_t c2 = __ldcg(reinterpret_cast<const unsigned short *>(P.c2s) + i2);
+                        const uint32_t c2 = (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(P.c2s) + i2) >> 2;
                         const int32_t cell = a * k_v + (int32_t)c2;
                         const uint32_t x = __ldcg(Tcur + cell) + (cell == prev1 ? 1u : 0u);
                         pay = ((unsigned long long)a << 48) | ((unsigned long long)c2 << 32) | x;
@@ -580,7 +592,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         const int32_t c1 = (int32_t)(wpayload >> 48), c2w = (int32_t)((wpayload >> 32) & 0xFFFFu);
         if (threadIdx.x == 0) {
             if (sh_best_key == win) {                          // keys are unique: exactly one owner CTA
-                P.c2s[sh_best_idx] = (uint16_t)k_v;            // remove_idx_all mi.py:104-106 (k_v = removed)
+                P.c2s[sh_best_idx] = (uint16_t)(k_v << 2);     // remove_idx_all mi.py:104-106 (offset of the -inf slot)
                 s.cells[(int64_t)key_pos(win) - s.pos_base] = 0xFFFFFFFFu;     // list-order view stays in sync
             }
             const uint32_t x = (uint32_t)(wpayload & 0xFFFFFFFFull), y = a_cnt[c2w], z = b_cnt[c1];
