@@ -21,10 +21,12 @@ SIGNATURES = {
     "acav_kmeans_create": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i64]),
     "acav_kmeans_destroy": (ctypes.c_int, [c_vp]),
     "acav_kmeans_workspace_bytes": (c_i64, [c_vp]),
+    "acav_kmeans_set_tile_variant": (ctypes.c_int, [c_vp, c_i32]),
     "acav_kmeans_assign": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_f32, c_f32,
                                           c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "acav_kmeans_prepare_centers": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f32, c_f32, c_vp]),
     "acav_kmeans_prepare_batch": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "acav_kmeans_prepare_batch_background": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "acav_kmeans_assign_prepared": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_f32, c_f32,
                                                    c_vp, c_vp, c_vp, c_vp, c_vp]),
     "acav_kmeans_assign_noise": (ctypes.c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
@@ -53,6 +55,7 @@ SIGNATURES = {
 }
 
 ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1
+TILE_AUTO, TILE_SINGLE, TILE_PAIR_256, TILE_PAIR_512 = 0, 1, 2, 3
 MI_LOOP_KERNELS, MI_LOOP_PERSISTENT = 0, 1
 PERSISTENT_READY = True         # persistent greedy-MI kernel validated against the C oracle on a B200
 TENSOR_PATH_READY = True        # tcgen05 assignment validated against the exact kernel on a B200

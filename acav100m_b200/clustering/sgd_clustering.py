@@ -22,8 +22,9 @@ from .. import _lib, parallel
 class KMeans:
     def __init__(self, args=None, d=None, k=None, lr=1e-2,
                  initial_rounds=10, reinit=(.7, 5.0), saved_dt=None,
-                 assign_mode="auto", warmup_rng="cpu"):
+                 assign_mode="auto", warmup_rng="cpu", tile_variant=0):
         self._ws = None
+        self.tile_variant = tile_variant              # _lib.TILE_*: which tcgen05 distance-GEMM kernel (0 = by shape)
         self._ws_batch = 0
         self._fallback_base = 0
         self._fallback_dev = None
@@ -123,6 +124,8 @@ class KMeans:
             handle = _lib.c_vp()
             with torch.cuda.device(dev):
                 _lib.call("acav_kmeans_create", _lib.ctypes.byref(handle), k, d, cap)
+                if getattr(self, "tile_variant", 0):
+                    _lib.call("acav_kmeans_set_tile_variant", handle, int(self.tile_variant))
             self._ws, self._ws_batch = handle, cap
         if self._fallback_dev is None or self._fallback_dev.device != dev:
             self._fallback_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -224,33 +227,40 @@ class KMeans:
                 for _ in range(2):
                     h = _lib.c_vp()
                     _lib.call("acav_kmeans_create", _lib.ctypes.byref(h), k, d, chunk)
+                    if getattr(self, "tile_variant", 0):
+                        _lib.call("acav_kmeans_set_tile_variant", h, int(self.tile_variant))
                     hs.append(h)
-            self._ws_pair = (hs[0], hs[1], chunk, torch.cuda.Stream(device=dev))
-        ws, side = self._ws_pair[:2], self._ws_pair[3]
+            # the distance GEMM runs on a HIGH-priority stream: its 148 persistent CTAs must win the SMs against
+            # the thousands of short preparation blocks of the next chunk, which then fill the remaining
+            # thread slots and stream HBM underneath the tensor-core work (equal priorities serialise the two)
+            self._ws_pair = (hs[0], hs[1], chunk, torch.cuda.Stream(device=dev, priority=-1))
+        ws, hot = self._ws_pair[:2], self._ws_pair[3]
         thr, r = self.underused_threshold(), float(self.reinit[1])
         main = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
             mp = _lib.ctypes.c_void_p(main.cuda_stream)
-            sp = _lib.ctypes.c_void_p(side.cuda_stream)
+            hp = _lib.ctypes.c_void_p(hot.cuda_stream)
             for h in ws:
                 _lib.call("acav_kmeans_prepare_centers", h, _lib.ptr(self.centers), _lib.ptr(self.counts), thr, r, mp)
-            side.wait_stream(main)
             done = [None, None]
             for i, lo in enumerate(range(0, n, chunk)):
                 xb = x[lo:lo + chunk]
                 h = ws[i % 2]
                 if done[i % 2] is not None:
-                    side.wait_event(done[i % 2])                   # workspace free again
-                _lib.call("acav_kmeans_prepare_batch", h, _lib.ptr(xb, row_strided=True), xb.shape[0],
-                          xb.stride(0), sp)
+                    main.wait_event(done[i % 2])                   # workspace free again
+                # chunk 0 has the GPU to itself; later chunks are prepared underneath the previous chunk's GEMM
+                _lib.call("acav_kmeans_prepare_batch" if i == 0 else "acav_kmeans_prepare_batch_background",
+                          h, _lib.ptr(xb, row_strided=True), xb.shape[0], xb.stride(0), mp)
                 ready = torch.cuda.Event()
-                ready.record(side)
-                main.wait_event(ready)
+                ready.record(main)
+                hot.wait_event(ready)
                 _lib.call("acav_kmeans_assign_prepared", h, _lib.ptr(xb, row_strided=True), xb.shape[0],
                           xb.stride(0), _lib.ptr(self.centers), _lib.ptr(self.counts), thr, r,
-                          _lib.c_vp(best.data_ptr() + 8 * lo), None, None, None, mp)
+                          _lib.c_vp(best.data_ptr() + 8 * lo), None, None, None, hp)
                 done[i % 2] = torch.cuda.Event()
-                done[i % 2].record(main)
+                done[i % 2].record(hot)
+            main.wait_stream(hot)
+            best.record_stream(hot)
         return best
 
     def _release_pair(self):

@@ -1,4 +1,5 @@
 // extern "C" surface of libacav_b200.so (declared in include/acav_b200.h).
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -22,7 +23,9 @@ struct acav_kmeans {
     int32_t *cand_rows, *cand_ids, *full_rows, *counters;      // counters = {n_cand, n_full}
     alignas(64) unsigned char tmap_x[128];
     alignas(64) unsigned char tmap_c[128];
+    alignas(64) unsigned char tmap_c128[128];      // centroid map with 128-row boxes (CTA-pair kernels)
     bool tensor_ready;
+    int32_t tile_variant;            // ACAV_TILE_*
     // partition scratch
     uint32_t *blockhist, *lrank, *total, *seg_start, *sorted_rows;
     float *lr_eff;
@@ -219,13 +222,29 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (rc) { acav_kmeans_destroy(h); return rc; }
     if (max_batch > 0 &&
         make_bf16_tensor_map(h->tmap_x, h->xb, max_batch, h->dp, 128) == 0 &&
-        make_bf16_tensor_map(h->tmap_c, h->cb, k, h->dp, umma_tile_n(k)) == 0)
+        make_bf16_tensor_map(h->tmap_c, h->cb, k, h->dp, umma_tile_n(k)) == 0 &&
+        make_bf16_tensor_map(h->tmap_c128, h->cb, k, h->dp, 128) == 0)
         h->tensor_ready = true;
+    h->tile_variant = ACAV_TILE_AUTO;
+    if (const char *e = std::getenv("ACAV_TILE_VARIANT")) h->tile_variant = std::atoi(e);
     *out = h;
     return 0;
 }
 
 int64_t acav_kmeans_workspace_bytes(const acav_kmeans_t *h) { return h ? h->bytes : 0; }
+
+int acav_kmeans_set_tile_variant(acav_kmeans_t *h, int32_t variant) {
+    if (!h || variant < ACAV_TILE_AUTO || variant > ACAV_TILE_PAIR_512) return ACAV_E_INVALID;
+    h->tile_variant = variant;
+    return 0;
+}
+
+// which distance-GEMM kernel runs for this shape
+static int32_t resolve_tile_variant(const acav_kmeans *h) {
+    if (h->tile_variant != ACAV_TILE_AUTO) return h->tile_variant;
+    if (h->k >= 256) return ACAV_TILE_PAIR_256;     // measured fastest at K = 1024, D = 2048 (profiles/README.md)
+    return ACAV_TILE_SINGLE;
+}
 
 int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                        const float *centers, const float *counts,
@@ -269,6 +288,12 @@ int acav_kmeans_prepare_batch(acav_kmeans_t *h, const float *x, int64_t b, int64
     return launch_prep_rows(x, b, h->d, ldx, h->dp, h->xb, h->xn, (cudaStream_t)stream);
 }
 
+int acav_kmeans_prepare_batch_background(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream) {
+    if (!h || b < 0 || b > h->max_batch || (b > 0 && (!x || ldx < h->d))) return ACAV_E_INVALID;
+    if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
+    return launch_prep_rows_background(x, b, h->d, ldx, h->dp, h->xb, h->xn, h->sm_count, (cudaStream_t)stream);
+}
+
 int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                                 const float *centers, const float *counts,
                                 float underused_threshold, float reinit_r,
@@ -279,9 +304,13 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
     if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     // tcgen05 distance GEMM + top-4 screen; merge / classify; exact re-check of near-ties
-    int32_t n_split = 1;
-    int rc = launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
-                                h->partial, &n_split, st);
+    int32_t n_split = 1;                       // partial top-4 lists per row
+    const int32_t variant = resolve_tile_variant(h);
+    int rc = variant == ACAV_TILE_SINGLE
+                 ? launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
+                                      h->partial, &n_split, st)
+                 : launch_assign_pair(h->tmap_x, h->tmap_c128, h->xn, h->cparams, (int32_t)b, h->k, h->dp,
+                                      h->sm_count, variant == ACAV_TILE_PAIR_512 ? 2 : 1, h->partial, &n_split, st);
     float *mind = min_dist ? min_dist : h->mind;
     if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cmax, best, mind, h->cand_rows,
                                         h->cand_ids, h->full_rows, h->counters, st);

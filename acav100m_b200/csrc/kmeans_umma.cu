@@ -18,61 +18,10 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "kmeans_umma.cuh"
 #include "sm100_ptx.cuh"
 
 namespace acav {
-
-constexpr int kBM = 128;                 // rows of X per tile (UMMA M)
-constexpr int kBK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kBNMax = 256;              // centroids per accumulator stage (UMMA N <= 256)
-constexpr int kStages = 4;
-constexpr int kABytes = kBM * kBK * 2;           // 16 KiB
-constexpr int kBBytesMax = kBNMax * kBK * 2;     // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kTmemCols = 512;
-constexpr int kUmmaThreads = 192;
-constexpr int kEpiThreads = 128;
-
-struct UmmaSmem {
-    // dynamic smem, 1024-byte aligned base:
-    //   [kStages][A 16K | B 32K] | cparams[2][256] float4 | barriers
-    static constexpr int kParamsOff = kStages * kStageBytes;
-    static constexpr int kBarOff = kParamsOff + 2 * kBNMax * 16;
-    static constexpr int kBytes = kBarOff + 256;
-};
-
-struct __align__(16) CentroidParam {     // dist = s*|x|^2 + (a*dot + b)
-    float a, b, s, pad;
-};
-
-// Screening state per row: the four smallest approximate distances (sorted, earliest index first on
-// ties) and the fifth smallest value.  The exact arg-min is guaranteed to be among the entries within
-// the error bound of d[0]; if d5 is outside the bound those are all in this list.
-struct Top4 {
-    float d[4];
-    int32_t i[4];
-    float d5;
-};
-
-__device__ __forceinline__ void top4_init(Top4 &t) {
-#pragma unroll
-    for (int s = 0; s < 4; ++s) { t.d[s] = INFINITY; t.i[s] = 0x7fffffff; }
-    t.d5 = INFINITY;
-}
-
-// stable insertion (strict <: an equal value stays behind the earlier index)
-__device__ __forceinline__ void top4_insert(Top4 &t, float v, int32_t vi) {
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const bool lt = v < t.d[s];
-        const float dv = lt ? t.d[s] : v;
-        const int32_t di = lt ? t.i[s] : vi;
-        t.d[s] = lt ? v : t.d[s];
-        t.i[s] = lt ? vi : t.i[s];
-        v = dv; vi = di;
-    }
-    t.d5 = fminf(t.d5, v);
-}
 
 // fp32 [rows, d] -> bf16 [rows, dp] (zero padded) + |row|^2 as the reference computes it (norm ** 2).
 __global__ void km_prep_rows_kernel(const float *__restrict__ x, int64_t rows, int32_t d, int64_t ldx,
@@ -106,6 +55,52 @@ __global__ void km_prep_rows_kernel(const float *__restrict__ x, int64_t rows, i
     if (lane == 0) {
         float nrm = sqrtf((float)s);
         xn[r] = __fmul_rn(nrm, nrm);
+    }
+}
+
+// Same result as km_prep_rows_kernel, shaped to run UNDERNEATH a resident distance GEMM: two small blocks per SM
+// (grid-stride over rows, one row per warp at a time, <= 40 registers per thread) with four 16-byte loads in
+// flight per thread, launched with the GEMM's shared-memory carve-out so both kernels can share an SM.  A wide grid would fill every thread slot and the GEMM's large
+// CTAs (> 200 KiB of shared memory, 320 threads) could not be placed until it had drained -- the two kernels
+// would run back to back.  Per lane the elements are accumulated in the same order as above: bit-identical.
+constexpr int kBgUnroll = 4;
+constexpr int kBgBlocksPerSm = 2;
+__global__ void __launch_bounds__(256, 6)
+km_prep_rows_bg_kernel(const float *__restrict__ x, int64_t rows, int32_t d, int64_t ldx, int32_t dp,
+                       __nv_bfloat16 *__restrict__ xb, float *__restrict__ xn) {
+    const int lane = threadIdx.x % kWarp;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x / kWarp);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp; r < rows; r += nwarps) {
+        const float *p = x + r * ldx;
+        __nv_bfloat16 *q = xb + r * dp;
+        double s = 0.0;
+        for (int32_t i0 = lane * 4; i0 < dp; i0 += kWarp * 4 * kBgUnroll) {
+            float4 v[kBgUnroll];
+#pragma unroll
+            for (int u = 0; u < kBgUnroll; ++u) {
+                const int32_t i = i0 + u * kWarp * 4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < d) v[u] = __ldcs(reinterpret_cast<const float4 *>(p + i));
+            }
+#pragma unroll
+            for (int u = 0; u < kBgUnroll; ++u) {
+                const int32_t i = i0 + u * kWarp * 4;
+                if (i < dp) {
+                    s += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z +
+                         (double)v[u].w * v[u].w;
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                    *reinterpret_cast<uint2 *>(q + i) = pk;
+                }
+            }
+        }
+        s = warp_sum_f64(s);
+        if (lane == 0) {
+            float nrm = sqrtf((float)s);
+            xn[r] = __fmul_rn(nrm, nrm);
+        }
     }
 }
 
@@ -420,6 +415,21 @@ int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32
     const int wpb = 8;
     km_prep_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * kWarp, 0, st>>>(
         x, rows, d, ldx, dp, reinterpret_cast<__nv_bfloat16 *>(xb), xn);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_prep_rows_background(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
+                                int32_t sm_count, cudaStream_t st) {
+    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (!vec || rows < 8 * (int64_t)sm_count) return launch_prep_rows(x, rows, d, ldx, dp, xb, xn, st);
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_prep_rows_bg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
+        carveout_set = true;
+    }
+    km_prep_rows_bg_kernel<<<sm_count * kBgBlocksPerSm, 256, 0, st>>>(x, rows, d, ldx, dp, reinterpret_cast<__nv_bfloat16 *>(xb), xn);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

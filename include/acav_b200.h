@@ -51,6 +51,15 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
 int acav_kmeans_destroy(acav_kmeans_t *h);
 int64_t acav_kmeans_workspace_bytes(const acav_kmeans_t *h);
 
+/* Tile shape of the tcgen05 distance GEMM behind ACAV_ASSIGN_TENSOR (the reference's `-2*matmul`,
+ * sgd_clustering.py:72).  AUTO picks by K; the others pin one kernel (benchmarking / debugging).
+ * Results are identical for every choice (the exact re-check decides near-ties). */
+#define ACAV_TILE_AUTO      0
+#define ACAV_TILE_SINGLE    1      /* one CTA per 128 x 256 tile (cta_group::1)                     */
+#define ACAV_TILE_PAIR_256  2      /* CTA pair, 256 x 256 tile, two TMEM accumulator stages         */
+#define ACAV_TILE_PAIR_512  3      /* CTA pair, 256 x 512 tile, X read once per 512 centroids       */
+int acav_kmeans_set_tile_variant(acav_kmeans_t *h, int32_t variant);
+
 /* Assignment modes */
 #define ACAV_ASSIGN_EXACT   0      /* fp32 inputs, fp64-accumulated dot products on CUDA cores     */
 #define ACAV_ASSIGN_TENSOR  1      /* tcgen05 bf16 distance GEMM + top-2 screening + exact refine  */
@@ -80,6 +89,11 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
 int acav_kmeans_prepare_centers(acav_kmeans_t *h, const float *centers, const float *counts,
                                 float underused_threshold, float reinit_r, void *stream);
 int acav_kmeans_prepare_batch(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream);
+/* Same result as acav_kmeans_prepare_batch, launched as one small block per SM so that it can share the SMs
+ * with the distance GEMM of ANOTHER workspace that is already resident (a wide grid would keep the GEMM's
+ * large CTAs from being placed and the two kernels would run back to back).  Use it for chunk i+1 while
+ * acav_kmeans_assign_prepared works on chunk i (the assignment pass, run_clustering.py:225-229). */
+int acav_kmeans_prepare_batch_background(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream);
 int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                                 const float *centers, const float *counts,
                                 float underused_threshold, float reinit_r,

@@ -203,14 +203,14 @@ def test_assign_strided_batch_and_empty_batch():
 
 # ---- tcgen05 tensor-core assignment ---------------------------------------------------------------
 
-def _assign_both_modes(x, centers, counts, count):
+def _assign_both_modes(x, centers, counts, count, tile_variant=0):
     from acav100m_b200 import _lib
     outs = {}
     b, d = x.shape
     k = centers.shape[0]
     for mode in ("exact", "tensor"):
         st = ko.SgdKMeansState(centers=centers.clone(), counts=counts.clone(), count=count)
-        km = state_to_gpu(st, assign_mode=mode)
+        km = state_to_gpu(st, assign_mode=mode, tile_variant=tile_variant)
         ws = km._workspace(b)
         xg = x.cuda()
         best = torch.empty(b, dtype=torch.int64, device="cuda")
@@ -228,9 +228,11 @@ def _assign_both_modes(x, centers, counts, count):
     (128, 64, 16, True), (1, 64, 16, True), (129, 64, 256, True), (1000, 128, 256, True), (300, 88, 13, True),
     (4097, 512, 300, True), (8192, 2048, 1024, True), (20000, 704, 1024, True), (3000, 2304, 32, True),
     (2048, 256, 512, False), (5000, 128, 1500, False)])
-def test_assign_tensor_equals_exact(b, d, k, clustered):
+@pytest.mark.parametrize("tile_variant", [1, 2, 3])
+def test_assign_tensor_equals_exact(b, d, k, clustered, tile_variant):
     """Screen + re-check must reproduce the exact kernel's ids on EVERY row (that is the design claim),
-    and the distances handed back must be the exact ones."""
+    and the distances handed back must be the exact ones -- for each of the three tcgen05 tile shapes
+    (one CTA 128x256, CTA pair 256x256, CTA pair 256x512)."""
     if clustered:
         x = torch.from_numpy(synth.gaussian_mixture(b, d, max(k // 2, 2), b + d))
         c = torch.from_numpy(synth.gaussian_mixture(k, d, max(k // 2, 2), b + d))
@@ -239,7 +241,7 @@ def test_assign_tensor_equals_exact(b, d, k, clustered):
         x, c = torch.randn(b, d, generator=g), torch.randn(k, d, generator=g)
     counts = torch.full((k,), 100.0)
     counts[::3] = 0.0                                          # a third of the centroids get the /5 scaling
-    outs = _assign_both_modes(x, c, counts, 50 * k)
+    outs = _assign_both_modes(x, c, counts, 50 * k, tile_variant)
     be, me, mean_e, _ = outs["exact"]
     bt, mt, mean_t, nref = outs["tensor"]
     assert np.array_equal(be, bt), "%d rows differ" % int((be != bt).sum())
