@@ -87,8 +87,8 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     const int ntiles = mi_partition_scratch_tiles(s.w);
     int rc = 0;
     if (!h->c2s) {
-        if (!rc) rc = dev_alloc(&h->c2s, (size_t)s.w + 32, nullptr);
-        if (!rc) rc = dev_alloc(&h->pos_s, (size_t)s.w + 8, nullptr);
+        if (!rc) rc = dev_alloc(&h->c2s, (size_t)mi_stream_capacity(s.w, s.k_a), nullptr);
+        if (!rc) rc = dev_alloc(&h->pos_s, (size_t)mi_stream_capacity(s.w, s.k_a), nullptr);
         if (!rc) rc = dev_alloc(&h->row_start, (size_t)s.k_a + 1, nullptr);
         if (!rc) rc = dev_alloc(&h->row_total, (size_t)s.k_a, nullptr);
         if (!rc) rc = dev_alloc(&h->tilehist, (size_t)ntiles * s.k_a, nullptr);
@@ -99,13 +99,15 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
         if (rc) return rc;
     }
     rc = launch_mi_partition(s.cells, s.w, s.k_a, h->tilehist, h->row_total, h->row_start, h->c2s, h->pos_s,
-                             s.w + 32, st);
+                             mi_stream_capacity(s.w, s.k_a), (uint16_t)(s.k_v << 2), st);
     if (rc) return rc;
     std::vector<uint32_t> rs((size_t)s.k_a + 1);
     ACAV_CUDA_TRY(cudaMemcpyAsync(rs.data(), h->row_start, sizeof(uint32_t) * rs.size(), cudaMemcpyDeviceToHost, st));
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));
-    h->w_sorted = rs[s.k_a];
-    // balanced cut: cost(e) = e + row_cost * (#non-empty rows that start before e)
+    h->w_sorted = rs[s.k_a];                       // rows padded to whole blocks
+    rc = launch_mi_block_sort(h->c2s, h->pos_s, h->w_sorted, st);
+    if (rc) return rc;
+    // balanced cut: cost(e) = e + row_cost * (#non-empty rows that start before e); chunk edges block aligned
     const int32_t grid = h->sm_count;
     const double row_cost = 6.0 * s.k_v;          // building one gain row ~ scanning 6*K_v candidates (measured)
     std::vector<double> cum((size_t)s.k_a + 1);
@@ -128,7 +130,7 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
             double off = t - cum[r] - row_cost;
             if (off < 0) off = 0;
             if (off > (double)n) off = (double)n;
-            e = rs[r] + (uint32_t)off;
+            e = rs[r] + ((uint32_t)off / (uint32_t)mi_stream_block()) * (uint32_t)mi_stream_block();
         }
         chunks[g] = e;
     }

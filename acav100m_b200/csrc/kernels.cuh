@@ -87,7 +87,10 @@ int launch_mi_apply(const MiState &s, const unsigned long long *key_cells, int32
 int mi_partition_scratch_tiles(int64_t w);
 int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t *tilehist, uint32_t *row_total,
                         uint32_t *row_start, uint16_t *c2s, uint32_t *pos_s, int64_t stream_capacity,
-                        cudaStream_t st);
+                        uint16_t pad_marker, cudaStream_t st);
+int launch_mi_block_sort(uint16_t *c2s, uint32_t *pos_s, int64_t w_padded, cudaStream_t st);
+int64_t mi_stream_capacity(int64_t w, int32_t k_a);
+int mi_stream_block();
 int mi_persistent_rows_that_fit(int32_t k_a, int32_t k_v);
 size_t mi_pub_bytes(int32_t grid);
 size_t mi_mail_bytes(int32_t world);

@@ -27,6 +27,8 @@ constexpr int kTileElems = 32768;            // elements per partition tile
 constexpr int kPartThreads = 512;
 constexpr int kSmallCounts = 256;            // per-iteration table of tN(x) for counts below this
 constexpr int kRing = 4;                     // 16-byte stream loads in flight per thread (cp.async ring)
+constexpr int kBlk = 256;                    // stream block: 32 lanes x one 16-byte vector of 8 candidates; rows are
+                                             // padded to whole blocks and each block is sorted by shared-memory bank
 
 __device__ __forceinline__ float xlogx_cnt(uint32_t k, float f0, const float *__restrict__ logs) {
     return k == 0 ? f0 : __fmul_rn((float)k, __ldg(logs + k));
@@ -78,7 +80,7 @@ mi_part_rowstart_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t 
     const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
     for (int32_t base = 0; base < k; base += 1024) {
         const int32_t i = base + threadIdx.x;
-        const uint32_t v = i < k ? total[i] : 0u;
+        const uint32_t v = i < k ? ((total[i] + (kBlk - 1)) & ~(uint32_t)(kBlk - 1)) : 0u;    // rows padded to blocks
         uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < kWarp; o <<= 1) {
@@ -152,6 +154,44 @@ __global__ void mi_fill_u16_kernel(uint16_t *p, int64_t lo, int64_t hi, uint16_t
     if (i < hi) p[i] = v;
 }
 
+// Sort every 256-candidate block of the (row-partitioned, row-padded) stream by (shared-memory bank of its gain
+// slot, c2, original order).  In the scan, lane l of a warp owns the 8 consecutive entries [8l, 8l+8) of a block
+// and gather step j reads entry 8l+j in all lanes: in a bank-sorted block those 32 entries lie 8 apart, i.e. in
+// (about) 32 different banks, or they are the same c2 (one address, broadcast) -- the random gather of the
+// unsorted stream needed ~3.5 shared-memory wavefronts per load, this needs ~1.  Order inside a block no longer
+// is list order, so the scan breaks gain ties inside a vector by original position (pos_s is permuted along).
+__global__ void __launch_bounds__(kBlk)
+mi_block_sort_kernel(uint16_t *__restrict__ c2s, uint32_t *__restrict__ pos_s, int64_t n_blocks) {
+    __shared__ uint32_t key[kBlk];
+    __shared__ uint16_t c2v[kBlk];
+    __shared__ uint32_t posv[kBlk];
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t base = blk * kBlk;
+        const int t = threadIdx.x;
+        const uint16_t c = c2s[base + t];
+        c2v[t] = c;
+        posv[t] = pos_s[base + t];
+        const uint32_t idx = (uint32_t)c >> 2;                   // column index (k_v for padding / removed)
+        key[t] = ((idx & 31u) << 24) | (idx << 8) | (uint32_t)t;  // idx < 2^14 (checked on the host)
+        __syncthreads();
+        for (int size = 2; size <= kBlk; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const int partner = t ^ stride;
+                if (partner > t) {
+                    const uint32_t a = key[t], b = key[partner];
+                    const bool up = (t & size) == 0;
+                    if ((a > b) == up) { key[t] = b; key[partner] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        const int src = (int)(key[t] & 255u);
+        c2s[base + t] = c2v[src];
+        pos_s[base + t] = posv[src];
+        __syncthreads();
+    }
+}
+
 // ---- the persistent kernel -----------------------------------------------------------------------
 
 struct MiPub {                       // one per CTA and iteration parity: the CTA's best candidate
@@ -188,7 +228,7 @@ struct MiPersist {
     unsigned int seq_base;
     MiMail *mail_local;              // [2][world] in this GPU's memory
     MiMail *mail_peer[kMaxWorld];    // the same array on every rank (peer-mapped pointers)
-    long long *dbg;                  // optional [grid][4] cycle counters of the LAST iteration (nullptr = off)
+    long long *dbg;                  // optional [grid][8] counters of the LAST iteration (nullptr = off)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks) {
@@ -258,23 +298,6 @@ __device__ __forceinline__ void scan_consider(ScanBest &b, float g, uint32_t e, 
     else if (g == b.bs && b.bi != 0xFFFFFFFFu && e >= b.bend) scan_tie(b, e, rend, pos_s);
 }
 
-// generic path for the few vectors that straddle a row boundary or a chunk edge
-__device__ __forceinline__ void scan_vector_slow(ScanBest &b, const uint4 q, uint32_t e0, uint32_t s_lo,
-                                                 uint32_t s_hi, int32_t &crow, const uint32_t *__restrict__ rs_local,
-                                                 const float *__restrict__ gain, int32_t gstride,
-                                                 const uint32_t *__restrict__ pos_s) {
-    uint32_t rend = rs_local[crow + 1];
-#pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t e = e0 + j;
-        if (e < s_lo || e >= s_hi) continue;
-        while (e >= rend) { ++crow; rend = rs_local[crow + 1]; }
-        const uint32_t word = j < 4 ? (j < 2 ? q.x : q.y) : (j < 6 ? q.z : q.w);
-        const uint32_t c2 = ((word >> ((j & 1) * 16)) & 0xFFFFu) >> 2;             // stream holds c2 * 4
-        scan_consider(b, gain[crow * gstride + c2], e, rend, pos_s);      // removed entries read -inf
-    }
-}
-
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -333,11 +356,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
     int32_t prev1 = -1, prev2 = -1;                            // table cell of picks it-1, it-2
     int64_t done = 0;
     bool broke = false;
+    long long t_learn = 0;
 
     for (int64_t it = 0; it < P.n_picks; ++it) {
         const int cur = (int)(it & 1);
         const long long t0 = P.dbg ? clock64() : 0;
-        long long t_gain = 0;
+        long long t_gain = 0, t_pre = 0;
         const uint32_t *Tcur = cur ? P.n_alt : s.n_cells;
         uint32_t *Toth = cur ? s.n_cells : P.n_alt;
         if (blockIdx.x == 0 && threadIdx.x == 0) {             // lagged writer of the other table copy
@@ -355,6 +379,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         ScanBest B;
         B.bs = -INFINITY; B.bi = 0xFFFFFFFFu; B.bend = 0; B.ntie = 0;
         B.tie[0] = B.tie[1] = B.tie[2] = 0;
+        if (P.dbg) t_pre = clock64() - t0;
         for (int32_t rb = r_lo; rb <= r_hi; rb += P.rows_smem) {
             const int32_t nr = min(P.rows_smem, r_hi - rb + 1);
             const uint32_t *rs_local = rs_all + rb;
@@ -391,75 +416,76 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             }
             __syncthreads();
             if (P.dbg) t_gain += clock64() - tg0;
+            // rows are padded to whole 256-candidate blocks and chunk edges are block aligned: a block never
+            // straddles a row or a chunk, so the row is uniform per warp-iteration and there is no slow path
             const uint32_t s_lo = max(e_lo, rs_local[0]), s_hi = min(e_hi, rs_local[nr]);
             if (s_hi <= s_lo) continue;
-            const uint32_t v_lo = s_lo >> 3, v_hi = (s_hi + 7) >> 3;
+            const uint32_t b_lo = s_lo / kBlk, b_hi = s_hi / kBlk;
             const uint4 *vec = reinterpret_cast<const uint4 *>(P.c2s_ro);
-            // cached row of this thread: index, element range clipped to my chunk, byte address of its gain row
-            int32_t crow = 0;
-            uint32_t rend = rs_local[1];
-            uint32_t lim_lo = max(s_lo, rs_local[0]), lim_hi = min(s_hi, rend);
-            const uint32_t gain_b = (uint32_t)__cvta_generic_to_shared(gain);
-            uint32_t grow_b = gain_b;
-            // each WARP walks its own contiguous span of vectors, 32 at a time (coalesced 512-byte
-            // loads), so consecutive vectors of a thread are 256 candidates apart and usually stay in
-            // the same table row: the cached row hits and the binary search below stays rare even
-            // where rows are short.  Per thread the elements are still visited in increasing order.
+            // each WARP walks its own contiguous span of blocks (coalesced 512-byte loads); lane l owns vector l.
+            // Measured alternatives on B200 (W = 1e8): warps interleaved over one contiguous CTA window 2.3x
+            // slower; ring depth 6 / 8 / 12 instead of 4 (more bytes in flight) 10-30 % slower.
             const uint32_t nwarps = kPersistThreads / kWarp;
-            const uint32_t span = (((v_hi - v_lo) + nwarps - 1) / nwarps + kWarp - 1) & ~(uint32_t)(kWarp - 1);
-            const uint32_t wv_lo = v_lo + (threadIdx.x / kWarp) * span;
-            const uint32_t wv_hi = min(v_hi, wv_lo + span);
-            const uint32_t vfirst = wv_lo + (threadIdx.x % kWarp);
+            const uint32_t span = (b_hi - b_lo + nwarps - 1) / nwarps;
+            const uint32_t wb_lo = min(b_hi, b_lo + (threadIdx.x / kWarp) * span);
+            const uint32_t wb_hi = min(b_hi, wb_lo + span);
+            const uint32_t lane = threadIdx.x % kWarp;
+            const uint32_t gain_b = (uint32_t)__cvta_generic_to_shared(gain);
+            int32_t crow = 0;
+            if (wb_lo < wb_hi) {                                 // row of my first block (uniform per warp)
+                const uint32_t ef = wb_lo * kBlk;
+                int32_t a = 0, b = nr;
+                while (a < b) { const int32_t m = (a + b) >> 1; if (rs_local[m + 1] > ef) b = m; else a = m + 1; }
+                crow = a;
+            }
+            uint32_t rend = rs_local[crow + 1];
+            uint32_t grow_b = gain_b + (uint32_t)(crow * gstride) * 4u;
 #pragma unroll
             for (int r = 0; r < kRing - 1; ++r) {
-                const uint32_t v = vfirst + (uint32_t)r * kWarp;
-                if (v < wv_hi) cp_async16(ring + r * kPersistThreads, vec + v);
+                const uint32_t blk = wb_lo + (uint32_t)r;
+                if (blk < wb_hi) cp_async16(ring + r * kPersistThreads, vec + (size_t)blk * kWarp + lane);
                 cp_async_commit();
             }
             int slot = 0;
-            for (uint32_t v = vfirst; v < wv_hi; v += kWarp) {
+            for (uint32_t blk = wb_lo; blk < wb_hi; ++blk) {
                 {
-                    const uint32_t vn = v + (kRing - 1) * kWarp;
+                    const uint32_t bn = blk + (kRing - 1);
                     int sn = slot + kRing - 1;
                     if (sn >= kRing) sn -= kRing;
-                    if (vn < wv_hi) cp_async16(ring + sn * kPersistThreads, vec + vn);
+                    if (bn < wb_hi) cp_async16(ring + sn * kPersistThreads, vec + (size_t)bn * kWarp + lane);
                     cp_async_commit();
                 }
                 cp_async_wait<kRing - 1>();
                 const uint4 q = ring[slot * kPersistThreads];
                 if (++slot == kRing) slot = 0;
-                const uint32_t e0 = v << 3;
-                if (e0 >= lim_lo && e0 + 8 <= lim_hi) {
-                    // fast path: all 8 candidates in the cached row segment; the stream holds byte offsets
-                    // into a gain row and removed entries point at its -inf slot: 2 instructions + 1 LDS each
-                    float g[8];
-                    const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+                const uint32_t eb = blk * kBlk;
+                while (eb >= rend) {                             // next non-empty row (uniform per warp)
+                    ++crow;
+                    rend = rs_local[crow + 1];
+                    grow_b = gain_b + (uint32_t)(crow * gstride) * 4u;
+                }
+                // the stream holds byte offsets into a gain row; removed / padding entries point at its -inf slot
+                const uint32_t e0 = eb + lane * 8u;
+                float g[8];
+                const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = (j & 1) ? (words[j >> 1] >> 16) : (words[j >> 1] & 0xFFFFu);
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[j]) : "r"(grow_b + off));
+                }
+                const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
+                                      fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                if (m > B.bs || (m == B.bs && B.bi != 0xFFFFFFFFu && e0 >= B.bend)) {
+                    // rare: of the maxima in this vector take the one that came first in the candidate list
+                    uint32_t bj = 0, bp = 0xFFFFFFFFu;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const uint32_t off = (j & 1) ? (words[j >> 1] >> 16) : (words[j >> 1] & 0xFFFFu);
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g[j]) : "r"(grow_b + off));
+                        if (g[j] == m) {
+                            const uint32_t pj = __ldg(P.pos_s + e0 + j);
+                            if (pj < bp) { bp = pj; bj = (uint32_t)j; }
+                        }
                     }
-                    const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
-                                          fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-                    if (m > B.bs || (m == B.bs && B.bi != 0xFFFFFFFFu && e0 >= B.bend)) {
-                        int j = 0;
-#pragma unroll
-                        for (int t = 7; t >= 0; --t) j = g[t] == m ? t : j;       // first of the maxima
-                        scan_consider(B, m, e0 + j, rend, P.pos_s);
-                    }
-                } else {
-                    // vector leaves the cached row (or straddles a boundary / chunk edge): generic path, then
-                    // re-cache the row the walk ended in
-                    const uint32_t ef = max(e0, s_lo);
-                    if (ef < rs_local[crow] || ef >= rs_local[crow + 1]) {
-                        int32_t a = 0, b = nr;             // row with rs_local[row] <= ef < rs_local[row+1]
-                        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_local[m + 1] > ef) b = m; else a = m + 1; }
-                        crow = a;
-                    }
-                    scan_vector_slow(B, q, e0, s_lo, s_hi, crow, rs_local, gain, gstride, P.pos_s);
-                    rend = rs_local[crow + 1];
-                    lim_lo = max(s_lo, rs_local[crow]); lim_hi = min(s_hi, rend);
-                    grow_b = gain_b + (uint32_t)(crow * gstride) * 4u;
+                    if (m > -INFINITY) scan_consider(B, m, e0 + bj, rend, P.pos_s);
                 }
             }
             cp_async_wait<0>();
@@ -529,9 +555,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         }
         const long long t2 = P.dbg ? clock64() : 0;
         grid_barrier(P.bar, grid);
+        const long long t3 = P.dbg ? clock64() : 0;
         if (P.dbg && threadIdx.x == 0) {
-            long long *d = P.dbg + 4 * blockIdx.x;
+            long long *d = P.dbg + 8 * blockIdx.x;
             d[0] = t_gain; d[1] = t1 - t0 - t_gain; d[2] = t2 - t1; d[3] = clock64() - t2;
+            d[4] = (long long)(e_hi - e_lo) / kBlk; d[5] = r_hi - r_lo + 1; d[6] = t_pre; d[7] = t_learn;
         }
         // ---------------- everyone learns the winner ----------------
         {
@@ -610,6 +638,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
         prev1 = c1 * k_v + c2w;
         done = it + 1;
         __syncthreads();
+        if (P.dbg) t_learn = clock64() - t3;
     }
     // ---------------- write the replicated state back (CTA 0) ----------------
     if (blockIdx.x == 0) {
@@ -635,7 +664,7 @@ int mi_partition_scratch_tiles(int64_t w) { return (int)ceil_div(w > 0 ? w : 1, 
 
 int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t *tilehist, uint32_t *row_total,
                         uint32_t *row_start, uint16_t *c2s, uint32_t *pos_s, int64_t stream_capacity,
-                        cudaStream_t st) {
+                        uint16_t pad_marker, cudaStream_t st) {
     const int ntiles = mi_partition_scratch_tiles(w);
     const size_t smem = (size_t)k_a * sizeof(uint32_t);
     if (smem > 96 * 1024) return ACAV_E_UNSUPPORTED;
@@ -651,11 +680,26 @@ int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t 
     ACAV_LAUNCH_CHECK();
     mi_part_rowstart_kernel<<<1, 1024, 0, st>>>(row_total, k_a, row_start);
     ACAV_LAUNCH_CHECK();
+    // padding entries of every row: "removed" marker (the -inf slot of a gain row)
+    mi_fill_u16_kernel<<<(unsigned)ceil_div(stream_capacity, 256), 256, 0, st>>>(c2s, 0, stream_capacity, pad_marker);
+    ACAV_LAUNCH_CHECK();
     mi_part_scatter_kernel<<<ntiles, kPartThreads, smem, st>>>(cells, w, k_a, tilehist, row_start, c2s, pos_s);
     ACAV_LAUNCH_CHECK();
-    (void)stream_capacity;
     return 0;
 }
+
+// second step, once the padded stream length is known on the host (row_start[k_a]): bank-sort every block
+int launch_mi_block_sort(uint16_t *c2s, uint32_t *pos_s, int64_t w_padded, cudaStream_t st) {
+    const int64_t n_blocks = w_padded / kBlk;
+    if (n_blocks == 0) return 0;
+    const unsigned grid = (unsigned)(n_blocks < 65535 * 16 ? n_blocks : 65535 * 16);
+    mi_block_sort_kernel<<<grid, kBlk, 0, st>>>(c2s, pos_s, n_blocks);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t mi_stream_capacity(int64_t w, int32_t k_a) { return w + (int64_t)kBlk * k_a + kBlk; }
+int mi_stream_block() { return kBlk; }
 
 
 // dynamic shared memory: [col_term k_v | tn_small | a_cnt k_v | b_cnt k_a | rs_all k_a+1 | rt_local rows |

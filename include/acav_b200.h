@@ -192,9 +192,10 @@ int acav_mi_comm_handle_bytes(void);
 int acav_mi_comm_export(acav_mi_t *h, int32_t world, int32_t rank, void *handle_out);
 int acav_mi_comm_connect(acav_mi_t *h, const void *handles);
 
-/* Profiling aid: when `cycles` (device int64 [4 * #SMs]) is non-NULL the persistent loop records, per
+/* Profiling aid: when `cycles` (device int64 [8 * #SMs]) is non-NULL the persistent loop records, per
  * CTA and for the last iteration it ran, SM cycles spent in {gain rows, candidate scan, block reduce +
- * publish, grid-barrier wait}.  NULL switches it off (default). */
+ * publish, grid-barrier wait}, then {stream blocks, table rows} of the CTA's chunk and the cycles of
+ * {per-iteration prologue, winner hand-over of the previous iteration}.  NULL switches it off (default). */
 int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles);
 
 /* Introspection for tests: copies table counts (uint32 [k_a*k_v], [k_v], [k_a]) and the four running
