@@ -56,7 +56,7 @@ SIGNATURES = {
 
 ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1
 TILE_AUTO, TILE_SINGLE, TILE_PAIR_256, TILE_PAIR_512 = 0, 1, 2, 3
-MI_LOOP_KERNELS, MI_LOOP_PERSISTENT = 0, 1
+MI_LOOP_KERNELS, MI_LOOP_PERSISTENT, MI_LOOP_CELLS = 0, 1, 2
 PERSISTENT_READY = True         # persistent greedy-MI kernel validated against the C oracle on a B200
 TENSOR_PATH_READY = True        # tcgen05 assignment validated against the exact kernel on a B200
 

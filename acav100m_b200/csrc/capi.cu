@@ -55,6 +55,9 @@ struct acav_mi {
     void *mail_peer[kMiMaxWorld];
     bool comm_connected;
     long long *dbg;              // optional per-CTA phase timers of the persistent loop
+    // cell-index loop resources (candidates sorted by table cell), built on first use
+    uint32_t *cx_sorted_pos, *cx_cell_start, *cx_head, *cx_first_pos;
+    bool cells_valid;
 };
 
 namespace {
@@ -143,6 +146,42 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `chunks` is a host temporary
     h->grid = grid;
     h->sorted_valid = true;
+    return 0;
+}
+
+// Build (or rebuild) the cell index from the list-order view.
+int mi_prepare_cells(acav_mi *h, cudaStream_t st) {
+    if (h->cells_valid) return 0;
+    MiState &s = h->s;
+    const size_t n_cells = (size_t)s.k_a * s.k_v;
+    if (s.k_a > 16384 || s.k_v > 16384) return ACAV_E_UNSUPPORTED;
+    int rc = 0;
+    if (!h->cx_sorted_pos) {
+        if (!rc) rc = dev_alloc(&h->cx_sorted_pos, (size_t)s.w + 4, nullptr);
+        if (!rc) rc = dev_alloc(&h->cx_cell_start, n_cells + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->cx_head, n_cells, nullptr);
+        if (!rc) rc = dev_alloc(&h->cx_first_pos, n_cells, nullptr);
+        if (!h->pub && !rc) rc = dev_alloc(&h->pub, mi_pub_bytes(h->sm_count), nullptr);
+        if (!h->bar && !rc) rc = dev_alloc(&h->bar, 2, nullptr);
+        if (rc) return rc;
+    }
+    // scratch of the two sort passes, released again after the build
+    const int32_t kmax = s.k_a > s.k_v ? s.k_a : s.k_v;
+    uint32_t *tilehist = nullptr, *total = nullptr, *start = nullptr, *tmp_cells = nullptr, *tmp_pos = nullptr,
+             *sorted_cells = nullptr;
+    if (!rc) rc = dev_alloc(&tilehist, (size_t)mi_cells_tiles(s.w) * kmax, nullptr);
+    if (!rc) rc = dev_alloc(&total, (size_t)kmax, nullptr);
+    if (!rc) rc = dev_alloc(&start, (size_t)kmax + 1, nullptr);
+    if (!rc) rc = dev_alloc(&tmp_cells, (size_t)s.w + 4, nullptr);
+    if (!rc) rc = dev_alloc(&tmp_pos, (size_t)s.w + 4, nullptr);
+    if (!rc) rc = dev_alloc(&sorted_cells, (size_t)s.w + 4, nullptr);
+    int64_t n_live = 0;
+    if (!rc) rc = launch_mi_cells_build(s, tilehist, total, start, tmp_cells, tmp_pos, sorted_cells, h->cx_sorted_pos,
+                                        h->cx_cell_start, h->cx_head, h->cx_first_pos, &n_live, st);
+    if (!rc) rc = (int)cudaStreamSynchronize(st);
+    cudaFree(tilehist); cudaFree(total); cudaFree(start); cudaFree(tmp_cells); cudaFree(tmp_pos); cudaFree(sorted_cells);
+    if (rc) return rc;
+    h->cells_valid = true;
     return 0;
 }
 
@@ -392,6 +431,7 @@ int acav_mi_destroy(acav_mi_t *h) {
         for (int r = 0; r < h->world; ++r)
             if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
     cudaFree(h->mail_local);
+    cudaFree(h->cx_sorted_pos); cudaFree(h->cx_cell_start); cudaFree(h->cx_head); cudaFree(h->cx_first_pos);
     delete h;
     return 0;
 }
@@ -414,6 +454,8 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     for (int r = 0; r < kMiMaxWorld; ++r) h->mail_peer[r] = nullptr;
     h->dbg = nullptr;
     h->sorted_valid = false;
+    h->cx_sorted_pos = nullptr; h->cx_cell_start = nullptr; h->cx_head = nullptr; h->cx_first_pos = nullptr;
+    h->cells_valid = false;
     int rc = query_sm_count(&h->sm_count);
     const size_t cells = (size_t)k_a * k_v;
     if (!rc) rc = dev_alloc(&s.cells, (size_t)w + 4, nullptr);
@@ -436,6 +478,7 @@ int acav_mi_load_candidates(acav_mi_t *h, const int64_t *cells, void *stream) {
     int rc = launch_mi_pack(cells, h->s.w, h->s.cells, (cudaStream_t)stream);
     h->loaded = (rc == 0);
     h->sorted_valid = false;
+    h->cells_valid = false;
     return rc;
 }
 
@@ -471,6 +514,7 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n, int64_t *o
     if (!h || !key_cells || n <= 0) return ACAV_E_INVALID;
     if (!h->tabled || !h->loaded) return ACAV_E_STATE;
     h->sorted_valid = false;                 // the row-partitioned stream does not see this removal
+    h->cells_valid = false;                  // nor does the cell index
     return launch_mi_apply(h->s, reinterpret_cast<const unsigned long long *>(key_cells), n, out_pos, out_gain,
                            (cudaStream_t)stream);
 }
@@ -479,8 +523,21 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
     if (!h || n_picks < 0 || (n_picks > 0 && (!out_pos || !out_gain))) return ACAV_E_INVALID;
     if (!h->tabled || !h->loaded) return ACAV_E_STATE;
     cudaStream_t st = (cudaStream_t)stream;
+    if (mode == ACAV_MI_LOOP_CELLS) {
+        if (n_picks == 0) return 0;
+        if (h->world > 1 && !h->comm_connected) return ACAV_E_STATE;
+        int rc = mi_prepare_cells(h, st);
+        if (rc) return rc;
+        const int32_t grid = h->sm_count < h->s.k_a ? h->sm_count : h->s.k_a;
+        h->sorted_valid = false;                 // the candidate stream does not see these removals
+        rc = launch_mi_cells(h->s, h->cx_cell_start, h->cx_sorted_pos, h->cx_head, h->cx_first_pos, grid, h->pub, h->bar,
+                             n_picks, out_pos, out_gain, h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer, st);
+        h->seq_base += (unsigned int)n_picks + 1u;
+        if (!rc) rc = launch_mi_refresh_terms(h->s, st);
+        return rc;
+    }
     if (mode == ACAV_MI_LOOP_KERNELS) {
-        if (n_picks > 0) h->sorted_valid = false;
+        if (n_picks > 0) { h->sorted_valid = false; h->cells_valid = false; }
         for (int64_t it = 0; it < n_picks; ++it) {
             int rc = launch_mi_gain_table(h->s, st);
             if (!rc) rc = launch_mi_scan(h->s, h->sm_count, st);
@@ -494,6 +551,7 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
     if (h->world > 1 && !h->comm_connected) return ACAV_E_STATE;
     int rc = mi_prepare_persistent(h, st);
     if (rc) return rc;
+    h->cells_valid = false;                      // the cell index does not see these removals
     rc = launch_mi_persistent(h->s, h->n_alt, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->pub, h->bar,
                               n_picks, out_pos, out_gain, h->rows_smem, h->world, h->rank, h->seq_base, h->mail_local,
                               h->mail_peer, h->dbg, st);

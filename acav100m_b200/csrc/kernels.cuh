@@ -101,6 +101,16 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
                          long long *dbg, cudaStream_t st);
 
+// mi_cells.cu (cell-index loop)
+int mi_cells_tiles(int64_t w);
+int launch_mi_cells_build(const MiState &s, uint32_t *tilehist, uint32_t *total, uint32_t *start, uint32_t *tmp_cells,
+                          uint32_t *tmp_pos, uint32_t *sorted_cells, uint32_t *sorted_pos, uint32_t *cell_start,
+                          uint32_t *head, uint32_t *first_pos, int64_t *n_live_host, cudaStream_t st);
+int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t *sorted_pos, uint32_t *head,
+                    uint32_t *first_pos, int32_t grid, void *pub, unsigned int *bar, int64_t n_picks,
+                    int64_t *out_pos, float *out_gain, int32_t world, int32_t rank, unsigned int seq_base,
+                    void *mail_local, void *const *mail_peer, cudaStream_t st);
+
 // mi_dense.cu
 struct MiDense {
     uint32_t *n_cells;     // [P, C, C]

@@ -19,23 +19,16 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "mi_loop.cuh"
 
 namespace acav {
 
 constexpr int kPersistThreads = 1024;
 constexpr int kTileElems = 32768;            // elements per partition tile
 constexpr int kPartThreads = 512;
-constexpr int kSmallCounts = 256;            // per-iteration table of tN(x) for counts below this
 constexpr int kRing = 4;                     // 16-byte stream loads in flight per thread (cp.async ring)
 constexpr int kBlk = 256;                    // stream block: 32 lanes x one 16-byte vector of 8 candidates; rows are
                                              // padded to whole blocks and each block is sorted by shared-memory bank
-
-__device__ __forceinline__ float xlogx_cnt(uint32_t k, float f0, const float *__restrict__ logs) {
-    return k == 0 ? f0 : __fmul_rn((float)k, __ldg(logs + k));
-}
-__device__ __forceinline__ float bump_sum(float prev, uint32_t k, float f0, const float *__restrict__ logs) {
-    return __fadd_rn(__fsub_rn(prev, xlogx_cnt(k, f0, logs)), xlogx_cnt(k + 1, 0.f, logs));
-}
 
 // ---- stable partition of the candidate list by table row ------------------------------------------
 
@@ -194,20 +187,6 @@ mi_block_sort_kernel(uint16_t *__restrict__ c2s, uint32_t *__restrict__ pos_s, i
 
 // ---- the persistent kernel -----------------------------------------------------------------------
 
-struct MiPub {                       // one per CTA and iteration parity: the CTA's best candidate
-    unsigned long long key;          // (orderable gain << 32) | (0xFFFFFFFF - global position), 0 = none
-    unsigned long long payload;      // (c1 << 48) | (c2 << 32) | table count x of that cell
-};
-
-struct MiMail {                      // one per (parity, source rank), written by peers over NVLink
-    unsigned long long key;
-    unsigned long long payload;
-    unsigned int seq;                // iteration tag, stored last with release semantics
-    unsigned int pad[3];
-};
-
-constexpr int kMaxWorld = 16;
-
 struct MiPersist {
     MiState s;                       // canonical state in global memory (read at entry, written back at exit)
     uint32_t *n_alt;                 // second copy of the table counts (double buffering, see kernel)
@@ -230,24 +209,6 @@ struct MiPersist {
     MiMail *mail_peer[kMaxWorld];    // the same array on every rank (peer-mapped pointers)
     long long *dbg;                  // optional [grid][8] counters of the LAST iteration (nullptr = off)
 };
-
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned int *gen = bar + 1;
-        const unsigned int g = *gen;
-        __threadfence();
-        if (atomicAdd(bar, 1u) == nblocks - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*gen == g) { }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 __device__ __forceinline__ uint4 ldcg_u4(const uint4 *p) { return __ldcg(p); }
 
@@ -296,15 +257,6 @@ __device__ __forceinline__ void scan_consider(ScanBest &b, float g, uint32_t e, 
                                               const uint32_t *__restrict__ pos_s) {
     if (g > b.bs) { b.bs = g; b.bi = e; b.bend = rend; b.ntie = 0; }
     else if (g == b.bs && b.bi != 0xFFFFFFFFu && e >= b.bend) scan_tie(b, e, rend, pos_s);
-}
-
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // One cooperative launch = n_picks greedy iterations with ONE grid barrier each.

@@ -96,12 +96,15 @@ class EfficientMemMI:
     def launches_per_iteration(self):
         if self._dist is not None and not self._nvlink:
             return 4                                   # gain, scan, emit, apply (+ one NCCL all-gather)
-        return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0      # persistent: one launch per select()
+        return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0      # persistent / cells: one launch per select()
 
     def loop_name(self):
         if self._dist is not None:
-            return "persistent+nvlink-mailbox" if self._nvlink else "kernels+allgather"
-        return "kernels" if self._loop_mode() == _lib.MI_LOOP_KERNELS else "persistent"
+            if self._nvlink:
+                return ("cells" if self._loop_mode() == _lib.MI_LOOP_CELLS else "persistent") + "+nvlink-mailbox"
+            return "kernels+allgather"
+        return {_lib.MI_LOOP_KERNELS: "kernels", _lib.MI_LOOP_PERSISTENT: "persistent",
+                _lib.MI_LOOP_CELLS: "cells"}[self._loop_mode()]
 
     def init_cache(self, max_picks=None):
         """``init_cache`` :32-39, :297-308 on the device."""
@@ -123,7 +126,7 @@ class EfficientMemMI:
                       consts.ctypes.data_as(_lib.c_vp), st)
         self._picked = 0
         self._nvlink = False
-        if self._dist is not None and self._loop_mode() == _lib.MI_LOOP_PERSISTENT:
+        if self._dist is not None and self._loop_mode() in (_lib.MI_LOOP_PERSISTENT, _lib.MI_LOOP_CELLS):
             self._connect_ranks()
 
     def _connect_ranks(self):
@@ -171,6 +174,8 @@ class EfficientMemMI:
             return _lib.MI_LOOP_KERNELS
         if self.loop in ('persistent', _lib.MI_LOOP_PERSISTENT):
             return _lib.MI_LOOP_PERSISTENT
+        if self.loop in ('cells', _lib.MI_LOOP_CELLS):
+            return _lib.MI_LOOP_CELLS
         # "auto": the persistent row-partitioned kernel whenever its gain rows fit in shared memory
         return _lib.MI_LOOP_PERSISTENT if self.ncentroids <= 16384 else _lib.MI_LOOP_KERNELS
 

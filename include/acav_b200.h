@@ -174,10 +174,15 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n,
 
 /* Single-GPU greedy loop (EfficientMI.run_greedy, mi.py:150-192, body of the for loop x n_picks):
  * out_pos[i] = position in the candidate list of the i-th pick, out_gain[i] = its score.
- * mode 0: three kernels per iteration (reference-shaped); mode 1: persistent cooperative kernel.
- * Continues from the engine's current state. */
+ * mode 0: three kernels per iteration (reference-shaped); mode 1: persistent cooperative kernel
+ * streaming every remaining candidate per iteration; mode 2: persistent kernel over a cell index --
+ * candidates sorted once by table cell, every iteration scans the K_a x K_v cells (gain of the cell,
+ * earliest remaining candidate of the cell) instead of the candidates; the score depends on a candidate
+ * only through its cell (mi.py:322-381) and `max` keeps the first of equal scores (:79), so the picks and
+ * gains are identical.  All modes continue from the engine's current state and can be mixed. */
 #define ACAV_MI_LOOP_KERNELS     0
 #define ACAV_MI_LOOP_PERSISTENT  1
+#define ACAV_MI_LOOP_CELLS       2
 int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain,
                 int32_t mode, void *stream);
 

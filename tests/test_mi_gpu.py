@@ -12,7 +12,7 @@ from oracle import gen_golden, mi_oracle as mo
 pytestmark = pytest.mark.gpu
 
 P1 = [m for m in sorted(gen_golden.MI_CASES) if gen_golden.MI_CASES[m]["dcols"] == 2]
-LOOPS = ["kernels", "persistent"]
+LOOPS = ["kernels", "persistent", "cells"]
 
 
 def load(golden_dir, name):
@@ -142,13 +142,14 @@ def test_errors():
 
 @pytest.mark.parametrize("W,C,picks,seed", [(50_000, 16, 4000, 21), (300_000, 1024, 600, 22), (40, 4, 39, 23),
                                             (1_000_003, 256, 300, 24), (9000, 2048, 500, 25)])
-def test_persistent_loop_matches_c_oracle(W, C, picks, seed):
+@pytest.mark.parametrize("loop", ["persistent", "cells"])
+def test_persistent_loop_matches_c_oracle(W, C, picks, seed, loop):
     """Row-partitioned persistent kernel: massive early ties (every cell scores the same at first),
     rows split across CTAs, more rows per CTA than fit in shared memory, resumed runs."""
     a = synth.zipf_pairs(W, C, seed)
     a[0] = C - 1
     pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
-    m = gpu_measure(a, C, loop="persistent")
+    m = gpu_measure(a, C, loop=loop)
     m.init([(0, 1)], list(range(W)))
     first = picks // 3
     p1, g1 = m.select(first)
@@ -166,7 +167,7 @@ def test_loops_can_be_mixed():
     m = gpu_measure(a, C, loop="persistent")
     m.init([(0, 1)], list(range(W)))
     out = []
-    for loop, n in (("persistent", 300), ("kernels", 300), ("persistent", 300)):
+    for loop, n in (("persistent", 200), ("cells", 150), ("kernels", 200), ("cells", 150), ("persistent", 200)):
         m.loop = loop
         out.append(m.select(n))
     pos = torch.cat([o[0] for o in out]).cpu().numpy()
@@ -174,13 +175,14 @@ def test_loops_can_be_mixed():
     assert np.array_equal(pos, pos_want) and np.array_equal(gain, gain_want)
 
 
-def test_persistent_loop_uniform_ids_all_ties():
+@pytest.mark.parametrize("loop", ["persistent", "cells"])
+def test_persistent_loop_uniform_ids_all_ties(loop):
     """Every candidate in one cell: all scores tie on every iteration, list order must be kept."""
     W = 5000
     a = np.zeros((W, 2), dtype=np.int64)
     a[:, 1] = 3
     a[0] = (7, 7)
-    m = gpu_measure(a, 8, loop="persistent")
+    m = gpu_measure(a, 8, loop=loop)
     m.init([(0, 1)], list(range(W)))
     pos, _ = m.select(200)
     want, _ = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], 8, 200, bucketed=False)
