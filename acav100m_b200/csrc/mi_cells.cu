@@ -172,6 +172,7 @@ struct MiCells {
     int64_t *out_pos;
     float *out_gain;
     int32_t rows_per_cta;
+    int32_t cache_rows;              // 1: the CTA keeps counts + first positions of its rows in shared memory
     int32_t world, rank;
     unsigned int seq_base;
     MiMail *mail_local;
@@ -186,6 +187,9 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
     float *tn_small = col_term + k_v;                                               // [kSmallCounts]
     uint32_t *a_cnt = reinterpret_cast<uint32_t *>(tn_small + kSmallCounts);        // [k_v] column marginals
     uint32_t *b_cnt = a_cnt + k_v;                                                  // [k_a] row marginals
+    float *rt_local = reinterpret_cast<float *>(b_cnt + k_a);                       // [rows_per_cta]
+    uint32_t *n_loc = reinterpret_cast<uint32_t *>(rt_local + P.rows_per_cta);      // [rows_per_cta * k_v] if cached
+    uint32_t *fp_loc = n_loc + (P.cache_rows ? P.rows_per_cta * k_v : 0);           // [rows_per_cta * k_v] if cached
     __shared__ unsigned long long wkey[32];
     __shared__ unsigned long long wpay[32];
     __shared__ unsigned long long sh_best_key, sh_win_key, sh_win_pay;
@@ -199,6 +203,13 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
     const int32_t r_lo = min(k_a, (int32_t)blockIdx.x * P.rows_per_cta);
     const int32_t r_hi = min(k_a, r_lo + P.rows_per_cta);                 // my table rows [r_lo, r_hi)
     const int32_t n_my = (r_hi - r_lo) * k_v;
+    if (P.cache_rows) {                                                   // only this CTA ever touches these cells
+        for (int32_t j = threadIdx.x; j < n_my; j += kCellThreads) {
+            n_loc[j] = __ldcg(s.n_cells + (int64_t)r_lo * k_v + j);
+            fp_loc[j] = __ldcg(P.first_pos + (int64_t)r_lo * k_v + j);
+        }
+        __syncthreads();
+    }
     const uint32_t base_pos = (uint32_t)s.pos_base;
     const uint32_t grid = gridDim.x;
     int64_t done = 0;
@@ -212,6 +223,8 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
             col_term[i] = __fdiv_rn(-bump_sum(aloga, a_cnt[i], fa0, s.logs), np);
         for (int32_t i = threadIdx.x; i < kSmallCounts; i += blockDim.x)
             tn_small[i] = __fdiv_rn(bump_sum(NlogN, (uint32_t)i, fN0, s.logs), np);
+        for (int32_t i = threadIdx.x; i < r_hi - r_lo; i += blockDim.x)
+            rt_local[i] = __fdiv_rn(-bump_sum(blogb, b_cnt[r_lo + i], fa0, s.logs), np);
         __syncthreads();
         // ---------------- score my cells ----------------
         unsigned long long key = 0ull, pay = 0ull;
@@ -219,12 +232,11 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
             const int32_t rr = j / k_v, c2 = j - rr * k_v;
             const int32_t c1 = r_lo + rr;
             const int64_t cell = (int64_t)c1 * k_v + c2;
-            const uint32_t fp = __ldcg(P.first_pos + cell);
+            const uint32_t fp = P.cache_rows ? fp_loc[j] : __ldcg(P.first_pos + cell);
             if (fp == kNoPos) continue;
-            const uint32_t x = __ldcg(s.n_cells + cell);
+            const uint32_t x = P.cache_rows ? n_loc[j] : __ldcg(s.n_cells + cell);
             const float tN = x < (uint32_t)kSmallCounts ? tn_small[x] : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
-            const float rt = __fdiv_rn(-bump_sum(blogb, b_cnt[c1], fa0, s.logs), np);
-            const float g = __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt), lognp);
+            const float g = __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt_local[rr]), lognp);
             const unsigned long long kk = make_key(g, base_pos + fp);
             if (kk > key) { key = kk; pay = ((unsigned long long)c1 << 48) | ((unsigned long long)c2 << 32) | x; }
         }
@@ -315,12 +327,17 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
             if (sh_best_key == win) {                          // keys are unique: exactly one publishing CTA (on one rank)
                 const uint32_t h = __ldcg(P.head + cell) + 1u;             // remove_idx_all mi.py:104-106
                 const uint32_t lo = __ldg(P.cell_start + cell), hi = __ldg(P.cell_start + cell + 1);
+                const uint32_t nfp = lo + h < hi ? __ldg(P.sorted_pos + lo + h) : kNoPos;
                 __stcg(P.head + cell, h);
-                __stcg(P.first_pos + cell, lo + h < hi ? __ldg(P.sorted_pos + lo + h) : kNoPos);
+                __stcg(P.first_pos + cell, nfp);
+                if (P.cache_rows) fp_loc[cell - (int64_t)r_lo * k_v] = nfp;     // the publisher owns the cell's row
                 s.cells[(int64_t)key_pos(win) - s.pos_base] = 0xFFFFFFFFu;  // list-order view stays in sync
             }
             const uint32_t x = (uint32_t)(wpayload & 0xFFFFFFFFull), y = a_cnt[c2w], z = b_cnt[c1];
-            if (c1 >= r_lo && c1 < r_hi) __stcg(s.n_cells + cell, x + 1);  // update_mats :401-406 (row owner, every rank)
+            if (c1 >= r_lo && c1 < r_hi) {                     // update_mats :401-406 (row owner, on every rank)
+                __stcg(s.n_cells + cell, x + 1);
+                if (P.cache_rows) n_loc[cell - (int64_t)r_lo * k_v] = x + 1;
+            }
             ps[0] = bump_sum(ps[0], x, ps[4], s.logs);         // update_cache mi.py:383-389
             ps[1] = bump_sum(ps[1], y, ps[5], s.logs);
             ps[2] = bump_sum(ps[2], z, ps[5], s.logs);
@@ -409,8 +426,11 @@ int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t
     P.mail_local = reinterpret_cast<MiMail *>(mail_local);
     for (int r = 0; r < kMaxWorld; ++r)
         P.mail_peer[r] = (world > 1 && r < world) ? reinterpret_cast<MiMail *>(mail_peer[r]) : nullptr;
-    const size_t smem = ((size_t)2 * s.k_v + kSmallCounts + (size_t)s.k_a) * 4 + 16;
+    size_t smem = ((size_t)2 * s.k_v + kSmallCounts + (size_t)s.k_a + P.rows_per_cta) * 4 + 16;
     if (smem > 200 * 1024) return ACAV_E_UNSUPPORTED;
+    const size_t cache = (size_t)P.rows_per_cta * s.k_v * 8;
+    P.cache_rows = smem + cache <= 200 * 1024 ? 1 : 0;
+    if (P.cache_rows) smem += cache;
     static size_t attr_set = 0;
     if (smem > attr_set && smem > 48 * 1024) {
         ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
