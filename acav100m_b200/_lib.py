@@ -26,7 +26,6 @@ SIGNATURES = {
                                           c_vp, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "acav_kmeans_prepare_centers": (ctypes.c_int, [c_vp, c_vp, c_vp, c_f32, c_f32, c_vp]),
     "acav_kmeans_prepare_batch": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "acav_kmeans_prepare_batch_background": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "acav_kmeans_assign_prepared": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_f32, c_f32,
                                                    c_vp, c_vp, c_vp, c_vp, c_vp]),
     "acav_kmeans_assign_noise": (ctypes.c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),

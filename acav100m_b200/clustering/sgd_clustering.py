@@ -206,8 +206,8 @@ class KMeans:
 
     def assign_all(self, x, chunk=131072):
         """Labels for a whole resident feature matrix (the assignment pass, run_clustering.py:225-229),
-        walked in chunks with the fp32->bf16 preparation of chunk i+1 running on a second stream and
-        workspace while the tensor-core kernel works on chunk i.  Returns LongTensor[n] on the device."""
+        walked in chunks over two workspaces and two streams (preparation of chunk i+1 / tensor-core kernel
+        of chunk i).  Returns LongTensor[n] on the device."""
         x = self._prep_batch(x)
         dev = self._device()
         n = x.shape[0]
@@ -230,9 +230,9 @@ class KMeans:
                     if getattr(self, "tile_variant", 0):
                         _lib.call("acav_kmeans_set_tile_variant", h, int(self.tile_variant))
                     hs.append(h)
-            # the distance GEMM runs on a HIGH-priority stream: its 148 persistent CTAs must win the SMs against
-            # the thousands of short preparation blocks of the next chunk, which then fill the remaining
-            # thread slots and stream HBM underneath the tensor-core work (equal priorities serialise the two)
+            # second stream for the distance GEMM.  Measured on B200: the preparation of chunk i+1 and the GEMM
+            # of chunk i do share the SMs, but both run at the board's power limit (~1 kW), so the pass takes
+            # the SUM of their times either way (tools/km_overlap_probe.py)
             self._ws_pair = (hs[0], hs[1], chunk, torch.cuda.Stream(device=dev, priority=-1))
         ws, hot = self._ws_pair[:2], self._ws_pair[3]
         thr, r = self.underused_threshold(), float(self.reinit[1])
@@ -248,9 +248,7 @@ class KMeans:
                 h = ws[i % 2]
                 if done[i % 2] is not None:
                     main.wait_event(done[i % 2])                   # workspace free again
-                # chunk 0 has the GPU to itself; later chunks are prepared underneath the previous chunk's GEMM
-                _lib.call("acav_kmeans_prepare_batch" if i == 0 else "acav_kmeans_prepare_batch_background",
-                          h, _lib.ptr(xb, row_strided=True), xb.shape[0], xb.stride(0), mp)
+                _lib.call("acav_kmeans_prepare_batch", h, _lib.ptr(xb, row_strided=True), xb.shape[0], xb.stride(0), mp)
                 ready = torch.cuda.Event()
                 ready.record(main)
                 hot.wait_event(ready)

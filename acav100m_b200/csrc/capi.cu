@@ -257,7 +257,7 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) { rc = dev_alloc(&raw, (size_t)umma_partial_bytes(max_batch ? max_batch : 1), &h->bytes); h->partial = raw; }
     if (!rc) rc = dev_alloc(&h->cmax, 1, &h->bytes);
     if (!rc) rc = dev_alloc(&h->cand_rows, (size_t)max_batch, &h->bytes);
-    if (!rc) rc = dev_alloc(&h->cand_ids, (size_t)max_batch * 4, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->cand_ids, (size_t)max_batch * 16, &h->bytes);       // kMaxCand per row
     if (!rc) rc = dev_alloc(&h->full_rows, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->counters, 2, &h->bytes);
     if (rc) { acav_kmeans_destroy(h); return rc; }
@@ -329,12 +329,6 @@ int acav_kmeans_prepare_batch(acav_kmeans_t *h, const float *x, int64_t b, int64
     return launch_prep_rows(x, b, h->d, ldx, h->dp, h->xb, h->xn, (cudaStream_t)stream);
 }
 
-int acav_kmeans_prepare_batch_background(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream) {
-    if (!h || b < 0 || b > h->max_batch || (b > 0 && (!x || ldx < h->d))) return ACAV_E_INVALID;
-    if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
-    return launch_prep_rows_background(x, b, h->d, ldx, h->dp, h->xb, h->xn, h->sm_count, (cudaStream_t)stream);
-}
-
 int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                                 const float *centers, const float *counts,
                                 float underused_threshold, float reinit_r,
@@ -353,7 +347,7 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
                  : launch_assign_pair(h->tmap_x, h->tmap_c128, h->xn, h->cparams, (int32_t)b, h->k, h->dp,
                                       h->sm_count, variant == ACAV_TILE_PAIR_512 ? 2 : 1, h->partial, &n_split, st);
     float *mind = min_dist ? min_dist : h->mind;
-    if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cmax, best, mind, h->cand_rows,
+    if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cparams, h->cn, h->k, best, mind, h->cand_rows,
                                         h->cand_ids, h->full_rows, h->counters, st);
     if (!rc) rc = launch_candidate_refine(x, ldx, h->d, centers, h->xn, h->cn, counts, underused_threshold, reinit_r,
                                           h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind, st);

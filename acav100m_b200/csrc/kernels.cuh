@@ -24,8 +24,6 @@ int64_t umma_partial_bytes(int64_t max_batch);
 int64_t umma_param_bytes(int32_t k);
 int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
                      cudaStream_t st);
-int launch_prep_rows_background(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
-                                int32_t sm_count, cudaStream_t st);
 int launch_centroid_params(const float *cn, const float *counts, int32_t k, float thr, float r, void *params,
                            float *cmax, cudaStream_t st);
 int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, const void *cparams, int32_t b,
@@ -34,8 +32,8 @@ int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, 
 int launch_assign_pair(const void *tmap_x, const void *tmap_c128, const float *xn, const void *cparams, int32_t b,
                        int32_t k, int32_t dp, int32_t sm_count, int32_t halves, void *partial, int32_t *n_lists_out,
                        cudaStream_t st);
-int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const float *cmax,
-                          int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
+int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const void *cparams,
+                          const float *cn, int32_t k, int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
                           int32_t *counters, cudaStream_t st);
 int launch_candidate_refine(const float *x, int64_t ldx, int32_t d, const float *centers, const float *xn,
                             const float *cn, const float *counts, float thr, float r, const int32_t *cand_rows,

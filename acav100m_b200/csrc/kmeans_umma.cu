@@ -58,52 +58,6 @@ __global__ void km_prep_rows_kernel(const float *__restrict__ x, int64_t rows, i
     }
 }
 
-// Same result as km_prep_rows_kernel, shaped to run UNDERNEATH a resident distance GEMM: two small blocks per SM
-// (grid-stride over rows, one row per warp at a time, <= 40 registers per thread) with four 16-byte loads in
-// flight per thread, launched with the GEMM's shared-memory carve-out so both kernels can share an SM.  A wide grid would fill every thread slot and the GEMM's large
-// CTAs (> 200 KiB of shared memory, 320 threads) could not be placed until it had drained -- the two kernels
-// would run back to back.  Per lane the elements are accumulated in the same order as above: bit-identical.
-constexpr int kBgUnroll = 4;
-constexpr int kBgBlocksPerSm = 2;
-__global__ void __launch_bounds__(256, 6)
-km_prep_rows_bg_kernel(const float *__restrict__ x, int64_t rows, int32_t d, int64_t ldx, int32_t dp,
-                       __nv_bfloat16 *__restrict__ xb, float *__restrict__ xn) {
-    const int lane = threadIdx.x % kWarp;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x / kWarp);
-    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp; r < rows; r += nwarps) {
-        const float *p = x + r * ldx;
-        __nv_bfloat16 *q = xb + r * dp;
-        double s = 0.0;
-        for (int32_t i0 = lane * 4; i0 < dp; i0 += kWarp * 4 * kBgUnroll) {
-            float4 v[kBgUnroll];
-#pragma unroll
-            for (int u = 0; u < kBgUnroll; ++u) {
-                const int32_t i = i0 + u * kWarp * 4;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < d) v[u] = __ldcs(reinterpret_cast<const float4 *>(p + i));
-            }
-#pragma unroll
-            for (int u = 0; u < kBgUnroll; ++u) {
-                const int32_t i = i0 + u * kWarp * 4;
-                if (i < dp) {
-                    s += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z +
-                         (double)v[u].w * v[u].w;
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                    pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                    *reinterpret_cast<uint2 *>(q + i) = pk;
-                }
-            }
-        }
-        s = warp_sum_f64(s);
-        if (lane == 0) {
-            float nrm = sqrtf((float)s);
-            xn[r] = __fmul_rn(nrm, nrm);
-        }
-    }
-}
-
 // Per-centroid epilogue parameters and max |c| (for the error bound).  scale s = 1/r for under-used
 // centroids (sgd_clustering.py:76-77), else 1.
 __global__ void __launch_bounds__(1024)
@@ -114,7 +68,10 @@ km_centroid_params_kernel(const float *__restrict__ cn, const float *__restrict_
     for (int32_t i = threadIdx.x; i < k; i += blockDim.x) {
         const float s = counts[i] < thr ? 1.0f / r : 1.0f;
         CentroidParam p;
-        p.a = -2.0f * s; p.b = cn[i] * s; p.s = s; p.pad = 0.f;
+        p.a = -2.0f * s;
+        p.b = cn[i] * s * (1.0f - kScreenEps32);
+        p.s = s * (1.0f - kScreenEps32);
+        p.e = kScreenKappa * s * sqrtf(cn[i]) * 1.000001f;
         params[i] = p;
         m = fmaxf(m, cn[i]);
     }
@@ -224,6 +181,7 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int32_t nt_end = min(n_tiles, (g + 1) * tpg);
             const int32_t row = mb * kBM + row_in_tile;
             const float xnr = row < b ? xn[row] : 0.f;
+            const float nxs = -sqrtf(xnr) * 1.000001f;                 // -|x| (rounded away from zero)
             Top4 t4;
             top4_init(t4);
             for (int32_t nt = g * tpg; nt < nt_end; ++nt) {
@@ -234,7 +192,7 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     const int32_t c = nt * kBNMax + i;
                     CentroidParam p;
                     if (c < k) p = cparams[c];
-                    else { p.a = 0.f; p.b = INFINITY; p.s = 0.f; p.pad = 0.f; }
+                    else { p.a = 0.f; p.b = INFINITY; p.s = 0.f; p.e = 0.f; }
                     sp[i] = p;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -248,7 +206,7 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const CentroidParam p = sp[c0 + j];
-                        const float dist = fmaf(p.s, xnr, fmaf(p.a, __uint_as_float(v[j]), p.b));
+                        const float dist = fmaf(p.e, nxs, fmaf(p.s, xnr, fmaf(p.a, __uint_as_float(v[j]), p.b)));
                         if (dist < t4.d5) top4_insert(t4, dist, nt * kBNMax + c0 + j);   // rare after the first columns
                     }
                 }
@@ -264,44 +222,69 @@ km_assign_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// Merge the n_split partial lists of every row, write the screened arg-min, and route near-ties:
-//   |dist_bf16 - dist_exact| <= 2 * |<x,c>_bf16 - <x,c>| <= 2 * 1.25 * 2^-8 * |x| |c|  =: e
-// (two bf16 roundings per product, 2^-9 each, plus fp32 accumulation slack).  With B = 2e:
-//   d[1] - d[0] > B          -> the arg-min is certain;
-//   else if d5 - d[0] > B    -> the exact arg-min is one of the listed entries within B of d[0]:
-//                               queue the row for the candidate re-check (<= 4 exact dot products);
-//   else                     -> more than four near-ties: queue for the full exact kernel.
+// Classify every row from its partial top-4 lists (one list per centroid group / epilogue warp set) and route
+// near-ties.  The lists rank centroids by the lower bound L_c of their exact distance (see CentroidParam).
+// With c0 = the centroid of the smallest L over all lists:
+//   U = L_c0 + 2 * err_c0(row)  is an upper bound of the exact distance of c0, hence of the exact minimum;
+//   every centroid with L <= U is a possible winner.  A partial list holds ALL of its group's possible winners
+//   iff its fifth-smallest value d5 is > U;
+//   only c0 has L <= U                         -> c0 is the arg-min for certain;
+//   all lists complete, <= kMaxCand candidates -> queue the row for the candidate re-check (exact dot products
+//                                                 of exactly those centroids);
+//   otherwise                                  -> queue for the full exact kernel.
 __global__ void km_merge_classify_kernel(const Top4 *__restrict__ partial, int32_t b, int32_t n_split,
-                                         const float *__restrict__ xn, const float *__restrict__ cmax,
+                                         const float *__restrict__ xn, const CentroidParam *__restrict__ cparams,
+                                         const float *__restrict__ cn, int32_t k,
                                          int64_t *__restrict__ best, float *__restrict__ mind,
                                          int32_t *__restrict__ cand_rows, int32_t *__restrict__ cand_ids,
                                          int32_t *__restrict__ full_rows, int32_t *__restrict__ counters) {
     const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= b) return;
-    Top4 t = partial[row];
-    for (int32_t g = 1; g < n_split; ++g) {
-        const Top4 o = partial[(int64_t)g * b + row];        // later groups hold larger centroid indices
-#pragma unroll
-        for (int s = 0; s < 4; ++s) top4_insert(t, o.d[s], o.i[s]);
-        t.d5 = fminf(t.d5, o.d5);
+    float d0 = INFINITY, d5min = INFINITY;
+    int32_t i0 = 0x7fffffff;
+    for (int32_t g = 0; g < n_split; ++g) {
+        const Top4 &o = partial[(int64_t)g * b + row];
+        const float od = o.d[0];
+        const int32_t oi = o.i[0];
+        if (od < d0 || (od == d0 && oi < i0)) { d0 = od; i0 = oi; }
+        d5min = fminf(d5min, o.d5);
     }
-    best[row] = t.i[0];
-    if (mind) mind[row] = t.d[0];
-    const float bound = 5.0f * 0.00390625f * sqrtf(xn[row]) * (*cmax) + 1e-30f;
-    if (t.d[1] - t.d[0] > bound) return;
-    if (t.d5 - t.d[0] > bound) {
+    best[row] = i0;
+    if (mind) mind[row] = d0;
+    if (i0 < 0 || i0 >= k) {                                   // no finite distance at all (NaN / inf input)
+        full_rows[atomicAdd(&counters[1], 1)] = row;
+        return;
+    }
+    const CentroidParam p0 = cparams[i0];
+    const float xnr = xn[row];
+    const float s0 = p0.a * -0.5f;
+    const float err0 = p0.e * sqrtf(xnr) * 1.000001f + kScreenEps32 * s0 * (xnr + cn[i0]);
+    const float upper = d0 + 2.0f * err0 * 1.000001f + 1e-30f;
+    int32_t n_cand = 0;
+    for (int32_t g = 0; g < n_split; ++g) {
+        const Top4 &o = partial[(int64_t)g * b + row];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) n_cand += (o.d[s] <= upper) ? 1 : 0;
+    }
+    if (n_cand <= 1) return;
+    if (d5min > upper && n_cand <= kMaxCand) {
         const int32_t slot = atomicAdd(&counters[0], 1);
         cand_rows[slot] = row;
+        int32_t w = 0;
+        for (int32_t g = 0; g < n_split; ++g) {
+            const Top4 &o = partial[(int64_t)g * b + row];
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-            cand_ids[4 * slot + s] = (t.d[s] - t.d[0] <= bound) ? t.i[s] : -1;
+            for (int s = 0; s < 4; ++s)
+                if (o.d[s] <= upper) cand_ids[kMaxCand * slot + w++] = o.i[s];
+        }
+        for (; w < kMaxCand; ++w) cand_ids[kMaxCand * slot + w] = -1;
     } else {
         full_rows[atomicAdd(&counters[1], 1)] = row;
     }
 }
 
-// Candidate re-check: one thread per (row, candidate) evaluates the exact distance with the SAME
-// operation order as assign_exact_kernel (sequential fp64 FMA over k, one rounding to fp32, then the
+// Candidate re-check: kMaxCand threads per row, one per candidate, each evaluates the exact distance with the
+// SAME operation order as assign_exact_kernel (sequential fp64 FMA over k, one rounding to fp32, then the
 // reference's three fp32 operations), so both kernels agree bit for bit; lowest index wins ties.
 __global__ void __launch_bounds__(128)
 km_candidate_refine_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
@@ -311,15 +294,15 @@ km_candidate_refine_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
                            const int32_t *__restrict__ counters, int32_t capacity,
                            int64_t *__restrict__ best, float *__restrict__ mind) {
     const int32_t n = min(counters[0], capacity);
-    const int32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) / 4;
-    const int sub = threadIdx.x % 4;
+    const int32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) / kMaxCand;
+    const int sub = threadIdx.x % kMaxCand;
     const bool live = slot < n;
     float dist = INFINITY;
     int32_t c = 0x7fffffff;
     int32_t row = 0;
     if (live) {
         row = cand_rows[slot];
-        const int32_t cid = cand_ids[4 * slot + sub];
+        const int32_t cid = cand_ids[kMaxCand * slot + sub];
         if (cid >= 0) {
             c = cid;
             const float *p = x + (int64_t)row * ldx, *q = centers + (int64_t)c * d;
@@ -342,7 +325,7 @@ km_candidate_refine_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
         }
     }
 #pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
+    for (int o = kMaxCand / 2; o > 0; o >>= 1) {
         const float od = __shfl_xor_sync(0xffffffffu, dist, o);
         const int32_t oc = __shfl_xor_sync(0xffffffffu, c, o);
         if (od < dist || (od == dist && oc < c)) { dist = od; c = oc; }
@@ -419,21 +402,6 @@ int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32
     return 0;
 }
 
-int launch_prep_rows_background(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
-                                int32_t sm_count, cudaStream_t st) {
-    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    if (!vec || rows < 8 * (int64_t)sm_count) return launch_prep_rows(x, rows, d, ldx, dp, xb, xn, st);
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_prep_rows_bg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           cudaSharedmemCarveoutMaxShared));
-        carveout_set = true;
-    }
-    km_prep_rows_bg_kernel<<<sm_count * kBgBlocksPerSm, 256, 0, st>>>(x, rows, d, ldx, dp, reinterpret_cast<__nv_bfloat16 *>(xb), xn);
-    ACAV_LAUNCH_CHECK();
-    return 0;
-}
-
 int launch_centroid_params(const float *cn, const float *counts, int32_t k, float thr, float r, void *params,
                            float *cmax, cudaStream_t st) {
     km_centroid_params_kernel<<<1, 1024, 0, st>>>(cn, counts, k, thr, r, reinterpret_cast<CentroidParam *>(params), cmax);
@@ -467,14 +435,14 @@ int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, 
     return 0;
 }
 
-int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const float *cmax,
-                          int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
+int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const void *cparams,
+                          const float *cn, int32_t k, int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
                           int32_t *counters, cudaStream_t st) {
     ACAV_CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
     if (b == 0) return 0;
     km_merge_classify_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, st>>>(
-        reinterpret_cast<const Top4 *>(partial), b, n_split, xn, cmax, best, mind, cand_rows, cand_ids, full_rows,
-        counters);
+        reinterpret_cast<const Top4 *>(partial), b, n_split, xn, reinterpret_cast<const CentroidParam *>(cparams), cn, k,
+        best, mind, cand_rows, cand_ids, full_rows, counters);
     ACAV_LAUNCH_CHECK();
     return 0;
 }
@@ -485,7 +453,7 @@ int launch_candidate_refine(const float *x, int64_t ldx, int32_t d, const float 
                             const int32_t *cand_ids, const int32_t *counters, int32_t b, int64_t *best, float *mind,
                             cudaStream_t st) {
     if (b == 0) return 0;
-    km_candidate_refine_kernel<<<(unsigned)ceil_div((int64_t)b * 4, 128), 128, 0, st>>>(
+    km_candidate_refine_kernel<<<(unsigned)ceil_div((int64_t)b * kMaxCand, 128), 128, 0, st>>>(
         x, ldx, d, centers, xn, cn, counts, thr, r, cand_rows, cand_ids, counters, b, best, mind);
     ACAV_LAUNCH_CHECK();
     return 0;

@@ -26,18 +26,31 @@ struct UmmaSmem {
     static constexpr int kBytes = kBarOff + 256;
 };
 
-struct __align__(16) CentroidParam {     // dist = s*|x|^2 + (a*dot + b)
-    float a, b, s, pad;
+// Epilogue parameters of one centroid.  The kernels rank centroids by a LOWER BOUND of the exact distance
+//     L = s*|x|^2 + (a*dot + b) - e*|x|
+// where a = -2 s_c, s = s_c (1 - eps32), b = s_c |c|^2 (1 - eps32), s_c in {1, 1/r} (re-init scaling), and
+// e*|x| + eps32 s_c (|x|^2 + |c|^2) bounds the error of the bf16 screen against the exact evaluation:
+//     |<x,c>_bf16 - <x,c>| <= 1.03 * 2^-7 |x| |c|   (bf16 has 8 significant bits: unit roundoff 2^-8 per
+//     operand, 2^-7 per product; Cauchy-Schwarz; 3 % slack for the second-order term and the fp32
+//     accumulation over D <= 64 K terms), times 2 s_c for the distance  ->  e = 2.06 * 2^-7 s_c |c| ;
+//     eps32 = 2^-19 covers the fp32 roundings of both evaluations of the three-term formula (< 8e-7 relative
+//     to |x|^2 + |c|^2 in total).
+constexpr float kScreenKappa = 2.06f * 0.0078125f;
+constexpr float kScreenEps32 = 1.9073486328125e-6f;
+struct __align__(16) CentroidParam {
+    float a, b, s, e;
 };
 
-// Screening state per row: the four smallest approximate distances (sorted, earliest index first on
-// ties) and the fifth smallest value.  The exact arg-min is guaranteed to be among the entries within
-// the error bound of d[0]; if d5 is outside the bound those are all in this list.
+// Screening state per row: the four smallest distance LOWER BOUNDS (sorted, earliest index first on ties)
+// and the fifth smallest value.  With U = upper bound of centroid i[0] (= d[0] + 2 * its error), the exact
+// arg-min is one of the centroids whose lower bound is <= U; if d5 > U those are all in this list.
 struct Top4 {
     float d[4];
     int32_t i[4];
     float d5;
 };
+
+constexpr int kMaxCand = 16;             // candidates per row the re-check evaluates exactly (over all partial lists)
 
 __device__ __forceinline__ void top4_init(Top4 &t) {
 #pragma unroll

@@ -60,11 +60,11 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
 }
 
 __device__ __forceinline__ void screen_32(Top4 &t4, const uint32_t (&v)[32], const CentroidParam *__restrict__ sp,
-                                          float xnr, int32_t c_first) {
+                                          float xnr, float nxs, int32_t c_first) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const CentroidParam p = sp[j];
-        const float dist = fmaf(p.s, xnr, fmaf(p.a, __uint_as_float(v[j]), p.b));
+        const float dist = fmaf(p.e, nxs, fmaf(p.s, xnr, fmaf(p.a, __uint_as_float(v[j]), p.b)));   // lower bound
         if (dist < t4.d5) top4_insert(t4, dist, c_first + j);           // rare after the first columns
     }
 }
@@ -184,6 +184,7 @@ km_assign_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int32_t nt_end = min(n_tiles, (g + 1) * tpg);
             const int32_t row = mb * 2 * kBM + (int32_t)cta_rank * kBM + row_in_cta;
             const float xnr = row < b ? xn[row] : 0.f;
+            const float nxs = -sqrtf(xnr) * 1.000001f;                 // -|x| (rounded away from zero)
             Top4 t4;
             top4_init(t4);
             for (int32_t nt = g * tpg; nt < nt_end; ++nt) {
@@ -195,7 +196,7 @@ km_assign_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                     const int32_t c = nt * Cfg::kTileN + i;
                     CentroidParam p;
                     if (c < k) p = cparams[c];
-                    else { p.a = 0.f; p.b = INFINITY; p.s = 0.f; p.pad = 0.f; }
+                    else { p.a = 0.f; p.b = INFINITY; p.s = 0.f; p.e = 0.f; }
                     sp[i] = p;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kPairEpiThreads) : "memory");
@@ -210,10 +211,10 @@ km_assign_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 for (int32_t c0 = 0; c0 < Cfg::kColsPerWarpSet; c0 += 64) {
                     tmem_ld_wait_dep(va);
                     ptx::tmem_ld_32x32(taddr + c0 + 32, vb);              // in flight while va is screened
-                    screen_32(t4, va, spw + c0, xnr, cbase + c0);
+                    screen_32(t4, va, spw + c0, xnr, nxs, cbase + c0);
                     tmem_ld_wait_dep(vb);
                     if (c0 + 64 < Cfg::kColsPerWarpSet) ptx::tmem_ld_32x32(taddr + c0 + 64, va);
-                    screen_32(t4, vb, spw + c0 + 32, xnr, cbase + c0 + 32);
+                    screen_32(t4, vb, spw + c0 + 32, xnr, nxs, cbase + c0 + 32);
                 }
                 ptx::tc_fence_before();
                 __syncwarp();

@@ -53,6 +53,7 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=10_000_000)
     p.add_argument("--skip-cpu-baseline", action="store_true")
     p.add_argument("--skip-kmeans", action="store_true")
+    p.add_argument("--skip-mi", action="store_true", help="development only: the line then has no headline value")
     p.add_argument("--skip-e2e", action="store_true")
     return p.parse_args()
 
@@ -400,6 +401,11 @@ def main():
     dist, rank, world, local = dist_setup(args.gpus)
     sampler = ClockSampler(local)
     sampler.start()
+    if args.skip_mi:
+        km = run_kmeans(args, dist, rank, world)
+        if rank == 0:
+            print(json.dumps({"kmeans": km}), flush=True)
+        return
     mi, e2e = run_mi(args, dist, rank, world)
     km = None if args.skip_kmeans else run_kmeans(args, dist, rank, world)
     clocks = sampler.stop()

@@ -89,11 +89,6 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
 int acav_kmeans_prepare_centers(acav_kmeans_t *h, const float *centers, const float *counts,
                                 float underused_threshold, float reinit_r, void *stream);
 int acav_kmeans_prepare_batch(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream);
-/* Same result as acav_kmeans_prepare_batch, launched as one small block per SM so that it can share the SMs
- * with the distance GEMM of ANOTHER workspace that is already resident (a wide grid would keep the GEMM's
- * large CTAs from being placed and the two kernels would run back to back).  Use it for chunk i+1 while
- * acav_kmeans_assign_prepared works on chunk i (the assignment pass, run_clustering.py:225-229). */
-int acav_kmeans_prepare_batch_background(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, void *stream);
 int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                                 const float *centers, const float *counts,
                                 float underused_threshold, float reinit_r,

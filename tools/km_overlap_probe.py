@@ -1,5 +1,5 @@
 """Do the background preparation kernel and the distance GEMM really share the SMs?  Runs each alone, then both
-on two streams with no dependencies between them:  python tools/km_overlap_probe.py [variant] [bg|wide]"""
+on two streams with no dependencies between them, sampling SM clock and board power:  python tools/km_overlap_probe.py [variant]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -7,7 +7,7 @@ from acav100m_b200 import _lib, synth
 from acav100m_b200.clustering import KMeans
 
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-prep_fn = "acav_kmeans_prepare_batch_background" if (len(sys.argv) < 3 or sys.argv[2] == "bg") else "acav_kmeans_prepare_batch"
+prep_fn = "acav_kmeans_prepare_batch"
 n, d, k, chunk, reps = 262144, 2048, 1024, 131072, 10
 dev = torch.device("cuda", 0)
 x = synth.gaussian_mixture_torch(n, d, k, 1003, dev)
