@@ -152,9 +152,11 @@ class KMeans:
 
     def launches_per_step(self):
         """CUDA kernels of this library launched by one add() past warm-up (bench.py gpu_launches)."""
-        assign = 4 if self._mode() == _lib.ASSIGN_EXACT else 6
+        # tensor mode: centroid prep (2) + row prep + distance GEMM + classify + candidate re-check + exact kernel
+        # + exact distance of the winner + mean; then partition (4) + effective lr + 2 update kernels (+ apply on > 1 rank)
+        assign = 4 if self._mode() == _lib.ASSIGN_EXACT else 9
         _, world = self._world()
-        return assign + 4 + 2 + (1 if world > 1 else 0)
+        return assign + 4 + 3 + (1 if world > 1 else 0)
 
     # -- operator ------------------------------------------------------------------------------
 

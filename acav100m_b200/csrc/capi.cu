@@ -244,7 +244,7 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) rc = dev_alloc(&h->blockhist, (size_t)(nblk * k), &h->bytes);
     if (!rc) rc = dev_alloc(&h->lrank, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->total, (size_t)k, &h->bytes);
-    if (!rc) rc = dev_alloc(&h->seg_start, (size_t)k + 1, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->seg_start, (size_t)2 * k + 2, &h->bytes);     // offsets [k+1] + heavy-centroid list
     if (!rc) rc = dev_alloc(&h->sorted_rows, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->lr_eff, 1, &h->bytes);
     // tensor-core path (bf16 operands padded to a multiple of 64 columns)

@@ -62,12 +62,16 @@ __global__ void km_block_prefix_kernel(uint32_t *__restrict__ blockhist, int32_t
     counts_b[i] = (float)run;
 }
 
-// seg_start[0..k] = exclusive scan of total[0..k) (single block, chunks of 1024 with carry).
+constexpr uint32_t kUpdHeavyRows = 128;              // centroids with at least this many batch rows take the ring kernel
+
+// seg_start[0..k] = exclusive scan of total[0..k) (single block, chunks of 1024 with carry); also the list of
+// "heavy" centroids (>= kUpdHeavyRows rows of this batch): seg_start[k+1] = their number, seg_start[k+2..] = ids.
 __global__ void __launch_bounds__(1024)
 km_segment_start_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t *__restrict__ seg_start) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ uint32_t n_heavy;
+    if (threadIdx.x == 0) { carry = 0; n_heavy = 0; }
     __syncthreads();
     const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
     for (int32_t base = 0; base < k; base += 1024) {
@@ -94,11 +98,12 @@ km_segment_start_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t 
         __syncthreads();
         uint32_t excl = carry + warp_sums[warp] + inc - v;
         if (i < k) seg_start[i] = excl;
+        if (i < k && v >= kUpdHeavyRows) seg_start[k + 2 + atomicAdd(&n_heavy, 1u)] = (uint32_t)i;
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) seg_start[k] = carry;
+    if (threadIdx.x == 0) { seg_start[k] = carry; seg_start[k + 1] = n_heavy; }
 }
 
 __global__ void __launch_bounds__(kRankRows)
@@ -154,6 +159,7 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
     constexpr int kChunk = 256, kGroup = 32 / VEC;          // rows per register buffer
     __shared__ uint32_t sidx[kChunk];
     const int32_t c = blockIdx.x;
+    if (VEC == 4 && seg_start[c + 1] - seg_start[c] >= kUpdHeavyRows) return;   // heavy centroid: km_update_stream_kernel's
     const int32_t col = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
     const bool active = col < d;
     const float lr = *lr_eff_p;
@@ -217,6 +223,94 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
     }
 }
 
+// Same result as km_update_kernel<4, FUSED>, for centroids that own MANY rows of the batch: the per-(centroid,
+// column) add chain is serial, so what bounds a skewed batch is how many row loads a thread keeps in flight.
+// Here every thread streams its 16 bytes of each row through its own shared-memory ring with cp.async --
+// kUpdGroups x kUpdGroupRows = 128 rows in flight per thread instead of the 16 that fit in registers -- and
+// consumes the groups in order (wait_group), so the fp32 sum order is unchanged.  One warp x 4 columns per
+// block (16 blocks per centroid at D = 2048, so a handful of heavy centroids still spreads over dozens of SMs),
+// 64 KiB of ring.  Centroids below kUpdHeavyRows stay with km_update_kernel (blocks of the other class exit).
+constexpr int kUpdThreads = 32;                      // one warp x 4 columns = 128 columns per block
+constexpr int kUpdGroupRows = 8;
+constexpr int kUpdGroups = 16;                       // 128 rows x 512 B = 64 KiB in flight per block
+constexpr int kUpdChunk = 1024;                      // row indices staged per pass
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kUpdThreads)
+km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32_t d,
+                        const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
+                        const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
+                        float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas) {
+    extern __shared__ __align__(16) unsigned char usmem[];
+    float4 *ring = reinterpret_cast<float4 *>(usmem);                                   // [groups][rows][threads]
+    uint32_t *sidx = reinterpret_cast<uint32_t *>(usmem + (size_t)kUpdGroups * kUpdGroupRows * kUpdThreads * 16);
+    const int32_t col = (blockIdx.y * kUpdThreads + threadIdx.x) * 4;
+    const bool active = col < d;
+    const float lr = *lr_eff_p;
+    const uint32_t n_heavy = seg_start[k + 1];
+    for (uint32_t hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
+    const int32_t c = (int32_t)seg_start[k + 2 + hidx];
+    const float cb = counts_b[c];
+    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
+    const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float *xcol = x + (active ? col : 0);
+    const uint32_t my = (uint32_t)__cvta_generic_to_shared(ring + threadIdx.x);
+    auto issue_group = [&](int slot, uint32_t s, uint32_t n) {
+#pragma unroll
+        for (int u = 0; u < kUpdGroupRows; ++u) {
+            if (s + u < n) {
+                const float *p = xcol + (int64_t)sidx[s + u] * ldx;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(my + (uint32_t)((slot * kUpdGroupRows + u) * kUpdThreads * 16)),
+                             "l"(p) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (uint32_t chunk = lo; chunk < hi; chunk += kUpdChunk) {
+        const uint32_t n = min((uint32_t)kUpdChunk, hi - chunk);
+        __syncwarp();
+        for (uint32_t t = threadIdx.x; t < n; t += kUpdThreads) sidx[t] = sorted_rows[chunk + t];
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < kUpdGroups - 1; ++g) issue_group(g, (uint32_t)g * kUpdGroupRows, n);
+        int slot = 0;
+        for (uint32_t s = 0; s < n; s += kUpdGroupRows) {
+            int pre = slot + kUpdGroups - 1;
+            if (pre >= kUpdGroups) pre -= kUpdGroups;
+            issue_group(pre, s + (kUpdGroups - 1) * kUpdGroupRows, n);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kUpdGroups - 1) : "memory");
+#pragma unroll
+            for (int u = 0; u < kUpdGroupRows; ++u) {
+                if (s + u < n) {
+                    const float4 t = ring[(slot * kUpdGroupRows + u) * kUpdThreads + threadIdx.x];
+                    acc[0] = __fadd_rn(acc[0], __fmul_rn(t.x, lr));                          // :123
+                    acc[1] = __fadd_rn(acc[1], __fmul_rn(t.y, lr));
+                    acc[2] = __fadd_rn(acc[2], __fmul_rn(t.z, lr));
+                    acc[3] = __fadd_rn(acc[3], __fmul_rn(t.w, lr));
+                }
+            }
+            if (++slot == kUpdGroups) slot = 0;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (active) {
+        const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                // :121
+        float *cp = centers + (int64_t)c * d + col;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            float scaled = __fmul_rn(cp[v], decay);
+            if (FUSED) {
+                cp[v] = __fadd_rn(scaled, acc[v]);                                             // :127
+            } else {
+                cp[v] = scaled;
+                deltas[(int64_t)c * d + col + v] = acc[v];
+            }
+        }
+    }
+    }   // heavy centroids of this block
+}
+
 __global__ void km_apply_deltas_kernel(float *__restrict__ centers, const float *__restrict__ deltas,
                                        int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,6 +354,25 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
                   float *centers, float *counts, float *deltas, cudaStream_t st) {
     const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
+    if (vec4) {
+        // heavy centroids (>= kUpdHeavyRows rows of this batch): cp.async ring kernel; its blocks for light
+        // centroids exit at once, and km_update_kernel below skips the heavy ones
+        const size_t smem = (size_t)kUpdGroups * kUpdGroupRows * kUpdThreads * 16 + (size_t)kUpdChunk * 4;
+        static bool attr = false;
+        if (!attr) {
+            ACAV_CUDA_TRY(cudaFuncSetAttribute(km_update_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ACAV_CUDA_TRY(cudaFuncSetAttribute(km_update_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        dim3 sgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kUpdThreads * 4));   // loops over the heavy list
+        if (deltas)
+            km_update_stream_kernel<false><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                               centers, counts, deltas);
+        else
+            km_update_stream_kernel<true><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                              centers, counts, nullptr);
+        ACAV_LAUNCH_CHECK();
+    }
     dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128 * vec));
     if (deltas) {
         if (vec4)

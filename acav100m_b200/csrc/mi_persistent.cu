@@ -220,6 +220,9 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
                  "l"(gmem_src)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -390,34 +393,36 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                 while (a < b) { const int32_t m = (a + b) >> 1; if (rs_local[m + 1] > ef) b = m; else a = m + 1; }
                 crow = a;
             }
-            uint32_t rend = rs_local[crow + 1];
+            uint32_t rend_blk = rs_local[crow + 1] / kBlk;       // first block of the next row
             uint32_t grow_b = gain_b + (uint32_t)(crow * gstride) * 4u;
+            // pointer form of the ring: shared addresses as 32-bit offsets (slot stride 16 KiB, 4 slots = 64 KiB,
+            // so "next slot" is an add and a mask), the global source as a running pointer
+            static_assert(kRing == 4 && kPersistThreads * 16 == 0x4000, "ring arithmetic below assumes 4 x 16 KiB");
+            const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+            const char *src = reinterpret_cast<const char *>(vec + (size_t)wb_lo * kWarp + lane);
 #pragma unroll
             for (int r = 0; r < kRing - 1; ++r) {
-                const uint32_t blk = wb_lo + (uint32_t)r;
-                if (blk < wb_hi) cp_async16(ring + r * kPersistThreads, vec + (size_t)blk * kWarp + lane);
+                if (wb_lo + (uint32_t)r < wb_hi) cp_async16_u32(ring_u32 + r * 0x4000u, src + r * 512);
                 cp_async_commit();
             }
-            int slot = 0;
+            src += (kRing - 1) * 512;
+            uint32_t slot_off = 0, pre_off = (kRing - 1) * 0x4000u;
             for (uint32_t blk = wb_lo; blk < wb_hi; ++blk) {
-                {
-                    const uint32_t bn = blk + (kRing - 1);
-                    int sn = slot + kRing - 1;
-                    if (sn >= kRing) sn -= kRing;
-                    if (bn < wb_hi) cp_async16(ring + sn * kPersistThreads, vec + (size_t)bn * kWarp + lane);
-                    cp_async_commit();
-                }
+                if (blk + (kRing - 1) < wb_hi) cp_async16_u32(ring_u32 + pre_off, src);
+                cp_async_commit();
+                src += 512;
+                pre_off = (pre_off + 0x4000u) & 0xFFFFu;
                 cp_async_wait<kRing - 1>();
-                const uint4 q = ring[slot * kPersistThreads];
-                if (++slot == kRing) slot = 0;
-                const uint32_t eb = blk * kBlk;
-                while (eb >= rend) {                             // next non-empty row (uniform per warp)
+                uint4 q;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(ring_u32 + slot_off));
+                slot_off = (slot_off + 0x4000u) & 0xFFFFu;
+                while (blk >= rend_blk) {                        // next non-empty row (uniform per warp)
                     ++crow;
-                    rend = rs_local[crow + 1];
+                    rend_blk = rs_local[crow + 1] / kBlk;
                     grow_b = gain_b + (uint32_t)(crow * gstride) * 4u;
                 }
                 // the stream holds byte offsets into a gain row; removed / padding entries point at its -inf slot
-                const uint32_t e0 = eb + lane * 8u;
                 float g[8];
                 const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -427,17 +432,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                 }
                 const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])),
                                       fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-                if (m > B.bs || (m == B.bs && B.bi != 0xFFFFFFFFu && e0 >= B.bend)) {
-                    // rare: of the maxima in this vector take the one that came first in the candidate list
-                    uint32_t bj = 0, bp = 0xFFFFFFFFu;
+                if (m >= B.bs) {                                 // rare once the thread has seen a good candidate
+                    const uint32_t e0 = blk * kBlk + lane * 8u;
+                    if (m > B.bs || (B.bi != 0xFFFFFFFFu && e0 >= B.bend)) {
+                        // of the maxima in this vector take the one that came first in the candidate list
+                        uint32_t bj = 0, bp = 0xFFFFFFFFu;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (g[j] == m) {
-                            const uint32_t pj = __ldg(P.pos_s + e0 + j);
-                            if (pj < bp) { bp = pj; bj = (uint32_t)j; }
+                        for (int j = 0; j < 8; ++j) {
+                            if (g[j] == m) {
+                                const uint32_t pj = __ldg(P.pos_s + e0 + j);
+                                if (pj < bp) { bp = pj; bj = (uint32_t)j; }
+                            }
                         }
+                        if (m > -INFINITY) scan_consider(B, m, e0 + bj, rend_blk * kBlk, P.pos_s);
                     }
-                    if (m > -INFINITY) scan_consider(B, m, e0 + bj, rend, P.pos_s);
                 }
             }
             cp_async_wait<0>();

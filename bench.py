@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--skip-kmeans", action="store_true")
     p.add_argument("--skip-mi", action="store_true", help="development only: the line then has no headline value")
     p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--skip-cells", action="store_true")
     return p.parse_args()
 
 
@@ -179,6 +180,20 @@ def run_mi(args, dist, rank, world):
         "launches": max(m.launches_per_iteration() * args.steps, 2),     # persistent: one launch per select()
         "loop": m.loop_name(), "bytes_per_candidate": bytes_per_cand,
     }
+    # the same job through the cell-index loop (ACAV_MI_LOOP_CELLS): identical picks, O(K^2) work per iteration
+    res["cell_index_loop"] = None
+    if not args.skip_cells and world == 1:
+        mc = mi_engine(cells, args.k, rank, world, "cells", W * world, W * rank)
+        ms_c, _ = timed(dist, lambda: mc.select(args.warmup), lambda: mc.select(args.steps))
+        # both engines have now made warmup + steps picks from the same list: compare their tables
+        Ns, _, _, sums_s = m.read_state()
+        Nc, _, _, sums_c = mc.read_state()
+        res["cell_index_loop"] = {
+            "us_per_iteration": ms_c * 1e3 / args.steps, "value": scored / (ms_c * 1e-3), "unit": UNIT,
+            "same_table_as_streaming_loop": bool(torch.equal(Ns, Nc) and torch.equal(sums_s, sums_c)),
+            "what": "same candidate list and iterations through acav_mi_run(ACAV_MI_LOOP_CELLS): candidates sorted once by "
+                    "table cell, each iteration scans the K_a x K_v cells instead of the candidates (identical picks)"}
+        del mc
     e2e = None
     if not args.skip_e2e:
         del m
@@ -268,10 +283,38 @@ def run_kmeans(args, dist, rank, world):
     # whole assignment pass over the resident shard (KMeans.assign_all: 131072-row chunks, the fp32->bf16
     # preparation of chunk i+1 overlapped with the tensor-core kernel of chunk i)
     ms_pass, _ = timed(dist, lambda: km_sep.assign_all(x[:262144]), lambda: km_sep.assign_all(x))
+    # the dominant kernel by itself: the tcgen05 distance GEMM (+ classification) over the whole shard on operands
+    # prepared beforehand, chunk by chunk through the C ABI (acav_kmeans_assign_prepared)
+    from acav100m_b200 import _lib
+    chunk = 131072
+    ws = km_sep._workspace(chunk)
+    thr, rr = km_sep.underused_threshold(), float(km_sep.reinit[1])
+    st = _lib.stream_ptr(dev)
+    best_all = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.call("acav_kmeans_prepare_centers", ws, _lib.ptr(km_sep.centers), _lib.ptr(km_sep.counts), thr, rr, st)
+    ms_gemm, n_gemm_launch = 0.0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):                                   # first repetition warms up
+        ms_gemm, n_gemm_launch = 0.0, 0
+        for lo in range(0, n, chunk):
+            xb = x[lo:lo + chunk]
+            _lib.call("acav_kmeans_prepare_batch", ws, _lib.ptr(xb), xb.shape[0], d, st)
+            e0.record()
+            _lib.call("acav_kmeans_assign_prepared", ws, _lib.ptr(xb), xb.shape[0], d, _lib.ptr(km_sep.centers),
+                      _lib.ptr(km_sep.counts), thr, rr, _lib.c_vp(best_all.data_ptr() + 8 * lo), None, None, None, st)
+            e1.record()
+            e1.synchronize()
+            ms_gemm += e0.elapsed_time(e1)
+            n_gemm_launch += 1
+    t_ms = torch.tensor([ms_gemm], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_gemm = float(t_ms.item())
     pk = peaks()
     flops = 2.0 * b * k * d
     t_assign = ms_sep_assign * 1e-3 / steps
     pass_tflops = 2.0 * n * k * d / (ms_pass * 1e-3) / 1e12
+    gemm_tflops = 2.0 * n * k * d / (ms_gemm * 1e-3) / 1e12
     out = {
         "metric": "kmeans_iter_per_sec", "value": steps / (ms_step * 1e-3), "unit": "iter/s",
         "global_batch": b * world, "k": k, "d": d, "rows_resident_per_gpu": n, "steps": steps,
@@ -288,13 +331,23 @@ def run_kmeans(args, dist, rank, world):
             "assign_rows_per_sec": steps * b * world / (ms_sep_assign * 1e-3),
             "assign_ms_per_batch": ms_sep_assign / steps,
             "batch_assign_tflops": flops / t_assign / 1e12,
-            "assign_pass_ms": ms_pass, "assign_pass_rows_per_sec": n * world / (ms_pass * 1e-3)},
+            "assign_pass_ms": ms_pass, "assign_pass_rows_per_sec": n * world / (ms_pass * 1e-3),
+            "assign_pass_tflops": pass_tflops,
+            "assign_pass_note": "fp32->bf16 preparation (HBM-bound, ~980 W) and the GEMM (~930 W) both run at the "
+                                "board power limit, so the pass is the sum of the two (DESIGN.md 2.4)"},
         "gpu_launches": km.launches_per_step() * steps,
-        "roofline": {"bound": "tensor", "achieved": pass_tflops, "peak": pk["bf16_tflops"],
-                     "unit": "TFLOP/s", "frac": pass_tflops / pk["bf16_tflops"], "traffic": None,
-                     "kernel": "k-means assignment pass over the resident shard (KMeans.assign_all: fp32->bf16 prep "
-                               "+ tcgen05 distance GEMM + classify + exact re-check), converged state, 2*N*K*D flop",
-                     "peak_source": pk["source"] + " bf16 burst"},
+        "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": pk["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": gemm_tflops / pk["bf16_tflops"],
+                     "frac_of_sustained_peak": gemm_tflops / pk["bf16_tflops_sustained"] if pk.get("bf16_tflops_sustained") else None,
+                     "traffic": 613.3e6 + 11.4e6,
+                     "traffic_source": "ncu dram__bytes_read+write per launch (131072 x 2048 bf16 rows = 537 MB + centroids), "
+                                       "profiles/r01_km_pair256.ncu.txt",
+                     "kernel": "km_assign_pair_kernel<1> (tcgen05 cta_group::2 distance GEMM, 256x256 pair tiles) + top-4 "
+                               "classification, per 131072-row launch; 2*b*K*D flop; converged state",
+                     "launches_timed": n_gemm_launch, "ms_per_launch": ms_gemm / max(n_gemm_launch, 1),
+                     "algorithmic_flops_per_launch": 2.0 * chunk * k * d,
+                     "tensor_pipe_active_pct_ncu": 81.5,
+                     "peak_source": pk["source"] + " bf16 burst (cuBLAS 8192^3)"},
     }
     if not args.skip_e2e:
         host = torch.empty((steps, b, d), dtype=torch.float32).pin_memory()
@@ -433,6 +486,7 @@ def main():
                          "kernel": "greedy-MI iteration (gain table + candidate scan + apply), per GPU",
                          "algorithmic_bytes_per_launch": mi["algorithmic_bytes_per_launch"],
                          "peak_source": pk["source"] + " copy bandwidth"},
+            "cell_index_loop": mi.get("cell_index_loop"),
             "cpu_baseline": cpu, "cpu_model": cpu_model(), "kmeans": km, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -69,7 +69,7 @@ for mode in ("exact", "tensor"):
 W, C, picks = 200_003, 64, 700
 a = synth.zipf_pairs(W, C, 23)
 pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks)
-for loop in ("kernels", "persistent"):
+for loop in ("kernels", "persistent", "cells"):
     m = get_measure("mem_mi")(a, ncentroids=C, device="cuda", shard=(rank, world), loop=loop)
     m.init([(0, 1)], list(range(W)))
     p1, g1 = m.select(picks // 2)
