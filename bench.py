@@ -322,8 +322,9 @@ def run_kmeans(args, dist, rank, world):
         "assign_rows_per_sec": steps * b * world / (ms_assign * 1e-3),
         "assign_ms_per_batch": ms_assign / steps, "assign_mode": km.mode_name(),
         "steps_before_timing": warm, "lr_fallbacks": km.fallback,
-        "state": "trained from the reference init (torch.rand*1e-5, random-assignment warm-up); in this early, "
-                 "collapsed state ~K centroids are fp32-near-tied per row and rows take the exact re-check",
+        "state": "trained from the reference init (torch.rand*1e-5, random-assignment warm-up): an early, skewed state in "
+                 "which a handful of centroids own the batch and about half of the rows have 2-16 possible winners "
+                 "after the bf16 screen (exact candidate re-check)",
         "converged": {
             "state": "centroids at the mixture means (one clear nearest centroid per row)",
             "value": steps / (ms_sep_step * 1e-3), "unit": "iter/s", "ms_per_step": ms_sep_step / steps,
@@ -357,15 +358,32 @@ def run_kmeans(args, dist, rank, world):
             dist.barrier()
         t0 = time.perf_counter()
         last = None
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        bufs = [torch.empty((b, d), dtype=torch.float32, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        with torch.cuda.stream(copy_stream):
+            bufs[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
         for i in range(steps):
-            last = km.add(host[i].to(dev, non_blocking=True), sync=False)
+            if i + 1 < steps:                              # H2D of batch i+1 overlaps the step on batch i
+                j = (i + 1) % 2
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(freed[j])
+                    bufs[j].copy_(host[i + 1], non_blocking=True)
+                    ready[j].record(copy_stream)
+            cur.wait_event(ready[i % 2])
+            last = km.add(bufs[i % 2], sync=False)
+            freed[i % 2].record(cur)
         float(last)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         out["e2e"] = {"value": steps / float(dt.item()), "unit": "iter/s", "h2d_bytes_per_step": b * d * 4,
-                      "d2h_bytes_per_step": 4, "what": "KMeans.add on pinned host batches, mean distance read back"}
+                      "d2h_bytes_per_step": 4, "what": "KMeans.add on pinned host batches (H2D of batch i+1 on a copy stream while step i runs), mean distance read back"}
     del x
     return out
 
