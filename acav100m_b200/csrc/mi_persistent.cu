@@ -223,6 +223,17 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async16_u32(uint32_t smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+// same, with an L2 eviction-priority hint: the candidate stream (hundreds of MB, read once per iteration) is marked
+// evict-first so that it does not push the table counts, row offsets and positions out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_u32_hint(uint32_t smem_dst, const void *gmem_src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -308,6 +319,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
     }
     const uint32_t base_pos = (uint32_t)s.pos_base;
     const uint32_t grid = gridDim.x;
+    const uint64_t stream_pol = l2_policy_evict_first();
     int32_t prev1 = -1, prev2 = -1;                            // table cell of picks it-1, it-2
     int64_t done = 0;
     bool broke = false;
@@ -402,13 +414,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             const char *src = reinterpret_cast<const char *>(vec + (size_t)wb_lo * kWarp + lane);
 #pragma unroll
             for (int r = 0; r < kRing - 1; ++r) {
-                if (wb_lo + (uint32_t)r < wb_hi) cp_async16_u32(ring_u32 + r * 0x4000u, src + r * 512);
+                if (wb_lo + (uint32_t)r < wb_hi) cp_async16_u32_hint(ring_u32 + r * 0x4000u, src + r * 512, stream_pol);
                 cp_async_commit();
             }
             src += (kRing - 1) * 512;
             uint32_t slot_off = 0, pre_off = (kRing - 1) * 0x4000u;
             for (uint32_t blk = wb_lo; blk < wb_hi; ++blk) {
-                if (blk + (kRing - 1) < wb_hi) cp_async16_u32(ring_u32 + pre_off, src);
+                if (blk + (kRing - 1) < wb_hi) cp_async16_u32_hint(ring_u32 + pre_off, src, stream_pol);
                 cp_async_commit();
                 src += 512;
                 pre_off = (pre_off + 0x4000u) & 0xFFFFu;
