@@ -112,7 +112,8 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     if (rc) return rc;
     // balanced cut: cost(e) = e + row_cost * (#non-empty rows that start before e); chunk edges block aligned
     const int32_t grid = h->sm_count;
-    const double row_cost = 6.0 * s.k_v;          // building one gain row ~ scanning 6*K_v candidates (measured)
+    double row_cost = 6.0 * s.k_v;                // building one gain row ~ scanning 6*K_v candidates (measured)
+    if (const char *e = std::getenv("ACAV_MI_ROWCOST")) row_cost = std::atof(e) * s.k_v;
     std::vector<double> cum((size_t)s.k_a + 1);
     double run = 0.0;
     for (int32_t r = 0; r < s.k_a; ++r) {

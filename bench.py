@@ -496,9 +496,9 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": mi["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": mi["achieved_gbs"] / pk["hbm_gbs"],
-                         "traffic": 2.44 * args.mi_candidates if mi["loop"].startswith("persistent") else None,
-                         "traffic_source": "ncu dram__bytes_read+write per iteration, profiles/r01_mi_persist_v2.ncu.txt "
-                                           "(2-byte row-partitioned stream + table)",
+                         "traffic": 2.125 * args.mi_candidates if mi["loop"].startswith("persistent") else None,
+                         "traffic_source": "ncu dram__bytes_read+write per iteration at W = 1e8 (850 MB over a 4-iteration "
+                                           "launch), profiles/r01_mi_persist_v3.ncu.txt (2-byte row-partitioned stream + table)",
                          "bytes_per_candidate_accounted": mi["bytes_per_candidate"],
                          "list_order_equivalent_gbs": mi["achieved_gbs"] * 4.0 / mi["bytes_per_candidate"],
                          "kernel": "greedy-MI iteration (gain table + candidate scan + apply), per GPU",

@@ -142,3 +142,62 @@ def test_selection_cli_path_handling(tmp_path):
     assert args.data.meta.path == tmp_path / "clusters"                  # meta defaults to the shard dir
     assert args.measure_name == "mem_mi" and args.subset.ratio == 0.1 and args.computation.device == "cuda"
     assert args.batch.batch_size == 20 and args.log_times == 10
+
+
+# ---- chunked selection (reference subset_selection/code/chunk.py) ---------------------------------------
+
+def _chunk_fixture(tmp_path, n_shards=5, clips=7):
+    rng = np.random.RandomState(1)
+    cargs_ = cargs.get_args(**{"data.output.path": str(tmp_path / "clusters")})
+    for s in range(n_shards):
+        name = "shard-%06d" % s
+        _fake_cluster_shard(cargs_, name, clips, rng)
+        json.dump([{"filename": "clip_%06d_%04d.mp4" % (s, c), "id": "yt%d_%d" % (s, c), "segment": [0.0, 1.0]}
+                   for c in range(clips)], open(tmp_path / "clusters" / (name + ".json"), "w"))
+    return tmp_path / "clusters"
+
+
+def test_chunk_planning_follows_the_reference(tmp_path):
+    from acav100m_b200.subset_selection import chunk as schunk
+    clusters = _chunk_fixture(tmp_path)
+    assert list(schunk.get_chunks(list(range(5)), 2)) == [[0, 1], [2, 3], [4]]
+    assert list(schunk.split_chunks(list(range(5)), 2)) == [[0, 1, 2], [3, 4]]
+    args = scli.prepare(out_path=str(tmp_path / "out"), shards_path=str(clusters / "shard-{000000..000007}.pkl"),
+                        **{"chunk_size": 2, "subset.size": 10, "computation.num_workers": 8})
+    args.computation.num_gpus = 2
+    chunk_args, nodes, num_chunks = schunk.plan_chunks(args)
+    assert num_chunks == 3                                       # 5 existing shards of the 8 globbed, 2 per chunk
+    assert chunk_args.subset.size == 4                           # ceil(10 / 3), chunk.py:45-46
+    assert chunk_args.computation.num_workers == 4               # chunk.py:47-48
+    assert [[num for num, _ in run] for run in nodes] == [[0, 1], [2]]
+    assert [Path(p).name for p in nodes[1][0][1]] == ["shard-000004.pkl"]
+    args.computation.num_gpus = 9                                # more GPUs than chunks -> thresholded, chunk.py:31-35
+    _, nodes, _ = schunk.plan_chunks(args)
+    assert args.computation.num_gpus == 3 and len(nodes) == 3
+
+
+def test_chunk_caches_reduce_to_the_output_csv(tmp_path):
+    from acav100m_b200.subset_selection import chunk as schunk
+    clusters = _chunk_fixture(tmp_path)
+    out = tmp_path / "out" / "output.csv"
+    args = scli.prepare(out_path=str(out), shards_path=str(clusters / "shard-{000000..000004}.pkl"),
+                        meta_path=str(clusters), **{"chunk_size": 2, "subset.size": 3, "verbose": False})
+    args.parent_pid = "4242"
+    parts, metas = sdata.load_data(str(clusters / "shard-{000000..000001}.pkl"), clusters)
+    res = [{"filename": r["filename"], "shard_name": r["shard_name"]} for r in parts[sorted(parts)[0]][:5]]
+    # pickled cache of chunk 0 and CSV cache of chunk 1 (the two --save_cache_as_csvs settings)
+    schunk.save_chunk_cache(args, 0, 0, res, metas)
+    cache = tmp_path / "out" / "caches" / "cache_4242_0_0.pkl"
+    assert cache.is_file() and set(pickle.load(open(cache, "rb"))) == {"res", "metas"}
+    p, n = schunk._reduce_single_cache(args, "cache_4242_0_1", res[::-1], metas)
+    assert p.name == "cache_4242_0_1_output.csv" and n == 3      # truncated to the per-chunk quota
+    rows = list(csv.reader(open(p)))
+    assert rows[0][1] == res[-1]["filename"] and rows[0][2].startswith("yt")     # metadata joined by clip stem
+    assert ssave.group_cache_paths([cache, p]) == {"cache_4242": [cache, p]}
+    ssave.merge_all_csvs(args)                                   # `cli reduce_csvs`
+    assert [r[1] for r in csv.reader(open(out))] == [r["filename"] for r in res[::-1][:3]]
+    out.unlink()
+    p.unlink()
+    schunk.reduce_all_pkls(args)                                 # `cli reduce_pkls`
+    assert [r[1] for r in csv.reader(open(out))] == [r["filename"] for r in res[:3]]
+    assert (tmp_path / "out" / "caches" / "cache_4242_0_0_output.csv").is_file()

@@ -109,3 +109,35 @@ def test_cli_default_measure_runs_on_all_pairs(tmp_path):
     names = [l[1] for l in lines]
     assert len(set(names)) == len(names) and all(n.endswith(".mp4") for n in names)
     assert all(l[2].startswith("yt") for l in lines)
+
+
+def test_cli_chunked_selection_and_reduce(tmp_path):
+    """`cli run --chunk_size=2` (reference chunk.py): every chunk of two shards is its own greedy selection
+    with quota ceil(size / num_chunks), cached as a CSV; `cli reduce` appends the caches to output.csv."""
+    feat_dir, meta_dir = write_feature_shards(tmp_path / "data", n_shards=4, clips_per_shard=50, seed=6)
+    clusters, out_csv = tmp_path / "data" / "clusters", tmp_path / "data" / "sel" / "output.csv"
+    torch.manual_seed(2)
+    ccli.main(["cluster", "--feature_path=" + str(feat_dir / "shard-{000000..000003}.pkl"),
+               "--out_path=" + str(clusters), "--meta_path=" + str(meta_dir), "--clustering.ncentroids=6",
+               "--data.batch_size=32", "--computation.num_gpus=1"])
+    cols = [("layer_vggish", "layer_4"), ("layer_slow_fast", "layer_4")]
+    common = ["--shards_path=" + str(clusters / "shard-{000000..000003}.pkl"), "--meta_path=" + str(meta_dir),
+              "--out_path=" + str(out_csv), "--verbose=False"]
+    scli.main(["run", *common, "--measure_name=mem_mi", "--subset.size=30", "--shuffle_candidates=False",
+               "--chunk_size=2", "--computation.num_gpus=1", "--computation.load_async=True",
+               "--clustering.columns=" + repr(cols).replace(" ", "")])
+    caches = sorted((out_csv.parent / "caches").glob("cache_*_0_*_output.csv"))
+    assert len(caches) == 2 and not out_csv.exists()
+    want_all = []
+    for i, cache in enumerate(caches):
+        shard_glob = str(clusters / ("shard-{00000%d..00000%d}.pkl" % (2 * i, 2 * i + 1)))
+        parts, _ = sdata.load_data(shard_glob, meta_dir)
+        a, shard_names, filenames, _ = sdata.preprocess(parts[sorted(parts)[0]], columns=cols)
+        S, _ = mo.run_greedy_driver(a, subset_size=15, shuffle_candidates=False)       # ceil(30 / 2) per chunk
+        want = [filenames[s] for s in sorted(S)]
+        got = [l[1] for l in csv.reader(open(cache))]
+        assert got == want and len(got) == 14                   # run_greedy returns size - 1 picks (mi.py:150-192)
+        want_all += want
+    scli.main(["reduce", *common, "--subset.size=30"])
+    lines = list(csv.reader(open(out_csv)))
+    assert [l[1] for l in lines] == want_all and all(l[2].startswith("yt") for l in lines)
