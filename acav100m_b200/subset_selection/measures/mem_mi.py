@@ -120,7 +120,7 @@ class EfficientMemMI:
             _lib.call("acav_mi_create", _lib.ctypes.byref(handle), hi - lo, C, C, self._max_picks, lo)
             self._engine = handle
             _lib.call("acav_mi_load_candidates", handle, _lib.ptr(self._cells), st)
-            self._logs = tables.log_table(self._max_picks + 4).to(self.device)
+            self._logs = tables.log_table_device(self._max_picks + 4, self.device)
             consts = tables.empty_table_constants(C)
             _lib.call("acav_mi_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
                       consts.ctypes.data_as(_lib.c_vp), st)

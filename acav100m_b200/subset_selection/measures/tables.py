@@ -20,6 +20,21 @@ def log_table(n):
     return t
 
 
+_DEVICE_TABLES = {}
+
+
+def log_table_device(n, device):
+    """`log_table(n)` resident on `device`, shared by every engine of the process: the table is a constant of the
+    torch build (not of the data), so the longest one made so far is kept per device and reused (the chunked runner
+    and multi-layer jobs create many engines; 2^24 entries take ~30 ms to produce and upload)."""
+    key = str(device)
+    have = _DEVICE_TABLES.get(key)
+    if have is None or have.numel() < n:
+        have = log_table(n).to(device)
+        _DEVICE_TABLES[key] = have
+    return have
+
+
 def empty_table_constants(C):
     """{fN0, fa0, n0, NlogN0, aloga0, blogb0} of an empty C x C table (one clustering pair)."""
     N = torch.full((1, C, C), EPS)

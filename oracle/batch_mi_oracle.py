@@ -89,3 +89,31 @@ def greedy_batch_mi(assignments, ncentroids, pairs, candidates, subset_size, sta
         S += chosen.tolist()
         GAIN += top.tolist()
     return S[:subset_size], GAIN
+
+
+def greedy_dense_mi(assignments, ncentroids, pairs, candidates, subset_size, start_indices, follow=None):
+    """``EfficientMI.run_greedy`` mi.py:150-192 with the dense ``calc_MI`` (:85-91) -> (S, GAIN, per-iteration
+    score vectors).  The start indices are in S but never in the table.  `follow`: optional list of picks to
+    adopt instead of the arg-max (teacher forcing for the GPU tests)."""
+    a = torch.from_numpy(np.asarray(assignments)).to(torch.long)
+    C, P = ncentroids, len(pairs)
+    N = torch.full((P, C, C), EPS)                                # init_cache mi.py:32-39
+    cache = {'N': N, 'a': N.sum(dim=1), 'b': N.sum(dim=2)}
+    cache['n'] = cache['a'].sum(dim=-1)
+    cand = torch.as_tensor(list(candidates), dtype=torch.long)
+    S, GAIN, ALL = list(start_indices), [], []
+    for j in range(len(start_indices), subset_size - 1):
+        tabs = sample_tables(a, pairs, cand, C)
+        last = {key: cache[key].unsqueeze(0) + tabs[key] for key in tabs}   # get_last mi.py:93-98
+        scores = dense_mi(last).mean(dim=-1)                                # calc_score :76-80
+        score, idx = scores.max(dim=0)
+        ALL.append((scores.clone(), cand.clone()))
+        if follow is not None:
+            idx = (cand == follow[len(GAIN)]).nonzero()[0, 0]
+        idx = int(idx)
+        for key in cache:                                                   # update_cache :100-102
+            cache[key] = last[key][idx]
+        S.append(int(cand[idx]))
+        GAIN.append(float(scores[idx]))
+        cand = torch.cat((cand[:idx], cand[idx + 1:]))                      # remove_idx_all :104-125
+    return S, GAIN, ALL

@@ -135,7 +135,7 @@ def test_errors():
         bad.init([(0, 1)], list(range(50)))
     from acav100m_b200.subset_selection import get_measure
     with pytest.raises(NotImplementedError):
-        get_measure("mi")
+        get_measure("ami")
     with pytest.raises(AssertionError):
         get_measure("nope")
 

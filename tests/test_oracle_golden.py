@@ -167,3 +167,16 @@ def test_live_reference_agrees_with_oracle_on_fresh_seeds():
     d_or = [ko.sgd_step(st, xb)[1] for xb in batches]
     assert d_ref == d_or
     assert torch.equal(km.centers, st.centers) and torch.equal(km.counts, st.counts)
+
+
+def test_dense_mi_restatement_reproduces_reference_run(golden_dir):
+    """oracle.batch_mi_oracle.greedy_dense_mi (mi.py:150-192 with the dense calc_MI) against the reference's own
+    `mi` run: same picks, same fp32 scores."""
+    from oracle import batch_mi_oracle as bo
+    g = load(golden_dir, "mi_dense_small_mi")
+    a = g["assignments"].astype(np.int64)
+    order = g["candidate_order"].tolist()
+    S, GAIN, _ = bo.greedy_dense_mi(a, int(g["c"]), [tuple(p) for p in g["pairs"].tolist()], order[1:],
+                                    int(g["subset"]), [order[0]])
+    assert S == g["S"].tolist()
+    assert np.array_equal(np.array(GAIN), g["GAIN"])
