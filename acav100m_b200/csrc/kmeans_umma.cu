@@ -309,7 +309,25 @@ km_candidate_refine_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
             double acc = 0.0;
             if ((d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                 ((reinterpret_cast<uintptr_t>(centers) & 15) == 0)) {
-                for (int32_t i = 0; i < d; i += 4) {
+                // 16 independent 16-byte loads in flight per thread, then the 32 FMAs in k order (the chain is the
+                // definition of "exact"; only the loads are hoisted) -- the kernel was bound by load latency
+                int32_t i = 0;
+                for (; i + 32 <= d; i += 32) {
+                    float4 a[8], w[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        a[u] = __ldg(reinterpret_cast<const float4 *>(p + i) + u);
+                        w[u] = __ldg(reinterpret_cast<const float4 *>(q + i) + u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        acc = fma((double)a[u].x, (double)w[u].x, acc);
+                        acc = fma((double)a[u].y, (double)w[u].y, acc);
+                        acc = fma((double)a[u].z, (double)w[u].z, acc);
+                        acc = fma((double)a[u].w, (double)w[u].w, acc);
+                    }
+                }
+                for (; i < d; i += 4) {
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(p + i));
                     const float4 w = __ldg(reinterpret_cast<const float4 *>(q + i));
                     acc = fma((double)a.x, (double)w.x, acc);
