@@ -19,7 +19,6 @@ struct acav_kmeans {
     // tensor-core path: bf16 copies, epilogue parameters, screening results, TMA descriptors
     int32_t dp;
     void *xb, *cb, *cparams, *partial;
-    float *cmax;
     int32_t *cand_rows, *cand_ids, *full_rows, *counters;      // counters = {n_cand, n_full}
     alignas(64) unsigned char tmap_x[128];
     alignas(64) unsigned char tmap_c[128];
@@ -222,7 +221,7 @@ int acav_kmeans_destroy(acav_kmeans_t *h) {
     cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind); cudaFree(h->packed);
     cudaFree(h->blockhist); cudaFree(h->lrank); cudaFree(h->total); cudaFree(h->seg_start);
     cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
-    cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial); cudaFree(h->cmax);
+    cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial);
     cudaFree(h->cand_rows); cudaFree(h->cand_ids); cudaFree(h->full_rows); cudaFree(h->counters);
     delete h;
     return 0;
@@ -256,7 +255,6 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) { rc = dev_alloc(&raw, (size_t)k * h->dp * 2, &h->bytes); h->cb = raw; }
     if (!rc) { rc = dev_alloc(&raw, (size_t)umma_param_bytes(k), &h->bytes); h->cparams = raw; }
     if (!rc) { rc = dev_alloc(&raw, (size_t)umma_partial_bytes(max_batch ? max_batch : 1), &h->bytes); h->partial = raw; }
-    if (!rc) rc = dev_alloc(&h->cmax, 1, &h->bytes);
     if (!rc) rc = dev_alloc(&h->cand_rows, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->cand_ids, (size_t)max_batch * 16, &h->bytes);       // kMaxCand per row
     if (!rc) rc = dev_alloc(&h->full_rows, (size_t)max_batch, &h->bytes);
@@ -320,7 +318,7 @@ int acav_kmeans_prepare_centers(acav_kmeans_t *h, const float *centers, const fl
     if (!h->tensor_ready) return ACAV_E_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_prep_rows(centers, h->k, h->d, h->d, h->dp, h->cb, h->cn, st);
-    if (!rc) rc = launch_centroid_params(h->cn, counts, h->k, underused_threshold, reinit_r, h->cparams, h->cmax, st);
+    if (!rc) rc = launch_centroid_params(h->cn, counts, h->k, underused_threshold, reinit_r, h->cparams, st);
     return rc;
 }
 

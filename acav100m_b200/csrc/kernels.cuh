@@ -25,7 +25,7 @@ int64_t umma_param_bytes(int32_t k);
 int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32_t dp, void *xb, float *xn,
                      cudaStream_t st);
 int launch_centroid_params(const float *cn, const float *counts, int32_t k, float thr, float r, void *params,
-                           float *cmax, cudaStream_t st);
+                           cudaStream_t st);
 int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, const void *cparams, int32_t b,
                        int32_t k, int32_t dp, int32_t sm_count, void *partial, int32_t *n_split_out, cudaStream_t st);
 // kmeans_umma2.cu (CTA pairs): halves = 1 -> 256 x 256 pair tiles, 2 -> 256 x 512; *n_lists_out partial lists per row

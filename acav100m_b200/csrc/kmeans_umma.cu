@@ -58,32 +58,19 @@ __global__ void km_prep_rows_kernel(const float *__restrict__ x, int64_t rows, i
     }
 }
 
-// Per-centroid epilogue parameters and max |c| (for the error bound).  scale s = 1/r for under-used
-// centroids (sgd_clustering.py:76-77), else 1.
-__global__ void __launch_bounds__(1024)
-km_centroid_params_kernel(const float *__restrict__ cn, const float *__restrict__ counts, int32_t k,
-                          float thr, float r, CentroidParam *__restrict__ params, float *__restrict__ cmax) {
-    __shared__ float wmax[32];
-    float m = 0.f;
-    for (int32_t i = threadIdx.x; i < k; i += blockDim.x) {
-        const float s = counts[i] < thr ? 1.0f / r : 1.0f;
-        CentroidParam p;
-        p.a = -2.0f * s;
-        p.b = cn[i] * s * (1.0f - kScreenEps32);
-        p.s = s * (1.0f - kScreenEps32);
-        p.e = kScreenKappa * s * sqrtf(cn[i]) * 1.000001f;
-        params[i] = p;
-        m = fmaxf(m, cn[i]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x % kWarp == 0) wmax[threadIdx.x / kWarp] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float mm = 0.f;
-        for (int w = 0; w < 32; ++w) mm = fmaxf(mm, wmax[w]);
-        *cmax = sqrtf(mm);
-    }
+// Per-centroid epilogue parameters (see CentroidParam): scale s_c = 1/r for under-used centroids
+// (sgd_clustering.py:76-77), else 1, and the per-centroid error term of the bf16 screen.
+__global__ void km_centroid_params_kernel(const float *__restrict__ cn, const float *__restrict__ counts, int32_t k,
+                                          float thr, float r, CentroidParam *__restrict__ params) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const float s = counts[i] < thr ? 1.0f / r : 1.0f;
+    CentroidParam p;
+    p.a = -2.0f * s;
+    p.b = cn[i] * s * (1.0f - kScreenEps32);
+    p.s = s * (1.0f - kScreenEps32);
+    p.e = kScreenKappa * s * sqrtf(cn[i]) * 1.000001f;
+    params[i] = p;
 }
 
 __global__ void __launch_bounds__(kUmmaThreads, 1)
@@ -421,8 +408,9 @@ int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32
 }
 
 int launch_centroid_params(const float *cn, const float *counts, int32_t k, float thr, float r, void *params,
-                           float *cmax, cudaStream_t st) {
-    km_centroid_params_kernel<<<1, 1024, 0, st>>>(cn, counts, k, thr, r, reinterpret_cast<CentroidParam *>(params), cmax);
+                           cudaStream_t st) {
+    km_centroid_params_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(cn, counts, k, thr, r,
+                                                                         reinterpret_cast<CentroidParam *>(params));
     ACAV_LAUNCH_CHECK();
     return 0;
 }

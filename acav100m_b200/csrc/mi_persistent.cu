@@ -478,8 +478,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
         __syncthreads();                                       // widx is reused below
-        unsigned long long key = 0ull;
+        unsigned long long key = 0ull, pay = 0ull;
         if (my32 != 0u && my32 == m32) {
+            // this thread holds the block-maximum gain: its candidate's original position and column are loaded
+            // together, the table count of its cell right after (two memory latencies; thread 0 only publishes)
             uint32_t bp = __ldg(P.pos_s + bi);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -488,40 +490,41 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                     if (pt < bp) { bp = pt; bi = tie[t]; }
                 }
             }
+            const uint32_t c2 = (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(P.c2s) + bi) >> 2;
+            int32_t a = 0, b = k_a;                            // table row of the stream index
+            while (a < b) { const int32_t m = (a + b) >> 1; if (rs_all[m + 1] > bi) b = m; else a = m + 1; }
+            const int32_t cell = a * k_v + (int32_t)c2;
+            const uint32_t x = __ldcg(Tcur + cell) + (cell == prev1 ? 1u : 0u);
             key = ((unsigned long long)m32 << 32) | (unsigned long long)(0xFFFFFFFFu - (base_pos + bp));
+            pay = ((unsigned long long)a << 48) | ((unsigned long long)c2 << 32) | x;
         }
-        {   // block arg-max of (key, stream index); thread 0 publishes the CTA's candidate
-            unsigned long long k2 = key;
+        {   // block arg-max of (key, payload, stream index); thread 0 publishes the CTA's candidate
+            unsigned long long k2 = key, p2 = pay;
             uint32_t i2 = bi;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k2, o);
+                const unsigned long long op = __shfl_xor_sync(0xffffffffu, p2, o);
                 const uint32_t oi = __shfl_xor_sync(0xffffffffu, i2, o);
-                if (ok > k2) { k2 = ok; i2 = oi; }
+                if (ok > k2) { k2 = ok; p2 = op; i2 = oi; }
             }
-            if (threadIdx.x % kWarp == 0) { wkey[threadIdx.x / kWarp] = k2; widx[threadIdx.x / kWarp] = i2; }
+            if (threadIdx.x % kWarp == 0) {
+                wkey[threadIdx.x / kWarp] = k2; wpay[threadIdx.x / kWarp] = p2; widx[threadIdx.x / kWarp] = i2;
+            }
             __syncthreads();
             if (threadIdx.x < kWarp) {
-                k2 = wkey[threadIdx.x]; i2 = widx[threadIdx.x];
+                k2 = wkey[threadIdx.x]; p2 = wpay[threadIdx.x]; i2 = widx[threadIdx.x];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k2, o);
+                    const unsigned long long op = __shfl_xor_sync(0xffffffffu, p2, o);
                     const uint32_t oi = __shfl_xor_sync(0xffffffffu, i2, o);
-                    if (ok > k2) { k2 = ok; i2 = oi; }
+                    if (ok > k2) { k2 = ok; p2 = op; i2 = oi; }
                 }
                 if (threadIdx.x == 0) {
-                    unsigned long long pay = 0ull;
-                    if (k2) {
-                        int32_t a = 0, b = k_a;                // row of the stream index
-                        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_all[m + 1] > i2) b = m; else a = m + 1; }
-                        const uint32_t c2 = (uint32_t)__ldcg(reinterpret_cast<const unsigned short *>(P.c2s) + i2) >> 2;
-                        const int32_t cell = a * k_v + (int32_t)c2;
-                        const uint32_t x = __ldcg(Tcur + cell) + (cell == prev1 ? 1u : 0u);
-                        pay = ((unsigned long long)a << 48) | ((unsigned long long)c2 << 32) | x;
-                    }
                     sh_best_key = k2; sh_best_idx = i2;
                     MiPub *pb = P.pub + (size_t)cur * grid + blockIdx.x;
-                    pb->key = k2; pb->payload = pay;
+                    pb->key = k2; pb->payload = k2 ? p2 : 0ull;
                 }
             }
         }
@@ -539,7 +542,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             for (uint32_t t = threadIdx.x; t < grid; t += blockDim.x) {
                 const MiPub *pb = P.pub + (size_t)cur * grid + t;
                 const unsigned long long kk = __ldcg(&pb->key);
-                if (kk > k2) { k2 = kk; p2 = __ldcg(&pb->payload); }
+                const unsigned long long pp = __ldcg(&pb->payload);      // unconditional: one memory latency, not two
+                if (kk > k2) { k2 = kk; p2 = pp; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
