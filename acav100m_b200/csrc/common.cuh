@@ -20,6 +20,21 @@
 namespace acav {
 
 constexpr int kWarp = 32;
+constexpr int kMaxDevices = 64;
+
+// Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device, once per device and size (function
+// attributes are per device; a process may drive several).  `done` is a zero-initialised static of the call site.
+template <typename F>
+inline int ensure_dynamic_smem(F *func, size_t bytes, size_t (&done)[kMaxDevices]) {
+    int dev = 0;
+    ACAV_CUDA_TRY(cudaGetDevice(&dev));
+    const int slot = dev >= 0 && dev < kMaxDevices ? dev : 0;
+    if (bytes > done[slot] || dev != slot) {                   // devices beyond the table: set every time
+        ACAV_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        done[slot] = bytes;
+    }
+    return 0;
+}
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

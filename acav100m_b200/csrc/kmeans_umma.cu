@@ -417,12 +417,9 @@ int launch_centroid_params(const float *cn, const float *counts, int32_t k, floa
 
 int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, const void *cparams, int32_t b,
                        int32_t k, int32_t dp, int32_t sm_count, void *partial, int32_t *n_split_out, cudaStream_t st) {
-    static bool attr_set = false;
+    static size_t attr_done[kMaxDevices];
     const int smem_bytes = UmmaSmem::kBytes + 1024;
-    if (!attr_set) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_assign_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_set = true;
-    }
+    { int rc = ensure_dynamic_smem(km_assign_umma_kernel, (size_t)smem_bytes, attr_done); if (rc) return rc; }
     const int32_t bn = umma_tile_n(k);
     const int32_t n_tiles = (int32_t)ceil_div(k, kBNMax);
     const int32_t num_m = (int32_t)ceil_div(b, kBM);

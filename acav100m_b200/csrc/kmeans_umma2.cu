@@ -236,13 +236,9 @@ static int launch_pair_t(const void *tmap_x, const void *tmap_c128, const float 
                          int32_t k, int32_t dp, int32_t sm_count, void *partial, int32_t *n_lists_out,
                          cudaStream_t st) {
     using Cfg = PairCfg<kHalves>;
-    static bool attr_set = false;
+    static size_t attr_done[kMaxDevices];
     const int smem_bytes = Cfg::kBytes + 1024;
-    if (!attr_set) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_assign_pair_kernel<kHalves>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-        attr_set = true;
-    }
+    { int rc = ensure_dynamic_smem(km_assign_pair_kernel<kHalves>, (size_t)smem_bytes, attr_done); if (rc) return rc; }
     const int32_t n_tiles = (int32_t)ceil_div(k, Cfg::kTileN);
     const int32_t num_m = (int32_t)ceil_div(b, 2 * kBM);
     const int32_t clusters = sm_count / 2;

@@ -358,12 +358,9 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
         // heavy centroids (>= kUpdHeavyRows rows of this batch): cp.async ring kernel; its blocks for light
         // centroids exit at once, and km_update_kernel below skips the heavy ones
         const size_t smem = (size_t)kUpdGroups * kUpdGroupRows * kUpdThreads * 16 + (size_t)kUpdChunk * 4;
-        static bool attr = false;
-        if (!attr) {
-            ACAV_CUDA_TRY(cudaFuncSetAttribute(km_update_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ACAV_CUDA_TRY(cudaFuncSetAttribute(km_update_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        static size_t done_fused[kMaxDevices], done_split[kMaxDevices];
+        { int rc = ensure_dynamic_smem(km_update_stream_kernel<true>, smem, done_fused); if (rc) return rc; }
+        { int rc = ensure_dynamic_smem(km_update_stream_kernel<false>, smem, done_split); if (rc) return rc; }
         dim3 sgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kUpdThreads * 4));   // loops over the heavy list
         if (deltas)
             km_update_stream_kernel<false><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,

@@ -372,11 +372,11 @@ static int cells_sort_pass(const uint32_t *cells_in, const uint32_t *pos_in, int
     const int ntiles = mi_cells_tiles(w);
     const size_t smem = (size_t)k * sizeof(uint32_t);
     if (smem > 200 * 1024) return ACAV_E_UNSUPPORTED;
-    static size_t attr = 0;
-    if (smem > attr && smem > 48 * 1024) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(cells_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(cells_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+    static size_t done_count[kMaxDevices], done_scatter[kMaxDevices];
+    if (smem > 48 * 1024) {
+        int rc = ensure_dynamic_smem(cells_count_kernel, smem, done_count);
+        if (!rc) rc = ensure_dynamic_smem(cells_scatter_kernel, smem, done_scatter);
+        if (rc) return rc;
     }
     cells_count_kernel<<<ntiles, kCellSortThreads, smem, st>>>(cells_in, w, shift, k, tilehist);
     ACAV_LAUNCH_CHECK();
@@ -431,11 +431,8 @@ int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t
     const size_t cache = (size_t)P.rows_per_cta * s.k_v * 8;
     P.cache_rows = smem + cache <= 200 * 1024 ? 1 : 0;
     if (P.cache_rows) smem += cache;
-    static size_t attr_set = 0;
-    if (smem > attr_set && smem > 48 * 1024) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    static size_t attr_done[kMaxDevices];
+    if (smem > 48 * 1024) { int rc = ensure_dynamic_smem(mi_cells_kernel, smem, attr_done); if (rc) return rc; }
     ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
     void *args[] = {&P};

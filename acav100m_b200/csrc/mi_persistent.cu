@@ -644,11 +644,11 @@ int launch_mi_partition(const uint32_t *cells, int64_t w, int32_t k_a, uint32_t 
     const int ntiles = mi_partition_scratch_tiles(w);
     const size_t smem = (size_t)k_a * sizeof(uint32_t);
     if (smem > 96 * 1024) return ACAV_E_UNSUPPORTED;
-    static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_part_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+    static size_t done_count[kMaxDevices], done_scatter[kMaxDevices];
+    if (smem > 48 * 1024) {
+        int rc = ensure_dynamic_smem(mi_part_count_kernel, (size_t)96 * 1024, done_count);
+        if (!rc) rc = ensure_dynamic_smem(mi_part_scatter_kernel, (size_t)96 * 1024, done_scatter);
+        if (rc) return rc;
     }
     mi_part_count_kernel<<<ntiles, kPartThreads, smem, st>>>(cells, w, k_a, tilehist);
     ACAV_LAUNCH_CHECK();
@@ -712,11 +712,8 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
         P.mail_peer[r] = (world > 1 && r < world) ? reinterpret_cast<MiMail *>(mail_peer[r]) : nullptr;
     P.ring_offset = (int32_t)persist_table_bytes(s.k_a, s.k_v, rows_smem);
     const size_t smem = persist_table_bytes(s.k_a, s.k_v, rows_smem) + persist_ring_bytes();
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(mi_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    static size_t attr_done[kMaxDevices];
+    { int rc = ensure_dynamic_smem(mi_persistent_kernel, smem, attr_done); if (rc) return rc; }
     // both table copies start equal; the barrier words start at zero
     ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
     ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
