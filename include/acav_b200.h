@@ -62,7 +62,7 @@ int acav_kmeans_set_tile_variant(acav_kmeans_t *h, int32_t variant);
 
 /* Assignment modes */
 #define ACAV_ASSIGN_EXACT   0      /* fp32 inputs, fp64-accumulated dot products on CUDA cores     */
-#define ACAV_ASSIGN_TENSOR  1      /* tcgen05 bf16 distance GEMM + top-2 screening + exact refine  */
+#define ACAV_ASSIGN_TENSOR  1      /* tcgen05 bf16 distance GEMM + top-4 screening + exact refine  */
 
 /* Replaces the distance branch of KMeans.calc_best (sgd_clustering.py:70-79):
  *   dist[i,j] = (-2<c_i,x_j> + |x_j|^2) + |c_i|^2 ; rows i with counts[i] < underused_threshold
@@ -70,7 +70,7 @@ int acav_kmeans_set_tile_variant(acav_kmeans_t *h, int32_t variant);
  * x: [b, d] fp32 row-major with row stride ldx (elements).  best: int64[b] (torch.long, :78).
  * min_dist: fp32[b] or NULL.  mean_dist: fp32[1] on the device or NULL (no host sync here; the
  * reference's .item() at :79 is the caller's choice).  n_refined: int32[2] device or NULL -- in
- * ACAV_ASSIGN_TENSOR mode the number of rows re-checked on <= 4 candidates and the number sent
+ * ACAV_ASSIGN_TENSOR mode the number of rows re-checked on <= 16 candidates and the number sent
  * through the full exact kernel (both 0 in ACAV_ASSIGN_EXACT mode). */
 int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                        const float *centers, const float *counts,
