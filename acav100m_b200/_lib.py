@@ -43,6 +43,16 @@ SIGNATURES = {
     "acav_mi_apply": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "acav_mi_run": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp]),
     "acav_mi_read_state": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "acav_mi_pairs_create": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i64, c_i64]),
+    "acav_mi_pairs_destroy": (ctypes.c_int, [c_vp]),
+    "acav_mi_pairs_load_candidates": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "acav_mi_pairs_set_tables": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "acav_mi_pairs_add_sample": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "acav_mi_pairs_record_words": (ctypes.c_int, [c_vp]),
+    "acav_mi_pairs_local_best": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "acav_mi_pairs_apply": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "acav_mi_pairs_run": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "acav_mi_pairs_read_state": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "acav_mi_dense_create": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp]),
     "acav_mi_dense_destroy": (ctypes.c_int, [c_vp]),
     "acav_mi_dense_add": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -6,9 +6,12 @@ candidates)``, ``add_samples(ids)``, ``run_greedy(...) -> (S, GAIN, timelapse, L
 selected indices and the same fp32 scores bit for bit.  All per-iteration work (score every
 remaining candidate, first arg-max, table update, removal) happens inside ``libacav_b200.so``.
 
-Scope: one clustering pair (P = 1, the K_a x K_v audio-visual table of BASELINE.json); P > 1 raises.
+One clustering pair (P = 1, the K_a x K_v audio-visual table of BASELINE.json) runs on the persistent
+kernels of ``acav_mi_*``; several pairs (the reference's `combination` / `bipartite` / `diagonal` pairings,
+P = 45 by default) run on ``acav_mi_pairs_*`` (``pairs_engine.py``, csrc/mi_pairs.cu), the mean over pairs
+added in torch's CPU summation order so that scores stay bit-identical.
 New (not in the reference): ``shard=(rank, world)`` splits the candidate list into contiguous ranges
-across ranks with one 16-byte all-gather per iteration; every rank returns the same S and GAIN.
+across ranks with one small all-gather per iteration; every rank returns the same S and GAIN.
 """
 import time
 
@@ -17,6 +20,7 @@ import torch
 
 from ... import _lib, parallel
 from . import tables
+from .pairs_engine import PairsEngine
 
 
 class EfficientMemMI:
@@ -34,6 +38,7 @@ class EfficientMemMI:
         self.shard = shard
         self.loop = loop
         self._engine = None
+        self._pairs = None                        # PairsEngine when P > 1
         self._picked = 0
 
     # -- setup -----------------------------------------------------------------------------------
@@ -41,9 +46,8 @@ class EfficientMemMI:
     def init(self, clustering_combinations, candidates):
         """reference :27-30 -- empty table + candidate list."""
         self.combinations = [tuple(p) for p in clustering_combinations]
-        if len(self.combinations) != 1 or len(self.combinations[0]) != 2:
-            raise NotImplementedError(
-                "the CUDA engine handles one clustering pair (P = 1); got pairs %r" % (self.combinations,))
+        if not self.combinations or any(len(p) != 2 for p in self.combinations):
+            raise ValueError("every clustering combination must name two columns, got %r" % (self.combinations,))
         self.init_candidates(candidates)
         self.init_cache()
 
@@ -62,9 +66,14 @@ class EfficientMemMI:
             lo, hi = parallel.shard_bounds(W, rank, world)
             self._dist = dist
         self._range = (lo, hi)
-        pair = self.combinations[0]
+        self._W = W
         ids = self.candidate_ids[lo:hi]
         a = self.assignments
+        if len(self.combinations) > 1:            # rows of all clustering ids; PairsEngine keeps the columns it needs
+            self._cells = None
+            self._rows = a.index_select(0, ids.to(a.device))
+            return
+        pair = self.combinations[0]
         if a.device.type == 'cuda':
             cells = a.index_select(0, ids.to(a.device))[:, list(pair)].to(self.device).contiguous()
         else:
@@ -94,11 +103,15 @@ class EfficientMemMI:
         self.init_cache(max_picks=max_picks if max_picks is not None else min(self._W + 8, (1 << 24) - 8))
 
     def launches_per_iteration(self):
+        if self._pairs is not None:
+            return self._pairs.launches_per_iteration()
         if self._dist is not None and not self._nvlink:
             return 4                                   # gain, scan, emit, apply (+ one NCCL all-gather)
         return 3 if self._loop_mode() == _lib.MI_LOOP_KERNELS else 0      # persistent / cells: one launch per select()
 
     def loop_name(self):
+        if self._pairs is not None:
+            return "pairs" + ("+allgather" if self._dist is not None else "")
         if self._dist is not None:
             if self._nvlink:
                 return ("cells" if self._loop_mode() == _lib.MI_LOOP_CELLS else "persistent") + "+nvlink-mailbox"
@@ -114,6 +127,13 @@ class EfficientMemMI:
         if max_picks is None:
             max_picks = min(self._W + 8, (1 << 24) - 8)
         self._max_picks = int(max_picks)
+        self._picked = 0
+        self._nvlink = False
+        if len(self.combinations) > 1:
+            world = self.shard[1] if self.shard is not None else 1
+            self._pairs = PairsEngine(self.device, C, self.combinations, self._rows, lo, self._W, self._max_picks,
+                                      dist=self._dist, world=world)
+            return
         handle = _lib.c_vp()
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)
@@ -147,6 +167,9 @@ class EfficientMemMI:
         self._nvlink = True
 
     def _release(self):
+        if self._pairs is not None:
+            self._pairs.release()
+            self._pairs = None
         if self._engine is not None:
             _lib.load().acav_mi_destroy(self._engine)
             self._engine = None
@@ -161,6 +184,11 @@ class EfficientMemMI:
 
     def add_samples(self, ids):
         """reference :408-412 -- count samples into the table without selecting them."""
+        if self._pairs is not None:
+            for idx in ids:
+                self._pairs.add_sample(self.assignments[int(idx)].tolist())
+            self._picked += len(ids)
+            return
         pair = self.combinations[0]
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)
@@ -184,6 +212,9 @@ class EfficientMemMI:
         gains fp32[n]) as device tensors, without a host sync."""
         if self._picked + n_picks + 2 > self._max_picks:
             raise RuntimeError("engine was sized for %d picks" % self._max_picks)
+        if self._pairs is not None:
+            self._picked += n_picks
+            return self._pairs.select(n_picks)
         pos = torch.empty(n_picks, dtype=torch.int64, device=self.device)
         gain = torch.empty(n_picks, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -232,7 +263,10 @@ class EfficientMemMI:
         return (S, GAIN, timelapse, LOOKUPS)
 
     def read_state(self):
-        """Table counts and running sums (N [C,C], a [C], b [C], {NlogN, aloga, blogb, n}) for tests."""
+        """Table counts and running sums (N [C,C], a [C], b [C], {NlogN, aloga, blogb, n}) for tests; with P > 1
+        pairs every item gains a leading P axis."""
+        if self._pairs is not None:
+            return self._pairs.read_state()
         C = self.ncentroids
         N = torch.empty(C * C, dtype=torch.int32, device=self.device)
         a = torch.empty(C, dtype=torch.int32, device=self.device)

@@ -46,3 +46,21 @@ def empty_table_constants(C):
               xlogx(b).sum(-1)[0]]
     assert float(N[0, 0, 0] + 1) == 1.0 and float(a[0, 0] + 1) == 1.0 and float(n[0] + 1) == 1.0
     return np.array([float(c) for c in consts], dtype=np.float32)
+
+
+def pair_table_constants(P, C):
+    """fp32 [P, 6]: per clustering pair {fN0, fa0, n0, NlogN0, aloga0, blogb0} of the empty tables, as the reference's
+    ``init_cache`` (measures/mi.py:32-39, :297-308) produces them on its [P, C, C] tensors.  With two or more pairs every
+    output element of those reductions is summed serially by one thread (torch parallelises over outputs, not inside a
+    row), so the values do not depend on P; they are computed on a [2, C, C] tensor and repeated (checked against the
+    full shape in tests/test_mi_pairs_math_cpu.py).  One pair goes through `empty_table_constants`."""
+    if P == 1:
+        return empty_table_constants(C).reshape(1, 6)
+    N = torch.full((2, C, C), EPS)
+    a = N.sum(dim=1)
+    b = N.sum(dim=2)
+    n = a.sum(dim=-1)
+    xlogx = lambda v: v * v.log()
+    row = [xlogx(N[0, 0, 0]), xlogx(a[0, 0]), n[0], xlogx(N).sum([-1, -2])[0], xlogx(a).sum(-1)[0], xlogx(b).sum(-1)[0]]
+    assert float(N[0, 0, 0] + 1) == 1.0 and float(a[0, 0] + 1) == 1.0 and float(n[0] + 1) == 1.0
+    return np.tile(np.array([float(c) for c in row], dtype=np.float32), (P, 1))

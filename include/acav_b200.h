@@ -204,6 +204,53 @@ int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32
                        float *sums, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * greedy MI over P > 1 clustering pairs (EfficientMemMI with the `combination` / `bipartite` / `diagonal`
+ * pairings of subset_selection/code/pairing.py:5-41; the reference default is P = 45 pairs of ten clusterings)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct acav_mi_pairs acav_mi_pairs_t;
+
+/* Engine for `p` contingency tables of c x c cells over `w` candidates that carry `d` cluster ids each.
+ * pairs: HOST int32 [p, 2], the id columns (0..d-1) holding (c1, c2) of every pair (pairing.py, gather_pairs
+ * mi.py:310-320).  Limits: d <= 64, p <= 256, c <= 65535 (ACAV_E_UNSUPPORTED beyond).  `pos_base` as in
+ * acav_mi_create. */
+int acav_mi_pairs_create(acav_mi_pairs_t **out, int64_t w, int32_t d, int32_t c, int32_t p, const int32_t *pairs,
+                         int64_t max_picks, int64_t pos_base);
+int acav_mi_pairs_destroy(acav_mi_pairs_t *h);
+
+/* Candidate rows as the reference holds them (get_assignments mi.py:41-45): int64 [w, d] row-major on the
+ * device, row i = the d cluster ids of candidate i.  Stored as d uint16 columns inside the engine. */
+int acav_mi_pairs_load_candidates(acav_mi_pairs_t *h, const int64_t *ids, void *stream);
+
+/* logs as in acav_mi_set_tables; consts: HOST fp32 [p, 6] = per pair { x*log(x) of an empty cell, of an empty
+ * marginal, n0, NlogN0, aloga0, blogb0 } as init_cache (mi.py:32-39, 297-308) produces them for THIS p and c
+ * (the fp32 sums over the empty tables depend on the tensor shape).  Resets the tables. */
+int acav_mi_pairs_set_tables(acav_mi_pairs_t *h, const float *logs, int64_t n_logs, const float *consts,
+                             void *stream);
+
+/* add_samples (mi.py:408-412): counts one sample (HOST int64 [d] ids) into every table. */
+int acav_mi_pairs_add_sample(acav_mi_pairs_t *h, const int64_t *ids, void *stream);
+
+/* One greedy iteration split for multi-GPU use, as acav_mi_local_best / acav_mi_apply.  A record is
+ * acav_mi_pairs_record_words(h) = 1 + ceil(d / 4) uint64: the key ((orderable(mean score) << 32) |
+ * (0xFFFFFFFF - global position), 0 = no candidate left) followed by the winner's d ids, 16 bits each.
+ * The mean over pairs is added in the order torch's CPU `mean` uses (calc_score mi.py:76-80), so scores are
+ * bit-identical to the reference's.  apply: `records` = n consecutive records (all-gathered by the caller;
+ * n = 1 on one GPU); every rank applies the record with the largest key. */
+int acav_mi_pairs_record_words(const acav_mi_pairs_t *h);
+int acav_mi_pairs_local_best(acav_mi_pairs_t *h, uint64_t *record, void *stream);
+int acav_mi_pairs_apply(acav_mi_pairs_t *h, const uint64_t *records, int32_t n,
+                        int64_t *out_pos, float *out_gain, void *stream);
+
+/* Single-GPU greedy loop (run_greedy mi.py:150-192): n_picks iterations of local_best + apply. */
+int acav_mi_pairs_run(acav_mi_pairs_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain, void *stream);
+
+/* Introspection for tests: table counts (uint32 [p*c*c], [p*c], [p*c]) and running sums
+ * {NlogN, aloga, blogb, n} per pair (fp32 [p, 4]) to device buffers (any may be NULL). */
+int acav_mi_pairs_read_state(acav_mi_pairs_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows,
+                             float *sums, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * batch_mi, the reference CLI's default measure (subset_selection/code/measures/batch.py)
  * ---------------------------------------------------------------------------------------------- */
 

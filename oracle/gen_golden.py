@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU (this container only).
 
-TEST INFRASTRUCTURE ONLY.  Usage:  python oracle/gen_golden.py   (needs /root/reference mounted).
+TEST INFRASTRUCTURE ONLY.  Usage:  python oracle/gen_golden.py [case ...]   (needs /root/reference mounted).
 The reference never seeds its RNGs (SURVEY.md headline fact 4); this harness seeds torch / random /
 numpy itself and records the seed with every fixture.  Inputs are regenerated from the seed by
 ``acav100m_b200.synth`` (numpy legacy RandomState, frozen stream); a float64 checksum of the inputs
@@ -37,6 +37,10 @@ MI_CASES = {
     "mi_c20_shuffled": dict(v=600, c=20, dcols=2, subset=150, pairing="combination", shuffle=True, seed=1004),
     "mi_p3": dict(v=400, c=8, dcols=3, subset=80, pairing="combination", shuffle=False, seed=1005),
     "mi_dense_small": dict(v=300, c=6, dcols=2, subset=299, pairing="combination", shuffle=False, seed=1006),
+    # P = 10 and the reference default P = 45 (ten clusterings, `combination`): the mean over pairs goes through
+    # torch's vectorised inner-dimension sum (P >= 8), whose addition order the C oracle and the device restate
+    "mi_p10": dict(v=300, c=6, dcols=5, subset=60, pairing="combination", shuffle=False, seed=1008),
+    "mi_p45": dict(v=250, c=5, dcols=10, subset=50, pairing="combination", shuffle=True, seed=1009),
 }
 
 
@@ -142,6 +146,10 @@ def run_reference_batch_mi(case):
 def main():
     assert ref_shims.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
+    only = set(sys.argv[1:])                                        # optional: regenerate the named cases only
+    pick = lambda cases: {k: v for k, v in cases.items() if not only or k in only}
+    global KMEANS_CASES, MI_CASES, BATCH_MI_CASES
+    KMEANS_CASES, MI_CASES, BATCH_MI_CASES = pick(KMEANS_CASES), pick(MI_CASES), pick(BATCH_MI_CASES)
     for name, case in KMEANS_CASES.items():
         out = run_reference_kmeans(case)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)

@@ -179,3 +179,135 @@ double mi_oracle_scan_once(const int32_t *c1, const int32_t *c2, int64_t W, int3
     free(N); free(a); free(b); free(tbest); free(tvals);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * P > 1 clustering pairs.
+ *
+ *   measures/mi.py:285-295,310-320  calc_N / gather_pairs   candidate w, pair p -> (c1, c2) = (ids[w][pairs[p][0]],
+ *                                                           ids[w][pairs[p][1]])
+ *   measures/mi.py:76-80            calc_score              scores.mean(dim=-1) over the P pairs, then first max
+ *
+ * `mean(dim=-1)` of a contiguous fp32 [W, P] tensor is torch's CPU sum over the inner dimension followed by one
+ * division by P.  The sum is NOT a left-to-right loop: it is ATen's cascade_sum (ATen/native/cpu/SumKernel.cpp, an
+ * un-vendored dependency of the reference: torch, requirements.txt:2), restated below in the structure of that
+ * file -- multi_row_sum / row_sum / the inner-reduction drivers -- for its 8-lane float vectors.  The restatement
+ * is pinned against torch itself on random rows for P = 1..600 (tests/test_oracle_golden.py) and, through the
+ * greedy loop, against goldens produced by the unmodified reference for P = 3, 10 and 45.
+ * ---------------------------------------------------------------------------------------------- */
+
+#define ATEN_LANES 8          /* Vectorized<float>::size() of the sum kernel on this x86 build */
+#define ATEN_ILP 4
+#define ATEN_LEVELS 4
+
+static int ceil_log2_i64(int64_t x) {
+    int r = 0;
+    if (x <= 2) return 1;                       /* utils::CeilLog2 */
+    --x;
+    while (x > 0) { x >>= 1; ++r; }
+    return r;
+}
+
+/* multi_row_sum: `nrows` interleaved running sums (each `width` lanes wide) over `size` steps with cascade levels.
+ * in(i, k, l) = data[(i * row_stride + k * col_stride) + l]; out[k][l]. */
+static void multi_row_sum(const float *data, int64_t row_stride, int64_t col_stride, int64_t size, int width,
+                          float out[ATEN_ILP][ATEN_LANES]) {
+    int level_power = ceil_log2_i64(size) / ATEN_LEVELS;
+    if (level_power < 4) level_power = 4;
+    const int64_t level_step = (int64_t)1 << level_power, level_mask = level_step - 1;
+    float acc[ATEN_LEVELS][ATEN_ILP][ATEN_LANES];
+    memset(acc, 0, sizeof(acc));
+    int64_t i = 0;
+    for (; i + level_step <= size;) {
+        for (int64_t j = 0; j < level_step; ++j, ++i)
+            for (int k = 0; k < ATEN_ILP; ++k)
+                for (int l = 0; l < width; ++l) acc[0][k][l] += data[i * row_stride + k * col_stride + l];
+        for (int j = 1; j < ATEN_LEVELS; ++j) {
+            for (int k = 0; k < ATEN_ILP; ++k)
+                for (int l = 0; l < width; ++l) { acc[j][k][l] += acc[j - 1][k][l]; acc[j - 1][k][l] = 0.f; }
+            const int64_t mask = level_mask << (j * level_power);
+            if ((i & mask) != 0) break;
+        }
+    }
+    for (; i < size; ++i)
+        for (int k = 0; k < ATEN_ILP; ++k)
+            for (int l = 0; l < width; ++l) acc[0][k][l] += data[i * row_stride + k * col_stride + l];
+    for (int j = 1; j < ATEN_LEVELS; ++j)
+        for (int k = 0; k < ATEN_ILP; ++k)
+            for (int l = 0; l < width; ++l) acc[0][k][l] += acc[j][k][l];
+    memcpy(out, acc[0], sizeof(acc[0]));
+}
+
+/* row_sum over `size` elements of `width` lanes, consecutive elements `stride` floats apart */
+static void row_sum(const float *data, int64_t stride, int64_t size, int width, float out[ATEN_LANES]) {
+    float part[ATEN_ILP][ATEN_LANES];
+    const int64_t size_ilp = size / ATEN_ILP;
+    multi_row_sum(data, stride * ATEN_ILP, stride, size_ilp, width, part);
+    for (int64_t i = size_ilp * ATEN_ILP; i < size; ++i)
+        for (int l = 0; l < width; ++l) part[0][l] += data[i * stride + l];
+    for (int k = 1; k < ATEN_ILP; ++k)
+        for (int l = 0; l < width; ++l) part[0][l] += part[k][l];
+    memcpy(out, part[0], sizeof(float) * ATEN_LANES);
+}
+
+/* sum of one contiguous row of P floats: vectorized_inner_sum (P >= lanes) or scalar_inner_sum */
+float mi_oracle_aten_row_sum(const float *x, int64_t P) {
+    float v[ATEN_LANES];
+    if (P < ATEN_LANES) {
+        row_sum(x, 1, P, 1, v);
+        return v[0];
+    }
+    const int64_t vec_size = P / ATEN_LANES;
+    row_sum(x, ATEN_LANES, vec_size, ATEN_LANES, v);
+    float acc = 0.f;
+    for (int64_t k = vec_size * ATEN_LANES; k < P; ++k) acc += x[k];
+    for (int l = 0; l < ATEN_LANES; ++l) acc += v[l];
+    return acc;
+}
+
+float mi_oracle_aten_row_mean(const float *x, int64_t P) { return mi_oracle_aten_row_sum(x, P) / (float)P; }
+
+/* Literal greedy scan over P pairs.  ids: int32 [W, D] row-major; pairs: int32 [P, 2] columns of ids;
+ * consts: [P, 6] as load_consts, per pair.  out_sums (may be NULL): final [P, 4] NlogN, aloga, blogb, n. */
+int64_t mi_oracle_greedy_pairs(const int32_t *ids, int64_t W, int32_t D, int32_t C, const int32_t *pairs, int32_t P,
+                               const float *logs, int64_t nlogs, const float *consts, int64_t n_picks,
+                               int64_t *out_pos, float *out_gain, float *out_sums) {
+    (void)nlogs;
+    mi_scalars *s = malloc(sizeof(mi_scalars) * (size_t)P);
+    for (int p = 0; p < P; ++p) load_consts(&s[p], consts + 6 * p);
+    const int64_t cc = (int64_t)C * C;
+    int64_t *N = calloc((size_t)P * cc, sizeof(int64_t));
+    int64_t *a = calloc((size_t)P * C, sizeof(int64_t));
+    int64_t *b = calloc((size_t)P * C, sizeof(int64_t));
+    uint8_t *gone = calloc((size_t)(W > 0 ? W : 1), 1);
+    float *row = malloc(sizeof(float) * (size_t)P);
+    float *tmp = malloc(sizeof(float) * 3 * (size_t)P), *win = malloc(sizeof(float) * 3 * (size_t)P);
+    int64_t it;
+    for (it = 0; it < n_picks; ++it) {
+        int64_t best = -1; float bs = 0.f;
+        for (int64_t w = 0; w < W; ++w) {
+            if (gone[w]) continue;
+            for (int p = 0; p < P; ++p) {
+                const int64_t c1 = ids[w * D + pairs[2 * p]], c2 = ids[w * D + pairs[2 * p + 1]];
+                row[p] = cell_score(&s[p], N[p * cc + c1 * C + c2], a[(int64_t)p * C + c2], b[(int64_t)p * C + c1], logs,
+                                    &tmp[3 * p], &tmp[3 * p + 1], &tmp[3 * p + 2]);
+            }
+            const float sc = mi_oracle_aten_row_mean(row, P);
+            if (best < 0 || sc > bs) { best = w; bs = sc; memcpy(win, tmp, sizeof(float) * 3 * (size_t)P); }
+        }
+        if (best < 0) break;
+        out_pos[it] = best; out_gain[it] = bs;
+        for (int p = 0; p < P; ++p) {
+            const int64_t c1 = ids[best * D + pairs[2 * p]], c2 = ids[best * D + pairs[2 * p + 1]];
+            s[p].NlogN = win[3 * p]; s[p].aloga = win[3 * p + 1]; s[p].blogb = win[3 * p + 2]; s[p].n = s[p].n + 1.0f;
+            N[p * cc + c1 * C + c2] += 1; a[(int64_t)p * C + c2] += 1; b[(int64_t)p * C + c1] += 1;
+        }
+        gone[best] = 1;
+    }
+    if (out_sums)
+        for (int p = 0; p < P; ++p) {
+            out_sums[4 * p] = s[p].NlogN; out_sums[4 * p + 1] = s[p].aloga; out_sums[4 * p + 2] = s[p].blogb;
+            out_sums[4 * p + 3] = s[p].n;
+        }
+    free(s); free(N); free(a); free(b); free(gone); free(row); free(tmp); free(win);
+    return it;
+}

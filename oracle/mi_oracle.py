@@ -14,7 +14,9 @@ Two forms are provided:
 * ``greedy_mem_mi``      -- torch restatement, any number of clustering pairs P, O(W*P) per iteration;
 * ``greedy_mem_mi_c``    -- the plain-C restatement in ``oracle/mi_oracle.c`` (P = 1), either as the
                            literal per-candidate scan or bucketed by contingency-table cell
-                           (same picks, O(C*C) per iteration) so that full-size configs finish on CPU.
+                           (same picks, O(C*C) per iteration) so that full-size configs finish on CPU;
+* ``greedy_mem_mi_pairs_c`` -- plain C, any P: literal scan with the mean over pairs added in the order of torch's
+                           CPU reduction kernel (restated in mi_oracle.c, pinned against torch and the goldens).
 """
 import ctypes
 import itertools
@@ -207,6 +209,12 @@ def _lib():
             fn.restype = ctypes.c_int64
             fn.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int32, f32p, ctypes.c_int64,
                            f32p, ctypes.c_int64, i64p, f32p]
+        lib.mi_oracle_aten_row_mean.restype = ctypes.c_float
+        lib.mi_oracle_aten_row_mean.argtypes = [f32p, ctypes.c_int64]
+        lib.mi_oracle_greedy_pairs.restype = ctypes.c_int64
+        lib.mi_oracle_greedy_pairs.argtypes = [i32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, i32p,
+                                               ctypes.c_int32, f32p, ctypes.c_int64, f32p, ctypes.c_int64, i64p,
+                                               f32p, f32p]
         lib.mi_oracle_scan_once.restype = ctypes.c_double
         lib.mi_oracle_scan_once.argtypes = [i32p, i32p, ctypes.c_int64, ctypes.c_int32, f32p,
                                             ctypes.c_int64, f32p, ctypes.c_int32, ctypes.c_int32]
@@ -239,6 +247,46 @@ def greedy_mem_mi_c(c1, c2, C, n_picks, bucketed=True):
               as_p(pos, ctypes.c_int64), as_p(gain, ctypes.c_float))
     assert done == n_picks, (done, n_picks)
     return pos, gain
+
+
+def pair_constants(P, C):
+    """Per pair {fN0, fa0, n0, NlogN0, aloga0, blogb0} of the empty tables, computed on the [P, C, C] tensors the
+    reference builds (mi.py:32-39, :297-308): the fp32 sums over the empty tables depend on the tensor shape."""
+    tab = init_table(P, C)
+    out = np.zeros((P, 6), dtype=np.float32)
+    for p in range(P):
+        out[p] = [float(_xlogx(tab['N'][p, 0, 0])), float(_xlogx(tab['a'][p, 0])), float(tab['n'][p]),
+                  float(tab['NlogN'][p]), float(tab['aloga'][p]), float(tab['blogb'][p])]
+        assert float(tab['N'][p, 0, 0] + 1) == 1.0 and float(tab['a'][p, 0] + 1) == 1.0 and float(tab['n'][p] + 1) == 1.0
+    return out
+
+
+def aten_row_mean(row):
+    """`row.mean()` of a contiguous fp32 row as torch's CPU inner-dimension reduction adds it (mi_oracle.c)."""
+    row = np.ascontiguousarray(row, dtype=np.float32)
+    return float(_lib().mi_oracle_aten_row_mean(row.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), len(row)))
+
+
+def greedy_mem_mi_pairs_c(ids, C, pairs, n_picks, return_sums=False):
+    """Exact greedy over P clustering pairs (literal scan, plain C).  ids: int [W, D] cluster ids of the candidates in
+    list order; pairs: [(col1, col2)] * P.  Returns (positions int64[n], gains fp32[n]) (+ final sums [P, 4])."""
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    W, D = ids.shape
+    pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    P = len(pr)
+    n_picks = int(min(n_picks, W))
+    logs = log_table(n_picks + 2)
+    consts = np.ascontiguousarray(pair_constants(P, C))
+    pos = np.zeros(n_picks, dtype=np.int64)
+    gain = np.zeros(n_picks, dtype=np.float32)
+    sums = np.zeros((P, 4), dtype=np.float32)
+    as_p = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    done = _lib().mi_oracle_greedy_pairs(as_p(ids, ctypes.c_int32), W, D, C, as_p(pr, ctypes.c_int32), P,
+                                         as_p(logs, ctypes.c_float), len(logs), as_p(consts, ctypes.c_float), n_picks,
+                                         as_p(pos, ctypes.c_int64), as_p(gain, ctypes.c_float),
+                                         as_p(sums, ctypes.c_float))
+    assert done == n_picks, (done, n_picks)
+    return (pos, gain, sums) if return_sums else (pos, gain)
 
 
 def scan_once_seconds(c1, c2, C, repeats, threads):

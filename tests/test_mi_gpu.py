@@ -125,8 +125,8 @@ def test_two_engines_sharded_equal_one_engine():
 def test_errors():
     a = synth.zipf_pairs(50, 4, 1)
     m = gpu_measure(a, 4)
-    with pytest.raises(NotImplementedError):
-        m.init([(0, 1), (0, 1)], list(range(50)))
+    with pytest.raises(ValueError):
+        m.init([(0, 1, 1)], list(range(50)))
     m.init([(0, 1)], list(range(1, 50)))
     with pytest.raises(RuntimeError):
         m.run_greedy(80, [0])
