@@ -592,12 +592,14 @@ struct acav_mi_dense {
     MiDense s;
     float *per_pair;
     int64_t per_pair_cap;
+    double *ami_scratch;         // 4*P*C + P doubles, allocated on the first acav_mi_dense_score_ami
 };
 
 int acav_mi_dense_destroy(acav_mi_dense_t *h) {
     if (!h) return 0;
     cudaFree(h->s.n_cells); cudaFree(h->s.a_cols); cudaFree(h->s.b_rows); cudaFree(h->s.n); cudaFree(h->s.sums);
     cudaFree(h->per_pair);
+    cudaFree(h->ami_scratch);
     delete h;
     return 0;
 }
@@ -607,7 +609,7 @@ int acav_mi_dense_create(acav_mi_dense_t **out, int32_t p, int32_t c, void *stre
     *out = nullptr;
     acav_mi_dense *h = new (std::nothrow) acav_mi_dense();
     if (!h) return (int)cudaErrorMemoryAllocation;
-    h->s = MiDense(); h->s.p = p; h->s.c = c; h->per_pair = nullptr; h->per_pair_cap = 0;
+    h->s = MiDense(); h->s.p = p; h->s.c = c; h->per_pair = nullptr; h->per_pair_cap = 0; h->ami_scratch = nullptr;
     int rc = dev_alloc(&h->s.n_cells, (size_t)p * c * c, nullptr);
     if (!rc) rc = dev_alloc(&h->s.a_cols, (size_t)p * c, nullptr);
     if (!rc) rc = dev_alloc(&h->s.b_rows, (size_t)p * c, nullptr);
@@ -624,22 +626,46 @@ int acav_mi_dense_add(acav_mi_dense_t *h, const int64_t *cells, int64_t m, void 
     return launch_mi_dense_add(h->s, cells, m, (cudaStream_t)stream);
 }
 
+namespace {
+// per-(candidate, pair) scratch of the dense scorers when the caller does not ask for the per-pair values
+int dense_per_pair(acav_mi_dense *h, int64_t nb, float *per_pair, float **out, cudaStream_t st) {
+    *out = per_pair;
+    if (per_pair) return 0;
+    if (h->per_pair_cap < nb * h->s.p) {
+        ACAV_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(h->per_pair);
+        h->per_pair = nullptr;
+        h->per_pair_cap = 0;
+        int rc = dev_alloc(&h->per_pair, (size_t)(nb * h->s.p), nullptr);
+        if (rc) return rc;
+        h->per_pair_cap = nb * h->s.p;
+    }
+    *out = h->per_pair;
+    return 0;
+}
+}  // namespace
+
 int acav_mi_dense_score(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, float *scores, float *per_pair,
                         void *stream) {
     if (!h || nb < 0 || (nb > 0 && (!cells || !scores))) return ACAV_E_INVALID;
-    float *pp = per_pair;
-    if (!pp) {
-        if (h->per_pair_cap < nb * h->s.p) {
-            ACAV_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-            cudaFree(h->per_pair);
-            h->per_pair = nullptr;
-            int rc = dev_alloc(&h->per_pair, (size_t)(nb * h->s.p), nullptr);
-            if (rc) return rc;
-            h->per_pair_cap = nb * h->s.p;
-        }
-        pp = h->per_pair;
-    }
+    float *pp = nullptr;
+    int rc = dense_per_pair(h, nb, per_pair, &pp, (cudaStream_t)stream);
+    if (rc) return rc;
     return launch_mi_dense_score(h->s, cells, nb, pp, scores, (cudaStream_t)stream);
+}
+
+int acav_mi_dense_score_ami(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, int32_t average_method,
+                            float *scores, float *per_pair, void *stream) {
+    if (!h || nb < 0 || (nb > 0 && (!cells || !scores)) || average_method < 0 || average_method > 2) return ACAV_E_INVALID;
+    if (h->s.p > 65535) return ACAV_E_UNSUPPORTED;                     // grid.y of the line sums
+    float *pp = nullptr;
+    int rc = dense_per_pair(h, nb, per_pair, &pp, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (!h->ami_scratch) {
+        rc = dev_alloc(&h->ami_scratch, (size_t)4 * h->s.p * h->s.c + (size_t)h->s.p, nullptr);
+        if (rc) return rc;
+    }
+    return launch_mi_dense_score_ami(h->s, cells, nb, h->ami_scratch, average_method, pp, scores, (cudaStream_t)stream);
 }
 
 int acav_mi_read_state(acav_mi_t *h, uint32_t *n_cells, uint32_t *a_cols, uint32_t *b_rows, float *sums,

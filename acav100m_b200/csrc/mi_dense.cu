@@ -14,6 +14,7 @@
 // for this measure; scores are checked to 1e-5 (tests/test_batch_mi_gpu.py).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "mi_ami_math.h"
 
 namespace acav {
 
@@ -80,6 +81,98 @@ __global__ void mi_dense_mean_kernel(const float *__restrict__ per_pair, int64_t
     float acc = 0.f;
     for (int32_t j = 0; j < p; ++j) acc = __fadd_rn(acc, per_pair[b * p + j]);
     scores[b] = __fdiv_rn(acc, (float)p);
+}
+
+// ---- adjusted MI (`ami`, reference measures/mi.py:212-262) -------------------------------------------------------------
+// The reference evaluates nine lgamma per cell of every candidate's dense table: O(W*P*C*C) per iteration.  Adding one
+// sample to cell (i, j) changes n (every cell), a_j (column j) and b_i (row i), so with the per-iteration sums of
+// mi_ami_math.h -- over the whole table, per row and per column, each with and without the marginal bumped, all at
+// n + 1 samples -- a candidate's EMI is four corrections: O(P*C*C) per iteration for the sums, O(1) per candidate.
+
+__device__ __forceinline__ double block_sum_f64(double v, double *scratch) {
+    v = warp_sum_f64(v);
+    if (threadIdx.x % kWarp == 0) scratch[threadIdx.x / kWarp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int wi = 0; wi < (int)(blockDim.x / kWarp); ++wi) t += scratch[wi];
+    __syncthreads();
+    return t;                                   // valid in thread 0
+}
+
+// grid (C, P, 2): z = 0 sums row blockIdx.x over its columns, z = 1 sums column blockIdx.x over its rows
+__global__ void __launch_bounds__(128) mi_dense_ami_lines_kernel(MiDense s, double *__restrict__ line,
+                                                                 double *__restrict__ line_up) {
+    __shared__ double scratch[4];
+    const int32_t q = blockIdx.x, p = blockIdx.y;
+    const bool rows = blockIdx.z == 0;
+    const int64_t o = (int64_t)p * s.c;
+    const uint32_t m = s.n[p] + 1u;
+    const double c = (double)s.c;
+    double acc = 0.0, acc_up = 0.0;
+    for (int32_t t = threadIdx.x; t < s.c; t += blockDim.x) {
+        const int32_t i = rows ? q : t, j = rows ? t : q;
+        const uint32_t x = s.n_cells[(o + i) * s.c + j], y = s.a_cols[o + j], z = s.b_rows[o + i];
+        acc += ami_emi_term(x, y, z, m, c);
+        acc_up += rows ? ami_emi_term(x, y, z + 1u, m, c) : ami_emi_term(x, y + 1u, z, m, c);
+    }
+    const int64_t out = ((int64_t)blockIdx.z * s.p + p) * s.c + q;
+    acc = block_sum_f64(acc, scratch);
+    acc_up = block_sum_f64(acc_up, scratch);
+    if (threadIdx.x == 0) { line[out] = acc; line_up[out] = acc_up; }
+}
+
+// base[p] = sum over the rows of pair p
+__global__ void __launch_bounds__(128) mi_dense_ami_base_kernel(MiDense s, const double *__restrict__ line,
+                                                                double *__restrict__ base) {
+    __shared__ double scratch[4];
+    const int32_t p = blockIdx.x;
+    double acc = 0.0;
+    for (int32_t i = threadIdx.x; i < s.c; i += blockDim.x) acc += line[(int64_t)p * s.c + i];
+    acc = block_sum_f64(acc, scratch);
+    if (threadIdx.x == 0) base[p] = acc;
+}
+
+// AMI of (table + one sample) for every (candidate, pair)
+__global__ void mi_dense_ami_score_kernel(MiDense s, const int64_t *__restrict__ cells, int64_t nb,
+                                          const double *__restrict__ line, const double *__restrict__ line_up,
+                                          const double *__restrict__ base, int32_t average_method,
+                                          float *__restrict__ per_pair) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb * s.p) return;
+    const int p = (int)(i % s.p);
+    const double e = dense_eps(), c = (double)s.c;
+    const int32_t c1 = (int32_t)cells[i * 2], c2 = (int32_t)cells[i * 2 + 1];
+    const int64_t o = (int64_t)p * s.c;
+    const uint32_t x = s.n_cells[(o + c1) * s.c + c2], y = s.a_cols[o + c2], z = s.b_rows[o + c1];
+    const double nlogn = s.sums[3 * p] + xlogx_d(x + 1, e) - xlogx_d(x, e);
+    const double aloga = s.sums[3 * p + 1] + xlogx_d(y + 1, c * e) - xlogx_d(y, c * e);
+    const double blogb = s.sums[3 * p + 2] + xlogx_d(z + 1, c * e) - xlogx_d(z, c * e);
+    const uint32_t m = s.n[p] + 1u;
+    const double n1 = (double)m, logn = log(n1);
+    const double mi = (nlogn - aloga - blogb) / n1 + logn;
+    const double ha = logn - aloga / n1, hb = logn - blogb / n1;         // -sum a/n log(a/n), sum a = n
+    const int64_t cols = (int64_t)s.p * s.c;                               // lines of z = 1 follow those of z = 0
+    const double emi = ami_emi_with_sample(base[p], line[o + c1], line_up[o + c1], line[cols + o + c2],
+                                           line_up[cols + o + c2], x, y, z, m, c);
+    per_pair[i] = (float)ami_from_parts(mi, emi, ha, hb, average_method);
+}
+
+int launch_mi_dense_score_ami(const MiDense &s, const int64_t *cells, int64_t nb, double *scratch, int32_t average_method,
+                              float *per_pair, float *scores, cudaStream_t st) {
+    if (nb == 0) return 0;
+    const int64_t lines = 2 * (int64_t)s.p * s.c;
+    double *line = scratch, *line_up = scratch + lines, *base = scratch + 2 * lines;
+    mi_dense_ami_lines_kernel<<<dim3((unsigned)s.c, (unsigned)s.p, 2), 128, 0, st>>>(s, line, line_up);
+    ACAV_LAUNCH_CHECK();
+    mi_dense_ami_base_kernel<<<(unsigned)s.p, 128, 0, st>>>(s, line, base);
+    ACAV_LAUNCH_CHECK();
+    mi_dense_ami_score_kernel<<<(unsigned)ceil_div(nb * s.p, 128), 128, 0, st>>>(s, cells, nb, line, line_up, base,
+                                                                                 average_method, per_pair);
+    ACAV_LAUNCH_CHECK();
+    mi_dense_mean_kernel<<<(unsigned)ceil_div(nb, 128), 128, 0, st>>>(per_pair, nb, s.p, scores);
+    ACAV_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_mi_dense_reset(const MiDense &s, cudaStream_t st) {

@@ -270,6 +270,17 @@ int acav_mi_dense_add(acav_mi_dense_t *h, const int64_t *cells, int64_t m, void 
 int acav_mi_dense_score(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, float *scores, float *per_pair,
                         void *stream);
 
+/* The same for the adjusted-MI measure `ami` (EfficientAMI, mi.py:212-262): scores[i] = mean over pairs of
+ * (MI - EMI) / max(generalized_mean(H_a, H_b) - EMI, eps) of (table_p + one-hot(candidate i)), with the reference's
+ * single-term EMI (calc_EMI :217-231), evaluated in fp64.  average_method: 0 arithmetic, 1 max, 2 min
+ * (generalized_mean :200-209).  Cost per call: O(P*C*C) for the row / column sums of the EMI terms plus O(1) per
+ * (candidate, pair) -- the reference's dense evaluation is O(nb*P*C*C). */
+#define ACAV_AMI_ARITHMETIC 0
+#define ACAV_AMI_MAX        1
+#define ACAV_AMI_MIN        2
+int acav_mi_dense_score_ami(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, int32_t average_method,
+                            float *scores, float *per_pair, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

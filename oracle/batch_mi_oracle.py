@@ -45,6 +45,43 @@ def dense_mi(last):
     return (N / n * (N.log() + n.log() - (a.log() + b.log()))).sum([2, 3])
 
 
+def dense_emi(last):
+    """``EfficientAMI.calc_EMI`` mi.py:217-231 -> [m, P].  (One hypergeometric term per cell, evaluated at the cell's
+    own count -- not sklearn's sum over all possible counts; restated as the reference has it.)"""
+    N = last['N']
+    a = last['a'].unsqueeze(2)
+    b = last['b'].unsqueeze(3)
+    n = last['n'].unsqueeze(-1).unsqueeze(-1)
+    term1 = (N / n * (N.log() + n.log() - (a.log() + b.log())))
+    log_term2 = (a + 1).lgamma() + (b + 1).lgamma() + (n - a + 1).lgamma() + (n - b + 1).lgamma() \
+        - ((n + 1).lgamma() + (N + 1).lgamma() + (a - N + 1).lgamma() + (b - N + 1).lgamma()
+           + (n - a - b + N + 1).lgamma())
+    return (term1 * log_term2.exp()).sum([2, 3])
+
+
+def entropies(last):
+    """``calc_entropy`` / ``calc_entropies`` mi.py:233-245 -> (ha [m, P], hb [m, P])."""
+    n = last['n'].unsqueeze(-1)
+    pa, pb = last['a'] / n, last['b'] / n
+    return -(pa * pa.log()).sum(dim=-1), -(pb * pb.log()).sum(dim=-1)
+
+
+def dense_ami(last, average_method='arithmetic'):
+    """``EfficientAMI.calc_AMI`` mi.py:247-262 with ``generalized_mean`` :200-209 and ``ensure_nonzero`` :193-198."""
+    mi = dense_mi(last)
+    emi = dense_emi(last)
+    ha, hb = entropies(last)
+    if average_method == 'max':
+        normalizer = torch.max(ha, hb)
+    elif average_method == 'min':
+        normalizer = torch.min(ha, hb)
+    else:
+        normalizer = (ha + hb) / 2
+    denominator = normalizer - emi
+    denominator = torch.max(denominator, torch.full(denominator.shape, EPS, dtype=denominator.dtype))
+    return (mi - emi) / denominator
+
+
 def modify_k(k, B, subset_size, dataset_size, keep_unselected):
     """batch.py:173-188."""
     term = B * subset_size / dataset_size
@@ -91,21 +128,25 @@ def greedy_batch_mi(assignments, ncentroids, pairs, candidates, subset_size, sta
     return S[:subset_size], GAIN
 
 
-def greedy_dense_mi(assignments, ncentroids, pairs, candidates, subset_size, start_indices, follow=None):
-    """``EfficientMI.run_greedy`` mi.py:150-192 with the dense ``calc_MI`` (:85-91) -> (S, GAIN, per-iteration
-    score vectors).  The start indices are in S but never in the table.  `follow`: optional list of picks to
-    adopt instead of the arg-max (teacher forcing for the GPU tests)."""
+def greedy_dense_mi(assignments, ncentroids, pairs, candidates, subset_size, start_indices, follow=None,
+                    measure='mi', average_method='arithmetic', dtype=torch.float32):
+    """``EfficientMI.run_greedy`` mi.py:150-192 with the dense ``calc_MI`` (:85-91) -- or, measure='ami', with
+    ``EfficientAMI.calc_AMI`` (:247-262) -- -> (S, GAIN, per-iteration score vectors).  The start indices are in S but
+    never in the table.  `follow`: optional list of picks to adopt instead of the arg-max (teacher forcing for the GPU
+    tests).  dtype=float64 evaluates the same expressions in double precision: the value the reference's fp32 tensors
+    approximate (its lgamma differences cancel catastrophically, see tests/test_ami_cpu.py)."""
     a = torch.from_numpy(np.asarray(assignments)).to(torch.long)
     C, P = ncentroids, len(pairs)
-    N = torch.full((P, C, C), EPS)                                # init_cache mi.py:32-39
+    N = torch.full((P, C, C), EPS, dtype=dtype)                   # init_cache mi.py:32-39
     cache = {'N': N, 'a': N.sum(dim=1), 'b': N.sum(dim=2)}
     cache['n'] = cache['a'].sum(dim=-1)
     cand = torch.as_tensor(list(candidates), dtype=torch.long)
     S, GAIN, ALL = list(start_indices), [], []
     for j in range(len(start_indices), subset_size - 1):
         tabs = sample_tables(a, pairs, cand, C)
-        last = {key: cache[key].unsqueeze(0) + tabs[key] for key in tabs}   # get_last mi.py:93-98
-        scores = dense_mi(last).mean(dim=-1)                                # calc_score :76-80
+        last = {key: cache[key].unsqueeze(0) + tabs[key].to(dtype) for key in tabs}   # get_last mi.py:93-98
+        per_pair = dense_mi(last) if measure == 'mi' else dense_ami(last, average_method)
+        scores = per_pair.mean(dim=-1)                                      # calc_score :76-80
         score, idx = scores.max(dim=0)
         ALL.append((scores.clone(), cand.clone()))
         if follow is not None:

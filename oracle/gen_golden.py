@@ -44,6 +44,12 @@ MI_CASES = {
 }
 
 
+AMI_CASES = {
+    # adjusted MI (measures/mi.py:212-262): dense toy-size measure, reachable as --measure_name=ami
+    "ami_small": dict(v=200, c=5, dcols=2, subset=60, pairing="combination", shuffle=False, seed=1010),
+    "ami_p3": dict(v=150, c=4, dcols=3, subset=40, pairing="combination", shuffle=False, seed=1011),
+}
+
 BATCH_MI_CASES = {
     # the reference CLI's default measure (config.py:45): B = 20 candidates per iteration, keep top k = 4
     "bmi_p3": dict(v=400, c=8, dcols=3, subset=80, seed=1005, keep_unselected=True),
@@ -148,8 +154,9 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     only = set(sys.argv[1:])                                        # optional: regenerate the named cases only
     pick = lambda cases: {k: v for k, v in cases.items() if not only or k in only}
-    global KMEANS_CASES, MI_CASES, BATCH_MI_CASES
+    global KMEANS_CASES, MI_CASES, BATCH_MI_CASES, AMI_CASES
     KMEANS_CASES, MI_CASES, BATCH_MI_CASES = pick(KMEANS_CASES), pick(MI_CASES), pick(BATCH_MI_CASES)
+    AMI_CASES = pick(AMI_CASES)
     for name, case in KMEANS_CASES.items():
         out = run_reference_kmeans(case)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
@@ -160,6 +167,10 @@ def main():
             out = run_reference_mi(case, measure)
             np.savez_compressed(os.path.join(GOLDEN, f"{name}_{measure}.npz"), **out)
             print(name, measure, "|S|", len(out["S"]), out["S"][:8].tolist(), out["GAIN"][:3].tolist())
+    for name, case in AMI_CASES.items():
+        out = run_reference_mi(case, "ami")
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, "ami |S|", len(out["S"]), out["S"][:8].tolist(), out["GAIN"][:3].tolist())
     for name, case in BATCH_MI_CASES.items():
         out = run_reference_batch_mi(case)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)

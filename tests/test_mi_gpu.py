@@ -134,8 +134,6 @@ def test_errors():
     with pytest.raises(ValueError):
         bad.init([(0, 1)], list(range(50)))
     from acav100m_b200.subset_selection import get_measure
-    with pytest.raises(NotImplementedError):
-        get_measure("ami")
     with pytest.raises(AssertionError):
         get_measure("nope")
 
