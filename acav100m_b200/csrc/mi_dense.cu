@@ -86,8 +86,9 @@ __global__ void mi_dense_mean_kernel(const float *__restrict__ per_pair, int64_t
 // ---- adjusted MI (`ami`, reference measures/mi.py:212-262) -------------------------------------------------------------
 // The reference evaluates nine lgamma per cell of every candidate's dense table: O(W*P*C*C) per iteration.  Adding one
 // sample to cell (i, j) changes n (every cell), a_j (column j) and b_i (row i), so with the per-iteration sums of
-// mi_ami_math.h -- over the whole table, per row and per column, each with and without the marginal bumped, all at
-// n + 1 samples -- a candidate's EMI is four corrections: O(P*C*C) per iteration for the sums, O(1) per candidate.
+// mi_ami_math.h -- the per-cell shares of MI - EMI over the whole table, per row and per column, each with and without
+// the marginal bumped, all at n + 1 samples -- a candidate's MI - EMI is four corrections: O(P*C*C) per iteration for
+// the sums, O(1) per candidate.
 
 __device__ __forceinline__ double block_sum_f64(double v, double *scratch) {
     v = warp_sum_f64(v);
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(128) mi_dense_ami_lines_kernel(MiDense s, doub
     for (int32_t t = threadIdx.x; t < s.c; t += blockDim.x) {
         const int32_t i = rows ? q : t, j = rows ? t : q;
         const uint32_t x = s.n_cells[(o + i) * s.c + j], y = s.a_cols[o + j], z = s.b_rows[o + i];
-        acc += ami_emi_term(x, y, z, m, c);
-        acc_up += rows ? ami_emi_term(x, y, z + 1u, m, c) : ami_emi_term(x, y + 1u, z, m, c);
+        acc += ami_gap_term(x, y, z, m, c);
+        acc_up += rows ? ami_gap_term(x, y, z + 1u, m, c) : ami_gap_term(x, y + 1u, z, m, c);
     }
     const int64_t out = ((int64_t)blockIdx.z * s.p + p) * s.c + q;
     acc = block_sum_f64(acc, scratch);
@@ -153,9 +154,9 @@ __global__ void mi_dense_ami_score_kernel(MiDense s, const int64_t *__restrict__
     const double mi = (nlogn - aloga - blogb) / n1 + logn;
     const double ha = logn - aloga / n1, hb = logn - blogb / n1;         // -sum a/n log(a/n), sum a = n
     const int64_t cols = (int64_t)s.p * s.c;                               // lines of z = 1 follow those of z = 0
-    const double emi = ami_emi_with_sample(base[p], line[o + c1], line_up[o + c1], line[cols + o + c2],
+    const double gap = ami_gap_with_sample(base[p], line[o + c1], line_up[o + c1], line[cols + o + c2],
                                            line_up[cols + o + c2], x, y, z, m, c);
-    per_pair[i] = (float)ami_from_parts(mi, emi, ha, hb, average_method);
+    per_pair[i] = (float)ami_from_parts(mi, gap, ha, hb, average_method);
 }
 
 int launch_mi_dense_score_ami(const MiDense &s, const int64_t *cells, int64_t nb, double *scratch, int32_t average_method,

@@ -32,10 +32,10 @@ void host_ami_scores(const uint32_t *N, int32_t C, const int32_t *cells, int64_t
     for (int i = 0; i < C; ++i)
         for (int j = 0; j < C; ++j) {
             const uint32_t x = N[i * C + j];
-            const double f = ami_emi_term(x, a[j], b[i], m, c);
+            const double f = ami_gap_term(x, a[j], b[i], m, c);
             row[i] += f; col[j] += f;
-            row_up[i] += ami_emi_term(x, a[j], b[i] + 1, m, c);
-            col_up[j] += ami_emi_term(x, a[j] + 1, b[i], m, c);
+            row_up[i] += ami_gap_term(x, a[j], b[i] + 1, m, c);
+            col_up[j] += ami_gap_term(x, a[j] + 1, b[i], m, c);
         }
     double base = 0;                                                              // mi_dense_ami_base_kernel
     for (int i = 0; i < C; ++i) base += row[i];
@@ -48,8 +48,8 @@ void host_ami_scores(const uint32_t *N, int32_t C, const int32_t *cells, int64_t
         const double n1 = (double)m, logn = log(n1);
         const double mi = (nl - al - bl) / n1 + logn;
         const double ha = logn - al / n1, hb = logn - bl / n1;
-        const double emi = ami_emi_with_sample(base, row[c1], row_up[c1], col[c2], col_up[c2], x, y, z, m, c);
-        out[w] = ami_from_parts(mi, emi, ha, hb, average_method);
+        const double gap = ami_gap_with_sample(base, row[c1], row_up[c1], col[c2], col_up[c2], x, y, z, m, c);
+        out[w] = ami_from_parts(mi, gap, ha, hb, average_method);
     }
 }
 

@@ -81,6 +81,52 @@ def test_kernel_arithmetic_equals_dense_fp64_evaluation(host_ami, C, n, method, 
         np.testing.assert_allclose(out, want32, rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", AMI)
+def test_kernel_arithmetic_follows_the_reference_run(host_ami, golden_dir, name):
+    """The GPU test's replay (tests/test_zz_ami_gpu.py) with the host build standing in for the kernels: teacher-forced
+    along the reference's own `ami` run, every candidate's score within 1e-5 of the reference's fp32 value and 1e-6 of
+    the fp64 evaluation at every iteration."""
+    g, a, order, pairs = _golden(golden_dir, name)
+    C, subset, S_ref = int(g["c"]), int(g["subset"]), g["S"].tolist()
+    _, _, ALL = bo.greedy_dense_mi(a, C, pairs, order[1:], subset, [order[0]], follow=S_ref[1:], measure="ami")
+    _, _, ALL64 = bo.greedy_dense_mi(a, C, pairs, order[1:], subset, [order[0]], follow=S_ref[1:], measure="ami",
+                                     dtype=torch.float64)
+    tables = [np.zeros((C, C), dtype=np.uint32) for _ in pairs]
+    for it, ((want, cand), (want64, _)) in enumerate(zip(ALL, ALL64)):
+        per_pair = np.zeros((len(cand), len(pairs)), dtype=np.float32)
+        for p, (c1, c2) in enumerate(pairs):
+            cells = np.ascontiguousarray(a[cand.numpy()][:, [c1, c2]], dtype=np.int32)
+            out = np.zeros(len(cells), dtype=np.float64)
+            host_ami.host_ami_scores(tables[p].ctypes.data, C, cells.ctypes.data, len(cells), 0, out.ctypes.data)
+            per_pair[:, p] = out.astype(np.float32)
+        got = np.zeros(len(cand), dtype=np.float32)
+        for p in range(len(pairs)):                                 # mi_dense_mean_kernel: pairs added in order
+            got = (got + per_pair[:, p]).astype(np.float32)
+        got = (got / np.float32(len(pairs))).astype(np.float32)
+        np.testing.assert_allclose(got, want.numpy(), rtol=1e-5, atol=1e-6, err_msg="iteration %d" % it)
+        np.testing.assert_allclose(got, want64.numpy(), rtol=1e-6, atol=1e-7, err_msg="iteration %d" % it)
+        row = a[S_ref[1 + it]]
+        for p, (c1, c2) in enumerate(pairs):
+            tables[p][row[c1], row[c2]] += 1
+
+
+@pytest.mark.parametrize("n_same", [1, 2, 37])
+def test_singular_start_of_a_run_matches_the_reference(host_ami, n_same):
+    """All picks so far in one cell: both entropies vanish, the denominator is a difference of 1e-14 terms, and the
+    reference returns exactly 0 for a candidate joining that cell (its MI and EMI are bit-identical there), ~0 for one
+    sharing its row or column, 1 for one on a fresh row and column."""
+    C = 5
+    N = np.zeros((C, C), dtype=np.uint32)
+    N[2, 3] = n_same
+    cells = np.ascontiguousarray(np.stack(np.meshgrid(np.arange(C), np.arange(C), indexing="ij"), -1).reshape(-1, 2),
+                                 dtype=np.int32)
+    out = np.zeros(len(cells), dtype=np.float64)
+    host_ami.host_ami_scores(N.ctypes.data, C, cells.ctypes.data, len(cells), 0, out.ctypes.data)
+    want32 = _dense_truth(N, cells, "arithmetic", torch.float32).numpy()
+    np.testing.assert_allclose(out, want32, rtol=1e-5, atol=1e-6)
+    assert out[2 * C + 3] == 0.0
+
+
 def test_reference_fp32_noise_grows_with_the_table():
     """Why parity for `ami` is stated against the fp64 value: the reference's fp32 lgamma terms are ~n*log(n) each and
     their difference is O(1), so its relative error grows with n (1e-6 at n = 400, > 1e-4 by n = 10^5)."""
