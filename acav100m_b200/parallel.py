@@ -57,6 +57,34 @@ def unpack_cell(cell):
     return (cell >> 16) & 0xFFFF, cell & 0xFFFF
 
 
+def record_words(d):
+    """uint64 words of a multi-pair winner record (device twin: acav_mi_pairs_record_words): the key, then the
+    winner's d cluster ids, 16 bits each, four per word."""
+    return 1 + (int(d) + 3) // 4
+
+
+def pack_record(key, ids):
+    """-> list of unsigned ints [key, ids 0..3, ids 4..7, ...] (mip_emit_kernel's layout)."""
+    words = [int(key) & 0xFFFFFFFFFFFFFFFF] + [0] * (record_words(len(ids)) - 1)
+    for j, c in enumerate(ids):
+        words[1 + j // 4] |= (int(c) & 0xFFFF) << (16 * (j % 4))
+    return words
+
+
+def unpack_record(words, d):
+    """-> (key, [d ids])."""
+    return int(words[0]) & 0xFFFFFFFFFFFFFFFF, [(int(words[1 + j // 4]) >> (16 * (j % 4))) & 0xFFFF for j in range(d)]
+
+
+def combine_records(records):
+    """records: iterable of word lists -> the one with the largest key (None if every key is 0)."""
+    best = None
+    for rec in records:
+        if (int(rec[0]) & 0xFFFFFFFFFFFFFFFF) > (0 if best is None else int(best[0]) & 0xFFFFFFFFFFFFFFFF):
+            best = rec
+    return best
+
+
 def combine_pairs(pairs):
     """pairs: iterable of (key, cell) as unsigned ints -> the winning (key, cell) or (0, 0)."""
     best = (0, 0)
@@ -73,7 +101,9 @@ def sharded_greedy(engine, dist, world, n_picks, new_pair_buffer, new_gather_buf
     engine.local_best(out_pair)         -> fills a 2 x int64 buffer with this rank's (key, cell)
     engine.apply(all_pairs, world, i)   -> every rank applies the winner among the gathered pairs
     The buffers are int64 tensors on the engine's device (bit patterns of uint64); the gather buffer is
-    flat [2 * world] = world consecutive (key, cell) pairs (a layout both NCCL and gloo accept)."""
+    flat [2 * world] = world consecutive (key, cell) pairs (a layout both NCCL and gloo accept).
+    The multi-pair engine (P > 1) runs the same loop with records of `record_words(d)` words -- key + the
+    winner's d cluster ids -- instead of (key, cell) pairs."""
     mine = new_pair_buffer()
     allp = new_gather_buffer(world)
     for i in range(n_picks):

@@ -134,6 +134,74 @@ def test_sharded_greedy_equals_single_process(world):
         assert [g for _, g in picks] == want_G
 
 
+class _OraclePairsEngine:
+    """CPU stand-in for acav_mi_pairs_local_best / acav_mi_pairs_apply (records = key + the winner's d ids)."""
+
+    def __init__(self, assignments, C, pairs, lo, hi):
+        self.pairs, self.d = pairs, assignments.shape[1]
+        self.tab = mo.init_table(len(pairs), C)
+        self.lo = lo
+        self.rows = torch.from_numpy(assignments[lo:hi])
+        self.cells = mo.candidate_cells(assignments, pairs, range(lo, hi))
+        self.alive = torch.ones(hi - lo, dtype=torch.bool)
+        self.picks = []
+
+    @staticmethod
+    def _i64(words):
+        return torch.from_numpy(np.array(words, dtype=np.uint64).view(np.int64).copy())
+
+    def local_best(self, out_rec):
+        idx = torch.nonzero(self.alive)[:, 0]
+        if idx.numel() == 0:
+            out_rec.zero_()
+            return
+        scores, _, _, _ = mo.candidate_scores(self.tab, self.cells[idx])
+        score, j = scores.mean(dim=-1).max(dim=0)
+        local = int(idx[j])
+        out_rec.copy_(self._i64(parallel.pack_record(parallel.pack_key(score.item(), self.lo + local),
+                                                     self.rows[local].tolist())))
+
+    def apply(self, all_recs, world, i):
+        words = all_recs.numpy().view(np.uint64).reshape(world, -1).tolist()
+        key, ids = parallel.unpack_record(parallel.combine_records(words), self.d)
+        score, pos = parallel.unpack_key(key)
+        cand = torch.tensor([[[ids[c1], ids[c2]] for c1, c2 in self.pairs]])
+        _, NlogN, aloga, blogb = mo.candidate_scores(self.tab, cand)
+        mo.apply_pick(self.tab, cand[0], NlogN[0], aloga[0], blogb[0])
+        if self.lo <= pos < self.lo + len(self.alive):
+            self.alive[pos - self.lo] = False
+        self.picks.append((pos, score))
+
+
+def _pairs_rank(rank, world, a, C, pairs, n_picks):
+    lo, hi = parallel.shard_bounds(len(a), rank, world)
+    eng = _OraclePairsEngine(a, C, pairs, lo, hi)
+    words = parallel.record_words(a.shape[1])
+    parallel.sharded_greedy(eng, dist, world, n_picks, lambda: torch.zeros(words, dtype=torch.int64),
+                            lambda w: torch.zeros(words * w, dtype=torch.int64))
+    return eng.picks
+
+
+def test_record_layout_round_trip():
+    ids = [0, 65534, 17, 1023, 5, 9, 77]
+    rec = parallel.pack_record(parallel.pack_key(0.5, 42), ids)
+    assert len(rec) == parallel.record_words(7) == 3
+    assert parallel.unpack_record(rec, 7) == (parallel.pack_key(0.5, 42), ids)
+    assert parallel.combine_records([[0, 1, 2], rec, parallel.pack_record(parallel.pack_key(0.5, 43), ids)]) == rec
+    assert parallel.combine_records([[0, 0, 0]]) is None
+
+
+def test_sharded_pairs_greedy_equals_single_process():
+    rng = np.random.RandomState(43)
+    a = rng.randint(0, 7, size=(500, 5)).astype(np.int64)
+    pairs = mo.cluster_pairing([("m%d" % i, "l") for i in range(5)], "combination")       # P = 10
+    n_picks = 60
+    want_pos, want_gain = mo.greedy_mem_mi_pairs_c(a, 7, pairs, n_picks)
+    for picks in _spawn(_pairs_rank, 2, a, 7, pairs, n_picks):
+        assert [p for p, _ in picks] == want_pos.tolist()
+        assert np.array_equal(np.array([g for _, g in picks], dtype=np.float32), want_gain)
+
+
 # ---- k-means distributed step --------------------------------------------------------------------
 
 def _cpu_protocol_kmeans(d, k, world):
