@@ -484,9 +484,9 @@ def main():
         pk = peaks()
         cpu = None
         if world == 1 and not args.skip_cpu_baseline:
-            cpu = cpu_mi(args, 200, 3)
+            cpu = cpu_mi(args, 2000, 3)                    # ~10 s of host work on 16 threads (bounded sample)
             if km is not None:
-                km["cpu_baseline"] = cpu_kmeans(args, 5)
+                km["cpu_baseline"] = cpu_kmeans(args, 200)  # ~5 s
         line = {
             "metric": METRIC, "value": mi["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": mi["ms"] / args.steps, "higher_is_better": True,
