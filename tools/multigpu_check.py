@@ -4,7 +4,8 @@
         tools/multigpu_check.py
 
 k-means: N-rank KMeans.add (NCCL all-reduce of histogram and deltas) vs the oracle's world step.
-greedy MI: candidate list sharded over the ranks vs the C oracle on the whole list.
+greedy MI: candidate list sharded over the ranks vs the C oracle on the whole list (one pair: all three loops; several
+pairs: the record all-gather of acav_mi_pairs_local_best / apply).
 """
 import os
 import sys
@@ -79,6 +80,21 @@ for loop in ("kernels", "persistent", "cells"):
     print(f"[rank {rank}] greedy MI sharded over {world} ranks, loop={m.loop_name()}: bit-exact={ok}", flush=True)
     assert ok
     del m
+# ---- greedy MI over several clustering pairs (records all-gathered per iteration) ----
+rng = np.random.RandomState(29)
+W, D, C, picks = 60_001, 6, 24, 150
+base = rng.randint(0, C, size=(W, 1))
+a = np.where(rng.random_sample((W, D)) < 0.5, (base + np.arange(D)) % C, rng.randint(0, C, size=(W, D))).astype(np.int64)
+pairs = mo.cluster_pairing([("m%d" % i, "l") for i in range(D)], "combination")
+pos_want, gain_want = mo.greedy_mem_mi_pairs_c(a, C, pairs, picks)
+m = get_measure("mem_mi")(a, ncentroids=C, device="cuda", shard=(rank, world))
+m.init(pairs, list(range(W)))
+pos, gain = m.select(picks)
+ok = np.array_equal(pos.cpu().numpy(), pos_want) and np.array_equal(gain.cpu().numpy(), gain_want)
+print(f"[rank {rank}] greedy MI over {len(pairs)} pairs sharded over {world} ranks, loop={m.loop_name()}: bit-exact={ok}",
+      flush=True)
+assert ok
+del m
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
