@@ -43,6 +43,24 @@ def test_aten_row_mean_restatement_matches_torch():
         assert np.array_equal(want, got), p
 
 
+@pytest.mark.parametrize("threads", [1, 4])
+def test_aten_row_mean_restatement_at_scale_and_any_thread_count(threads):
+    """torch parallelises the reduction over output rows, never inside a row: the order holds for W = 3*10^5 rows and does
+    not depend on the number of threads (the GPU box has twice the cores of the container the goldens were made in)."""
+    rng = np.random.RandomState(5)
+    before = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    try:
+        for w, p in [(300_000, 45), (400_000, 6)]:
+            x = (rng.standard_normal((w, p)) * 5).astype(np.float32)
+            want = torch.from_numpy(x).mean(dim=-1).numpy()
+            idx = rng.randint(0, w, size=1500)
+            got = np.array([mo.aten_row_mean(x[i]) for i in idx], dtype=np.float32)
+            assert np.array_equal(want[idx], got), (w, p)
+    finally:
+        torch.set_num_threads(before)
+
+
 @pytest.mark.parametrize("name", PAIR_CASES)
 def test_c_pairs_oracle_reproduces_reference_bits(golden_dir, name):
     g, a, start, cands, pairs = _golden(golden_dir, name)
