@@ -6,10 +6,8 @@ import math
 from collections import defaultdict
 from pathlib import Path
 
-import numpy as np
 import torch
 
-from .. import hostio
 from . import data as D
 from .config import MODELS
 from .save import save_assignments

@@ -1,6 +1,5 @@
 """The C-ABI library builds for sm_100a, loads without a GPU and exports exactly what
 include/acav_b200.h declares (no compute calls here)."""
-import ctypes
 import os
 import re
 import subprocess

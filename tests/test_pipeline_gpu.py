@@ -3,7 +3,6 @@
 import csv
 import pickle
 import random
-from pathlib import Path
 
 import numpy as np
 import pytest

@@ -1,11 +1,10 @@
 """Diagnostic for the tcgen05 assignment kernel (not a test): compares tensor-mode assignment with the
 exact mode and with a torch evaluation of the bf16-rounded distances."""
 import sys
-import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from acav100m_b200 import _lib, synth
+from acav100m_b200 import _lib
 from acav100m_b200.clustering import KMeans
 
 

@@ -58,7 +58,7 @@ def run(which):
     return e0.elapsed_time(e1) / reps
 
 
-import subprocess, time
+import subprocess
 for w in ("gemm", "prep", "both"):
     run(w)
     reps = 3000
