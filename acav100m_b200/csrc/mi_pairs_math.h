@@ -11,8 +11,10 @@
 
 #if defined(__CUDACC__)
 #define ACAV_HD __host__ __device__ __forceinline__
+#define ACAV_UNROLL _Pragma("unroll")
 #else
 #define ACAV_HD inline
+#define ACAV_UNROLL
 #endif
 
 namespace acav {
@@ -67,27 +69,27 @@ ACAV_HD float pairs_mean(int P, G g) {
     } else {
         const int V = P >> 3, Vf = V & ~3;
         float acc[4][8];
-#pragma unroll
+ACAV_UNROLL
         for (int k = 0; k < 4; ++k)
-#pragma unroll
+ACAV_UNROLL
             for (int l = 0; l < 8; ++l) acc[k][l] = 0.f;
         for (int v = 0; v < Vf; v += 4) {
-#pragma unroll
+ACAV_UNROLL
             for (int k = 0; k < 4; ++k)
-#pragma unroll
+ACAV_UNROLL
                 for (int l = 0; l < 8; ++l) acc[k][l] = acc[k][l] + g((v + k) * 8 + l);
         }
         for (int v = Vf; v < V; ++v) {
-#pragma unroll
+ACAV_UNROLL
             for (int l = 0; l < 8; ++l) acc[0][l] = acc[0][l] + g(v * 8 + l);
         }
-#pragma unroll
+ACAV_UNROLL
         for (int k = 1; k < 4; ++k)
-#pragma unroll
+ACAV_UNROLL
             for (int l = 0; l < 8; ++l) acc[0][l] = acc[0][l] + acc[k][l];
         s = 0.f;
         for (int p = V * 8; p < P; ++p) s = s + g(p);
-#pragma unroll
+ACAV_UNROLL
         for (int l = 0; l < 8; ++l) s = s + acc[0][l];
     }
     return s / (float)P;
