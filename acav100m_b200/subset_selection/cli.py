@@ -5,7 +5,8 @@ Drop-in for ``subset_selection/code/cli.py run`` (reference cli.py:17-104): same
 directory), same append-mode CSV.  ``--measure_name=mem_mi`` selects the exact greedy CUDA engine, the
 default ``batch_mi`` the reference's batched variant (scoring on the device); ``--chunk_size=n`` runs the
 reference's chunked multi-GPU mode (chunk.py) and ``reduce`` / ``reduce_csvs`` / ``reduce_pkls`` merge its
-caches.  The contrastive baseline (run_contrastive.py) is out of scope and says so.
+caches, ``compare_measures`` the reference's measure comparison (tests.py).  The contrastive baseline
+(run_contrastive.py) is out of scope and says so.
 """
 import copy
 import datetime
@@ -15,6 +16,7 @@ from pathlib import Path
 
 from .. import hostio
 from .chunk import reduce_all_pkls, run_chunks
+from .compare import compare_measures as _compare_measures
 from .config import defaults
 from .run import run_single
 from .save import merge_all_csvs
@@ -93,12 +95,20 @@ def reduce(**kwargs):
     _timed(lambda args: merge_all_csvs(args) if args.save_cache_as_csvs else reduce_all_pkls(args), **kwargs)
 
 
+def compare_measures(**kwargs):
+    """cli.py:80-83 (``--measure_names="['mem_mi','mi']"`` by default)."""
+    report = _compare_measures(prepare(**kwargs))
+    print('done')
+    return report
+
+
 def main(argv=None):
     command, kwargs = hostio.parse_cli(sys.argv[1:] if argv is None else argv)
-    commands = {'run': run, 'reduce': reduce, 'reduce_csvs': reduce_csvs, 'reduce_pkls': reduce_pkls}
+    commands = {'run': run, 'reduce': reduce, 'reduce_csvs': reduce_csvs, 'reduce_pkls': reduce_pkls,
+                'compare_measures': compare_measures}
     if command not in commands:
-        raise SystemExit("usage: cli.py run|reduce|reduce_csvs|reduce_pkls --shards_path=... --meta_path=... "
-                         "--out_path=... [--a.b.c=v ...]")
+        raise SystemExit("usage: cli.py run|reduce|reduce_csvs|reduce_pkls|compare_measures --shards_path=... "
+                         "--meta_path=... --out_path=... [--a.b.c=v ...]")
     commands[command](**kwargs)
 
 

@@ -1,7 +1,7 @@
 """Default flag tree of ``subset_selection/code/cli.py run`` (reference subset_selection/code/config.py:1-53).
-``clustering.columns`` is the only addition: an optional list of two ``(model_key, layer)`` tuples that
-restricts the selection to one audio-visual pair when the cluster shards hold more clusterings (the
-CUDA engine scores one contingency table; with all ten layer clusterings the reference forms 45)."""
+``clustering.columns`` is the only addition: an optional list of ``(model_key, layer)`` tuples that restricts
+the selection to those clusterings -- e.g. one audio-visual pair, which runs on the persistent one-table kernels --
+when the cluster shards hold more (with all ten layer clusterings the `combination` pairing forms 45 tables)."""
 
 defaults = {
     'data': {

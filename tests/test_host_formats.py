@@ -112,6 +112,38 @@ def test_cluster_shards_round_trip_into_selection_inputs(tmp_path):
                 sys.modules.pop(stale, None)
 
 
+def test_compare_measures_command_plumbing(tmp_path, monkeypatch, capsys):
+    """`cli compare_measures` (reference cli.py:80-83, tests.py): measure list from --measure_names, one report per
+    partition; the oracle stands in for the device measures here (the real ones run in the GPU tests)."""
+    from acav100m_b200.subset_selection import cli as scli, compare
+    from oracle import mi_oracle as mo
+    rng = np.random.RandomState(1)
+    args = cargs.get_args(**{"data.output.path": str(tmp_path / "clusters")})
+    paths = [_fake_cluster_shard(args, "shard-00000%d" % i, 9, rng) for i in range(2)]
+    csave.store_shards_set(args, paths)
+    calls = []
+
+    def fake_run_greedy(a, assignments, clustering_types, subset_size, subset_ratio, measure_name, cluster_pairing,
+                        shuffle_candidates, verbose):
+        calls.append((measure_name, cluster_pairing, assignments.shape))
+        S, GAIN = mo.run_greedy_driver(assignments, subset_size=subset_size, pairing=cluster_pairing,
+                                       clustering_types=clustering_types)
+        if measure_name == "mi":                                 # a second measure that disagrees on the last pick
+            S, GAIN = S[:-1] + [S[0]], GAIN[:-1] + [GAIN[-1] + 0.5]
+        return S, GAIN, [0.0] * len(GAIN)
+
+    monkeypatch.setattr(compare, "_run_greedy", fake_run_greedy)
+    report = scli.compare_measures(shards_path=str(tmp_path / "clusters" / "shard-{000000..000001}.pkl"),
+                                   meta_path=str(tmp_path), out_path=str(tmp_path / "out.csv"),
+                                   **{"subset.size": 6, "shuffle_candidates": False, "verbose": False,
+                                      "clustering.columns": [("layer_vggish", "layer_4"), ("layer_slow_fast", "layer_4")]})
+    assert [c[0] for c in calls] == ["mem_mi", "mi"] and calls[0][1] == "combination" and calls[0][2] == (18, 2)
+    assert len(report) == 1 and report[0][0][:2] == ("mem_mi", "mi")
+    assert report[0][0][2] == pytest.approx(4 / 5) and report[0][0][3] == pytest.approx(0.5 / 4)
+    out = capsys.readouterr().out
+    assert "mem_mi vs. mi" in out and "S equivalence" in out and out.strip().endswith("done")
+
+
 def test_partitions_follow_newest_log(tmp_path):
     d = tmp_path / "c"
     d.mkdir()
