@@ -1,7 +1,8 @@
-"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+"""Multi-GPU parity check against the oracle, run under torchrun (one rank per GPU; not collected by pytest -- the
+GPU test box has one device):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/multigpu_check.py
+        tests/multigpu_check.py
 
 k-means: N-rank KMeans.add (NCCL all-reduce of histogram and deltas) vs the oracle's world step.
 greedy MI: candidate list sharded over the ranks vs the C oracle on the whole list (one pair: all three loops; several
