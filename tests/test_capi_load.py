@@ -68,7 +68,8 @@ def test_operators_fail_loudly_without_gpu():
     with pytest.raises(RuntimeError, match="no CPU path"):
         km.add(torch.zeros(16, 8))
     import numpy as np
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
-        get_measure("mem_mi")(np.zeros((4, 2), dtype=np.int64), ncentroids=2)
+    for name in ("mem_mi", "batch_mi", "mi", "ami"):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            get_measure(name)(np.zeros((4, 2), dtype=np.int64), ncentroids=2, batch_size=2, selection_size=1)
     rc = _lib.load().acav_device_info(None, None, None)
     assert rc != 0                            # a cudaError, not a silent success
