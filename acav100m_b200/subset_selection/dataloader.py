@@ -32,16 +32,66 @@ def format_row(row):
     return row['filename'], row['shard_name'], res
 
 
+def _column_plan(row, clustering_types):
+    """Where each clustering of `clustering_types` sits inside a row: (feature list name, index in that list, model key,
+    key inside 'array') -- lets `preprocess` read the ten ids of a row without building a dict per row."""
+    plan = []
+    for model_key, layer in clustering_types:
+        hit = None
+        for feature_name in ('audio_assignments', 'video_assignments'):
+            for pos, feature in enumerate(row[feature_name]):
+                if feature['model_key'] != model_key:
+                    continue
+                array = feature['array']
+                if isinstance(array, dict):
+                    if layer in array:
+                        hit = (feature_name, pos, model_key, layer)
+                elif isinstance(array, (list, tuple)):
+                    if layer.startswith('layer_') and layer[6:].isdigit() and int(layer[6:]) < len(array):
+                        hit = (feature_name, pos, model_key, int(layer[6:]))
+                elif layer == 'model':
+                    hit = (feature_name, pos, model_key, None)
+        if hit is None:
+            return None
+        plan.append(hit)
+    return plan
+
+
+def _row_ids(row, plan):
+    """The row's cluster ids in plan order, or None when the row is laid out differently from the first one."""
+    out = []
+    try:
+        for feature_name, pos, model_key, key in plan:
+            feature = row[feature_name][pos]
+            if feature['model_key'] != model_key:
+                return None
+            out.append(feature['array'] if key is None else feature['array'][key])
+    except (IndexError, KeyError, TypeError):
+        return None
+    return out
+
+
 def preprocess(data, columns=None):
-    """dataloader.py:56-69 -> (assignments [V, D] int64, shard_names, filenames, clustering_types)."""
-    filenames, shard_names, rows = zip(*(format_row(r) for r in data))
-    clustering_types = sorted(rows[0].keys())
+    """dataloader.py:56-69 -> (assignments [V, D] int64, shard_names, filenames, clustering_types).  Same result as
+    formatting every row into a {(model_key, layer): id} dict (`format_row`); rows laid out like the first one -- all of
+    them, in shards written by the clustering stage -- are read through a precomputed column plan instead."""
+    clustering_types = sorted(format_row(data[0])[2].keys())
     if columns is not None:
         columns = [tuple(c) for c in columns]
         missing = [c for c in columns if c not in clustering_types]
         assert not missing, "clustering.columns not present in the shards: {}".format(missing)
         clustering_types = columns
-    assignments = np.array([[int(r[k]) for k in clustering_types] for r in rows], dtype=np.int64)
+    plan = _column_plan(data[0], clustering_types)
+    flat = []
+    for row in data:
+        ids = _row_ids(row, plan) if plan is not None else None
+        if ids is None:
+            formatted = format_row(row)[2]
+            ids = [formatted[k] for k in clustering_types]
+        flat.extend(ids)
+    assignments = np.array(flat, dtype=np.int64).reshape(len(data), len(clustering_types))
+    filenames = tuple(r['filename'] for r in data)
+    shard_names = tuple(r['shard_name'] for r in data)
     return assignments, shard_names, filenames, clustering_types
 
 

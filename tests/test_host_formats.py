@@ -112,6 +112,34 @@ def test_cluster_shards_round_trip_into_selection_inputs(tmp_path):
                 sys.modules.pop(stale, None)
 
 
+def test_preprocess_column_plan_equals_per_row_dicts():
+    """`preprocess` reads rows through a column plan taken from the first row; rows laid out differently (feature order
+    swapped, list- or scalar-valued 'array', dataloader.py:17-36) fall back to the per-row dict and give the same ids."""
+    rng = np.random.RandomState(2)
+
+    def row(i, swap=False, kind="dict"):
+        def feat(model, n):
+            vals = [np.int64(rng.randint(9)) for _ in range(n)]
+            arr = {"layer_%d" % j: v for j, v in enumerate(vals)} if kind == "dict" else (vals if kind == "list" else vals[0])
+            return {"model_key": model, "array": arr}
+        video = [feat("layer_slow_fast", 3), feat("layer_other", 3)]
+        return {"filename": "c%03d.mp4" % i, "shard_name": "shard-%06d" % (i // 4),
+                "audio_assignments": [feat("layer_vggish", 3)], "video_assignments": video[::-1] if swap else video}
+
+    for kind in ("dict", "list", "scalar"):
+        data = [row(i, swap=(i % 3 == 1), kind=kind) for i in range(12)]
+        a, shard_names, filenames, types_ = sdata.preprocess(data)
+        want_rows = [sdata.format_row(r)[2] for r in data]
+        assert types_ == sorted(want_rows[0].keys()) and len(types_) == (3 if kind == "scalar" else 9)
+        assert np.array_equal(a, np.array([[int(r[k]) for k in types_] for r in want_rows]))
+        assert a.dtype == np.int64 and filenames[5] == "c005.mp4" and shard_names[5] == "shard-000001"
+        cols = [types_[-1], types_[0]]
+        a2, _, _, t2 = sdata.preprocess(data, columns=cols)
+        assert t2 == cols and np.array_equal(a2, a[:, [len(types_) - 1, 0]])
+    with pytest.raises(AssertionError):
+        sdata.preprocess(data, columns=[("layer_vggish", "nope")])
+
+
 def test_compare_measures_command_plumbing(tmp_path, monkeypatch, capsys):
     """`cli compare_measures` (reference cli.py:80-83, tests.py): measure list from --measure_names, one report per
     partition; the oracle stands in for the device measures here (the real ones run in the GPU tests)."""
