@@ -71,7 +71,7 @@ def collate_features(rows):
                 res['/'.join((feat['extractor_name'], feat['dataset']))] = feature
         else:
             res[key] = [r[key] for r in rows]
-    res['idx'] = [Path(r['filename']).stem for r in rows]
+    res['idx'] = [hostio.file_stem(r['filename']) for r in rows]
     return res
 
 

@@ -36,6 +36,19 @@ def objectify(tree):
     return tree
 
 
+def file_stem(filename):
+    """``Path(filename).stem`` for the per-clip loops (pathlib builds a path object per call: ~10 us each, minutes at
+    10^8 clips): last path component without its final suffix; a leading dot or a trailing dot is not a suffix."""
+    name = str(filename)
+    if not name or name[-1] in '/\\' or '\\' in name:
+        return Path(name).stem
+    name = name.rsplit('/', 1)[-1]
+    if name in ('.', '..'):
+        return Path(str(filename)).stem
+    i = name.rfind('.')
+    return name[:i] if 0 < i < len(name) - 1 else name
+
+
 def update_args(args, overrides):
     """Merge ``{'a.b.c': v}`` into a nested dict (reference args.py `_update_args`)."""
     for key, value in overrides.items():

@@ -111,7 +111,7 @@ def load_metas(shard_paths, metas_path):
     for shard_path in shard_paths:
         meta_path = Path(metas_path) / "{}.json".format(shard_path.stem)
         if meta_path.is_file():
-            metas[shard_path.stem] = {Path(r['filename']).stem: r for r in hostio.load_json(meta_path)}
+            metas[shard_path.stem] = {hostio.file_stem(r['filename']): r for r in hostio.load_json(meta_path)}
     return metas
 
 

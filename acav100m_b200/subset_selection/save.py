@@ -5,13 +5,15 @@ import csv
 from collections import defaultdict
 from pathlib import Path
 
+from .. import hostio
+
 
 def save_output(data, metas, out_path, name='', sharded_meta=True):
     out_path = Path(out_path)
     out_path.parent.mkdir(exist_ok=True, parents=True)
     rows, keys = {}, []
     for row in data:
-        fname = Path(row['filename']).stem
+        fname = hostio.file_stem(row['filename'])
         meta = None
         if sharded_meta:
             meta = metas.get(row['shard_name'], {}).get(fname)

@@ -112,6 +112,15 @@ def test_cluster_shards_round_trip_into_selection_inputs(tmp_path):
                 sys.modules.pop(stale, None)
 
 
+def test_file_stem_equals_pathlib():
+    import random
+    from pathlib import Path as P
+    rnd = random.Random(0)
+    names = ["a.mp4", "x/y/a.b.mp4", ".hidden", "name.", "noext", "a/b/", "", "..", "x/y.z/.", "C:\\a\\b.mp4", "a.tar.gz"]
+    names += ["".join(rnd.choice("ab./_-") for _ in range(rnd.randint(0, 9))) for _ in range(3000)]
+    assert [hostio.file_stem(n) for n in names] == [P(n).stem for n in names]
+
+
 def test_preprocess_column_plan_equals_per_row_dicts():
     """`preprocess` reads rows through a column plan taken from the first row; rows laid out differently (feature order
     swapped, list- or scalar-valued 'array', dataloader.py:17-36) fall back to the per-row dict and give the same ids."""
