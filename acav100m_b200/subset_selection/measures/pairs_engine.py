@@ -34,23 +34,34 @@ class PairsEngine:
             raise ValueError("cluster ids must lie in [0, ncentroids)")
         self.w = ids.shape[0]
         handle = _lib.c_vp()
+        self._h = None
         with torch.cuda.device(device):
             st = _lib.stream_ptr(device)
             _lib.call("acav_mi_pairs_create", _lib.ctypes.byref(handle), self.w, self.D, self.C, self.P,
                       self.engine_pairs.ctypes.data_as(_lib.c_vp), self.max_picks, int(lo))
             self._h = handle
-            _lib.call("acav_mi_pairs_load_candidates", handle, _lib.ptr(ids), st)
-            self._logs = tables.log_table_device(self.max_picks + 4, device)
-            consts = np.ascontiguousarray(tables.pair_table_constants(self.P, self.C))
-            _lib.call("acav_mi_pairs_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
-                      consts.ctypes.data_as(_lib.c_vp), st)
-            torch.cuda.current_stream(device).synchronize()          # `ids` may be freed once packed
+            try:
+                _lib.call("acav_mi_pairs_load_candidates", handle, _lib.ptr(ids), st)
+                self._logs = tables.log_table_device(self.max_picks + 4, device)
+                consts = np.ascontiguousarray(tables.pair_table_constants(self.P, self.C))
+                _lib.call("acav_mi_pairs_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
+                          consts.ctypes.data_as(_lib.c_vp), st)
+                torch.cuda.current_stream(device).synchronize()      # `ids` may be freed once packed
+            except Exception:
+                self.release()
+                raise
         self.record_words = int(_lib.load().acav_mi_pairs_record_words(handle))
 
     def release(self):
         if getattr(self, "_h", None) is not None:
             _lib.load().acav_mi_pairs_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     def add_sample(self, row):
         """row: the sample's D cluster ids (all clustering columns)."""

@@ -64,3 +64,33 @@ def test_product_operators_have_no_cpu_path():
         src = _read(p)
         assert "_lib.call(" in src, p
         assert "require_cuda" in src or "no CPU path" in src or "pairs_engine" in p, p
+
+
+def test_no_undefined_names_in_gpu_only_code_paths():
+    """Most of the host code only runs on the GPU box; a name that is never bound anywhere in its module (a missing
+    import, a typo) must not wait for that run to show up."""
+    import ast
+    import builtins
+    known = set(dir(builtins)) | {"__file__"}
+    offenders = []
+    for rel in _python_files("acav100m_b200", "tools", "tests", "oracle", "bench.py", "__graft_entry__.py"):
+        tree = ast.parse(_read(rel))
+        bound = set(known)
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)):
+                bound.add(n.name)
+            elif isinstance(n, ast.Import):
+                bound.update((a.asname or a.name).split(".")[0] for a in n.names)
+            elif isinstance(n, ast.ImportFrom):
+                bound.update(a.asname or a.name for a in n.names)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                bound.add(n.id)
+            elif isinstance(n, ast.arg):
+                bound.add(n.arg)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                bound.add(n.name)
+            elif isinstance(n, (ast.Global, ast.Nonlocal)):
+                bound.update(n.names)
+        offenders += [(rel, n.id, n.lineno) for n in ast.walk(tree)
+                      if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in bound]
+    assert offenders == []
