@@ -50,3 +50,21 @@ def test_cli_ami_runs_on_all_pairs(clustered):
     names = [l[1] for l in lines]
     assert len(lines) == 24 and len(set(names)) == 24 and all(n.endswith(".mp4") for n in names)   # mi.py:161: size - 1
     assert np.all([l[2].startswith("yt") for l in lines])
+
+
+def test_run_sh_runs_both_stages_with_the_reference_defaults(tmp_path):
+    """`bash run.sh DATA_DIR`: the reference's two stage scripts (clustering/code/run.sh, subset_selection/code/run.sh)
+    with their default flags -- K = 32, two epochs at batch 32, then `batch_mi` over all 45 pairs -- on shard-000000."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    write_feature_shards(tmp_path / "data", n_shards=1, clips_per_shard=80, seed=12)
+    env = dict(os.environ, PATH=os.path.dirname(sys.executable) + os.pathsep + os.environ.get("PATH", ""))
+    out = subprocess.run(["bash", os.path.join(root, "run.sh"), str(tmp_path / "data"), "--subset.size=12",
+                          "--verbose=False"], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("done") >= 2
+    assert (tmp_path / "data" / "clusters" / "shard-000000.pkl").is_file()
+    lines = list(csv.reader(open(tmp_path / "data" / "output.csv")))
+    assert len(lines) == 12 and len({l[1] for l in lines}) == 12 and all(l[2].startswith("yt") for l in lines)
