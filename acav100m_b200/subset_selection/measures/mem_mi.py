@@ -80,7 +80,6 @@ class EfficientMemMI:
             cells = a.index_select(0, ids)[:, list(pair)].contiguous().to(self.device)
         if cells.numel() and (int(cells.min()) < 0 or int(cells.max()) >= self.ncentroids):
             raise ValueError("cluster ids must lie in [0, ncentroids)")
-        self._W = W
         self._cells = cells
 
     def init_from_cells(self, clustering_combinations, cells, w_global=None, lo=0, max_picks=None):
@@ -144,8 +143,6 @@ class EfficientMemMI:
             consts = tables.empty_table_constants(C)
             _lib.call("acav_mi_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
                       consts.ctypes.data_as(_lib.c_vp), st)
-        self._picked = 0
-        self._nvlink = False
         if self._dist is not None and self._loop_mode() in (_lib.MI_LOOP_PERSISTENT, _lib.MI_LOOP_CELLS):
             self._connect_ranks()
 
