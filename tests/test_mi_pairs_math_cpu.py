@@ -147,3 +147,20 @@ def test_device_header_data_flow_equals_oracle(host_math, d, c, w, picks, seed):
     assert np.array_equal(pos, want_pos)
     assert np.array_equal(gain, want_gain)
     assert np.array_equal(sums, want_sums)
+
+
+def test_device_header_data_flow_equals_oracle_on_random_instances(host_math):
+    """Random shapes (2..23 clusterings, 1..256 pairs in random order and orientation, lists that nearly run empty):
+    the kernels' arithmetic and the oracle agree on every pick, every fp32 score and the final running sums."""
+    import itertools
+    rng = np.random.RandomState(77)
+    for _ in range(40):
+        d, c, w = int(rng.randint(2, 24)), int(rng.randint(2, 40)), int(rng.randint(20, 500))
+        picks = int(rng.randint(5, min(w, 120)))
+        ids = rng.randint(0, c, size=(w, d))
+        allp = list(itertools.combinations(range(d), 2))
+        rng.shuffle(allp)
+        pairs = [tuple(int(v) for v in (p if rng.rand() < 0.7 else p[::-1])) for p in allp[:int(rng.randint(1, min(len(allp), 256) + 1))]]
+        want_pos, want_gain, want_sums = mo.greedy_mem_mi_pairs_c(ids, c, pairs, picks, return_sums=True)
+        pos, gain, sums = _host_greedy(host_math, ids, c, pairs, picks)
+        assert np.array_equal(pos, want_pos) and np.array_equal(gain, want_gain) and np.array_equal(sums, want_sums), (d, c, w)
