@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# compute-sanitizer passes over the GPU tests (run on a B200: `gpurun --timeout 1500 -- 'bash tools/sanitize.sh > gpurun_out/sanitize.log 2>&1'`).
+#   memcheck  : every kernel, on the small-shape tests (the sanitizer slows kernels 10-100x; the W >= 1e5 cases are deselected)
+#   racecheck : shared-memory hazards of the non-cooperative kernels (multi-pair engine, dense / ami scoring, k-means update)
+#   synccheck : barrier usage of the persistent cooperative kernels
+# Exit status: non-zero if any pass reports an error.
+set -uo pipefail
+cd "$(dirname "$0")/.."
+SAN=${SAN:-compute-sanitizer}
+SMALL='not 100003 and not 100_003 and not 300000 and not 1000003 and not 50000 and not 20000-10 and not pipeline and not run_sh'
+status=0
+run() { echo "=== $*"; "$@" || status=1; }
+run $SAN --tool memcheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "$SMALL" \
+    tests/test_zz_mi_pairs_gpu.py tests/test_zz_ami_gpu.py tests/test_dense_mi_gpu.py tests/test_batch_mi_gpu.py
+run $SAN --tool memcheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "ragged or strided or warmup or update_is_bit_exact" \
+    tests/test_kmeans_gpu.py
+run $SAN --tool racecheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "reference_bits or one_pair or subset_of_columns" \
+    tests/test_zz_mi_pairs_gpu.py tests/test_zz_ami_gpu.py
+run $SAN --tool synccheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "uniform_ids or mixed" tests/test_mi_gpu.py
+exit $status
