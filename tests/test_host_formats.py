@@ -112,6 +112,17 @@ def test_cluster_shards_round_trip_into_selection_inputs(tmp_path):
                 sys.modules.pop(stale, None)
 
 
+def test_stack_layer_equals_np_stack():
+    rng = np.random.RandomState(3)
+    dicts = [{"layer_0": rng.standard_normal(5).astype(np.float32), "layer_1": rng.standard_normal(3)} for _ in range(7)]
+    lists = [[d["layer_0"], d["layer_1"]] for d in dicts]
+    for arrays in (dicts, lists, dicts[:3] + lists[3:]):
+        for layer in ("layer_0", "layer_1"):
+            want = np.stack([np.asarray(cdata._get_layer(a, layer), dtype=np.float32) for a in arrays])
+            got = cdata._stack_layer(arrays, layer)
+            assert got.dtype == np.float32 and np.array_equal(got, want)
+
+
 def test_file_stem_equals_pathlib():
     import random
     from pathlib import Path as P
