@@ -62,6 +62,9 @@ SIGNATURES = {
     "acav_mi_comm_handle_bytes": (ctypes.c_int, []),
     "acav_mi_comm_export": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp]),
     "acav_mi_comm_connect": (ctypes.c_int, [c_vp, c_vp]),
+    "acav_mi_loop_supported": (ctypes.c_int, [c_i32, c_i32, c_i32]),
+    "acav_mi_prepare": (ctypes.c_int, [c_vp, c_i32, c_vp]),
+    "acav_mi_status": (ctypes.c_int, [c_vp, c_vp, c_vp]),
 }
 
 ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1

@@ -53,6 +53,8 @@ struct acav_mi {
     unsigned char *mail_local;
     void *mail_peer[kMiMaxWorld];
     bool comm_connected;
+    int *run_status;             // device word written by the persistent loops (kMiRun*)
+    unsigned long long spin_limit_ns;
     long long *dbg;              // optional per-CTA phase timers of the persistent loop
     // cell-index loop resources (candidates sorted by table cell), built on first use
     uint32_t *cx_sorted_pos, *cx_cell_start, *cx_head, *cx_first_pos;
@@ -423,7 +425,7 @@ int acav_mi_destroy(acav_mi_t *h) {
     if (h->comm_connected)
         for (int r = 0; r < h->world; ++r)
             if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
-    cudaFree(h->mail_local);
+    cudaFree(h->mail_local); cudaFree(h->run_status);
     cudaFree(h->cx_sorted_pos); cudaFree(h->cx_cell_start); cudaFree(h->cx_head); cudaFree(h->cx_first_pos);
     delete h;
     return 0;
@@ -445,7 +447,12 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     h->chunk_start = nullptr; h->n_alt = nullptr; h->pub = nullptr; h->bar = nullptr; h->grid = 0; h->rows_smem = 0;
     h->w_sorted = 0; h->world = 1; h->rank = 0; h->seq_base = 0; h->mail_local = nullptr; h->comm_connected = false;
     for (int r = 0; r < kMiMaxWorld; ++r) h->mail_peer[r] = nullptr;
-    h->dbg = nullptr;
+    h->dbg = nullptr; h->run_status = nullptr;
+    h->spin_limit_ns = 20ull * 1000000000ull;                             // 20 s; ACAV_MI_SPIN_TIMEOUT_MS overrides
+    if (const char *e = std::getenv("ACAV_MI_SPIN_TIMEOUT_MS")) {
+        const double ms = std::atof(e);
+        if (ms > 0) h->spin_limit_ns = (unsigned long long)(ms * 1e6);
+    }
     h->sorted_valid = false;
     h->cx_sorted_pos = nullptr; h->cx_cell_start = nullptr; h->cx_head = nullptr; h->cx_first_pos = nullptr;
     h->cells_valid = false;
@@ -461,6 +468,8 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     if (!rc) rc = dev_alloc(&s.sums, 8, nullptr);
     if (!rc) rc = dev_alloc(&s.key, 2, nullptr);
     if (!rc) rc = dev_alloc(&h->consts_dev, 8, nullptr);
+    if (!rc) rc = dev_alloc(&h->run_status, 1, nullptr);
+    if (!rc) rc = (int)cudaMemset(h->run_status, 0, sizeof(int));
     if (rc) { acav_mi_destroy(h); return rc; }
     *out = h;
     return 0;
@@ -524,7 +533,8 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         const int32_t grid = h->sm_count < h->s.k_a ? h->sm_count : h->s.k_a;
         h->sorted_valid = false;                 // the candidate stream does not see these removals
         rc = launch_mi_cells(h->s, h->cx_cell_start, h->cx_sorted_pos, h->cx_head, h->cx_first_pos, grid, h->pub, h->bar,
-                             n_picks, out_pos, out_gain, h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer, st);
+                             n_picks, out_pos, out_gain, h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer,
+                             h->run_status, h->spin_limit_ns, st);
         h->seq_base += (unsigned int)n_picks + 1u;
         if (!rc) rc = launch_mi_refresh_terms(h->s, st);
         return rc;
@@ -547,10 +557,37 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
     h->cells_valid = false;                      // the cell index does not see these removals
     rc = launch_mi_persistent(h->s, h->n_alt, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->pub, h->bar,
                               n_picks, out_pos, out_gain, h->rows_smem, h->world, h->rank, h->seq_base, h->mail_local,
-                              h->mail_peer, h->dbg, st);
+                              h->mail_peer, h->dbg, h->run_status, h->spin_limit_ns, st);
     h->seq_base += (unsigned int)n_picks + 1u;          // mailbox tags never repeat across runs
     if (!rc) rc = launch_mi_refresh_terms(h->s, st);
     return rc;
+}
+
+int acav_mi_loop_supported(int32_t k_a, int32_t k_v, int32_t mode) {
+    if (k_a <= 0 || k_v <= 0 || k_a > 65535 || k_v > 65535) return 0;
+    if (mode == ACAV_MI_LOOP_KERNELS) return 1;
+    if (mode == ACAV_MI_LOOP_PERSISTENT)       // one gain row must fit in shared memory, the stream holds 4*c2 in 16 bits
+        return mi_persistent_rows_that_fit(k_a, k_v) >= 1 && k_v <= 16383 && (int64_t)k_a * k_v < (1ll << 31);
+    if (mode == ACAV_MI_LOOP_CELLS) return k_a <= 16384 && k_v <= 16384 && mi_cells_smem_fits(k_a, k_v);
+    return 0;
+}
+
+int acav_mi_prepare(acav_mi_t *h, int32_t mode, void *stream) {
+    if (!h) return ACAV_E_INVALID;
+    if (!h->loaded) return ACAV_E_STATE;
+    if (!acav_mi_loop_supported(h->s.k_a, h->s.k_v, mode)) return ACAV_E_UNSUPPORTED;
+    if (mode == ACAV_MI_LOOP_PERSISTENT) return mi_prepare_persistent(h, (cudaStream_t)stream);
+    if (mode == ACAV_MI_LOOP_CELLS) return mi_prepare_cells(h, (cudaStream_t)stream);
+    return 0;
+}
+
+int acav_mi_status(acav_mi_t *h, int32_t *status_host, void *stream) {
+    if (!h || !status_host) return ACAV_E_INVALID;
+    int v = 0;
+    ACAV_CUDA_TRY(cudaMemcpyAsync(&v, h->run_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ACAV_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *status_host = v;
+    return 0;
 }
 
 int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles) {

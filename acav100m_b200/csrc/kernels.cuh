@@ -97,17 +97,19 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
                          unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
-                         long long *dbg, cudaStream_t st);
+                         long long *dbg, int *status, unsigned long long spin_limit_ns, cudaStream_t st);
 
 // mi_cells.cu (cell-index loop)
 int mi_cells_tiles(int64_t w);
+bool mi_cells_smem_fits(int32_t k_a, int32_t k_v);
 int launch_mi_cells_build(const MiState &s, uint32_t *tilehist, uint32_t *total, uint32_t *start, uint32_t *tmp_cells,
                           uint32_t *tmp_pos, uint32_t *sorted_cells, uint32_t *sorted_pos, uint32_t *cell_start,
                           uint32_t *head, uint32_t *first_pos, int64_t *n_live_host, cudaStream_t st);
 int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t *sorted_pos, uint32_t *head,
                     uint32_t *first_pos, int32_t grid, void *pub, unsigned int *bar, int64_t n_picks,
                     int64_t *out_pos, float *out_gain, int32_t world, int32_t rank, unsigned int seq_base,
-                    void *mail_local, void *const *mail_peer, cudaStream_t st);
+                    void *mail_local, void *const *mail_peer, int *status, unsigned long long spin_limit_ns,
+                    cudaStream_t st);
 
 // mi_dense.cu
 struct MiDense {

@@ -177,6 +177,8 @@ struct MiCells {
     unsigned int seq_base;
     MiMail *mail_local;
     MiMail *mail_peer[kMaxWorld];
+    int *status;                     // kMiRun* word of this launch (device)
+    unsigned long long spin_limit_ns;
 };
 
 __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
                 pb->key = key; pb->payload = pay;
             }
         }
-        grid_barrier(P.bar, grid);
+        if (grid_barrier(P.bar, grid, P.world > 1 ? P.status : nullptr)) break;      // a CTA gave up on a peer GPU
         // ---------------- everyone learns the winner ----------------
         {
             unsigned long long k2 = 0ull, p2 = 0ull;
@@ -301,11 +303,16 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
                         st_release_sys(&m->seq, tag);
                     }
                     unsigned long long gk = 0ull, gp = 0ull;
+                    bool timed_out = false;
                     if ((int)threadIdx.x < P.world) {
                         const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
-                        while (ld_acquire_sys(&m->seq) != tag) { }
+                        timed_out = !wait_mail_tag(&m->seq, tag, P.spin_limit_ns);
                         gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
                         gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
+                    }
+                    if (__any_sync(0xffffffffu, timed_out)) {      // a peer never delivered: stop here, say why
+                        gk = 0ull; gp = 0ull;
+                        if (threadIdx.x == 0) *reinterpret_cast<volatile int *>(P.status) = kMiRunPeerTimeout;
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -366,6 +373,12 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
 
 int mi_cells_tiles(int64_t w) { return (int)ceil_div(w > 0 ? w : 1, kCellTile); }
 
+// replicated marginals + per-CTA row terms must fit in shared memory (the per-row caches are optional)
+bool mi_cells_smem_fits(int32_t k_a, int32_t k_v) {
+    const size_t smem = ((size_t)2 * k_v + kSmallCounts + (size_t)2 * k_a) * 4 + 16;
+    return smem <= 200 * 1024;
+}
+
 static int cells_sort_pass(const uint32_t *cells_in, const uint32_t *pos_in, int64_t w, int shift, int32_t k,
                            uint32_t *tilehist, uint32_t *total, uint32_t *start, uint32_t *cells_out,
                            uint32_t *pos_out, cudaStream_t st) {
@@ -417,8 +430,10 @@ int launch_mi_cells_build(const MiState &s, uint32_t *tilehist, uint32_t *total,
 int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t *sorted_pos, uint32_t *head,
                     uint32_t *first_pos, int32_t grid, void *pub, unsigned int *bar, int64_t n_picks,
                     int64_t *out_pos, float *out_gain, int32_t world, int32_t rank, unsigned int seq_base,
-                    void *mail_local, void *const *mail_peer, cudaStream_t st) {
+                    void *mail_local, void *const *mail_peer, int *status, unsigned long long spin_limit_ns,
+                    cudaStream_t st) {
     MiCells P;
+    P.status = status; P.spin_limit_ns = spin_limit_ns;
     P.s = s; P.cell_start = cell_start; P.sorted_pos = sorted_pos; P.head = head; P.first_pos = first_pos;
     P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks; P.out_pos = out_pos; P.out_gain = out_gain;
     P.rows_per_cta = (int32_t)ceil_div(s.k_a, grid);
@@ -435,6 +450,7 @@ int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t
     if (smem > 48 * 1024) { int rc = ensure_dynamic_smem(mi_cells_kernel, smem, attr_done); if (rc) return rc; }
     ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
+    ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     void *args[] = {&P};
     ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_cells_kernel, dim3(grid), dim3(kCellThreads), args, smem, st));
     return 0;

@@ -208,6 +208,8 @@ struct MiPersist {
     MiMail *mail_local;              // [2][world] in this GPU's memory
     MiMail *mail_peer[kMaxWorld];    // the same array on every rank (peer-mapped pointers)
     long long *dbg;                  // optional [grid][8] counters of the LAST iteration (nullptr = off)
+    int *status;                     // kMiRun* word of this launch (device)
+    unsigned long long spin_limit_ns;    // how long a CTA waits for a peer GPU's entry before giving up
 };
 
 __device__ __forceinline__ uint4 ldcg_u4(const uint4 *p) { return __ldcg(p); }
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
             }
         }
         const long long t2 = P.dbg ? clock64() : 0;
-        grid_barrier(P.bar, grid);
+        if (grid_barrier(P.bar, grid, P.world > 1 ? P.status : nullptr)) { broke = true; break; }   // a CTA gave up on a peer GPU
         const long long t3 = P.dbg ? clock64() : 0;
         if (P.dbg && threadIdx.x == 0) {
             long long *d = P.dbg + 8 * blockIdx.x;
@@ -573,11 +575,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                         st_release_sys(&m->seq, tag);
                     }
                     unsigned long long gk = 0ull, gp = 0ull;
+                    bool timed_out = false;
                     if ((int)threadIdx.x < P.world) {
                         const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
-                        while (ld_acquire_sys(&m->seq) != tag) { }
+                        timed_out = !wait_mail_tag(&m->seq, tag, P.spin_limit_ns);
                         gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
                         gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
+                    }
+                    if (__any_sync(0xffffffffu, timed_out)) {      // a peer never delivered: stop here, say why
+                        gk = 0ull; gp = 0ull;
+                        if (threadIdx.x == 0) *reinterpret_cast<volatile int *>(P.status) = kMiRunPeerTimeout;
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -700,9 +707,9 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
                          unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
-                         long long *dbg, cudaStream_t st) {
+                         long long *dbg, int *status, unsigned long long spin_limit_ns, cudaStream_t st) {
     MiPersist P;
-    P.dbg = dbg;
+    P.dbg = dbg; P.status = status; P.spin_limit_ns = spin_limit_ns;
     P.s = s; P.n_alt = n_alt; P.c2s_ro = c2s; P.c2s = c2s; P.pos_s = pos_s; P.row_start = row_start;
     P.chunk_start = chunk_start; P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks;
     P.out_pos = out_pos; P.out_gain = out_gain; P.rows_smem = rows_smem;
@@ -718,6 +725,7 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
     ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
     ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
+    ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     void *args[] = {&P};
     ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_persistent_kernel, dim3(grid), dim3(kPersistThreads), args,
                                               smem, st));

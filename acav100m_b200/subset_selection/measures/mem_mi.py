@@ -128,6 +128,7 @@ class EfficientMemMI:
         self._max_picks = int(max_picks)
         self._picked = 0
         self._nvlink = False
+        self._ready_mode = None
         if len(self.combinations) > 1:
             world = self.shard[1] if self.shard is not None else 1
             self._pairs = PairsEngine(self.device, C, self.combinations, self._rows, lo, self._W, self._max_picks,
@@ -146,22 +147,40 @@ class EfficientMemMI:
         if self._dist is not None and self._loop_mode() in (_lib.MI_LOOP_PERSISTENT, _lib.MI_LOOP_CELLS):
             self._connect_ranks()
 
+    def _all_ranks_ok(self, ok):
+        """True iff `ok` holds on every rank (one tiny all-reduce; ranks must agree before any of them enters a
+        persistent kernel that waits for its peers)."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN)
+        return bool(flag.item())
+
     def _connect_ranks(self):
         """Exchange the mailbox IPC handles so the persistent kernel can push each iteration's winner
-        straight into the peers' memory over NVLink (include/acav_b200.h, acav_mi_comm_*)."""
+        straight into the peers' memory over NVLink (include/acav_b200.h, acav_mi_comm_*).  If any rank cannot
+        map its peers (no CUDA IPC / no P2P: other node, MIG, container without shared /dev/shm) every rank falls
+        back to the 3-kernel loop with one 16-byte all-gather per iteration."""
         rank, world = self.shard
         n = _lib.load().acav_mi_comm_handle_bytes()
         mine = (_lib.ctypes.c_ubyte * n)()
+        err = None
         with torch.cuda.device(self.device):
-            _lib.call("acav_mi_comm_export", self._engine, world, rank, mine)
+            try:
+                _lib.call("acav_mi_comm_export", self._engine, world, rank, mine)
+            except _lib.AcavError as e:
+                err = e
             local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device)
             gathered = torch.empty(world * n, dtype=torch.uint8, device=self.device)
             self._dist.all_gather_into_tensor(gathered, local)
-            blob = bytes(gathered.cpu().numpy().tobytes())
-            handles = (_lib.ctypes.c_ubyte * (world * n)).from_buffer_copy(blob)
-            _lib.call("acav_mi_comm_connect", self._engine, handles)
+            if self._all_ranks_ok(err is None):
+                blob = bytes(gathered.cpu().numpy().tobytes())
+                handles = (_lib.ctypes.c_ubyte * (world * n)).from_buffer_copy(blob)
+                try:
+                    _lib.call("acav_mi_comm_connect", self._engine, handles)
+                except _lib.AcavError as e:
+                    err = e
+            self._nvlink = self._all_ranks_ok(err is None)
+            self._nvlink_error = err
             self._dist.barrier()
-        self._nvlink = True
 
     def _release(self):
         if self._pairs is not None:
@@ -201,8 +220,24 @@ class EfficientMemMI:
             return _lib.MI_LOOP_PERSISTENT
         if self.loop in ('cells', _lib.MI_LOOP_CELLS):
             return _lib.MI_LOOP_CELLS
-        # "auto": the persistent row-partitioned kernel whenever its gain rows fit in shared memory
-        return _lib.MI_LOOP_PERSISTENT if self.ncentroids <= 16384 else _lib.MI_LOOP_KERNELS
+        # "auto": the persistent row-partitioned kernel whenever one of its gain rows fits in shared memory
+        # (K <= 8140 for a square table), else the cell index (K <= 16384), else three kernels per iteration
+        C = self.ncentroids
+        for mode in (_lib.MI_LOOP_PERSISTENT, _lib.MI_LOOP_CELLS):
+            if _lib.load().acav_mi_loop_supported(C, C, mode):
+                return mode
+        return _lib.MI_LOOP_KERNELS
+
+    def check_status(self):
+        """Raise if the last persistent launch gave up waiting for a peer GPU (synchronises the stream)."""
+        if self._engine is None or not self._nvlink:
+            return
+        st = _lib.ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.call("acav_mi_status", self._engine, _lib.ctypes.byref(st), _lib.stream_ptr(self.device))
+        if st.value != 0:
+            raise RuntimeError("greedy-MI persistent loop stopped: a peer GPU's winner did not arrive within the "
+                               "spin limit (a rank failed or ran a different number of iterations)")
 
     def select(self, n_picks):
         """Run `n_picks` greedy iterations; returns (positions int64[n] in the candidate list,
@@ -217,6 +252,17 @@ class EfficientMemMI:
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)
             if self._dist is None or self._nvlink:
+                if self._nvlink and getattr(self, "_ready_mode", None) != self._loop_mode():
+                    # every rank must have its layout ready (and have got here) before any enters the kernel
+                    try:
+                        _lib.call("acav_mi_prepare", self._engine, self._loop_mode(), st)
+                        err = None
+                    except _lib.AcavError as e:
+                        err = e
+                    if not self._all_ranks_ok(err is None):
+                        raise RuntimeError("greedy-MI setup failed on %s rank: %s"
+                                           % ("this" if err else "another", err))
+                    self._ready_mode = self._loop_mode()
                 _lib.call("acav_mi_run", self._engine, n_picks, _lib.ptr(pos), _lib.ptr(gain),
                           self._loop_mode(), st)
             else:
@@ -248,6 +294,7 @@ class EfficientMemMI:
             raise RuntimeError("cannot pick %d of %d candidates" % (n_picks, self._W))
         t0 = time.time()
         pos, gain = self.select(n_picks)
+        self.check_status()
         pos = pos.cpu()
         gains = gain.cpu().tolist()
         elapsed = time.time() - t0

@@ -56,6 +56,9 @@ def parse_args():
     p.add_argument("--skip-mi", action="store_true", help="development only: the line then has no headline value")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--skip-cells", action="store_true")
+    p.add_argument("--skip-parity", action="store_true")
+    p.add_argument("--parity-candidates", type=int, default=2_000_000, help="per rank, for the parity_n self-check")
+    p.add_argument("--parity-picks", type=int, default=256)
     return p.parse_args()
 
 
@@ -159,13 +162,53 @@ def mi_engine(cells_src, k, rank, world, loop, w_global, lo):
     return m
 
 
+def mi_parity(args, dist, rank, world, timed_pos, timed_gain):
+    """Self-certification of a (multi-GPU) run, printed as `parity_n` in the JSON line:
+      1. every rank returned the same (positions, gains) from the timed iterations;
+      2. a 2e6-candidates-per-rank list, sharded exactly like the timed one, run through the same loop(s), gives the
+         picks and fp32 gains of the C oracle (oracle/mi_oracle.c, bucketed scan) on the WHOLE list, bit for bit.
+    The oracle is the checker here, not the thing measured."""
+    from acav100m_b200 import synth
+    out = {"world": world}
+    ok = True
+    if world > 1:
+        mine = torch.cat([timed_pos.to(torch.float64), timed_gain.to(torch.float64)])
+        allr = torch.empty(world * mine.numel(), dtype=torch.float64, device=mine.device)
+        dist.all_gather_into_tensor(allr, mine)
+        same = bool((allr.view(world, -1) == allr.view(world, -1)[0]).all().item())
+        out["timed_picks_identical_on_all_ranks"] = same
+        ok &= same
+    w_small, picks = args.parity_candidates, args.parity_picks
+    lists = [synth.zipf_pairs(w_small, args.k, 7000 + r) for r in range(world)]      # every rank can rebuild every shard
+    want = None
+    if rank == 0:
+        want = cpu_oracle_picks(np.concatenate(lists), args.k, picks)
+    loops = {}
+    for loop in ("persistent", "cells"):
+        cells = torch.from_numpy(lists[rank]).cuda()
+        m = mi_engine(cells, args.k, rank, world, loop, w_small * world, w_small * rank)
+        pos, gain = m.select(picks)
+        m.check_status()
+        if rank == 0:
+            good = bool(np.array_equal(pos.cpu().numpy(), want[0]) and np.array_equal(gain.cpu().numpy(), want[1]))
+            loops[m.loop_name()] = good
+            ok &= good
+        del m
+    out["vs_c_oracle_bit_exact"] = loops
+    out["what"] = ("%d picks from %d candidates per rank x %d ranks vs oracle/mi_oracle.c on the whole list"
+                   % (picks, w_small, world))
+    out["result"] = "ok" if ok else "MISMATCH"
+    return out
+
+
 def run_mi(args, dist, rank, world):
     from acav100m_b200 import synth
     W = args.mi_candidates
     dev = torch.device("cuda", torch.cuda.current_device())
     cells = synth.zipf_pairs_torch(W, args.k, 1004 + rank, dev)
     m = mi_engine(cells, args.k, rank, world, args.mi_loop, W * world, W * rank)
-    ms, _ = timed(dist, lambda: m.select(args.warmup), lambda: m.select(args.steps))
+    ms, (t_pos, t_gain) = timed(dist, lambda: m.select(args.warmup), lambda: m.select(args.steps))
+    m.check_status()
     w_global = W * world
     scored = sum(w_global - args.warmup - i for i in range(args.steps))
     # algorithmic bytes per iteration and GPU in the layout the loop actually streams (DESIGN.md 3.3):
@@ -180,6 +223,7 @@ def run_mi(args, dist, rank, world):
         "launches": max(m.launches_per_iteration() * args.steps, 2),     # persistent: one launch per select()
         "loop": m.loop_name(), "bytes_per_candidate": bytes_per_cand,
     }
+    res["parity_n"] = None if args.skip_parity else mi_parity(args, dist, rank, world, t_pos, t_gain)
     # the same job through the cell-index loop (ACAV_MI_LOOP_CELLS): identical picks, O(K^2) work per iteration
     res["cell_index_loop"] = None
     if not args.skip_cells and world == 1:
@@ -406,6 +450,12 @@ def cpu_mi(args, repeats, warm=1):
                       "oracle/mi_oracle.c, OpenMP over %d threads" % (repeats, W, args.k, threads)}
 
 
+def cpu_oracle_picks(cells, k, picks):
+    """The C oracle's greedy picks and fp32 gains on a whole candidate list (checker of mi_parity)."""
+    from oracle import mi_oracle as mo
+    return mo.greedy_mem_mi_c(cells[:, 0], cells[:, 1], k, picks, bucketed=True)
+
+
 def cpu_kmeans(args, steps):
     from acav100m_b200 import synth
     from oracle import kmeans_oracle as ko
@@ -504,6 +554,7 @@ def main():
                          "kernel": "greedy-MI iteration (gain table + candidate scan + apply), per GPU",
                          "algorithmic_bytes_per_launch": mi["algorithmic_bytes_per_launch"],
                          "peak_source": pk["source"] + " copy bandwidth"},
+            "parity_n": (mi["parity_n"] or {}).get("result"), "parity": mi["parity_n"],
             "cell_index_loop": mi.get("cell_index_loop"),
             "cpu_baseline": cpu, "cpu_model": cpu_model(), "kmeans": km, "clocks": clocks,
         }

@@ -181,6 +181,25 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n,
 int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain,
                 int32_t mode, void *stream);
 
+/* Which loops can run a k_a x k_v table (1 / 0): ACAV_MI_LOOP_PERSISTENT needs at least one gain row of k_v + 1
+ * floats next to the replicated marginals in shared memory and 4*k_v < 65536 (k_v <= 8140 at k_a = k_v);
+ * ACAV_MI_LOOP_CELLS needs the marginals in shared memory (k <= 16384).  A host mirror picks the loop with this
+ * instead of catching ACAV_E_UNSUPPORTED from acav_mi_run. */
+int acav_mi_loop_supported(int32_t k_a, int32_t k_v, int32_t mode);
+
+/* Builds the candidate layout of `mode` now (the stable partition / cell index that acav_mi_run would otherwise
+ * build on first use) and returns its status, so that a multi-GPU caller can agree on success across ranks BEFORE
+ * any rank enters the persistent kernel. */
+int acav_mi_prepare(acav_mi_t *h, int32_t mode, void *stream);
+
+/* Why the last persistent launch ended: synchronises `stream`, then *status_host = 0 (all iterations done or no
+ * candidate left on any rank) or ACAV_MI_RUN_PEER_TIMEOUT (a peer GPU's per-iteration entry did not arrive within
+ * the spin limit -- 20 s, environment ACAV_MI_SPIN_TIMEOUT_MS -- and the loop stopped; out_pos of the iterations
+ * not run is -1).  The kernels never spin without bound on another GPU. */
+#define ACAV_MI_RUN_OK            0
+#define ACAV_MI_RUN_PEER_TIMEOUT  1
+int acav_mi_status(acav_mi_t *h, int32_t *status_host, void *stream);
+
 /* Multi-GPU persistent loop (one process per GPU on one node).  Every rank holds a contiguous range of
  * the candidate list (pos_base); inside ACAV_MI_LOOP_PERSISTENT each rank's per-iteration winner is
  * written straight into every peer's mailbox over NVLink (peer stores + release/acquire flags) -- no

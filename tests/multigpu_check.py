@@ -1,5 +1,5 @@
-"""Multi-GPU parity check against the oracle, run under torchrun (one rank per GPU; not collected by pytest -- the
-GPU test box has one device):
+"""Multi-GPU parity check against the oracle, run under torchrun (one rank per GPU).  tests/test_multigpu_gpu.py
+spawns it as a `-m gpu` test wherever at least two devices are visible; by hand:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/multigpu_check.py
@@ -66,6 +66,29 @@ for mode in ("exact", "tensor"):
     print(f"[rank {rank}] kmeans {mode}: counts/count/fallback ok={ok} max rel |dcenter| {rel:.2e} ids agree {agree:.4f}",
           flush=True)
     assert ok and agree > 0.999
+    # every rank holds the same centers bit for bit (replicated state must not drift)
+    ref = km.centers.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(ref, km.centers), "centers differ between ranks"
+
+# k-means with a skewed batch: a few centroids own >= 128 rows of every rank's slice (ring kernel, split variant)
+k, d, b = 6, 256, 2048
+gsk = torch.Generator().manual_seed(31)
+means = torch.randn(3, d, generator=gsk) * 3.0
+x = means[torch.randint(0, 3, (b * world * 4,), generator=gsk)] + torch.randn(b * world * 4, d, generator=gsk)
+c0 = torch.cat([means, means + 100.0])                        # three centroids own everything, three stay empty
+km = KMeans(args, d, k, assign_mode="exact", warmup_rng="cpu")
+km.centers = c0.clone()
+km.to("cuda")
+st = ko.SgdKMeansState(centers=c0.clone(), counts=torch.zeros(k))
+st.count = km.count = 10 * k                                  # past the warm-up: distance assignment from step 1
+for g0 in range(0, len(x), world * b):
+    km.add(x[g0 + rank * b: g0 + (rank + 1) * b])
+    ko.sgd_step_world(st, [x[g0 + r * b: g0 + (r + 1) * b] for r in range(world)])
+rel = ((km.centers.cpu() - st.centers).abs().max() / st.centers.abs().max()).item()
+ok = torch.equal(km.counts.cpu(), st.counts) and km.fallback == st.fallback and rel < 1e-5
+print(f"[rank {rank}] kmeans skewed batch (heavy centroids, split update): ok={ok} max rel |dcenter| {rel:.2e}", flush=True)
+assert ok
 
 # ---- greedy MI ----
 W, C, picks = 200_003, 64, 700
@@ -96,6 +119,28 @@ print(f"[rank {rank}] greedy MI over {len(pairs)} pairs sharded over {world} ran
       flush=True)
 assert ok
 del m
+# ---- a rank that does not show up must not hang the others: bounded peer wait (ACAV_MI_SPIN_TIMEOUT_MS) ----
+if os.environ.get("ACAV_MI_SPIN_TIMEOUT_MS"):
+    W, C = 50_000, 32
+    a = synth.zipf_pairs(W, C, 41)
+    for loop in ("persistent", "cells"):
+        m = get_measure("mem_mi")(a, ncentroids=C, device="cuda", shard=(rank, world), loop=loop)
+        m.init([(0, 1)], list(range(W)))
+        m.select(5)
+        m.check_status()
+        dist.barrier()
+        if rank == 0:                                         # the other ranks never launch this one
+            pos, _ = m.select(7)
+            try:
+                m.check_status()
+                raised = False
+            except RuntimeError:
+                raised = True
+            print(f"[rank 0] loop={loop}: lone rank gave up waiting and raised={raised}, unfinished picks {pos.cpu().tolist()}",
+                  flush=True)
+            assert raised and int(pos[0]) == -1
+        dist.barrier()
+        del m
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:

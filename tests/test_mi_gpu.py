@@ -185,3 +185,27 @@ def test_persistent_loop_uniform_ids_all_ties(loop):
     pos, _ = m.select(200)
     want, _ = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], 8, 200, bucketed=False)
     assert np.array_equal(pos.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("C,want_loop", [(8140, "persistent"), (8192, "cells"), (16384, "cells"), (16500, "kernels")])
+def test_auto_loop_falls_back_when_the_table_outgrows_shared_memory(C, want_loop):
+    """loop='auto' (the CLI default) must pick a loop that can run the table: the persistent stream needs one gain
+    row of K_v + 1 floats next to the replicated marginals in shared memory (K <= 8140), the cell index needs the
+    marginals (K <= 16384), beyond that three kernels per iteration -- and the picks stay the oracle's."""
+    W, picks = 6000, 12
+    a = synth.zipf_pairs(W, C, C)
+    a[0] = C - 1
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C)                                    # loop='auto'
+    m.init([(0, 1)], list(range(W)))
+    assert m.loop_name() == want_loop
+    pos, gain = m.select(picks)
+    assert np.array_equal(pos.cpu().numpy(), pos_want)
+    assert np.array_equal(gain.cpu().numpy(), gain_want)
+    if want_loop != "persistent":                            # asking for a loop that cannot run the shape is an error
+        from acav100m_b200 import _lib
+        bad = gpu_measure(a, C, loop="persistent")
+        bad.init([(0, 1)], list(range(W)))
+        with pytest.raises(_lib.AcavError) as e:
+            bad.select(1)
+        assert e.value.status == -2

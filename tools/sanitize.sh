@@ -9,11 +9,13 @@ cd "$(dirname "$0")/.."
 SAN=${SAN:-compute-sanitizer}
 SMALL='not 100003 and not 100_003 and not 300000 and not 1000003 and not 50000 and not 20000-10 and not pipeline and not run_sh'
 status=0
-run() { echo "=== $*"; "$@" || status=1; }
+run() { echo "=== $*"; timeout ${SAN_TIMEOUT:-600} "$@"; rc=$?; echo "=== exit $rc"; [ $rc -eq 0 ] || status=1; }
 run $SAN --tool memcheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "$SMALL" \
     tests/test_zz_mi_pairs_gpu.py tests/test_zz_ami_gpu.py tests/test_dense_mi_gpu.py tests/test_batch_mi_gpu.py
-run $SAN --tool memcheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "ragged or strided or warmup or update_is_bit_exact" \
+run $SAN --tool memcheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "ragged or strided or warmup or update_is_bit_exact or split_update or (tensor_equals_exact and (128-64-16 or 129-64-256 or 300-88-13))" \
     tests/test_kmeans_gpu.py
+run $SAN --tool memcheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "(matches_c_oracle and 257-3-256) or add_samples or errors or mixed or uniform_ids" tests/test_mi_gpu.py
+run $SAN --tool racecheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "update_is_bit_exact and (4096-128-8 or 65-88-17 or 4096-130-8)" tests/test_kmeans_gpu.py
 run $SAN --tool racecheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "reference_bits or one_pair or subset_of_columns" \
     tests/test_zz_mi_pairs_gpu.py tests/test_zz_ami_gpu.py
 run $SAN --tool synccheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "uniform_ids or mixed" tests/test_mi_gpu.py
