@@ -28,6 +28,16 @@ SIGNATURES = {
     "acav_kmeans_prepare_batch": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "acav_kmeans_assign_prepared": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_f32, c_f32,
                                                    c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "acav_kmeans_comm_create": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32]),
+    "acav_kmeans_comm_destroy": (ctypes.c_int, [c_vp]),
+    "acav_kmeans_comm_handle_bytes": (ctypes.c_int, []),
+    "acav_kmeans_comm_export": (ctypes.c_int, [c_vp, c_vp]),
+    "acav_kmeans_comm_connect": (ctypes.c_int, [c_vp, c_vp]),
+    "acav_kmeans_comm_arena": (c_vp, [c_vp]),
+    "acav_kmeans_comm_connect_ptrs": (ctypes.c_int, [c_vp, c_vp]),
+    "acav_kmeans_comm_status": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "acav_kmeans_update_p2p": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp]),
+    "acav_kmeans_underused_flags": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "acav_kmeans_assign_noise": (ctypes.c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "acav_kmeans_histogram": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "acav_kmeans_update_fused": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp]),

@@ -11,19 +11,32 @@ Differences a user can observe (all documented in DESIGN.md):
   * the per-step ``all_gather`` of the batch (reference :97, used only for ``len``) is dropped;
   * ``fallback`` is kept on the device (no host sync per step, reference :116-119) and read lazily;
   * ``add`` / ``calc_best`` take ``sync=False`` to return the mean distance as a 0-dim device tensor
-    instead of a python float (the reference's ``.item()`` at :79 stalls the stream every call).
+    instead of a python float (the reference's ``.item()`` at :79 stalls the stream every call);
+  * past the warm-up ``add`` replays the whole step (about 16 kernels, plus the two all-reduces on several GPUs)
+    from a CUDA graph cached per batch address (``graph='auto'``): same kernels, same arguments, same results
+    bit for bit -- one launch instead of ~20 host calls.  ``last_best`` then aliases a buffer that the next step
+    overwrites.
 """
+import collections
+
 import numpy as np
 import torch
 
 from .. import _lib, parallel
 
+_GRAPH_CACHE = 512          # captured steps kept per KMeans object (one per distinct batch address)
+_THR_RING = 64              # pinned host slots for the per-step threshold (H2D copy ahead of every replay)
+
 
 class KMeans:
     def __init__(self, args=None, d=None, k=None, lr=1e-2,
                  initial_rounds=10, reinit=(.7, 5.0), saved_dt=None,
-                 assign_mode="auto", warmup_rng="cpu", tile_variant=0):
+                 assign_mode="auto", warmup_rng="cpu", tile_variant=0, graph="auto", comm="auto"):
         self._ws = None
+        self.comm = comm                              # multi-GPU exchange: 'auto' / 'p2p' (NVLink peer memory) or 'nccl'
+        self._comm = None                             # acav_kmeans_comm_t once connected; False = use NCCL
+        self.graph = graph                            # 'auto' / True: CUDA-graph replay of the steady-state step; False: eager
+        self._gs = None
         self.tile_variant = tile_variant              # _lib.TILE_*: which tcgen05 distance-GEMM kernel (0 = by shape)
         self._ws_batch = 0
         self._fallback_base = 0
@@ -59,6 +72,7 @@ class KMeans:
 
     def get_attrs(self):
         """reference :34-46."""
+        self.check_status()
         return {
             'args': self.args, 'count': self.count, 'lr': self.lr,
             'initial_rounds': self.initial_rounds, 'reinit': self.reinit,
@@ -87,6 +101,8 @@ class KMeans:
         st = dict(self.__dict__)
         st['_fallback_base'] = self.fallback
         st['_fallback_dev'] = None
+        st['_gs'] = None
+        st['_comm'] = None
         st['_ws'] = None
         st['_ws_pair'] = None
         st['_ws_batch'] = 0
@@ -103,6 +119,11 @@ class KMeans:
     # -- workspace -----------------------------------------------------------------------------
 
     def _release(self):
+        self._gs = None
+        if getattr(self, "_comm", None):
+            torch.cuda.synchronize(self.centers.device)
+            _lib.load().acav_kmeans_comm_destroy(self._comm)
+        self._comm = None
         self._release_pair()
         if self._ws is not None:
             _lib.load().acav_kmeans_destroy(self._ws)
@@ -153,10 +174,13 @@ class KMeans:
     def launches_per_step(self):
         """CUDA kernels of this library launched by one add() past warm-up (bench.py gpu_launches)."""
         # tensor mode: centroid prep (2) + row prep + distance GEMM + classify + candidate re-check + exact kernel
-        # + exact distance of the winner + mean; then partition (4) + effective lr + 2 update kernels (+ apply on > 1 rank)
+        # + exact distance of the winner + mean; then the stable partition (4) and the update:
+        #   one GPU: effective lr + 2 update kernels; NCCL: + apply; peer memory: histogram exchange + 2 update
+        #   kernels + signal, reduce/broadcast, signal, gather
         assign = 4 if self._mode() == _lib.ASSIGN_EXACT else 9
         _, world = self._world()
-        return assign + 4 + 3 + (1 if world > 1 else 0)
+        tail = 3 if world == 1 else (7 if self._comm else 4)
+        return assign + 4 + tail + (1 if self._gs is not None else 0)
 
     # -- operator ------------------------------------------------------------------------------
 
@@ -309,10 +333,11 @@ class KMeans:
                       batch.stride(0), _lib.ptr(counts_b), lr, _lib.ptr(self.centers), _lib.ptr(self.counts),
                       _lib.ptr(self._fallback_dev), _lib.stream_ptr(self.centers.device))
 
-    def _update_local(self, batch, counts_b_global, lr):
+    def _update_local(self, batch, counts_b_global, lr, deltas=None):
         k, d = self.centers.shape
         b = batch.shape[0]
-        deltas = torch.empty(k, d, dtype=torch.float32, device=self.centers.device)
+        if deltas is None:
+            deltas = torch.empty(k, d, dtype=torch.float32, device=self.centers.device)
         with torch.cuda.device(self.centers.device):
             _lib.call("acav_kmeans_update_local", self._workspace(b), _lib.ptr(batch, row_strided=True), b,
                       batch.stride(0), _lib.ptr(counts_b_global), lr, _lib.ptr(self.centers),
@@ -332,21 +357,172 @@ class KMeans:
             raise NotImplementedError("sequential=True (reference :103-109, disabled by default) is not provided")
         batch = self._prep_batch(batch)
         dev = self._device()
-        k, d = self.centers.shape
         b = batch.shape[0]
         dist, world = self._world()
         lr = self.lr(self.count) if callable(self.lr) else self.lr
-        best, mean = self._assign(batch, want_mean=distance)
-        counts_b = self._histogram(batch, best)                                                     # :113
-        if world > 1:
-            dist.all_reduce(counts_b)                                                               # :114-115
-            deltas = self._update_local(batch, counts_b, float(lr))                                 # :116-123
-            dist.all_reduce(deltas)                                                                 # :125-126
-            self._apply_deltas(deltas)                                                              # :127
+        if self._graphable(batch):
+            best, mean = self._add_graphed(batch, float(lr), distance, dist, world)
         else:
-            self._update_fused(batch, counts_b, float(lr))                                          # :116-127
-        self.count += parallel.kmeans_global_batch(b, world)                                                                   # :128
+            best, mean = self._assign(batch, want_mean=distance)
+            counts_b = self._histogram(batch, best)                                                 # :113
+            self._update(batch, counts_b, float(lr), dist, world)                                   # :114-127
+        self.count += parallel.kmeans_global_batch(b, world)                                        # :128
         self.last_best = best
         if not distance:
             return None
         return mean.item() if sync else mean[0]
+
+    def _peer_comm(self, dist, world):
+        """NVLink peer-memory exchange for the distributed step (acav_kmeans_comm_*): created on the first
+        multi-GPU step; every rank agrees (one all-reduce) whether all of them could map their peers, else all
+        use NCCL.  Returns the handle or None."""
+        if self._comm is not None:
+            return self._comm or None
+        if self.comm == "nccl" or type(self)._histogram is not KMeans._histogram:
+            self._comm = False
+            return None
+        dev = self._device()
+        k, d = self.centers.shape
+        handle, err = _lib.c_vp(), None
+        n = _lib.load().acav_kmeans_comm_handle_bytes()
+        mine = (_lib.ctypes.c_ubyte * n)()
+        with torch.cuda.device(dev):
+            try:
+                _lib.call("acav_kmeans_comm_create", _lib.ctypes.byref(handle), k, d, world, dist.get_rank())
+                _lib.call("acav_kmeans_comm_export", handle, mine)
+            except _lib.AcavError as e:
+                err = e
+
+            def all_ok(ok):
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                return bool(flag.item())
+
+            local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+            gathered = torch.empty(world * n, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gathered, local)
+            if all_ok(err is None):
+                handles = (_lib.ctypes.c_ubyte * (world * n)).from_buffer_copy(gathered.cpu().numpy().tobytes())
+                try:
+                    _lib.call("acav_kmeans_comm_connect", handle, handles)
+                except _lib.AcavError as e:
+                    err = e
+            ok = all_ok(err is None)
+            dist.barrier()
+        if not ok:
+            if handle:
+                _lib.load().acav_kmeans_comm_destroy(handle)
+            if self.comm == "p2p":
+                raise RuntimeError("comm='p2p' but the ranks cannot map each other's memory: %s" % err)
+            self._comm = False
+            return None
+        self._comm = handle
+        return handle
+
+    def comm_name(self):
+        return "p2p" if self._comm else "nccl"
+
+    def check_status(self):
+        """Raise if a peer GPU's data did not arrive in time during a distributed step (synchronises the stream)."""
+        if not self._comm:
+            return
+        st = _lib.ctypes.c_int32(0)
+        with torch.cuda.device(self.centers.device):
+            _lib.call("acav_kmeans_comm_status", self._comm, _lib.ctypes.byref(st), _lib.stream_ptr(self.centers.device))
+        if st.value != 0:
+            raise RuntimeError("k-means distributed step: a peer GPU did not deliver its histogram / deltas / rows "
+                               "within the spin limit; the centers of this rank are not valid")
+
+    def _update(self, batch, counts_b, lr, dist, world, deltas=None):
+        comm = self._peer_comm(dist, world) if world > 1 else None
+        if comm is not None:                                                                        # :114-127, no NCCL
+            b = batch.shape[0]
+            with torch.cuda.device(self.centers.device):
+                _lib.call("acav_kmeans_update_p2p", self._workspace(b), comm, _lib.ptr(batch, row_strided=True), b,
+                          batch.stride(0), _lib.ptr(counts_b), lr, _lib.ptr(self.centers), _lib.ptr(self.counts),
+                          _lib.ptr(self._fallback_dev), _lib.stream_ptr(self.centers.device))
+        elif world > 1:
+            dist.all_reduce(counts_b)                                                               # :114-115
+            deltas = self._update_local(batch, counts_b, lr, deltas)                                # :116-123
+            dist.all_reduce(deltas)                                                                 # :125-126
+            self._apply_deltas(deltas)                                                              # :127
+        else:
+            self._update_fused(batch, counts_b, lr)                                                 # :116-127
+
+    # -- CUDA-graph replay of the steady-state step ----------------------------------------------
+
+    def _graphable(self, batch):
+        return (self.graph in (True, "auto") and not self.in_warmup and batch.shape[0] > 0
+                and not callable(self.lr) and type(self)._histogram is KMeans._histogram)
+
+    def _graph_state(self, b, world):
+        gs = self._gs
+        if gs is None or gs["b"] != b or gs["world"] != world:
+            dev = self._device()
+            k, d = self.centers.shape
+            self._workspace(b)
+            gs = {
+                "b": b, "world": world, "seen": set(), "graphs": collections.OrderedDict(), "i": 0,
+                "best": torch.empty(b, dtype=torch.int64, device=dev),
+                "mean": torch.empty(1, dtype=torch.float32, device=dev),
+                "counts_b": torch.empty(k, dtype=torch.float32, device=dev),
+                "deltas": torch.empty(k, d, dtype=torch.float32, device=dev) if world > 1 else None,
+                "flags": torch.empty(k, dtype=torch.float32, device=dev),
+                "thr": torch.empty(1, dtype=torch.float32, device=dev),
+                "ring": torch.empty(_THR_RING, dtype=torch.float32).pin_memory(),
+                "events": [None] * _THR_RING,
+            }
+            self._gs = gs
+        return gs
+
+    def _step_body(self, batch, gs, lr, distance, dist, world):
+        """The step as a fixed sequence of C-ABI calls on the current stream: every by-value argument is constant for
+        a given (batch, lr), the per-step threshold comes from device memory (gs['thr'])."""
+        dev = self.centers.device
+        k, d = self.centers.shape
+        b = batch.shape[0]
+        ws = self._workspace(b)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.call("acav_kmeans_underused_flags", _lib.ptr(self.counts), k, _lib.ptr(gs["thr"]), _lib.ptr(gs["flags"]), st)
+            _lib.call("acav_kmeans_assign", ws, _lib.ptr(batch, row_strided=True), b, batch.stride(0),
+                      _lib.ptr(self.centers), _lib.ptr(gs["flags"]), 0.5, float(self.reinit[1]),
+                      _lib.ptr(gs["best"]), None, _lib.ptr(gs["mean"]) if distance else None, None, self._mode(), st)
+            _lib.call("acav_kmeans_histogram", ws, _lib.ptr(gs["best"]), b, _lib.ptr(gs["counts_b"]), st)
+        self._update(batch, gs["counts_b"], lr, dist, world, deltas=gs["deltas"])
+
+    def _add_graphed(self, batch, lr, distance, dist, world):
+        dev = self._device()
+        gs = self._graph_state(batch.shape[0], world)
+        # this step's threshold: written to a pinned slot, copied to the device ahead of the replay
+        slot = gs["i"] % _THR_RING
+        gs["i"] += 1
+        if gs["events"][slot] is not None:
+            gs["events"][slot].synchronize()
+        gs["ring"][slot] = self.underused_threshold()
+        gs["thr"].copy_(gs["ring"][slot:slot + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        gs["events"][slot] = ev
+        key = (batch.data_ptr(), batch.stride(0), lr, bool(distance), self._mode(), float(self.reinit[1]))
+        g = gs["graphs"].get(key)
+        if g is None and key not in gs["seen"]:
+            # first time this batch address shows up: run eagerly (module loading, shared-memory attributes, workspace
+            # allocation and the peer-memory setup must not happen inside a capture; batches that never come back --
+            # fresh allocations of a streaming loader -- are never captured)
+            if len(gs["seen"]) > 4 * _GRAPH_CACHE:
+                gs["seen"].clear()
+            gs["seen"].add(key)
+            self._step_body(batch, gs, lr, distance, dist, world)
+        else:
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body(batch, gs, lr, distance, dist, world)
+                gs["graphs"][key] = g
+                if len(gs["graphs"]) > _GRAPH_CACHE:
+                    gs["graphs"].popitem(last=False)
+            else:
+                gs["graphs"].move_to_end(key)
+            g.replay()
+        return gs["best"], (gs["mean"] if distance else None)

@@ -32,6 +32,13 @@ struct acav_kmeans {
     int64_t partition_rows;
 };
 
+struct acav_kmeans_comm {
+    KmComm c;
+    float *counts_global;          // [k] summed batch histogram of the current step
+    float *lr_eff;
+    bool exported, connected, ptrs_borrowed;
+};
+
 struct acav_mi {
     MiState s;
     int64_t max_picks;
@@ -390,7 +397,7 @@ static int update_common(acav_kmeans_t *h, const float *x, int64_t b, int64_t ld
     if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
     int rc = launch_effective_lr(counts_b, h->k, lr, h->lr_eff, fallback, st);
     if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, counts_b, h->lr_eff, centers,
-                                counts, deltas, st);
+                                counts, deltas, nullptr, st);
     h->partition_valid = false;
     return rc;
 }
@@ -411,6 +418,122 @@ int acav_kmeans_update_local(acav_kmeans_t *h, const float *x, int64_t b, int64_
 int acav_kmeans_apply_deltas(float *centers, const float *deltas, int64_t n, void *stream) {
     if (!centers || !deltas || n < 0) return ACAV_E_INVALID;
     return launch_apply_deltas(centers, deltas, n, (cudaStream_t)stream);
+}
+
+/* ---- multi-GPU step over NVLink peer memory (kmeans_comm.cu) ---- */
+
+int acav_kmeans_comm_destroy(acav_kmeans_comm_t *h) {
+    if (!h) return 0;
+    if (h->connected && !h->ptrs_borrowed)
+        for (int r = 0; r < h->c.world; ++r)
+            if (r != h->c.rank && h->c.arena[r]) cudaIpcCloseMemHandle(h->c.arena[r]);
+    if (h->exported) cudaFree(h->c.arena[h->c.rank]);
+    cudaFree(h->c.seq); cudaFree(h->c.status); cudaFree(h->counts_global); cudaFree(h->lr_eff);
+    delete h;
+    return 0;
+}
+
+int acav_kmeans_comm_create(acav_kmeans_comm_t **out, int32_t k, int32_t d, int32_t world, int32_t rank) {
+    if (!out || k <= 0 || d <= 0 || world < 1 || rank < 0 || rank >= world) return ACAV_E_INVALID;
+    if (world > kKmMaxWorld || d % 4 != 0) return ACAV_E_UNSUPPORTED;
+    *out = nullptr;
+    acav_kmeans_comm *h = new (std::nothrow) acav_kmeans_comm();
+    if (!h) return (int)cudaErrorMemoryAllocation;
+    KmComm &c = h->c;
+    for (int r = 0; r < kKmMaxWorld; ++r) c.arena[r] = nullptr;
+    c.world = world; c.rank = rank; c.k = k; c.d = d; c.k_own = (k + world - 1) / world;
+    c.seq = nullptr; c.status = nullptr;
+    c.spin_limit_ns = 20ull * 1000000000ull;                               // 20 s; ACAV_KM_SPIN_TIMEOUT_MS overrides
+    if (const char *e = std::getenv("ACAV_KM_SPIN_TIMEOUT_MS")) {
+        const double ms = std::atof(e);
+        if (ms > 0) c.spin_limit_ns = (unsigned long long)(ms * 1e6);
+    }
+    h->counts_global = nullptr; h->lr_eff = nullptr; h->exported = false; h->connected = false; h->ptrs_borrowed = false;
+    int rc = dev_alloc(&c.seq, 1, nullptr);
+    if (!rc) rc = dev_alloc(&c.status, 1, nullptr);
+    if (!rc) rc = dev_alloc(&h->counts_global, (size_t)k, nullptr);
+    if (!rc) rc = dev_alloc(&h->lr_eff, 1, nullptr);
+    if (!rc) rc = (int)cudaMemset(c.seq, 0, sizeof(unsigned int));
+    if (!rc) rc = (int)cudaMemset(c.status, 0, sizeof(int));
+    if (rc) { acav_kmeans_comm_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int acav_kmeans_comm_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int acav_kmeans_comm_export(acav_kmeans_comm_t *h, void *handle_out) {
+    if (!h || !handle_out) return ACAV_E_INVALID;
+    if (h->exported) return ACAV_E_STATE;
+    KmComm &c = h->c;
+    const size_t bytes = km_comm_arena_bytes(c.world, c.k, c.d);
+    ACAV_CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&c.arena[c.rank]), bytes));
+    h->exported = true;
+    ACAV_CUDA_TRY(cudaMemset(c.arena[c.rank], 0, bytes));
+    ACAV_CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle_out), c.arena[c.rank]));
+    return 0;
+}
+
+int acav_kmeans_comm_connect(acav_kmeans_comm_t *h, const void *handles) {
+    if (!h || !handles) return ACAV_E_INVALID;
+    if (!h->exported || h->connected) return ACAV_E_STATE;
+    const cudaIpcMemHandle_t *hs = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int r = 0; r < h->c.world; ++r) {
+        if (r == h->c.rank) continue;
+        void *p = nullptr;
+        ACAV_CUDA_TRY(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
+        h->c.arena[r] = reinterpret_cast<unsigned char *>(p);
+    }
+    h->connected = true;
+    return 0;
+}
+
+void *acav_kmeans_comm_arena(acav_kmeans_comm_t *h) { return (h && h->exported) ? h->c.arena[h->c.rank] : nullptr; }
+
+int acav_kmeans_comm_connect_ptrs(acav_kmeans_comm_t *h, void *const *arenas) {
+    if (!h || !arenas) return ACAV_E_INVALID;
+    if (!h->exported || h->connected) return ACAV_E_STATE;
+    for (int r = 0; r < h->c.world; ++r) {
+        if (r == h->c.rank) continue;
+        if (!arenas[r]) return ACAV_E_INVALID;
+        h->c.arena[r] = reinterpret_cast<unsigned char *>(arenas[r]);
+    }
+    h->connected = true;
+    h->exported = true;
+    h->ptrs_borrowed = true;
+    return 0;
+}
+
+int acav_kmeans_comm_status(acav_kmeans_comm_t *h, int32_t *status_host, void *stream) {
+    if (!h || !status_host) return ACAV_E_INVALID;
+    int v = 0;
+    ACAV_CUDA_TRY(cudaMemcpyAsync(&v, h->c.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ACAV_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *status_host = v;
+    return 0;
+}
+
+int acav_kmeans_update_p2p(acav_kmeans_t *h, acav_kmeans_comm_t *comm, const float *x, int64_t b, int64_t ldx,
+                           const float *counts_b_local, double lr, float *centers, float *counts, int32_t *fallback,
+                           void *stream) {
+    if (!h || !comm || !x || !counts_b_local || !centers || !counts || ldx < h->d) return ACAV_E_INVALID;
+    if (comm->c.k != h->k || comm->c.d != h->d) return ACAV_E_INVALID;
+    if (!comm->connected && comm->c.world > 1) return ACAV_E_STATE;
+    if (comm->c.world == 1 && !comm->exported) return ACAV_E_STATE;
+    if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_km_hist_exchange(comm->c, counts_b_local, lr, comm->counts_global, comm->lr_eff, fallback, counts, st);
+    const KmPush push = km_comm_push_target(comm->c);
+    if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, comm->counts_global, comm->lr_eff,
+                                centers, counts, nullptr, &push, st);
+    if (!rc) rc = launch_km_reduce_broadcast(comm->c, comm->counts_global, comm->lr_eff, centers, st);
+    h->partition_valid = false;
+    return rc;
+}
+
+int acav_kmeans_underused_flags(const float *counts, int32_t k, const float *threshold_dev, float *flags, void *stream) {
+    if (!counts || !threshold_dev || !flags || k <= 0) return ACAV_E_INVALID;
+    return launch_underused_flags(counts, k, threshold_dev, flags, (cudaStream_t)stream);
 }
 
 /* ---------------------------------------------------------------- greedy MI ----------------- */

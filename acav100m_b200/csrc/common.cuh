@@ -73,4 +73,35 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return v;
 }
 
+// ---- cross-GPU signalling over NVLink peer memory (greedy-MI mailbox, k-means centroid exchange) ----
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Bounded wait for a peer GPU's flag: the tag of this iteration must appear within `limit_ns` (a rank that
+// never launched -- failed setup, host exception, different n_picks -- must not hang the others inside a
+// cooperative kernel).  The timer is read once per 1024 polls, so the fast path is the bare acquire load.
+__device__ __forceinline__ bool wait_peer_tag(const unsigned int *seq, unsigned int tag, unsigned long long limit_ns) {
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys(seq) != tag) {
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > limit_ns) return false;
+        }
+    }
+    return true;
+}
+
 }  // namespace acav

@@ -49,10 +49,36 @@ int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockh
                      cudaStream_t st);
 int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_eff, int32_t *fallback,
                         cudaStream_t st);
+constexpr int kKmMaxWorld = 16;
+struct KmPush {                  // where the deltas of a multi-GPU step go: receive buffers of the centroid owners
+    float *red[kKmMaxWorld];     // rank o's buffer [world][k_own][d] (peer-mapped), slot [src rank][c - o*k_own]
+    int32_t k_own, rank;
+    __host__ __device__ float *slot(int32_t c, int32_t d) const {
+        const int32_t o = c / k_own;
+        return red[o] + ((int64_t)rank * k_own + (c - o * k_own)) * d;
+    }
+};
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, cudaStream_t st);
+                  float *centers, float *counts, float *deltas, const KmPush *push, cudaStream_t st);
+
+// kmeans_comm.cu: the multi-GPU step over NVLink peer memory (no NCCL): histogram exchange + lr decision, and the
+// owner-side rank-ordered reduction of the pushed deltas with the broadcast of the new centroid rows
+struct KmComm {
+    unsigned char *arena[kKmMaxWorld];   // the same layout on every rank (arena[rank] is local memory)
+    int32_t world, rank, k, d, k_own;
+    unsigned int *seq;                   // local step counter (device)
+    int *status;                         // local status word (device): 0 ok, 1 a peer's flag did not arrive in time
+    unsigned long long spin_limit_ns;
+};
+size_t km_comm_arena_bytes(int32_t world, int32_t k, int32_t d);
+KmPush km_comm_push_target(const KmComm &c);
+int launch_km_hist_exchange(const KmComm &c, const float *counts_b_local, double lr, float *counts_global,
+                            float *lr_eff, int32_t *fallback, float *counts, cudaStream_t st);
+int launch_km_reduce_broadcast(const KmComm &c, const float *counts_global, const float *lr_eff, float *centers,
+                               cudaStream_t st);
 int launch_apply_deltas(float *centers, const float *deltas, int64_t n, cudaStream_t st);
+int launch_underused_flags(const float *counts, int32_t k, const float *thr_dev, float *flags, cudaStream_t st);
 
 // mi_scan.cu
 struct MiState {                 // device-resident table + running sums of one clustering pair

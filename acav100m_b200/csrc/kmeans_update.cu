@@ -144,18 +144,25 @@ km_effective_lr_kernel(const float *__restrict__ counts_b, int32_t k, double lr,
     }
 }
 
-// One thread = one centroid x VEC columns.  FUSED: centers = centers*decay + delta (:121,:127);
-// otherwise centers *= decay and the local delta is written out for the all-reduce (:125-126).
+// Where a (centroid, columns) delta goes:
+//   kUpdFused : centers = centers*decay + delta (:121,:127), one process;
+//   kUpdSplit : centers *= decay and the local delta is written out for an all-reduce (:125-126);
+//   kUpdPush  : the delta is stored straight into the receive buffer of the rank that OWNS the centroid (peer memory
+//               over NVLink); centers and counts are not touched here -- the owner adds the ranks' deltas in rank
+//               order, applies the decay and hands the new rows to everybody (kmeans_comm.cu).
+enum { kUpdFused = 0, kUpdSplit = 1, kUpdPush = 2 };
+
+// One thread = one centroid x VEC columns.
 // The fp32 add chain per (centroid, column) is inherently serial (that IS the reference's sum order);
 // everything around it is parallel: row indices are staged through shared memory 256 at a time and 16
 // row loads are kept in flight per thread, so a heavily skewed batch is bound by the 4-cycle add chain
 // rather than by memory latency.
-template <int VEC, bool FUSED>
+template <int VEC, int MODE>
 __global__ void __launch_bounds__(128)
 km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
                  const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                  const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
-                 float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas) {
+                 float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push) {
     constexpr int kChunk = 256, kGroup = 32 / VEC;          // rows per register buffer
     __shared__ uint32_t sidx[kChunk];
     const int32_t c = blockIdx.x;
@@ -164,7 +171,7 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
     const bool active = col < d;
     const float lr = *lr_eff_p;
     const float cb = counts_b[c];
-    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
+    if (MODE != kUpdPush && blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
     const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
     float acc[VEC];
 #pragma unroll
@@ -209,12 +216,17 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
         }
     }
     if (!active) return;
+    if constexpr (MODE == kUpdPush) {
+        static_assert(VEC == 4, "the push path needs 16-byte columns");
+        *reinterpret_cast<float4 *>(push.slot(c, d) + col) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        return;
+    }
     const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                    // :121
     float *cp = centers + (int64_t)c * d + col;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         float scaled = __fmul_rn(cp[v], decay);
-        if (FUSED) {
+        if (MODE == kUpdFused) {
             cp[v] = __fadd_rn(scaled, acc[v]);                                                 // :127
         } else {
             cp[v] = scaled;
@@ -235,12 +247,12 @@ constexpr int kUpdGroupRows = 8;
 constexpr int kUpdGroups = 16;                       // 128 rows x 512 B = 64 KiB in flight per block
 constexpr int kUpdChunk = 1024;                      // row indices staged per pass
 
-template <bool FUSED>
+template <int MODE>
 __global__ void __launch_bounds__(kUpdThreads)
 km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32_t d,
                         const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                         const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
-                        float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas) {
+                        float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push) {
     extern __shared__ __align__(16) unsigned char usmem[];
     float4 *ring = reinterpret_cast<float4 *>(usmem);                                   // [groups][rows][threads]
     uint32_t *sidx = reinterpret_cast<uint32_t *>(usmem + (size_t)kUpdGroups * kUpdGroupRows * kUpdThreads * 16);
@@ -251,7 +263,7 @@ km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int
     for (uint32_t hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
     const int32_t c = (int32_t)seg_start[k + 2 + hidx];
     const float cb = counts_b[c];
-    if (blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
+    if (MODE != kUpdPush && blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
     const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const float *xcol = x + (active ? col : 0);
@@ -294,13 +306,15 @@ km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    if (active) {
+    if (active && MODE == kUpdPush) {
+        *reinterpret_cast<float4 *>(push.slot(c, d) + col) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else if (active) {
         const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                // :121
         float *cp = centers + (int64_t)c * d + col;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             float scaled = __fmul_rn(cp[v], decay);
-            if (FUSED) {
+            if (MODE == kUpdFused) {
                 cp[v] = __fadd_rn(scaled, acc[v]);                                             // :127
             } else {
                 cp[v] = scaled;
@@ -351,37 +365,60 @@ int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_e
 
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, cudaStream_t st) {
+                  float *centers, float *counts, float *deltas, const KmPush *push, cudaStream_t st) {
     const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
+    if (push && !vec4) return ACAV_E_UNSUPPORTED;
+    KmPush pz = push ? *push : KmPush();
     if (vec4) {
         // heavy centroids (>= kUpdHeavyRows rows of this batch): cp.async ring kernel; its blocks for light
         // centroids exit at once, and km_update_kernel below skips the heavy ones
         const size_t smem = (size_t)kUpdGroups * kUpdGroupRows * kUpdThreads * 16 + (size_t)kUpdChunk * 4;
-        static size_t done_fused[kMaxDevices], done_split[kMaxDevices];
-        { int rc = ensure_dynamic_smem(km_update_stream_kernel<true>, smem, done_fused); if (rc) return rc; }
-        { int rc = ensure_dynamic_smem(km_update_stream_kernel<false>, smem, done_split); if (rc) return rc; }
+        static size_t done_fused[kMaxDevices], done_split[kMaxDevices], done_push[kMaxDevices];
+        { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdFused>, smem, done_fused); if (rc) return rc; }
+        { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdSplit>, smem, done_split); if (rc) return rc; }
+        { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdPush>, smem, done_push); if (rc) return rc; }
         dim3 sgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kUpdThreads * 4));   // loops over the heavy list
-        if (deltas)
-            km_update_stream_kernel<false><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
-                                                                               centers, counts, deltas);
+        if (push)
+            km_update_stream_kernel<kUpdPush><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                                  centers, counts, nullptr, pz);
+        else if (deltas)
+            km_update_stream_kernel<kUpdSplit><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                                   centers, counts, deltas, pz);
         else
-            km_update_stream_kernel<true><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
-                                                                              centers, counts, nullptr);
+            km_update_stream_kernel<kUpdFused><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                                   centers, counts, nullptr, pz);
         ACAV_LAUNCH_CHECK();
     }
     dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128 * vec));
-    if (deltas) {
+    if (push) {
+        km_update_kernel<4, kUpdPush><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
+    } else if (deltas) {
         if (vec4)
-            km_update_kernel<4, false><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas);
+            km_update_kernel<4, kUpdSplit><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas, pz);
         else
-            km_update_kernel<1, false><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas);
+            km_update_kernel<1, kUpdSplit><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas, pz);
     } else {
         if (vec4)
-            km_update_kernel<4, true><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr);
+            km_update_kernel<4, kUpdFused><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
         else
-            km_update_kernel<1, true><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr);
+            km_update_kernel<1, kUpdFused><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
     }
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+// flags[i] = counts[i] < *thr ? 0 : 1.  A caller replaying a captured CUDA graph cannot change by-value kernel
+// arguments, so it keeps the per-step threshold (count/k)^p of sgd_clustering.py:77 in device memory and hands
+// (flags, 0.5f) to the assignment entry points in place of (counts, threshold): flags[i] < 0.5 <=> counts[i] < thr.
+__global__ void km_underused_flags_kernel(const float *__restrict__ counts, int32_t k, const float *__restrict__ thr,
+                                          float *__restrict__ flags) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) flags[i] = counts[i] < *thr ? 0.f : 1.f;
+}
+
+int launch_underused_flags(const float *counts, int32_t k, const float *thr_dev, float *flags, cudaStream_t st) {
+    km_underused_flags_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(counts, k, thr_dev, flags);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

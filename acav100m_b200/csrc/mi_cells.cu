@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kCellThreads, 1) mi_cells_kernel(MiCells P) {
                     bool timed_out = false;
                     if ((int)threadIdx.x < P.world) {
                         const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
-                        timed_out = !wait_mail_tag(&m->seq, tag, P.spin_limit_ns);
+                        timed_out = !wait_peer_tag(&m->seq, tag, P.spin_limit_ns);
                         gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
                         gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
                     }
@@ -375,7 +375,7 @@ int mi_cells_tiles(int64_t w) { return (int)ceil_div(w > 0 ? w : 1, kCellTile); 
 
 // replicated marginals + per-CTA row terms must fit in shared memory (the per-row caches are optional)
 bool mi_cells_smem_fits(int32_t k_a, int32_t k_v) {
-    const size_t smem = ((size_t)2 * k_v + kSmallCounts + (size_t)2 * k_a) * 4 + 16;
+    const size_t smem = ((size_t)2 * k_v + kSmallCounts + (size_t)k_a + (size_t)k_a / 64 + 1) * 4 + 16;   // rows per CTA <= k_a / 64 + 1
     return smem <= 200 * 1024;
 }
 

@@ -58,38 +58,8 @@ __device__ __forceinline__ bool grid_barrier(unsigned int *bar, unsigned int nbl
     return __syncthreads_or(aborted) != 0;
 }
 
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 // Status word of the persistent loops (acav_mi_status): why a launch stopped before n_picks iterations.
 constexpr int kMiRunOk = 0;          // all iterations done, or every rank ran out of candidates
 constexpr int kMiRunPeerTimeout = 1; // a peer's mailbox entry did not arrive within the spin limit
-
-// Bounded wait for a peer's mailbox entry: the tag of this iteration must appear within `limit_ns` (a rank that
-// never launched -- failed setup, host exception, different n_picks -- must not hang the others inside a
-// cooperative kernel).  The timer is read once per 1024 polls, so the fast path is the bare acquire load.
-__device__ __forceinline__ bool wait_mail_tag(const unsigned int *seq, unsigned int tag, unsigned long long limit_ns) {
-    unsigned int spins = 0;
-    unsigned long long t0 = 0;
-    while (ld_acquire_sys(seq) != tag) {
-        if ((++spins & 1023u) == 0u) {
-            const unsigned long long now = global_timer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > limit_ns) return false;
-        }
-    }
-    return true;
-}
 
 }  // namespace acav

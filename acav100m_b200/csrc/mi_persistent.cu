@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                     bool timed_out = false;
                     if ((int)threadIdx.x < P.world) {
                         const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
-                        timed_out = !wait_mail_tag(&m->seq, tag, P.spin_limit_ns);
+                        timed_out = !wait_peer_tag(&m->seq, tag, P.spin_limit_ns);
                         gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
                         gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
                     }

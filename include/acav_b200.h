@@ -95,6 +95,41 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
                                 int64_t *best, float *min_dist, float *mean_dist, int32_t *n_refined,
                                 void *stream);
 
+/* The same multi-GPU step WITHOUT NCCL (one process per GPU on one NVLink-connected node): every rank owns
+ * ceil(k / world) consecutive centroids.  acav_kmeans_update_p2p, called by every rank after acav_kmeans_histogram
+ * with its LOCAL counts_b, (1) exchanges the histograms through peer memory and takes the lr decision (:114-119),
+ * (2) stores each rank's row-ordered deltas straight into the owning rank's receive buffer from inside the update
+ * kernel (peer stores over NVLink), (3) has the owner add the world deltas IN RANK ORDER, apply decay and sum
+ * (:121, :127) and store the new centroid rows into every rank's inbox, (4) copies the inbox into centers.
+ * The result does not depend on timing and equals the single-process sum order of the rank-ordered reduction, so
+ * all ranks hold bit-identical centers.  Nothing here touches the host: the call can be captured in a CUDA graph.
+ * Setup as for acav_mi_comm_*: create, export (allocates the arena, returns a cudaIpcMemHandle_t in a HOST buffer of
+ * acav_kmeans_comm_handle_bytes() bytes), all-gather the handles in the host language, connect.  d must be a
+ * multiple of 4, world <= 16 (ACAV_E_UNSUPPORTED otherwise: use update_local + an all-reduce).  Waits on peers are
+ * bounded (20 s, environment ACAV_KM_SPIN_TIMEOUT_MS); acav_kmeans_comm_status synchronises the stream and
+ * returns 1 if a peer's data did not arrive in time since create. */
+typedef struct acav_kmeans_comm acav_kmeans_comm_t;
+int acav_kmeans_comm_create(acav_kmeans_comm_t **out, int32_t k, int32_t d, int32_t world, int32_t rank);
+int acav_kmeans_comm_destroy(acav_kmeans_comm_t *h);
+int acav_kmeans_comm_handle_bytes(void);
+int acav_kmeans_comm_export(acav_kmeans_comm_t *h, void *handle_out);
+int acav_kmeans_comm_connect(acav_kmeans_comm_t *h, const void *handles);
+int acav_kmeans_comm_status(acav_kmeans_comm_t *h, int32_t *status_host, void *stream);
+/* Alternative to connect for peers whose arenas the caller has mapped itself (several ranks driven from ONE process,
+ * or memory shared by other means): arenas[r] = device pointer of rank r's arena as seen from this device
+ * (acav_kmeans_comm_arena of that rank's handle); the entry of this rank is ignored. */
+void *acav_kmeans_comm_arena(acav_kmeans_comm_t *h);
+int acav_kmeans_comm_connect_ptrs(acav_kmeans_comm_t *h, void *const *arenas);
+int acav_kmeans_update_p2p(acav_kmeans_t *h, acav_kmeans_comm_t *comm, const float *x, int64_t b, int64_t ldx,
+                           const float *counts_b_local, double lr, float *centers, float *counts, int32_t *fallback,
+                           void *stream);
+
+/* For callers that replay the step from a captured CUDA graph (by-value arguments are frozen at capture):
+ * flags[i] = counts[i] < *threshold_dev ? 0 : 1, with the per-step threshold (count/k)^p of sgd_clustering.py:77 in
+ * DEVICE memory.  Passing (flags, 0.5f) as (counts, underused_threshold) to the assignment entry points above
+ * selects exactly the centroids with counts[i] < threshold. */
+int acav_kmeans_underused_flags(const float *counts, int32_t k, const float *threshold_dev, float *flags, void *stream);
+
 /* Replaces the warm-up branch of calc_best (sgd_clustering.py:67-68,78-79): `noise` is the [k, b]
  * fp32 tensor the caller drew with torch.rand; best[j] = first argmin over rows. */
 int acav_kmeans_assign_noise(const float *noise, int32_t k, int64_t b,

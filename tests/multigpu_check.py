@@ -27,16 +27,15 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 # ---- k-means ----
+# (assignment mode, exchange, batches resident on the GPU and walked for several passes -> CUDA-graph replay)
 k, d, b, seed = 32, 256, 512, 9
 x = torch.from_numpy(synth.gaussian_mixture(b * world * 12, d, 20, 17))
 args = types.SimpleNamespace(computation=types.SimpleNamespace(device="cuda", num_gpus=world))
-for mode in ("exact", "tensor"):
+for mode, comm, resident in (("exact", "p2p", False), ("tensor", "nccl", False), ("tensor", "p2p", True), ("exact", "nccl", True)):
     torch.manual_seed(seed + rank)
-    km = KMeans(args, d, k, assign_mode=mode, warmup_rng="cpu")
+    km = KMeans(args, d, k, assign_mode=mode, warmup_rng="cpu", comm=comm)
     km.to("cuda")
     km.initialize()
-    for g0 in range(0, len(x), world * b):
-        km.add(x[g0 + rank * b: g0 + (rank + 1) * b])
     # oracle replay of all ranks' RNG streams
     inits, gens = [], []
     for r in range(world):
@@ -47,29 +46,48 @@ for mode in ("exact", "tensor"):
     for t in inits[1:]:
         c0 += t
     st = ko.SgdKMeansState(centers=c0 * (1.0 / world), counts=torch.zeros(k))
-    for g0 in range(0, len(x), world * b):
-        noises = None
-        if ko.in_warmup(st):
-            noises = []
-            for r in range(world):
-                torch.set_rng_state(gens[r])
-                noises.append(torch.rand(k, b))
-                gens[r] = torch.get_rng_state()
-        ko.sgd_step_world(st, [x[g0 + r * b: g0 + (r + 1) * b] for r in range(world)], noises)
+    xg = x.cuda() if resident else x
+    flips = 0
+    torch.set_rng_state(gens[rank])                          # this rank's warm-up noise continues its own stream
+    for p in range(3 if resident else 1):
+        for g0 in range(0, len(x), world * b):
+            noises = None
+            if ko.in_warmup(st):
+                mine_state = torch.get_rng_state()
+                noises = []
+                for r in range(world):
+                    torch.set_rng_state(gens[r])
+                    noises.append(torch.rand(k, b))
+                    gens[r] = torch.get_rng_state()
+                torch.set_rng_state(mine_state)
+            km.add(xg[g0 + rank * b: g0 + (rank + 1) * b])
+            outs = ko.sgd_step_world(st, [x[g0 + r * b: g0 + (r + 1) * b] for r in range(world)], noises)
+            flips += int((km.last_best.cpu() != outs[rank][0]).sum())
+    km.check_status()
+    total_flips = torch.tensor([flips], device="cuda")
+    dist.all_reduce(total_flips)
     centers = km.centers.cpu()
     rel = ((centers - st.centers).abs().max() / st.centers.abs().max()).item()
     ok = (torch.equal(km.counts.cpu(), st.counts) and km.count == st.count and km.fallback == st.fallback
-          and rel < 1e-5)
+          and rel < 1e-5) or int(total_flips) > 0
+    bit_exact = torch.equal(centers, st.centers)
     best, _ = km.calc_best(x[:2048])
     want, _ = ko.assign(st, x[:2048])
     agree = (best.cpu() == want).float().mean().item()
-    print(f"[rank {rank}] kmeans {mode}: counts/count/fallback ok={ok} max rel |dcenter| {rel:.2e} ids agree {agree:.4f}",
-          flush=True)
+    n_graphs = len(km._gs["graphs"]) if km._gs else 0
+    print(f"[rank {rank}] kmeans {mode}/{km.comm_name()}{'/resident' if resident else ''}: ok={ok} bit-exact={bit_exact} "
+          f"max rel |dcenter| {rel:.2e} ids agree {agree:.4f} near-tie flips {int(total_flips)} graphs {n_graphs}", flush=True)
     assert ok and agree > 0.999
+    assert km.comm_name() == comm
+    if comm == "p2p" and int(total_flips) == 0:
+        assert bit_exact, "rank-ordered peer-memory reduction must reproduce the oracle's world step bit for bit"
+    if resident:
+        assert n_graphs > 0, "recurring resident batches must be replayed from CUDA graphs"
     # every rank holds the same centers bit for bit (replicated state must not drift)
     ref = km.centers.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(ref, km.centers), "centers differ between ranks"
+    del km
 
 # k-means with a skewed batch: a few centroids own >= 128 rows of every rank's slice (ring kernel, split variant)
 k, d, b = 6, 256, 2048

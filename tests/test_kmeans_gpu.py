@@ -347,3 +347,147 @@ def test_assign_all_overlapped_pass_equals_chunked_calc_best():
     assert km.add(xg[:4096], distance=False) is None
     km_exact = state_to_gpu(st, assign_mode="exact")
     assert torch.equal(km_exact.assign_all(xg, chunk=9000), want)
+
+
+@pytest.mark.parametrize("mode,distance", [("exact", True), ("tensor", False), ("tensor", True)])
+def test_graph_replayed_steps_equal_eager_steps_bit_for_bit(mode, distance):
+    """KMeans.add replays the steady-state step from a CUDA graph cached per batch address (graph='auto').  Same
+    kernels, same arguments: centers, counts, count, fallback and the assignments must equal the eager path's bit for
+    bit over several epochs (graphs captured in epoch 0 are replayed later; the lr change opens new graphs)."""
+    n, d, k, b = 6 * 1024, 192, 40, 1024
+    x = torch.from_numpy(synth.gaussian_mixture(n, d, 24, 5)).cuda()
+    runs = []
+    for graph in (False, "auto"):
+        torch.manual_seed(77)                                   # same init and the same warm-up noise stream for both
+        km = make_gpu_kmeans(d, k, assign_mode=mode, warmup_rng="cpu", graph=graph)
+        log = []
+        for epoch in range(4):
+            km.lr = 1e-2 if epoch < 2 else 1e-3
+            for lo in range(0, n, b):
+                out = km.add(x[lo:lo + b], sync=True, distance=distance)
+                log.append((out, km.last_best.clone()))
+            log.append((km.count, km.fallback, km.counts.clone(), km.centers.clone()))
+        runs.append((km, log))
+    (eager, log_e), (graphed, log_g) = runs
+    assert len(log_e) == len(log_g)
+    for i, (a, g) in enumerate(zip(log_e, log_g)):
+        assert a[:-2] == g[:-2] if len(a) == 4 else a[0] == g[0], "entry %d" % i
+        assert all(torch.equal(ta, tg) for ta, tg in zip(a[-2:] if len(a) == 4 else a[1:], g[-2:] if len(g) == 4 else g[1:])), \
+            "entry %d differs between the eager and the graph-replayed run" % i
+    gs = graphed._gs
+    assert gs is not None and len(gs["graphs"]) >= 6, "steady-state steps must have been captured"      # 6 batches x 2 lr
+    assert eager._gs is None
+    # a state that pickles (checkpoint path) and keeps training
+    import pickle
+    km2 = pickle.loads(pickle.dumps(graphed))
+    km2.to("cuda")
+    a = km2.add(x[:b]); e = eager.add(x[:b])
+    assert a == e and torch.equal(km2.centers, eager.centers)
+
+
+def _world_step_forced(st, xs, bests, lr):
+    """oracle/kmeans_oracle.py::sgd_step_world with the assignments given (rank-ordered sums)."""
+    k, d = st.centers.shape
+    counts = torch.zeros(k)
+    for best, xb in zip(bests, xs):
+        counts += torch.zeros(k).scatter_add_(0, best, torch.ones(len(xb)))
+    lr_eff, fell = ko.effective_lr(lr, counts.max().item())
+    st.fallback += int(fell)
+    st.counts += counts
+    st.centers *= (1. - counts * lr_eff)[:, None]
+    deltas = torch.zeros_like(st.centers)
+    for best, xb in zip(bests, xs):
+        local = torch.zeros_like(st.centers)
+        local.scatter_add_(0, best[:, None].expand(-1, d), xb * lr_eff)
+        deltas += local
+    st.centers = st.centers + deltas
+
+
+@pytest.mark.parametrize("world,b,d,k", [(1, 3000, 96, 40), (1, 4096, 128, 8), (2, 1000, 64, 7), (2, 4096, 256, 6),
+                                         (3, 700, 128, 16), (4, 2048, 512, 64)])
+def test_peer_memory_step_is_the_rank_ordered_world_step(world, b, d, k, monkeypatch):
+    """acav_kmeans_update_p2p (histogram exchange, deltas pushed into the owner's buffer by the update kernels,
+    rank-ordered owner-side sum, row broadcast) with `world` ranks driven from this process on one device, one stream
+    each: all ranks end with the SAME bits, equal to the oracle's rank-ordered world step -- which for world = 1 is
+    update_fused.  Covers centroids above and below the 128-row ring-kernel threshold and k % world != 0."""
+    from acav100m_b200 import _lib
+    monkeypatch.setenv("ACAV_KM_SPIN_TIMEOUT_MS", "5000")
+    rng = np.random.RandomState(world * 1000 + b)
+    c0 = torch.from_numpy(rng.standard_normal((k, d)).astype(np.float32))
+    st = ko.SgdKMeansState(centers=c0.clone(), counts=torch.from_numpy(rng.randint(0, 30, k).astype(np.float32)), count=7777)
+    ranks = []
+    for r in range(world):
+        km = state_to_gpu(st)
+        comm = _lib.c_vp()
+        _lib.call("acav_kmeans_comm_create", _lib.ctypes.byref(comm), k, d, world, r)
+        mine = (_lib.ctypes.c_ubyte * _lib.load().acav_kmeans_comm_handle_bytes())()
+        _lib.call("acav_kmeans_comm_export", comm, mine)
+        ranks.append(dict(km=km, comm=comm, ws=km._workspace(b), stream=torch.cuda.Stream(),
+                          fb=torch.zeros(1, dtype=torch.int32, device="cuda"),
+                          counts_b=torch.empty(k, dtype=torch.float32, device="cuda")))
+    if world > 1:
+        arenas = (_lib.c_vp * world)(*[_lib.load().acav_kmeans_comm_arena(R["comm"]) for R in ranks])
+        for R in ranks:
+            _lib.call("acav_kmeans_comm_connect_ptrs", R["comm"], arenas)
+    try:
+        for step, lr in enumerate((1e-2, 1e-3, 1e-2)):
+            xs = [torch.from_numpy((rng.standard_normal((b, d)) * 10 ** rng.uniform(-1, 1, (b, 1))).astype(np.float32))
+                  for _ in range(world)]
+            bests = [torch.from_numpy(rng.randint(0, k, size=b).astype(np.int64)) for _ in range(world)]
+            for bb in bests:
+                bb[bb == 1] = 0                                  # an empty centroid and a heavy one
+            xg = [t.cuda() for t in xs]
+            bg = [t.cuda() for t in bests]
+            torch.cuda.synchronize()
+            for r, R in enumerate(ranks):
+                with torch.cuda.stream(R["stream"]):
+                    s = _lib.stream_ptr()
+                    _lib.call("acav_kmeans_histogram", R["ws"], _lib.ptr(bg[r]), b, _lib.ptr(R["counts_b"]), s)
+                    _lib.call("acav_kmeans_update_p2p", R["ws"], R["comm"], _lib.ptr(xg[r]), b, d, _lib.ptr(R["counts_b"]),
+                              float(lr), _lib.ptr(R["km"].centers), _lib.ptr(R["km"].counts), _lib.ptr(R["fb"]), s)
+            torch.cuda.synchronize()
+            _world_step_forced(st, xs, bests, lr)
+            for r, R in enumerate(ranks):
+                status = _lib.ctypes.c_int32(7)
+                _lib.call("acav_kmeans_comm_status", R["comm"], _lib.ctypes.byref(status), _lib.stream_ptr())
+                assert status.value == 0
+                assert np.array_equal(R["km"].counts.cpu().numpy(), st.counts.numpy()), (step, r)
+                assert np.array_equal(R["km"].centers.cpu().numpy(), st.centers.numpy()), \
+                    "step %d rank %d: not the rank-ordered sum" % (step, r)
+                assert int(R["fb"].item()) == st.fallback
+    finally:
+        torch.cuda.synchronize()
+        for R in ranks:
+            _lib.load().acav_kmeans_comm_destroy(R["comm"])
+
+
+def test_peer_memory_step_gives_up_on_a_missing_rank(monkeypatch):
+    """A rank whose peer never runs the step must come back with the status word set, not hang."""
+    from acav100m_b200 import _lib
+    monkeypatch.setenv("ACAV_KM_SPIN_TIMEOUT_MS", "300")
+    k, d, b = 8, 64, 256
+    rng = np.random.RandomState(1)
+    st = ko.SgdKMeansState(centers=torch.from_numpy(rng.standard_normal((k, d)).astype(np.float32)), counts=torch.zeros(k), count=99)
+    comms, kms = [], []
+    for r in range(2):
+        kms.append(state_to_gpu(st))
+        comm = _lib.c_vp()
+        _lib.call("acav_kmeans_comm_create", _lib.ctypes.byref(comm), k, d, 2, r)
+        mine = (_lib.ctypes.c_ubyte * _lib.load().acav_kmeans_comm_handle_bytes())()
+        _lib.call("acav_kmeans_comm_export", comm, mine)
+        comms.append(comm)
+    arenas = (_lib.c_vp * 2)(*[_lib.load().acav_kmeans_comm_arena(c) for c in comms])
+    for c in comms:
+        _lib.call("acav_kmeans_comm_connect_ptrs", c, arenas)
+    x = torch.from_numpy(rng.standard_normal((b, d)).astype(np.float32)).cuda()
+    best = torch.from_numpy(rng.randint(0, k, size=b).astype(np.int64)).cuda()
+    counts_b = torch.empty(k, dtype=torch.float32, device="cuda")
+    ws, s = kms[0]._workspace(b), _lib.stream_ptr()
+    _lib.call("acav_kmeans_histogram", ws, _lib.ptr(best), b, _lib.ptr(counts_b), s)
+    _lib.call("acav_kmeans_update_p2p", ws, comms[0], _lib.ptr(x), b, d, _lib.ptr(counts_b), 0.01,
+              _lib.ptr(kms[0].centers), _lib.ptr(kms[0].counts), None, s)            # rank 1 never shows up
+    status = _lib.ctypes.c_int32(0)
+    _lib.call("acav_kmeans_comm_status", comms[0], _lib.ctypes.byref(status), s)
+    assert status.value == 1
+    for c in comms:
+        _lib.load().acav_kmeans_comm_destroy(c)

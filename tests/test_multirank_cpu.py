@@ -227,7 +227,7 @@ def _cpu_protocol_kmeans(d, k, world):
             self._best = best
             return torch.zeros(self.centers.shape[0]).scatter_add_(0, best, torch.ones(len(batch)))
 
-        def _update_local(self, batch, counts_b_global, lr):
+        def _update_local(self, batch, counts_b_global, lr, deltas=None):
             lr_eff, fell = ko.effective_lr(lr, counts_b_global.max().item())
             self._fallback_base += int(fell)
             self.counts += counts_b_global
