@@ -74,12 +74,13 @@ SIGNATURES = {
     "acav_mi_comm_connect": (ctypes.c_int, [c_vp, c_vp]),
     "acav_mi_loop_supported": (ctypes.c_int, [c_i32, c_i32, c_i32]),
     "acav_mi_prepare": (ctypes.c_int, [c_vp, c_i32, c_vp]),
+    "acav_mi_set_stream_variant": (ctypes.c_int, [c_vp, c_i32, c_i32]),
     "acav_mi_status": (ctypes.c_int, [c_vp, c_vp, c_vp]),
 }
 
 ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1
 TILE_AUTO, TILE_SINGLE, TILE_PAIR_256, TILE_PAIR_512 = 0, 1, 2, 3
-MI_LOOP_KERNELS, MI_LOOP_PERSISTENT, MI_LOOP_CELLS = 0, 1, 2
+MI_LOOP_KERNELS, MI_LOOP_PERSISTENT, MI_LOOP_CELLS, MI_LOOP_BYTES = 0, 1, 2, 3
 PERSISTENT_READY = True         # persistent greedy-MI kernel validated against the C oracle on a B200
 TENSOR_PATH_READY = True        # tcgen05 assignment validated against the exact kernel on a B200
 

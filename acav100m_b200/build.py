@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libacav_b200.so")
-SOURCES = ["capi.cu", "kmeans_exact.cu", "kmeans_update.cu", "kmeans_comm.cu", "kmeans_umma.cu", "kmeans_umma2.cu", "mi_scan.cu", "mi_persistent.cu", "mi_cells.cu", "mi_dense.cu", "mi_pairs.cu"]
+SOURCES = ["capi.cu", "kmeans_exact.cu", "kmeans_update.cu", "kmeans_comm.cu", "kmeans_umma.cu", "kmeans_umma2.cu", "mi_scan.cu", "mi_persistent.cu", "mi_stream8.cu", "mi_cells.cu", "mi_dense.cu", "mi_pairs.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # parity-critical fp32 chains use explicit _rn intrinsics; keep the rest uncontracted too

@@ -66,6 +66,11 @@ struct acav_mi {
     // cell-index loop resources (candidates sorted by table cell), built on first use
     uint32_t *cx_sorted_pos, *cx_cell_start, *cx_head, *cx_first_pos;
     bool cells_valid;
+    // byte-stream loop resources (sub-row partitioned stream, one byte per candidate), built on first use
+    uint8_t *s8_stream;
+    uint32_t *s8_pos, *s8_row_start, *s8_row_total, *s8_tilehist, *s8_chunk_start;
+    int32_t s8_rows_smem, s8_variant, s8_use_cache;
+    bool s8_valid;
 };
 
 namespace {
@@ -86,6 +91,81 @@ int query_sm_count(int32_t *out) {
     int n = 0;
     ACAV_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     *out = n;
+    return 0;
+}
+
+// Balanced cut of a row-partitioned stream into `grid` contiguous chunks: cost(e) = e + row_cost * (#non-empty rows that
+// start before e); chunk edges are multiples of `blk` (rows are padded to whole blocks).  rs = row offsets [n_rows + 1].
+std::vector<uint32_t> cut_chunks(const std::vector<uint32_t> &rs, int32_t n_rows, double row_cost, uint32_t blk, int32_t grid) {
+    std::vector<double> cum((size_t)n_rows + 1);
+    double run = 0.0;
+    for (int32_t r = 0; r < n_rows; ++r) {
+        cum[r] = run;
+        const uint32_t n = rs[r + 1] - rs[r];
+        if (n) run += row_cost + (double)n;
+    }
+    cum[n_rows] = run;
+    std::vector<uint32_t> chunks((size_t)grid + 1);
+    int32_t r = 0;
+    for (int32_t g = 0; g <= grid; ++g) {
+        const double t = run * (double)g / (double)grid;
+        while (r < n_rows && cum[r + 1] <= t) ++r;
+        uint32_t e;
+        if (r >= n_rows) e = rs[n_rows];
+        else {
+            const uint32_t n = rs[r + 1] - rs[r];
+            double off = t - cum[r] - row_cost;
+            if (off < 0) off = 0;
+            if (off > (double)n) off = (double)n;
+            e = rs[r] + ((uint32_t)off / blk) * blk;
+        }
+        chunks[g] = e;
+    }
+    chunks[0] = 0;
+    chunks[grid] = rs[n_rows];
+    for (int32_t g = 1; g <= grid; ++g)
+        if (chunks[g] < chunks[g - 1]) chunks[g] = chunks[g - 1];
+    return chunks;
+}
+
+// Build (or rebuild) the sub-row partitioned one-byte stream of ACAV_MI_LOOP_BYTES and its per-CTA chunk table.
+int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
+    if (h->s8_valid) return 0;
+    MiState &s = h->s;
+    if (!mi_s8_supported(s.k_a, s.k_v)) return ACAV_E_UNSUPPORTED;
+    h->s8_rows_smem = mi_s8_rows_that_fit(s.k_a, s.k_v);
+    const int32_t k_rows = mi_s8_k_rows(s.k_a, s.k_v);
+    const int ntiles = mi_s8_tiles(s.w);
+    const int64_t cap = (mi_s8_stream_capacity(s.w, s.k_a, s.k_v) + 15) / 16 * 16;
+    int rc = 0;
+    if (!h->s8_stream) {
+        if (!rc) rc = dev_alloc(&h->s8_stream, (size_t)cap, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_pos, (size_t)cap, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_row_start, (size_t)k_rows + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_row_total, (size_t)k_rows, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_tilehist, (size_t)ntiles * k_rows, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_chunk_start, (size_t)h->sm_count + 1, nullptr);
+        if (!h->n_alt && !rc) rc = dev_alloc(&h->n_alt, (size_t)s.k_a * s.k_v, nullptr);
+        if (!h->pub && !rc) rc = dev_alloc(&h->pub, mi_pub_bytes(h->sm_count), nullptr);
+        if (!h->bar && !rc) rc = dev_alloc(&h->bar, 2, nullptr);
+        if (rc) return rc;
+    }
+    rc = launch_mi_s8_partition(s.cells, s.w, s.k_a, s.k_v, h->s8_tilehist, h->s8_row_total, h->s8_row_start,
+                                h->s8_stream, h->s8_pos, cap, st);
+    if (rc) return rc;
+    std::vector<uint32_t> rs((size_t)k_rows + 1);
+    ACAV_CUDA_TRY(cudaMemcpyAsync(rs.data(), h->s8_row_start, sizeof(uint32_t) * rs.size(), cudaMemcpyDeviceToHost, st));
+    ACAV_CUDA_TRY(cudaStreamSynchronize(st));
+    rc = launch_mi_s8_block_sort(h->s8_stream, h->s8_pos, rs[k_rows], st);
+    if (rc) return rc;
+    double row_cost = 512.0;                       // one sub-row's gain row ~ streaming one block (tuned on B200)
+    if (const char *e = std::getenv("ACAV_MI_S8_ROWCOST")) row_cost = std::atof(e);
+    const std::vector<uint32_t> chunks = cut_chunks(rs, k_rows, row_cost, (uint32_t)mi_s8_block(), h->sm_count);
+    ACAV_CUDA_TRY(cudaMemcpyAsync(h->s8_chunk_start, chunks.data(), sizeof(uint32_t) * chunks.size(),
+                                  cudaMemcpyHostToDevice, st));
+    ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `chunks` is a host temporary
+    h->grid = h->sm_count;
+    h->s8_valid = true;
     return 0;
 }
 
@@ -118,38 +198,10 @@ int mi_prepare_persistent(acav_mi *h, cudaStream_t st) {
     h->w_sorted = rs[s.k_a];                       // rows padded to whole blocks
     rc = launch_mi_block_sort(h->c2s, h->pos_s, h->w_sorted, st);
     if (rc) return rc;
-    // balanced cut: cost(e) = e + row_cost * (#non-empty rows that start before e); chunk edges block aligned
     const int32_t grid = h->sm_count;
     double row_cost = 6.0 * s.k_v;                // building one gain row ~ scanning 6*K_v candidates (measured)
     if (const char *e = std::getenv("ACAV_MI_ROWCOST")) row_cost = std::atof(e) * s.k_v;
-    std::vector<double> cum((size_t)s.k_a + 1);
-    double run = 0.0;
-    for (int32_t r = 0; r < s.k_a; ++r) {
-        cum[r] = run;
-        const uint32_t n = rs[r + 1] - rs[r];
-        if (n) run += row_cost + (double)n;
-    }
-    cum[s.k_a] = run;
-    std::vector<uint32_t> chunks((size_t)grid + 1);
-    int32_t r = 0;
-    for (int32_t g = 0; g <= grid; ++g) {
-        const double t = run * (double)g / (double)grid;
-        while (r < s.k_a && cum[r + 1] <= t) ++r;
-        uint32_t e;
-        if (r >= s.k_a) e = rs[s.k_a];
-        else {
-            const uint32_t n = rs[r + 1] - rs[r];
-            double off = t - cum[r] - row_cost;
-            if (off < 0) off = 0;
-            if (off > (double)n) off = (double)n;
-            e = rs[r] + ((uint32_t)off / (uint32_t)mi_stream_block()) * (uint32_t)mi_stream_block();
-        }
-        chunks[g] = e;
-    }
-    chunks[0] = 0;
-    chunks[grid] = rs[s.k_a];
-    for (int32_t g = 1; g <= grid; ++g)
-        if (chunks[g] < chunks[g - 1]) chunks[g] = chunks[g - 1];
+    const std::vector<uint32_t> chunks = cut_chunks(rs, s.k_a, row_cost, (uint32_t)mi_stream_block(), grid);
     ACAV_CUDA_TRY(cudaMemcpyAsync(h->chunk_start, chunks.data(), sizeof(uint32_t) * chunks.size(),
                                   cudaMemcpyHostToDevice, st));
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `chunks` is a host temporary
@@ -550,6 +602,8 @@ int acav_mi_destroy(acav_mi_t *h) {
             if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
     cudaFree(h->mail_local); cudaFree(h->run_status);
     cudaFree(h->cx_sorted_pos); cudaFree(h->cx_cell_start); cudaFree(h->cx_head); cudaFree(h->cx_first_pos);
+    cudaFree(h->s8_stream); cudaFree(h->s8_pos); cudaFree(h->s8_row_start); cudaFree(h->s8_row_total);
+    cudaFree(h->s8_tilehist); cudaFree(h->s8_chunk_start);
     delete h;
     return 0;
 }
@@ -579,6 +633,11 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     h->sorted_valid = false;
     h->cx_sorted_pos = nullptr; h->cx_cell_start = nullptr; h->cx_head = nullptr; h->cx_first_pos = nullptr;
     h->cells_valid = false;
+    h->s8_stream = nullptr; h->s8_pos = nullptr; h->s8_row_start = nullptr; h->s8_row_total = nullptr;
+    h->s8_tilehist = nullptr; h->s8_chunk_start = nullptr; h->s8_rows_smem = 0; h->s8_valid = false;
+    h->s8_variant = 0; h->s8_use_cache = 1;
+    if (const char *e = std::getenv("ACAV_MI_S8_VARIANT")) h->s8_variant = std::atoi(e);
+    if (const char *e = std::getenv("ACAV_MI_S8_CACHE")) h->s8_use_cache = std::atoi(e);
     int rc = query_sm_count(&h->sm_count);
     const size_t cells = (size_t)k_a * k_v;
     if (!rc) rc = dev_alloc(&s.cells, (size_t)w + 4, nullptr);
@@ -604,6 +663,7 @@ int acav_mi_load_candidates(acav_mi_t *h, const int64_t *cells, void *stream) {
     h->loaded = (rc == 0);
     h->sorted_valid = false;
     h->cells_valid = false;
+    h->s8_valid = false;
     return rc;
 }
 
@@ -640,6 +700,7 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n, int64_t *o
     if (!h->tabled || !h->loaded) return ACAV_E_STATE;
     h->sorted_valid = false;                 // the row-partitioned stream does not see this removal
     h->cells_valid = false;                  // nor does the cell index
+    h->s8_valid = false;
     return launch_mi_apply(h->s, reinterpret_cast<const unsigned long long *>(key_cells), n, out_pos, out_gain,
                            (cudaStream_t)stream);
 }
@@ -654,7 +715,8 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         int rc = mi_prepare_cells(h, st);
         if (rc) return rc;
         const int32_t grid = h->sm_count < h->s.k_a ? h->sm_count : h->s.k_a;
-        h->sorted_valid = false;                 // the candidate stream does not see these removals
+        h->sorted_valid = false;                 // the candidate streams do not see these removals
+        h->s8_valid = false;
         rc = launch_mi_cells(h->s, h->cx_cell_start, h->cx_sorted_pos, h->cx_head, h->cx_first_pos, grid, h->pub, h->bar,
                              n_picks, out_pos, out_gain, h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer,
                              h->run_status, h->spin_limit_ns, st);
@@ -663,7 +725,7 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         return rc;
     }
     if (mode == ACAV_MI_LOOP_KERNELS) {
-        if (n_picks > 0) { h->sorted_valid = false; h->cells_valid = false; }
+        if (n_picks > 0) { h->sorted_valid = false; h->cells_valid = false; h->s8_valid = false; }
         for (int64_t it = 0; it < n_picks; ++it) {
             int rc = launch_mi_gain_table(h->s, st);
             if (!rc) rc = launch_mi_scan(h->s, h->sm_count, st);
@@ -672,12 +734,28 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         }
         return 0;
     }
+    if (mode == ACAV_MI_LOOP_BYTES) {
+        if (n_picks == 0) return 0;
+        if (h->world > 1 && !h->comm_connected) return ACAV_E_STATE;
+        int rc = mi_prepare_stream8(h, st);
+        if (rc) return rc;
+        h->cells_valid = false;                  // neither the cell index nor the 2-byte stream see these removals
+        h->sorted_valid = false;
+        rc = launch_mi_stream8(h->s, h->n_alt, h->s8_stream, h->s8_pos, h->s8_row_start, h->s8_chunk_start, h->grid, h->pub,
+                               h->bar, n_picks, out_pos, out_gain, h->s8_rows_smem, h->s8_variant, h->s8_use_cache,
+                               h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer, h->dbg, h->run_status,
+                               h->spin_limit_ns, st);
+        h->seq_base += (unsigned int)n_picks + 1u;
+        if (!rc) rc = launch_mi_refresh_terms(h->s, st);
+        return rc;
+    }
     if (mode != ACAV_MI_LOOP_PERSISTENT) return ACAV_E_INVALID;
     if (n_picks == 0) return 0;
     if (h->world > 1 && !h->comm_connected) return ACAV_E_STATE;
     int rc = mi_prepare_persistent(h, st);
     if (rc) return rc;
     h->cells_valid = false;                      // the cell index does not see these removals
+    h->s8_valid = false;
     rc = launch_mi_persistent(h->s, h->n_alt, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->pub, h->bar,
                               n_picks, out_pos, out_gain, h->rows_smem, h->world, h->rank, h->seq_base, h->mail_local,
                               h->mail_peer, h->dbg, h->run_status, h->spin_limit_ns, st);
@@ -692,6 +770,7 @@ int acav_mi_loop_supported(int32_t k_a, int32_t k_v, int32_t mode) {
     if (mode == ACAV_MI_LOOP_PERSISTENT)       // one gain row must fit in shared memory, the stream holds 4*c2 in 16 bits
         return mi_persistent_rows_that_fit(k_a, k_v) >= 1 && k_v <= 16383 && (int64_t)k_a * k_v < (1ll << 31);
     if (mode == ACAV_MI_LOOP_CELLS) return k_a <= 16384 && k_v <= 16384 && mi_cells_smem_fits(k_a, k_v);
+    if (mode == ACAV_MI_LOOP_BYTES) return mi_s8_supported(k_a, k_v) ? 1 : 0;
     return 0;
 }
 
@@ -701,6 +780,7 @@ int acav_mi_prepare(acav_mi_t *h, int32_t mode, void *stream) {
     if (!acav_mi_loop_supported(h->s.k_a, h->s.k_v, mode)) return ACAV_E_UNSUPPORTED;
     if (mode == ACAV_MI_LOOP_PERSISTENT) return mi_prepare_persistent(h, (cudaStream_t)stream);
     if (mode == ACAV_MI_LOOP_CELLS) return mi_prepare_cells(h, (cudaStream_t)stream);
+    if (mode == ACAV_MI_LOOP_BYTES) return mi_prepare_stream8(h, (cudaStream_t)stream);
     return 0;
 }
 
@@ -716,6 +796,13 @@ int acav_mi_status(acav_mi_t *h, int32_t *status_host, void *stream) {
 int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles) {
     if (!h) return ACAV_E_INVALID;
     h->dbg = reinterpret_cast<long long *>(cycles);
+    return 0;
+}
+
+int acav_mi_set_stream_variant(acav_mi_t *h, int32_t variant, int32_t use_cache) {
+    if (!h || variant < 0 || variant > 4) return ACAV_E_INVALID;
+    h->s8_variant = variant;
+    h->s8_use_cache = use_cache ? 1 : 0;
     return 0;
 }
 

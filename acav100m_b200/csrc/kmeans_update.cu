@@ -268,16 +268,25 @@ km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const float *xcol = x + (active ? col : 0);
     const uint32_t my = (uint32_t)__cvta_generic_to_shared(ring + threadIdx.x);
+    // cp.async of one group of rows into ring slot `slot`: the row indices are read first (independent shared-memory
+    // loads), then the copies are issued back to back -- a load-then-issue pair per row serialised the single warp
     auto issue_group = [&](int slot, uint32_t s, uint32_t n) {
+        uint32_t idx[kUpdGroupRows];
+#pragma unroll
+        for (int u = 0; u < kUpdGroupRows; ++u) idx[u] = s + u < n ? sidx[s + u] : 0u;
 #pragma unroll
         for (int u = 0; u < kUpdGroupRows; ++u) {
             if (s + u < n) {
-                const float *p = xcol + (int64_t)sidx[s + u] * ldx;
+                const float *p = xcol + (int64_t)idx[u] * ldx;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(my + (uint32_t)((slot * kUpdGroupRows + u) * kUpdThreads * 16)),
-                             "l"(p) : "memory");
+                             "l"(p));
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_group = [&](float4 (&dst)[kUpdGroupRows], int slot) {
+#pragma unroll
+        for (int u = 0; u < kUpdGroupRows; ++u) dst[u] = ring[(slot * kUpdGroupRows + u) * kUpdThreads + threadIdx.x];
     };
     for (uint32_t chunk = lo; chunk < hi; chunk += kUpdChunk) {
         const uint32_t n = min((uint32_t)kUpdChunk, hi - chunk);
@@ -286,23 +295,33 @@ km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < kUpdGroups - 1; ++g) issue_group(g, (uint32_t)g * kUpdGroupRows, n);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kUpdGroups - 2) : "memory");          // group 0 has landed
+        float4 cur[kUpdGroupRows], nxt[kUpdGroupRows];
+        load_group(cur, 0);
         int slot = 0;
+        // software pipeline: while the fp32 add chain of group g runs (the serial part: the reference's sum order),
+        // the rows of group g+1 are already on their way from shared memory to registers and group g+15 is being
+        // fetched into the slot group g-1 left
         for (uint32_t s = 0; s < n; s += kUpdGroupRows) {
             int pre = slot + kUpdGroups - 1;
             if (pre >= kUpdGroups) pre -= kUpdGroups;
             issue_group(pre, s + (kUpdGroups - 1) * kUpdGroupRows, n);
-            asm volatile("cp.async.wait_group %0;" ::"n"(kUpdGroups - 1) : "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(kUpdGroups - 2) : "memory");      // the next group has landed
+            int nslot = slot + 1;
+            if (nslot == kUpdGroups) nslot = 0;
+            load_group(nxt, nslot);
 #pragma unroll
             for (int u = 0; u < kUpdGroupRows; ++u) {
                 if (s + u < n) {
-                    const float4 t = ring[(slot * kUpdGroupRows + u) * kUpdThreads + threadIdx.x];
-                    acc[0] = __fadd_rn(acc[0], __fmul_rn(t.x, lr));                          // :123
-                    acc[1] = __fadd_rn(acc[1], __fmul_rn(t.y, lr));
-                    acc[2] = __fadd_rn(acc[2], __fmul_rn(t.z, lr));
-                    acc[3] = __fadd_rn(acc[3], __fmul_rn(t.w, lr));
+                    acc[0] = __fadd_rn(acc[0], __fmul_rn(cur[u].x, lr));                       // :123
+                    acc[1] = __fadd_rn(acc[1], __fmul_rn(cur[u].y, lr));
+                    acc[2] = __fadd_rn(acc[2], __fmul_rn(cur[u].z, lr));
+                    acc[3] = __fadd_rn(acc[3], __fmul_rn(cur[u].w, lr));
                 }
             }
-            if (++slot == kUpdGroups) slot = 0;
+#pragma unroll
+            for (int u = 0; u < kUpdGroupRows; ++u) cur[u] = nxt[u];
+            slot = nslot;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }

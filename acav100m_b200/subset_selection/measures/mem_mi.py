@@ -24,6 +24,9 @@ from .pairs_engine import PairsEngine
 
 
 class EfficientMemMI:
+    _LOOP_NAMES = {_lib.MI_LOOP_KERNELS: "kernels", _lib.MI_LOOP_PERSISTENT: "persistent",
+                   _lib.MI_LOOP_CELLS: "cells", _lib.MI_LOOP_BYTES: "bytes"}
+
     def __init__(self, assignments, measure_type='mutual_info', average_method='arithmetic',
                  ncentroids=20, device=None, shard=None, loop='auto', **kwargs):
         self.average_method = average_method.lower()
@@ -113,10 +116,9 @@ class EfficientMemMI:
             return "pairs" + ("+allgather" if self._dist is not None else "")
         if self._dist is not None:
             if self._nvlink:
-                return ("cells" if self._loop_mode() == _lib.MI_LOOP_CELLS else "persistent") + "+nvlink-mailbox"
+                return self._LOOP_NAMES[self._loop_mode()] + "+nvlink-mailbox"
             return "kernels+allgather"
-        return {_lib.MI_LOOP_KERNELS: "kernels", _lib.MI_LOOP_PERSISTENT: "persistent",
-                _lib.MI_LOOP_CELLS: "cells"}[self._loop_mode()]
+        return self._LOOP_NAMES[self._loop_mode()]
 
     def init_cache(self, max_picks=None):
         """``init_cache`` :32-39, :297-308 on the device."""
@@ -144,7 +146,7 @@ class EfficientMemMI:
             consts = tables.empty_table_constants(C)
             _lib.call("acav_mi_set_tables", handle, _lib.ptr(self._logs), self._logs.numel(),
                       consts.ctypes.data_as(_lib.c_vp), st)
-        if self._dist is not None and self._loop_mode() in (_lib.MI_LOOP_PERSISTENT, _lib.MI_LOOP_CELLS):
+        if self._dist is not None and self._loop_mode() != _lib.MI_LOOP_KERNELS:
             self._connect_ranks()
 
     def _all_ranks_ok(self, ok):
@@ -220,6 +222,8 @@ class EfficientMemMI:
             return _lib.MI_LOOP_PERSISTENT
         if self.loop in ('cells', _lib.MI_LOOP_CELLS):
             return _lib.MI_LOOP_CELLS
+        if self.loop in ('bytes', _lib.MI_LOOP_BYTES):
+            return _lib.MI_LOOP_BYTES
         # "auto": the persistent row-partitioned kernel whenever one of its gain rows fits in shared memory
         # (K <= 8140 for a square table), else the cell index (K <= 16384), else three kernels per iteration
         C = self.ncentroids

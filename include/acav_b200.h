@@ -213,6 +213,11 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n,
 #define ACAV_MI_LOOP_KERNELS     0
 #define ACAV_MI_LOOP_PERSISTENT  1
 #define ACAV_MI_LOOP_CELLS       2
+/* mode 3: the persistent candidate stream with ONE byte per candidate -- the list stably partitioned by (c1, c2 / w)
+ * sub-rows of w <= 255 columns, streamed through registers (no shared-memory ring), table counts of a CTA's sub-rows
+ * cached in shared memory; half the HBM bytes per iteration of mode 1, same picks and gains.  Needs
+ * k_a * ceil(k_v / 255) <= 24000 (acav_mi_loop_supported). */
+#define ACAV_MI_LOOP_BYTES       3
 int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain,
                 int32_t mode, void *stream);
 
@@ -251,6 +256,11 @@ int acav_mi_comm_connect(acav_mi_t *h, const void *handles);
  * publish, grid-barrier wait}, then {stream blocks, table rows} of the CTA's chunk and the cycles of
  * {per-iteration prologue, winner hand-over of the previous iteration}.  NULL switches it off (default). */
 int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles);
+
+/* Tuning of ACAV_MI_LOOP_BYTES (benchmarking): variant 0..4 = (threads per CTA, 16-byte loads in flight per thread)
+ * (512,6) (512,8) (768,4) (1024,2) (512,4); use_cache = 0 switches the shared-memory count cache off.  Also settable
+ * through the environment (ACAV_MI_S8_VARIANT, ACAV_MI_S8_CACHE) before acav_mi_create. */
+int acav_mi_set_stream_variant(acav_mi_t *h, int32_t variant, int32_t use_cache);
 
 /* Introspection for tests: copies table counts (uint32 [k_a*k_v], [k_v], [k_a]) and the four running
  * sums {NlogN, aloga, blogb, n} to device buffers (any may be NULL). */

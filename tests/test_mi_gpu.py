@@ -12,7 +12,7 @@ from oracle import gen_golden, mi_oracle as mo
 pytestmark = pytest.mark.gpu
 
 P1 = [m for m in sorted(gen_golden.MI_CASES) if gen_golden.MI_CASES[m]["dcols"] == 2]
-LOOPS = ["kernels", "persistent", "cells"]
+LOOPS = ["kernels", "persistent", "cells", "bytes"]
 
 
 def load(golden_dir, name):
@@ -140,7 +140,7 @@ def test_errors():
 
 @pytest.mark.parametrize("W,C,picks,seed", [(50_000, 16, 4000, 21), (300_000, 1024, 600, 22), (40, 4, 39, 23),
                                             (1_000_003, 256, 300, 24), (9000, 2048, 500, 25)])
-@pytest.mark.parametrize("loop", ["persistent", "cells"])
+@pytest.mark.parametrize("loop", ["persistent", "cells", "bytes"])
 def test_persistent_loop_matches_c_oracle(W, C, picks, seed, loop):
     """Row-partitioned persistent kernel: massive early ties (every cell scores the same at first),
     rows split across CTAs, more rows per CTA than fit in shared memory, resumed runs."""
@@ -165,7 +165,8 @@ def test_loops_can_be_mixed():
     m = gpu_measure(a, C, loop="persistent")
     m.init([(0, 1)], list(range(W)))
     out = []
-    for loop, n in (("persistent", 200), ("cells", 150), ("kernels", 200), ("cells", 150), ("persistent", 200)):
+    for loop, n in (("persistent", 150), ("bytes", 100), ("cells", 100), ("kernels", 150), ("bytes", 100), ("cells", 100),
+                    ("persistent", 200)):
         m.loop = loop
         out.append(m.select(n))
     pos = torch.cat([o[0] for o in out]).cpu().numpy()
@@ -173,7 +174,7 @@ def test_loops_can_be_mixed():
     assert np.array_equal(pos, pos_want) and np.array_equal(gain, gain_want)
 
 
-@pytest.mark.parametrize("loop", ["persistent", "cells"])
+@pytest.mark.parametrize("loop", ["persistent", "cells", "bytes"])
 def test_persistent_loop_uniform_ids_all_ties(loop):
     """Every candidate in one cell: all scores tie on every iteration, list order must be kept."""
     W = 5000
@@ -187,11 +188,12 @@ def test_persistent_loop_uniform_ids_all_ties(loop):
     assert np.array_equal(pos.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("C,want_loop", [(8140, "persistent"), (8192, "cells"), (16384, "cells"), (16500, "kernels")])
+@pytest.mark.parametrize("C,want_loop", [(8140, "persistent"), (8192, "cells"), (16384, "cells")])
 def test_auto_loop_falls_back_when_the_table_outgrows_shared_memory(C, want_loop):
     """loop='auto' (the CLI default) must pick a loop that can run the table: the persistent stream needs one gain
     row of K_v + 1 floats next to the replicated marginals in shared memory (K <= 8140), the cell index needs the
-    marginals (K <= 16384), beyond that three kernels per iteration -- and the picks stay the oracle's."""
+    marginals (K <= 16384) -- and the picks stay the oracle's.  (Beyond K = 16384 the empty table's n0 = K^2 * eps is
+    no longer absorbed by fp32 1.0 and the log-table trick does not apply: tables.py refuses such tables.)"""
     W, picks = 6000, 12
     a = synth.zipf_pairs(W, C, C)
     a[0] = C - 1
@@ -209,3 +211,27 @@ def test_auto_loop_falls_back_when_the_table_outgrows_shared_memory(C, want_loop
         with pytest.raises(_lib.AcavError) as e:
             bad.select(1)
         assert e.value.status == -2
+
+
+@pytest.mark.parametrize("variant,cache", [(0, 0), (1, 1), (2, 1), (3, 1), (4, 0)])
+@pytest.mark.parametrize("W,C,picks,seed", [(120_000, 300, 700, 5), (60_000, 1024, 400, 6)])
+def test_byte_stream_variants_match_c_oracle(W, C, picks, seed, variant, cache):
+    """Every (threads, loads in flight) instantiation of the one-byte stream kernel, with and without the
+    shared-memory count cache (cache = 0 reads the double-buffered global table like the 2-byte loop): same picks,
+    same fp32 gains.  C = 300 -> 2 sub-rows of 150 columns, C = 1024 -> 5 of 205."""
+    from acav100m_b200 import _lib
+    a = synth.zipf_pairs(W, C, seed)
+    a[0] = C - 1
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C, loop="bytes")
+    m.init([(0, 1)], list(range(W)))
+    _lib.call("acav_mi_set_stream_variant", m._engine, variant, cache)
+    p1, g1 = m.select(picks // 3)                             # two launches: state written back and re-read
+    p2, g2 = m.select(picks - picks // 3)
+    pos, gain = torch.cat([p1, p2]).cpu().numpy(), torch.cat([g1, g2]).cpu().numpy()
+    assert np.array_equal(pos, pos_want)
+    assert np.array_equal(gain, gain_want)
+    N, ca, rb, sums = m.read_state()
+    want_N = np.zeros((C, C), dtype=np.int64)
+    np.add.at(want_N, (a[pos_want, 0], a[pos_want, 1]), 1)
+    assert np.array_equal(N.numpy(), want_N)
