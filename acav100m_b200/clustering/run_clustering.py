@@ -8,6 +8,7 @@ from pathlib import Path
 
 import torch
 
+from . import checkpoint
 from . import data as D
 from .config import MODELS
 from .save import save_assignments
@@ -62,39 +63,77 @@ def cache_path(args, epoch):
 
 
 def save_clusterings(args, epoch, clusterings):
-    """Checkpoint after every epoch.  Written in the reference's ``save_scheme_ver2`` layout (a tree of
-    ``get_attrs()`` dicts with numpy arrays), which does not pickle any class."""
+    """Checkpoint after every epoch (run_clustering.py:110-116).  ``--clustering.save_scheme_ver2`` (default True here):
+    a tree of ``get_attrs()`` dicts with numpy arrays, which pickles no class; False writes the reference's own default
+    layout (objects under the class path ``sgd_clustering.KMeans``) so that a reference run can resume from it."""
     tree = {m: {k: km.get_attrs() for k, km in per.items()} for m, per in clusterings.items()}
     for per in tree.values():
         for attrs in per.values():
             attrs['args'] = None
     path = cache_path(args, epoch)
     path.parent.mkdir(parents=True, exist_ok=True)
-    torch.save(tree, str(path))
+    if getattr(args.clustering, 'save_scheme_ver2', True) is False:
+        checkpoint.save_tree_ver1(tree, path)
+    else:
+        torch.save(tree, str(path))
     return path
 
 
+def get_shard_subset_cache(args, path, epoch, name):
+    """run_clustering.py:76-84 -- a checkpoint trained on a SUBSET of the shards asked for now: of the files
+    ``cache_epoch_{e}_*shard-{..}.pkl`` whose shard set lies inside ``name``'s, the reference takes the maximum by python's
+    set comparison (``max(..., key=set)``: the first candidate, in glob order, that no later one is a proper superset of);
+    kept as is.  Returns a path or None."""
+    cands = {}
+    for p in path.glob("cache_epoch_{}_*.pkl".format(epoch)):
+        at = p.name.find('shard-')
+        if at >= 0:
+            cands[p] = set(D.brace_expand(p.name[at:]))
+    shard_set = set(D.brace_expand(name))
+    cands = {p: v for p, v in cands.items() if len(v - shard_set) == 0}
+    if not cands:
+        return None
+    return max(list(cands.items()), key=lambda v: v[1])[0]
+
+
+def _load_path(args, path, model_names):
+    """run_clustering.py:87-107 -- ver1 (objects) and ver2 (dict trees) alike."""
+    tree = checkpoint.load_tree(path)
+    if not set(model_names) <= set(tree.keys()):
+        print("clustering cache features does not match with the given models")
+        return None
+    clusterings = {}
+    for m in model_names:
+        clusterings[m] = {}
+        for k, attrs in tree[m].items():
+            km = KMeans.load(dict(attrs))
+            km.args = args
+            clusterings[m][k] = km
+    print("loading from clustering cache: {}".format(path))
+    return _place_loaded(args, clusterings)
+
+
+def _place_loaded(args, clusterings):
+    # the reference calls initialize() on loaded models too (run_clustering.py:49-52,95): with several ranks that
+    # averages the (identical) replicas, a no-op up to rounding; kept
+    return _place(args, clusterings)
+
+
 def load_clusterings(args, model_names):
-    """run_clustering.py:55-107 -- resume from ``--clustering.cached_epoch``."""
+    """run_clustering.py:55-73 -- resume from ``--clustering.cached_epoch``."""
     epoch = args.clustering.cached_epoch
     if isinstance(epoch, int):
         path = cache_path(args, epoch)
+        loaded = None
         if path.is_file():
-            tree = torch.load(str(path), weights_only=False)
-            if set(model_names) <= set(tree.keys()):
-                clusterings = {}
-                for m in model_names:
-                    clusterings[m] = {}
-                    for k, v in tree[m].items():
-                        attrs = v if isinstance(v, dict) else v.get_attrs()
-                        km = KMeans.load(dict(attrs))
-                        km.args = args
-                        clusterings[m][k] = km
-                print("loading from clustering cache: {}".format(path))
-                return _place(args, clusterings), True
-            print("clustering cache features does not match with the given models")
-        else:
-            print("no clustering cache found.")
+            loaded = _load_path(args, path, model_names)
+        elif getattr(args.clustering, 'load_cache_from_shard_subset', False):
+            sub = get_shard_subset_cache(args, path.parent, epoch, Path(args.data.path).name)
+            if sub is not None:
+                loaded = _load_path(args, sub, model_names)
+        if loaded is not None:
+            return loaded, True
+        print("no clustering cache found.")
     return init_clusterings(args, model_names), False
 
 

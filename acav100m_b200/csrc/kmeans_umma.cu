@@ -296,22 +296,38 @@ km_candidate_refine_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
             double acc = 0.0;
             if ((d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                 ((reinterpret_cast<uintptr_t>(centers) & 15) == 0)) {
-                // 16 independent 16-byte loads in flight per thread, then the 32 FMAs in k order (the chain is the
-                // definition of "exact"; only the loads are hoisted) -- the kernel was bound by load latency
-                int32_t i = 0;
-                for (; i + 32 <= d; i += 32) {
-                    float4 a[8], w[8];
+                // the chain of d fp64 FMAs in k order is the definition of "exact" (same order as assign_exact_kernel)
+                // and stays serial; the loads are double-buffered in registers, 32 elements (16 x 16 bytes) per
+                // buffer, so the L2 latency of batch i+1 hides behind the FMA chain of batch i
+                float4 a0[8], w0[8], a1[8], w1[8];
+                auto ld = [&](float4 (&av)[8], float4 (&wv)[8], int32_t at) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        a[u] = __ldg(reinterpret_cast<const float4 *>(p + i) + u);
-                        w[u] = __ldg(reinterpret_cast<const float4 *>(q + i) + u);
+                        av[u] = __ldg(reinterpret_cast<const float4 *>(p + at) + u);
+                        wv[u] = __ldg(reinterpret_cast<const float4 *>(q + at) + u);
                     }
+                };
+                auto fm = [&](const float4 (&av)[8], const float4 (&wv)[8]) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        acc = fma((double)a[u].x, (double)w[u].x, acc);
-                        acc = fma((double)a[u].y, (double)w[u].y, acc);
-                        acc = fma((double)a[u].z, (double)w[u].z, acc);
-                        acc = fma((double)a[u].w, (double)w[u].w, acc);
+                        acc = fma((double)av[u].x, (double)wv[u].x, acc);
+                        acc = fma((double)av[u].y, (double)wv[u].y, acc);
+                        acc = fma((double)av[u].z, (double)wv[u].z, acc);
+                        acc = fma((double)av[u].w, (double)wv[u].w, acc);
+                    }
+                };
+                const int32_t nb = d / 32;
+                int32_t i = nb * 32;
+                if (nb > 0) {
+                    ld(a0, w0, 0);
+                    int32_t bi = 0;
+                    while (true) {
+                        if (bi + 1 < nb) ld(a1, w1, (bi + 1) * 32);
+                        fm(a0, w0);
+                        if (++bi >= nb) break;
+                        if (bi + 1 < nb) ld(a0, w0, (bi + 1) * 32);
+                        fm(a1, w1);
+                        if (++bi >= nb) break;
                     }
                 }
                 for (; i < d; i += 4) {

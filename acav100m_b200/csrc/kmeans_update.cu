@@ -6,8 +6,11 @@
 // To be bit-identical we (1) partition the batch rows by centroid with a STABLE counting sort and
 // (2) let one thread own one (centroid, 4 columns) slot and add its member rows sequentially.  Reads
 // are coalesced across columns; the only serial dependence is the fp32 add chain itself.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "sm100_ptx.cuh"
 
 namespace acav {
 
@@ -344,6 +347,106 @@ km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int
     }   // heavy centroids of this block
 }
 
+// Heavy centroids, TMA version (default): one CTA = (heavy centroid, 64 columns), two warps.  Warp 0 is the producer:
+// per stage of 32 rows every lane issues ONE bulk async copy (cp.async.bulk, 256 bytes of its row) completing on the
+// stage's mbarrier -- the copy engine keeps kBulkStages x 32 rows in flight per CTA without occupying load/store
+// slots (the cp.async ring above is limited by the outstanding-miss capacity of the SM: ~24 rows in flight measured).
+// Warp 1 is the consumer: lane l owns columns 2l, 2l+1 and adds its 8 bytes of every row in stage order -- the same
+// strict row-order fp32 chain.  32 CTAs per heavy centroid at D = 2048, so one centroid owning a third of the batch
+// is still pulled by 32 SMs.
+constexpr int kBulkCols = 64;                        // columns per CTA (256 bytes per row)
+constexpr int kBulkRows = 32;                        // rows per stage: one per producer lane
+constexpr int kBulkStages = 8;                       // 256 rows x 256 B = 64 KiB in flight per CTA
+
+template <int MODE>
+__global__ void __launch_bounds__(64)
+km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32_t d,
+                      const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
+                      const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
+                      float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push) {
+    extern __shared__ __align__(128) unsigned char bsmem[];
+    float *ring = reinterpret_cast<float *>(bsmem);                                     // [stages][rows][64]
+    uint64_t *full = reinterpret_cast<uint64_t *>(bsmem + (size_t)kBulkStages * kBulkRows * kBulkCols * 4);
+    uint64_t *empty = full + kBulkStages;
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int32_t col0 = blockIdx.y * kBulkCols;
+    const uint32_t row_bytes = (uint32_t)min(kBulkCols, d - col0) * 4u;                 // multiple of 16 (d % 4 == 0)
+    const float lr = *lr_eff_p;
+    const uint32_t n_heavy = seg_start[k + 1];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBulkStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t stage = 0, phase = 0;                    // both warps walk the stages in the same order, across centroids
+    for (uint32_t hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
+        const int32_t c = (int32_t)seg_start[k + 2 + hidx];
+        const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
+        if (warp == 0) {
+            // ===== producer =====
+            for (uint32_t base = lo; base < hi; base += kBulkRows) {
+                const uint32_t n = min((uint32_t)kBulkRows, hi - base);
+                const uint32_t row = (uint32_t)lane < n ? __ldg(sorted_rows + base + lane) : 0u;
+                ptx::mbar_wait(&empty[stage], phase ^ 1u);                              // slot free (first lap passes)
+                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[stage], n * row_bytes);
+                __syncwarp();
+                if ((uint32_t)lane < n) {
+                    const float *src = x + (int64_t)row * ldx + col0;
+                    float *dst = ring + ((size_t)stage * kBulkRows + lane) * kBulkCols;
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                        ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(row_bytes), "r"(ptx::smem_u32(&full[stage])) : "memory");
+                }
+                if (++stage == kBulkStages) { stage = 0; phase ^= 1u; }
+            }
+        } else {
+            // ===== consumer =====
+            const int32_t col = col0 + 2 * lane;
+            const bool active = col < d;
+            float acc0 = 0.f, acc1 = 0.f;
+            for (uint32_t base = lo; base < hi; base += kBulkRows) {
+                const uint32_t n = min((uint32_t)kBulkRows, hi - base);
+                ptx::mbar_wait(&full[stage], phase);
+                const float2 *rows = reinterpret_cast<const float2 *>(ring + (size_t)stage * kBulkRows * kBulkCols) + lane;
+                if (n == kBulkRows) {
+                    float2 v[kBulkRows];
+#pragma unroll
+                    for (int r = 0; r < kBulkRows; ++r) v[r] = rows[r * (kBulkCols / 2)];
+#pragma unroll
+                    for (int r = 0; r < kBulkRows; ++r) {
+                        acc0 = __fadd_rn(acc0, __fmul_rn(v[r].x, lr));                     // :123
+                        acc1 = __fadd_rn(acc1, __fmul_rn(v[r].y, lr));
+                    }
+                } else {
+                    for (uint32_t r = 0; r < n; ++r) {
+                        const float2 v = rows[r * (kBulkCols / 2)];
+                        acc0 = __fadd_rn(acc0, __fmul_rn(v.x, lr));
+                        acc1 = __fadd_rn(acc1, __fmul_rn(v.y, lr));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+                if (++stage == kBulkStages) { stage = 0; phase ^= 1u; }
+            }
+            const float cb = counts_b[c];
+            if (MODE != kUpdPush && blockIdx.y == 0 && lane == 0) counts[c] = __fadd_rn(counts[c], cb);      // :120
+            if (active && MODE == kUpdPush) {
+                *reinterpret_cast<float2 *>(push.slot(c, d) + col) = make_float2(acc0, acc1);
+            } else if (active) {
+                const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                    // :121
+                float *cp = centers + (int64_t)c * d + col;
+                const float s0 = __fmul_rn(cp[0], decay), s1 = __fmul_rn(cp[1], decay);
+                if (MODE == kUpdFused) {
+                    cp[0] = __fadd_rn(s0, acc0); cp[1] = __fadd_rn(s1, acc1);               // :127
+                } else {
+                    cp[0] = s0; cp[1] = s1;
+                    deltas[(int64_t)c * d + col] = acc0; deltas[(int64_t)c * d + col + 1] = acc1;
+                }
+            }
+        }
+    }
+}
+
 __global__ void km_apply_deltas_kernel(float *__restrict__ centers, const float *__restrict__ deltas,
                                        int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,8 +500,32 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
         { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdFused>, smem, done_fused); if (rc) return rc; }
         { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdSplit>, smem, done_split); if (rc) return rc; }
         { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdPush>, smem, done_push); if (rc) return rc; }
+        static int use_ring = -1;
+        if (use_ring < 0) {
+            const char *e = std::getenv("ACAV_KM_HEAVY");
+            use_ring = (e && e[0] == 'r') ? 1 : 0;                                       // "ring": the cp.async kernel
+        }
+        if (!use_ring) {
+            const size_t bsmem = (size_t)kBulkStages * kBulkRows * kBulkCols * 4 + 2 * kBulkStages * sizeof(uint64_t);
+            static size_t bdone[3][kMaxDevices];
+            { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdFused>, bsmem, bdone[0]); if (rc) return rc; }
+            { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdSplit>, bsmem, bdone[1]); if (rc) return rc; }
+            { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdPush>, bsmem, bdone[2]); if (rc) return rc; }
+            dim3 bgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kBulkCols));     // loops over the heavy list
+            if (push)
+                km_update_bulk_kernel<kUpdPush><<<bgrid, 64, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                         centers, counts, nullptr, pz);
+            else if (deltas)
+                km_update_bulk_kernel<kUpdSplit><<<bgrid, 64, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                          centers, counts, deltas, pz);
+            else
+                km_update_bulk_kernel<kUpdFused><<<bgrid, 64, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                          centers, counts, nullptr, pz);
+            ACAV_LAUNCH_CHECK();
+        }
         dim3 sgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kUpdThreads * 4));   // loops over the heavy list
-        if (push)
+        if (!use_ring) {
+        } else if (push)
             km_update_stream_kernel<kUpdPush><<<sgrid, kUpdThreads, smem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                                   centers, counts, nullptr, pz);
         else if (deltas)
