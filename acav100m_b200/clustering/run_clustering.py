@@ -8,6 +8,7 @@ from pathlib import Path
 
 import torch
 
+from .. import hostio
 from . import checkpoint
 from . import data as D
 from .config import MODELS
@@ -88,8 +89,8 @@ def get_shard_subset_cache(args, path, epoch, name):
     for p in path.glob("cache_epoch_{}_*.pkl".format(epoch)):
         at = p.name.find('shard-')
         if at >= 0:
-            cands[p] = set(D.brace_expand(p.name[at:]))
-    shard_set = set(D.brace_expand(name))
+            cands[p] = set(hostio.braceexpand(p.name[at:]))
+    shard_set = set(hostio.braceexpand(name))
     cands = {p: v for p, v in cands.items() if len(v - shard_set) == 0}
     if not cands:
         return None

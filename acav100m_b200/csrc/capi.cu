@@ -128,6 +128,58 @@ std::vector<uint32_t> cut_chunks(const std::vector<uint32_t> &rs, int32_t n_rows
     return chunks;
 }
 
+// The same with a cap on the rows a chunk may touch (so that every CTA's gain rows and table counts fit in its shared
+// memory and it never falls back to the multi-batch path).  Costs are in blocks: cost(chunk) = blocks + row_cost *
+// rows touched.  The smallest per-chunk budget T that needs <= grid chunks is found by bisection; rows are split at
+// block boundaries.  Returns grid + 1 offsets (trailing chunks may be empty).
+std::vector<uint32_t> cut_chunks_capped(const std::vector<uint32_t> &rs, int32_t n_rows, double row_cost, uint32_t blk,
+                                        int32_t grid, int32_t max_rows) {
+    auto fill = [&](double T, std::vector<uint32_t> *out) -> int64_t {
+        int64_t n_chunks = 0;
+        double cost = 0.0;
+        int32_t rows_in = 0;
+        uint32_t pos = 0;
+        if (out) { out->clear(); out->push_back(0); }
+        auto close = [&]() {
+            if (out) out->push_back(pos);
+            ++n_chunks;
+            cost = 0.0;
+            rows_in = 0;
+        };
+        for (int32_t r = 0; r < n_rows; ++r) {
+            uint32_t nb = (rs[r + 1] - rs[r]) / blk;
+            pos = rs[r];
+            while (nb > 0) {
+                if (rows_in > 0 && (rows_in >= max_rows || cost + row_cost + 1.0 > T)) close();
+                double room = T - cost - row_cost;
+                uint32_t take = room >= (double)nb ? nb : (room < 1.0 ? 1u : (uint32_t)room);
+                cost += row_cost + (double)take;
+                ++rows_in;
+                pos += take * blk;
+                nb -= take;
+                if (nb > 0) close();
+            }
+        }
+        pos = rs[n_rows];
+        if (rows_in > 0) close();
+        return n_chunks;
+    };
+    double total = 0.0;
+    for (int32_t r = 0; r < n_rows; ++r)
+        if (rs[r + 1] > rs[r]) total += row_cost + (double)((rs[r + 1] - rs[r]) / blk);
+    double lo = row_cost + 1.0, hi = total + row_cost + 1.0;
+    for (int it = 0; it < 48 && hi - lo > 0.5; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (fill(mid, nullptr) <= grid) hi = mid; else lo = mid;
+    }
+    std::vector<uint32_t> chunks;
+    fill(hi, &chunks);
+    while ((int32_t)chunks.size() < grid + 1) chunks.push_back(rs[n_rows]);
+    chunks[grid] = rs[n_rows];
+    chunks.resize((size_t)grid + 1);
+    return chunks;
+}
+
 // Build (or rebuild) the sub-row partitioned one-byte stream of ACAV_MI_LOOP_BYTES and its per-CTA chunk table.
 int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
     if (h->s8_valid) return 0;
@@ -158,9 +210,10 @@ int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));
     rc = launch_mi_s8_block_sort(h->s8_stream, h->s8_pos, rs[k_rows], st);
     if (rc) return rc;
-    double row_cost = 512.0;                       // one sub-row's gain row ~ streaming one block (tuned on B200)
+    double row_cost = 2.0;                         // blocks: building one cached gain row ~ streaming two blocks
     if (const char *e = std::getenv("ACAV_MI_S8_ROWCOST")) row_cost = std::atof(e);
-    const std::vector<uint32_t> chunks = cut_chunks(rs, k_rows, row_cost, (uint32_t)mi_s8_block(), h->sm_count);
+    const std::vector<uint32_t> chunks = cut_chunks_capped(rs, k_rows, row_cost, (uint32_t)mi_s8_block(), h->sm_count,
+                                                           h->s8_rows_smem);
     ACAV_CUDA_TRY(cudaMemcpyAsync(h->s8_chunk_start, chunks.data(), sizeof(uint32_t) * chunks.size(),
                                   cudaMemcpyHostToDevice, st));
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `chunks` is a host temporary

@@ -347,19 +347,23 @@ km_update_stream_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int
     }   // heavy centroids of this block
 }
 
-// Heavy centroids, TMA version (default): one CTA = (heavy centroid, 64 columns), two warps.  Warp 0 is the producer:
-// per stage of 32 rows every lane issues ONE bulk async copy (cp.async.bulk, 256 bytes of its row) completing on the
-// stage's mbarrier -- the copy engine keeps kBulkStages x 32 rows in flight per CTA without occupying load/store
-// slots (the cp.async ring above is limited by the outstanding-miss capacity of the SM: ~24 rows in flight measured).
-// Warp 1 is the consumer: lane l owns columns 2l, 2l+1 and adds its 8 bytes of every row in stage order -- the same
-// strict row-order fp32 chain.  32 CTAs per heavy centroid at D = 2048, so one centroid owning a third of the batch
-// is still pulled by 32 SMs.
+// Heavy centroids, TMA version (default): one CTA = (heavy centroid, 64 columns), five warps.  Warps 0-3 are
+// producers: per stage of 32 rows each of them issues eight bulk async copies (cp.async.bulk, 256 bytes of one row each,
+// one per lane 0..7; the instruction takes uniform operands, so a warp issues its lanes one after the other -- four
+// warps issue four at a time) completing on the stage's mbarrier; the row indices of the NEXT stage are loaded before
+// the copies of this one are issued.  The copy engine keeps kBulkStages x 32 rows in flight per CTA without occupying
+// load/store slots (the cp.async ring above is limited by the outstanding-miss capacity of the SM: ~24 rows in flight
+// measured).  Warp 4 is the consumer: lane l owns columns 2l, 2l+1 and adds its 8 bytes of every row in stage order --
+// the same strict row-order fp32 chain.  32 CTAs per heavy centroid at D = 2048, so one centroid owning a third of
+// the batch is still pulled by 32 SMs.
 constexpr int kBulkCols = 64;                        // columns per CTA (256 bytes per row)
-constexpr int kBulkRows = 32;                        // rows per stage: one per producer lane
+constexpr int kBulkRows = 32;                        // rows per stage
 constexpr int kBulkStages = 8;                       // 256 rows x 256 B = 64 KiB in flight per CTA
+constexpr int kBulkProducers = 4;                    // producer warps, kBulkRows / kBulkProducers rows each per stage
+constexpr int kBulkThreads = (kBulkProducers + 1) * kWarp;
 
 template <int MODE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kBulkThreads)
 km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32_t d,
                       const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                       const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
@@ -374,29 +378,36 @@ km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32
     const float lr = *lr_eff_p;
     const uint32_t n_heavy = seg_start[k + 1];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kBulkStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kBulkStages; ++s) { ptx::mbar_init(&full[s], kBulkProducers); ptx::mbar_init(&empty[s], 1); }
         ptx::fence_barrier_init();
     }
     __syncthreads();
-    uint32_t stage = 0, phase = 0;                    // both warps walk the stages in the same order, across centroids
+    constexpr int kPer = kBulkRows / kBulkProducers;  // rows of a stage issued by one producer warp
+    uint32_t stage = 0, phase = 0;                    // every warp walks the stages in the same order, across centroids
     for (uint32_t hidx = blockIdx.x; hidx < n_heavy; hidx += gridDim.x) {
         const int32_t c = (int32_t)seg_start[k + 2 + hidx];
         const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
-        if (warp == 0) {
-            // ===== producer =====
+        if (warp < kBulkProducers) {
+            // ===== producers =====
+            const uint32_t mine = (uint32_t)(warp * kPer + lane);                          // my row of a stage (lanes 0..7)
+            uint32_t row = (lane < kPer && lo + mine < hi) ? __ldg(sorted_rows + lo + mine) : 0u;
             for (uint32_t base = lo; base < hi; base += kBulkRows) {
                 const uint32_t n = min((uint32_t)kBulkRows, hi - base);
-                const uint32_t row = (uint32_t)lane < n ? __ldg(sorted_rows + base + lane) : 0u;
+                const uint32_t nxt = base + kBulkRows + mine;
+                const uint32_t row_next = (lane < kPer && nxt < hi) ? __ldg(sorted_rows + nxt) : 0u;
+                const uint32_t first = (uint32_t)(warp * kPer);
+                const uint32_t my_n = n > first ? min((uint32_t)kPer, n - first) : 0u;      // rows this warp issues
                 ptx::mbar_wait(&empty[stage], phase ^ 1u);                              // slot free (first lap passes)
-                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[stage], n * row_bytes);
+                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[stage], my_n * row_bytes);
                 __syncwarp();
-                if ((uint32_t)lane < n) {
+                if ((uint32_t)lane < my_n) {
                     const float *src = x + (int64_t)row * ldx + col0;
-                    float *dst = ring + ((size_t)stage * kBulkRows + lane) * kBulkCols;
+                    float *dst = ring + ((size_t)stage * kBulkRows + mine) * kBulkCols;
                     asm volatile(
                         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                         ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(row_bytes), "r"(ptx::smem_u32(&full[stage])) : "memory");
                 }
+                row = row_next;
                 if (++stage == kBulkStages) { stage = 0; phase ^= 1u; }
             }
         } else {
@@ -513,13 +524,13 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
             { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdPush>, bsmem, bdone[2]); if (rc) return rc; }
             dim3 bgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kBulkCols));     // loops over the heavy list
             if (push)
-                km_update_bulk_kernel<kUpdPush><<<bgrid, 64, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                km_update_bulk_kernel<kUpdPush><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                          centers, counts, nullptr, pz);
             else if (deltas)
-                km_update_bulk_kernel<kUpdSplit><<<bgrid, 64, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                km_update_bulk_kernel<kUpdSplit><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                           centers, counts, deltas, pz);
             else
-                km_update_bulk_kernel<kUpdFused><<<bgrid, 64, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                km_update_bulk_kernel<kUpdFused><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                           centers, counts, nullptr, pz);
             ACAV_LAUNCH_CHECK();
         }

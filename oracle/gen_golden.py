@@ -91,6 +91,33 @@ def run_reference_kmeans(case):
     )
 
 
+def write_reference_checkpoint(path):
+    """A ver1 centroid checkpoint exactly as the reference's default flags write it (run_clustering.py:110-116 with
+    `save_scheme_ver2` unset): ``torch.save`` of ``{model: {layer: <sgd_clustering.KMeans object>}}`` -- the objects of
+    the UNMODIFIED reference class after a few training steps.  tests/test_host_formats.py reads it back through
+    acav100m_b200.clustering.checkpoint without the reference on sys.path."""
+    KMeans = ref_shims.load_reference_kmeans()
+    seed_all(21)
+    tree = {}
+    expect = {}
+    with ref_shims.cuda_is_identity(), torch.no_grad():
+        for model, dims in (("layer_vggish", (8, 12)), ("layer_slow_fast", (16,))):
+            tree[model] = {}
+            for i, d in enumerate(dims):
+                km = KMeans(ref_shims.reference_kmeans_args(), d, 4)
+                x = torch.from_numpy(synth.gaussian_mixture(96, d, 3, 21 + i))
+                for xb in kmeans_batches(x, 16):
+                    km.add(xb)
+                km.args = None                                   # the reference pickles its munch tree here; not needed
+                tree[model]["layer_%d" % i] = km
+                expect["%s/layer_%d/centers" % (model, i)] = km.centers.numpy().copy()
+                expect["%s/layer_%d/counts" % (model, i)] = km.counts.numpy().copy()
+                expect["%s/layer_%d/count" % (model, i)] = np.int64(km.count)
+                expect["%s/layer_%d/fallback" % (model, i)] = np.int64(km.fallback)
+    torch.save(tree, path)
+    np.savez_compressed(path + ".expect.npz", **expect)
+
+
 def mi_assignments(case):
     if case["dcols"] == 2:
         return synth.zipf_pairs(case["v"], case["c"], case["seed"])
@@ -157,6 +184,9 @@ def main():
     global KMEANS_CASES, MI_CASES, BATCH_MI_CASES, AMI_CASES
     KMEANS_CASES, MI_CASES, BATCH_MI_CASES = pick(KMEANS_CASES), pick(MI_CASES), pick(BATCH_MI_CASES)
     AMI_CASES = pick(AMI_CASES)
+    if not only or "ref_ver1_checkpoint" in only:
+        write_reference_checkpoint(os.path.join(GOLDEN, "ref_ver1_cache_epoch_0.pkl"))
+        print("ref_ver1_cache_epoch_0.pkl written by the reference's KMeans class")
     for name, case in KMEANS_CASES.items():
         out = run_reference_kmeans(case)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)

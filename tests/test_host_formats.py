@@ -281,3 +281,93 @@ def test_chunk_caches_reduce_to_the_output_csv(tmp_path):
     schunk.reduce_all_pkls(args)                                 # `cli reduce_pkls`
     assert [r[1] for r in csv.reader(open(out))] == [r["filename"] for r in res[:3]]
     assert (tmp_path / "out" / "caches" / "cache_4242_0_0_output.csv").is_file()
+
+
+# ---- centroid checkpoints: both reference layouts, shard-subset lookup (run_clustering.py:55-116) ---------------
+
+def test_reference_written_ver1_checkpoint_loads_without_the_reference(golden_dir):
+    """tests/golden/ref_ver1_cache_epoch_0.pkl was written by the UNMODIFIED reference class (oracle/gen_golden.py::
+    write_reference_checkpoint): object pickles under the class path sgd_clustering.KMeans.  It must load here with no
+    `sgd_clustering` module importable."""
+    import sys
+    from acav100m_b200.clustering import checkpoint
+    assert "sgd_clustering" not in sys.modules
+    path = os.path.join(golden_dir, "ref_ver1_cache_epoch_0.pkl")
+    tree = checkpoint.load_tree(path)
+    want = dict(np.load(path + ".expect.npz"))
+    assert sorted(tree) == ["layer_slow_fast", "layer_vggish"] and sorted(tree["layer_vggish"]) == ["layer_0", "layer_1"]
+    for m, per in tree.items():
+        for layer, attrs in per.items():
+            key = "%s/%s/" % (m, layer)
+            assert isinstance(attrs["centers"], np.ndarray) and attrs["centers"].dtype == np.float32
+            assert np.array_equal(attrs["centers"], want[key + "centers"])
+            assert np.array_equal(attrs["counts"], want[key + "counts"])
+            assert attrs["count"] == int(want[key + "count"]) and attrs["fallback"] == int(want[key + "fallback"])
+            assert attrs["initial_rounds"] == 10 and tuple(attrs["reinit"]) == (.7, 5.0) and attrs["sequential"] is False
+    assert "sgd_clustering" not in sys.modules
+
+
+def test_ver1_checkpoint_written_here_is_what_the_reference_class_unpickles(tmp_path):
+    """save_scheme_ver2=False: objects pickled under `sgd_clustering.KMeans` carrying exactly the reference's attributes
+    as CPU tensors -- what the reference's load path needs (torch.load, then .to(device) on every object,
+    run_clustering.py:93, sgd_clustering.py:59-61).  Checked with a stand-in module of that name, and -- when
+    /root/reference is mounted -- with the reference class itself."""
+    import sys
+    import types
+    import torch
+    from acav100m_b200.clustering import checkpoint
+    from oracle import ref_shims
+    tree = {"layer_vggish": {"layer_0": {"args": None, "count": 320, "lr": 0.01, "initial_rounds": 10, "reinit": (.7, 5.0),
+                                         "fallback": 2, "sequential": False,
+                                         "centers": np.arange(12, dtype=np.float32).reshape(3, 4),
+                                         "counts": np.array([5, 0, 7], dtype=np.float32)}}}
+    path = tmp_path / "cache_epoch_0_shard-{000000..000001}.pkl"
+    checkpoint.save_tree_ver1(tree, path)
+    assert "sgd_clustering" not in sys.modules
+    # round trip through our own reader
+    back = checkpoint.load_tree(path)["layer_vggish"]["layer_0"]
+    assert np.array_equal(back["centers"], tree["layer_vggish"]["layer_0"]["centers"]) and back["count"] == 320
+
+    def check(cls):
+        objs = torch.load(str(path), weights_only=False)
+        km = objs["layer_vggish"]["layer_0"]
+        assert type(km) is cls
+        assert torch.is_tensor(km.centers) and km.centers.dtype == torch.float32 and km.centers.shape == (3, 4)
+        assert torch.equal(km.counts, torch.tensor([5., 0., 7.])) and km.count == 320 and km.fallback == 2
+        assert km.lr == 0.01 and km.initial_rounds == 10 and tuple(km.reinit) == (.7, 5.0) and km.sequential is False
+        return km
+
+    mod = types.ModuleType("sgd_clustering")
+    mod.KMeans = type("KMeans", (), {"__module__": "sgd_clustering"})
+    sys.modules["sgd_clustering"] = mod
+    try:
+        check(mod.KMeans)
+    finally:
+        del sys.modules["sgd_clustering"]
+    if ref_shims.reference_available():
+        RefKMeans = ref_shims.load_reference_kmeans()
+        try:
+            km = check(RefKMeans)
+            km.to("cpu")                                           # sgd_clustering.py:59-61
+            best, _ = km.calc_best(torch.zeros(2, 4))             # past warm-up (count >= 10 * k): distance branch
+            assert best.tolist() == [0, 0]
+            assert set(km.get_attrs()) >= {"centers", "counts", "count", "lr", "fallback"}
+        finally:
+            sys.modules.pop("sgd_clustering", None)
+
+
+def test_shard_subset_cache_lookup(tmp_path):
+    """get_shard_subset_cache (run_clustering.py:76-84): a checkpoint trained on a subset of the requested shards."""
+    import types
+    from acav100m_b200.clustering import run_clustering as rc
+    for name in ("cache_epoch_1_shard-{000000..000001}.pkl", "cache_epoch_1_shard-{000000..000003}.pkl",
+                 "cache_epoch_1_shard-{000004..000009}.pkl", "cache_epoch_2_shard-{000000..000001}.pkl", "log_x.json"):
+        (tmp_path / name).write_bytes(b"")
+    args = types.SimpleNamespace()
+    got = rc.get_shard_subset_cache(args, tmp_path, 1, "shard-{000000..000003}.pkl")
+    assert got is not None and got.name in ("cache_epoch_1_shard-{000000..000001}.pkl", "cache_epoch_1_shard-{000000..000003}.pkl")
+    # only subsets qualify: shards 4..9 are not inside 0..3; epoch must match
+    assert rc.get_shard_subset_cache(args, tmp_path, 1, "shard-{000002..000003}.pkl") is None
+    assert rc.get_shard_subset_cache(args, tmp_path, 3, "shard-{000000..000009}.pkl") is None
+    got2 = rc.get_shard_subset_cache(args, tmp_path, 2, "shard-{000000..000009}.pkl")
+    assert got2.name == "cache_epoch_2_shard-{000000..000001}.pkl"

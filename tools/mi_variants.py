@@ -23,7 +23,8 @@ ref = None
 CONFIGS = [("persistent", None, None, None), ("cells", None, None, None)]
 for variant in (0, 1, 4, 2, 3):
     CONFIGS.append(("bytes", variant, 1, None))
-CONFIGS += [("bytes", 0, 0, None), ("bytes", 0, 1, 128), ("bytes", 0, 1, 2048), ("bytes", 0, 1, 8192)]
+# row cost of the chunk cut, in 512-candidate blocks per sub-row touched (default 2)
+CONFIGS += [("bytes", 0, 0, None), ("bytes", 0, 1, 0.5), ("bytes", 0, 1, 4), ("bytes", 0, 1, 8), ("bytes", 2, 1, 4)]
 
 
 def timers(m, names=("gain rows", "scan", "reduce+publish", "barrier wait")):
