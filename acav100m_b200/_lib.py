@@ -41,6 +41,7 @@ SIGNATURES = {
     "acav_kmeans_assign_noise": (ctypes.c_int, [c_vp, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "acav_kmeans_histogram": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "acav_kmeans_update_fused": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp, c_vp]),
+    "acav_kmeans_update_sequential": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp]),
     "acav_kmeans_update_local": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_f64, c_vp, c_vp, c_vp,
                                                 c_vp, c_vp]),
     "acav_kmeans_apply_deltas": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -353,14 +353,24 @@ class KMeans:
     def add(self, batch, sync=True, distance=True):
         """reference :94-129 (fast parallel update) -> mean min-distance of the batch
         (None with `distance=False`: the training driver discards it, run_clustering.py:171-175)."""
-        if self.sequential:
-            raise NotImplementedError("sequential=True (reference :103-109, disabled by default) is not provided")
         batch = self._prep_batch(batch)
         dev = self._device()
         b = batch.shape[0]
         dist, world = self._world()
         lr = self.lr(self.count) if callable(self.lr) else self.lr
-        if self._graphable(batch):
+        if self.sequential:
+            # reference :96-109 -- the slow branch works on the all-gathered batch, every rank applies every row
+            if world > 1:
+                gbatch = torch.empty((b * world, batch.shape[1]), dtype=batch.dtype, device=dev)
+                dist.all_gather_into_tensor(gbatch, batch.contiguous())
+                batch = gbatch
+            best, mean = self._assign(batch, want_mean=distance)
+            counts_b = self._histogram(batch, best)
+            with torch.cuda.device(dev):
+                _lib.call("acav_kmeans_update_sequential", self._workspace(batch.shape[0]),
+                          _lib.ptr(batch, row_strided=True), batch.shape[0], batch.stride(0), _lib.ptr(counts_b),
+                          float(lr), _lib.ptr(self.centers), _lib.ptr(self.counts), _lib.stream_ptr(dev))
+        elif self._graphable(batch):
             best, mean = self._add_graphed(batch, float(lr), distance, dist, world)
         else:
             best, mean = self._assign(batch, want_mean=distance)

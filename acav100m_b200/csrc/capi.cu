@@ -360,7 +360,7 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) rc = dev_alloc(&h->total, (size_t)k, &h->bytes);
     if (!rc) rc = dev_alloc(&h->seg_start, (size_t)2 * k + 2, &h->bytes);     // offsets [k+1] + heavy-centroid list
     if (!rc) rc = dev_alloc(&h->sorted_rows, (size_t)max_batch, &h->bytes);
-    if (!rc) rc = dev_alloc(&h->lr_eff, 1, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->lr_eff, 2, &h->bytes);
     // tensor-core path (bf16 operands padded to a multiple of 64 columns)
     h->dp = (int32_t)ceil_div(d, 64) * 64;
     h->tensor_ready = false;
@@ -502,7 +502,7 @@ static int update_common(acav_kmeans_t *h, const float *x, int64_t b, int64_t ld
     if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
     int rc = launch_effective_lr(counts_b, h->k, lr, h->lr_eff, fallback, st);
     if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, counts_b, h->lr_eff, centers,
-                                counts, deltas, nullptr, st);
+                                counts, deltas, nullptr, false, st);
     h->partition_valid = false;
     return rc;
 }
@@ -511,6 +511,18 @@ int acav_kmeans_update_fused(acav_kmeans_t *h, const float *x, int64_t b, int64_
                              const float *counts_b, double lr,
                              float *centers, float *counts, int32_t *fallback, void *stream) {
     return update_common(h, x, b, ldx, counts_b, lr, centers, counts, nullptr, fallback, (cudaStream_t)stream);
+}
+
+int acav_kmeans_update_sequential(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, const float *counts_b,
+                                  double lr, float *centers, float *counts, void *stream) {
+    if (!h || !x || !counts_b || !centers || !counts || ldx < h->d) return ACAV_E_INVALID;
+    if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_sequential_lr(lr, h->lr_eff, st);
+    if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, counts_b, h->lr_eff, centers, counts,
+                                nullptr, nullptr, true, st);
+    h->partition_valid = false;
+    return rc;
 }
 
 int acav_kmeans_update_local(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
@@ -630,7 +642,7 @@ int acav_kmeans_update_p2p(acav_kmeans_t *h, acav_kmeans_comm_t *comm, const flo
     int rc = launch_km_hist_exchange(comm->c, counts_b_local, lr, comm->counts_global, comm->lr_eff, fallback, counts, st);
     const KmPush push = km_comm_push_target(comm->c);
     if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, comm->counts_global, comm->lr_eff,
-                                centers, counts, nullptr, &push, st);
+                                centers, counts, nullptr, &push, false, st);
     if (!rc) rc = launch_km_reduce_broadcast(comm->c, comm->counts_global, comm->lr_eff, centers, st);
     h->partition_valid = false;
     return rc;

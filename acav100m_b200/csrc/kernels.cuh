@@ -60,7 +60,8 @@ struct KmPush {                  // where the deltas of a multi-GPU step go: rec
 };
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, const KmPush *push, cudaStream_t st);
+                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st);
+int launch_sequential_lr(double lr, float *lr_eff, cudaStream_t st);
 
 // kmeans_comm.cu: the multi-GPU step over NVLink peer memory (no NCCL): histogram exchange + lr decision, and the
 // owner-side rank-ordered reduction of the pushed deltas with the broadcast of the new centroid rows

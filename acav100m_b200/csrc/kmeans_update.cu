@@ -153,7 +153,10 @@ km_effective_lr_kernel(const float *__restrict__ counts_b, int32_t k, double lr,
 //   kUpdPush  : the delta is stored straight into the receive buffer of the rank that OWNS the centroid (peer memory
 //               over NVLink); centers and counts are not touched here -- the owner adds the ranks' deltas in rank
 //               order, applies the decay and hands the new rows to everybody (kmeans_comm.cu).
-enum { kUpdFused = 0, kUpdSplit = 1, kUpdPush = 2 };
+//   kUpdSeq   : the reference's `sequential=True` branch (:103-109): the rows of a centroid are applied one after the
+//               other, c = fl(fl(c * w) + fl(lr * x)) with w = fl32(1 - lr); lr_eff_p[1] holds w.  Per centroid this is
+//               the same strict row-order chain, started from the centroid instead of from zero.
+enum { kUpdFused = 0, kUpdSplit = 1, kUpdPush = 2, kUpdSeq = 3 };
 
 // One thread = one centroid x VEC columns.
 // The fp32 add chain per (centroid, column) is inherently serial (that IS the reference's sum order);
@@ -179,6 +182,14 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    float wseq = 0.f;
+    if constexpr (MODE == kUpdSeq) {
+        wseq = lr_eff_p[1];
+        if (active) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = centers[(int64_t)c * d + col + v];
+        }
+    }
     const float *xcol = x + col;
     float buf[2][kGroup][VEC];                              // double buffer: loads of group g+1 fly during adds of g
     auto load_group = [&](float (&dst)[kGroup][VEC], uint32_t s, uint32_t n) {
@@ -200,7 +211,9 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
         for (int u = 0; u < kGroup; ++u) {
             if (s + u < n) {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(src[u][v], lr));     // :123
+                for (int v = 0; v < VEC; ++v)
+                    acc[v] = MODE == kUpdSeq ? __fadd_rn(__fmul_rn(acc[v], wseq), __fmul_rn(src[u][v], lr))   // :107-108
+                                             : __fadd_rn(acc[v], __fmul_rn(src[u][v], lr));                   // :123
             }
         }
     };
@@ -222,6 +235,11 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
     if constexpr (MODE == kUpdPush) {
         static_assert(VEC == 4, "the push path needs 16-byte columns");
         *reinterpret_cast<float4 *>(push.slot(c, d) + col) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        return;
+    }
+    if constexpr (MODE == kUpdSeq) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) centers[(int64_t)c * d + col + v] = acc[v];
         return;
     }
     const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                    // :121
@@ -415,6 +433,11 @@ km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32
             const int32_t col = col0 + 2 * lane;
             const bool active = col < d;
             float acc0 = 0.f, acc1 = 0.f;
+            float wseq = 0.f;
+            if constexpr (MODE == kUpdSeq) {
+                wseq = lr_eff_p[1];
+                if (active) { acc0 = centers[(int64_t)c * d + col]; acc1 = centers[(int64_t)c * d + col + 1]; }
+            }
             for (uint32_t base = lo; base < hi; base += kBulkRows) {
                 const uint32_t n = min((uint32_t)kBulkRows, hi - base);
                 ptx::mbar_wait(&full[stage], phase);
@@ -425,14 +448,24 @@ km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32
                     for (int r = 0; r < kBulkRows; ++r) v[r] = rows[r * (kBulkCols / 2)];
 #pragma unroll
                     for (int r = 0; r < kBulkRows; ++r) {
-                        acc0 = __fadd_rn(acc0, __fmul_rn(v[r].x, lr));                     // :123
-                        acc1 = __fadd_rn(acc1, __fmul_rn(v[r].y, lr));
+                        if constexpr (MODE == kUpdSeq) {
+                            acc0 = __fadd_rn(__fmul_rn(acc0, wseq), __fmul_rn(v[r].x, lr));   // :107-108
+                            acc1 = __fadd_rn(__fmul_rn(acc1, wseq), __fmul_rn(v[r].y, lr));
+                        } else {
+                            acc0 = __fadd_rn(acc0, __fmul_rn(v[r].x, lr));                 // :123
+                            acc1 = __fadd_rn(acc1, __fmul_rn(v[r].y, lr));
+                        }
                     }
                 } else {
                     for (uint32_t r = 0; r < n; ++r) {
                         const float2 v = rows[r * (kBulkCols / 2)];
-                        acc0 = __fadd_rn(acc0, __fmul_rn(v.x, lr));
-                        acc1 = __fadd_rn(acc1, __fmul_rn(v.y, lr));
+                        if constexpr (MODE == kUpdSeq) {
+                            acc0 = __fadd_rn(__fmul_rn(acc0, wseq), __fmul_rn(v.x, lr));
+                            acc1 = __fadd_rn(__fmul_rn(acc1, wseq), __fmul_rn(v.y, lr));
+                        } else {
+                            acc0 = __fadd_rn(acc0, __fmul_rn(v.x, lr));
+                            acc1 = __fadd_rn(acc1, __fmul_rn(v.y, lr));
+                        }
                     }
                 }
                 __syncwarp();
@@ -443,6 +476,8 @@ km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32
             if (MODE != kUpdPush && blockIdx.y == 0 && lane == 0) counts[c] = __fadd_rn(counts[c], cb);      // :120
             if (active && MODE == kUpdPush) {
                 *reinterpret_cast<float2 *>(push.slot(c, d) + col) = make_float2(acc0, acc1);
+            } else if (active && MODE == kUpdSeq) {
+                centers[(int64_t)c * d + col] = acc0; centers[(int64_t)c * d + col + 1] = acc1;
             } else if (active) {
                 const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                    // :121
                 float *cp = centers + (int64_t)c * d + col;
@@ -489,6 +524,19 @@ int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockh
     return 0;
 }
 
+// sequential branch: lr_eff[0] = fl32(lr), lr_eff[1] = fl32(1 - lr) (python-float subtraction, then the cast torch
+// applies to a python scalar multiplying an fp32 tensor)
+__global__ void km_sequential_lr_kernel(double lr, float *__restrict__ lr_eff) {
+    lr_eff[0] = (float)lr;
+    lr_eff[1] = (float)(1.0 - lr);
+}
+
+int launch_sequential_lr(double lr, float *lr_eff, cudaStream_t st) {
+    km_sequential_lr_kernel<<<1, 1, 0, st>>>(lr, lr_eff);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_eff, int32_t *fallback,
                         cudaStream_t st) {
     km_effective_lr_kernel<<<1, 1024, 0, st>>>(counts_b, k, lr, lr_eff, fallback);
@@ -498,10 +546,28 @@ int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_e
 
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, const KmPush *push, cudaStream_t st) {
+                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st) {
     const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     if (push && !vec4) return ACAV_E_UNSUPPORTED;
+    if (sequential) {                                  // :103-109: no histogram decay, no deltas
+        if (vec4) {
+            const size_t bsmem = (size_t)kBulkStages * kBulkRows * kBulkCols * 4 + 2 * kBulkStages * sizeof(uint64_t);
+            static size_t sdone[kMaxDevices];
+            { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdSeq>, bsmem, sdone); if (rc) return rc; }
+            dim3 bgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kBulkCols));
+            km_update_bulk_kernel<kUpdSeq><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                                                                                centers, counts, nullptr, KmPush());
+            ACAV_LAUNCH_CHECK();
+            dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128 * 4));
+            km_update_kernel<4, kUpdSeq><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, KmPush());
+        } else {
+            dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
+            km_update_kernel<1, kUpdSeq><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, KmPush());
+        }
+        ACAV_LAUNCH_CHECK();
+        return 0;
+    }
     KmPush pz = push ? *push : KmPush();
     if (vec4) {
         // heavy centroids (>= kUpdHeavyRows rows of this batch): cp.async ring kernel; its blocks for light

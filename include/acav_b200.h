@@ -152,6 +152,13 @@ int acav_kmeans_update_fused(acav_kmeans_t *h, const float *x, int64_t b, int64_
                              const float *counts_b, double lr,
                              float *centers, float *counts, int32_t *fallback, void *stream);
 
+/* The reference's `sequential=True` branch (sgd_clustering.py:103-109): the rows of the batch are applied one at a
+ * time, in batch order, each to its centroid: c = fl(fl(c * fl32(1 - lr)) + fl(fl32(lr) * x)); counts += 1.  No lr
+ * fallback, no decay by the histogram.  Rows of different centroids commute, so the result equals the per-centroid
+ * row-ordered recurrence the kernels run (same stable partition as the fast update). */
+int acav_kmeans_update_sequential(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx, const float *counts_b,
+                                  double lr, float *centers, float *counts, void *stream);
+
 /* Multi-GPU split of the same step: `update_local` applies the decay with the GLOBAL counts_b and
  * writes this rank's deltas[k,d] (to be all-reduced, sgd_clustering.py:125-126);
  * `apply_deltas` is centers += deltas (:127). */

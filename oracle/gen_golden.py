@@ -29,6 +29,8 @@ KMEANS_CASES = {
     "kmeans_bigbatch": dict(n=4096, d=64, k=32, k_true=20, batch=1024, epochs=3, seed=1002),
     # ragged feature dim / k not a power of two, epoch 5+ changes lr (run_clustering.py:168)
     "kmeans_ragged": dict(n=777, d=88, k=13, k_true=9, batch=37, epochs=6, seed=1003),
+    # the slow sequential update branch (sgd_clustering.py:103-109; `sequential` is an attribute, off by default :32)
+    "kmeans_sequential": dict(n=900, d=36, k=7, k_true=5, batch=150, epochs=2, seed=1004, sequential=True),
 }
 
 MI_CASES = {
@@ -75,6 +77,7 @@ def run_reference_kmeans(case):
     x = torch.from_numpy(synth.gaussian_mixture(case["n"], case["d"], case["k_true"], case["seed"]))
     seed_all(case["seed"])
     km = KMeans(ref_shims.reference_kmeans_args(), case["d"], case["k"])
+    km.sequential = bool(case.get("sequential", False))
     init_centers = km.centers.clone()
     dists, trace_best = [], []
     with ref_shims.cuda_is_identity(), torch.no_grad():

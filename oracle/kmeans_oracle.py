@@ -31,6 +31,7 @@ class SgdKMeansState:
     initial_rounds: int = 10
     reinit: tuple = (.7, 5.0)
     fallback: int = 0                # number of lr fallbacks taken (:119)
+    sequential: bool = False         # slow sequential update branch (:103-109), off by default (:32)
 
     def clone(self):
         return dataclasses.replace(self, centers=self.centers.clone(), counts=self.counts.clone())
@@ -88,12 +89,31 @@ def effective_lr(lr, max_count):
     return lr, False
 
 
+def sgd_step_sequential(state, batch, warmup_noise=None, best=None):
+    """``KMeans.add`` with ``sequential=True`` (sgd_clustering.py:103-109): rows are applied one at a time, in batch
+    order, each to its centroid: ``c *= 1 - lr; c += lr * x; counts += 1``.  No lr fallback, no decay by the histogram."""
+    lr = state.lr(state.count) if callable(state.lr) else state.lr
+    if best is None:
+        best, mean_dist = assign(state, batch, warmup_noise)
+    else:
+        mean_dist = float("nan")
+    for i, j in enumerate(best):
+        state.centers[j] *= 1 - lr                                                   # :107
+        state.centers[j] += lr * batch[i]                                            # :108
+        state.counts[j] += 1                                                         # :109
+    state.count += len(batch)                                                        # :128
+    return best, mean_dist
+
+
 def sgd_step(state, batch, warmup_noise=None, best=None):
-    """``KMeans.add`` sgd_clustering.py:94-129, single process (fast parallel update branch).
+    """``KMeans.add`` sgd_clustering.py:94-129, single process (fast parallel update branch; the sequential branch
+    when ``state.sequential``).
 
     Mutates `state`; returns (best, mean distance).  `best` may be forced (used to test the update
     in isolation).
     """
+    if state.sequential:
+        return sgd_step_sequential(state, batch, warmup_noise, best)
     k, d = state.centers.shape
     lr = state.lr(state.count) if callable(state.lr) else state.lr
     if best is None:

@@ -17,9 +17,10 @@ def load(golden_dir, name):
     return dict(np.load(os.path.join(golden_dir, name + ".npz")))
 
 
-def make_gpu_kmeans(d, k, **kw):
+def make_gpu_kmeans(d, k, sequential=False, **kw):
     from acav100m_b200.clustering import KMeans
     km = KMeans(None, d, k, **kw)
+    km.sequential = sequential
     km.to("cuda")
     return km
 
@@ -64,6 +65,7 @@ def _oracle_trajectory(case):
     x = torch.from_numpy(synth.gaussian_mixture(case["n"], case["d"], case["k_true"], case["seed"]))
     gen_golden.seed_all(case["seed"])
     st = ko.new_state(case["d"], case["k"])
+    st.sequential = bool(case.get("sequential", False))
     steps = []
     for epoch in range(case["epochs"]):
         st.lr = ko.epoch_lr(epoch)
@@ -80,7 +82,8 @@ def _check_trajectory(case, g, mode):
     x, st, steps = _oracle_trajectory(case)
     assert np.array_equal(st.centers.numpy(), g["centers"])      # the oracle is the reference
     gen_golden.seed_all(case["seed"])
-    km = make_gpu_kmeans(case["d"], case["k"], assign_mode=mode, warmup_rng="cpu")
+    km = make_gpu_kmeans(case["d"], case["k"], assign_mode=mode, warmup_rng="cpu",
+                         sequential=bool(case.get("sequential", False)))
     assert np.array_equal(km.centers.cpu().numpy(), g["init_centers"])
     dists, flips, i = [], 0, 0
     for epoch in range(case["epochs"]):
@@ -491,3 +494,28 @@ def test_peer_memory_step_gives_up_on_a_missing_rank(monkeypatch):
     assert status.value == 1
     for c in comms:
         _lib.load().acav_kmeans_comm_destroy(c)
+
+
+@pytest.mark.parametrize("b,d,k", [(64, 13, 5), (1000, 352, 33), (4096, 128, 8), (5003, 256, 3)])
+def test_sequential_update_is_bit_exact_given_assignments(b, d, k):
+    """`sequential=True` (sgd_clustering.py:103-109): one row at a time in batch order -- per centroid a row-ordered
+    recurrence, run by the same kernels as the fast update (light, scalar and TMA heavy-centroid paths)."""
+    from acav100m_b200 import _lib
+    rng = np.random.RandomState(b + d)
+    x = torch.from_numpy(rng.standard_normal((b, d)).astype(np.float32))
+    best = torch.from_numpy(rng.randint(0, k, size=b).astype(np.int64))
+    if k > 2:
+        best[best == 1] = 0
+    st = ko.SgdKMeansState(centers=torch.from_numpy(rng.standard_normal((k, d)).astype(np.float32)),
+                           counts=torch.from_numpy(rng.randint(0, 50, k).astype(np.float32)), count=999, lr=1e-2,
+                           sequential=True)
+    km = state_to_gpu(st)
+    ko.sgd_step(st, x, best=best)
+    xg, bg = x.cuda(), best.cuda()
+    counts_b = torch.empty(k, dtype=torch.float32, device="cuda")
+    ws, s = km._workspace(b), _lib.stream_ptr()
+    _lib.call("acav_kmeans_histogram", ws, _lib.ptr(bg), b, _lib.ptr(counts_b), s)
+    _lib.call("acav_kmeans_update_sequential", ws, _lib.ptr(xg), b, d, _lib.ptr(counts_b), 1e-2, _lib.ptr(km.centers),
+              _lib.ptr(km.counts), s)
+    assert np.array_equal(km.counts.cpu().numpy(), st.counts.numpy())
+    assert np.array_equal(km.centers.cpu().numpy(), st.centers.numpy())

@@ -37,6 +37,7 @@ def test_kmeans_oracle_reproduces_reference_bits(golden_dir, name):
     assert float(x.double().sum()) == float(g["x_checksum"]), "synthetic input stream drifted"
     gen_golden.seed_all(case["seed"])
     st = ko.new_state(case["d"], case["k"])
+    st.sequential = bool(case.get("sequential", False))
     assert np.array_equal(st.centers.numpy(), g["init_centers"])
     batches = gen_golden.kmeans_batches(x, case["batch"])
     dists = ko.train(st, lambda epoch: batches, case["epochs"])

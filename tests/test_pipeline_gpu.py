@@ -140,3 +140,85 @@ def test_cli_chunked_selection_and_reduce(tmp_path):
     scli.main(["reduce", *common, "--subset.size=30"])
     lines = list(csv.reader(open(out_csv)))
     assert [l[1] for l in lines] == want_all and all(l[2].startswith("yt") for l in lines)
+
+
+def _ckpt(path):
+    return torch.load(str(path), weights_only=False)
+
+
+def test_cli_resume_from_cached_epoch(tmp_path):
+    """--clustering.cached_epoch with and without --clustering.resume_training (run_clustering.py:55-73,132-177,
+    180-272): a loaded checkpoint skips training unless resume_training is set; resumed epochs continue the epoch
+    counter (and with it the lr schedule); cluster shards are prefixed `epoch_{e}_`; shards already written are
+    skipped; a checkpoint trained on a SUBSET of the shards is found through get_shard_subset_cache; a checkpoint in
+    the reference's own (object) layout resumes like ours."""
+    feat_dir, meta_dir = write_feature_shards(tmp_path / "data", n_shards=3, clips_per_shard=64, seed=9)
+    glob = str(feat_dir / "shard-{000000..000002}.pkl")
+    base = ["--meta_path=" + str(meta_dir), "--clustering.ncentroids=6", "--data.batch_size=32", "--computation.num_gpus=1"]
+    name = "shard-{000000..000002}.pkl"
+
+    # reference run: 3 epochs straight
+    full = tmp_path / "full"
+    torch.manual_seed(4)
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(full), *base, "--clustering.epochs=3"])
+    want = _ckpt(full / ("cache_epoch_2_" + name))
+
+    # 1 epoch, then resume for 2 more: same centers bit for bit (same data order, same lr per epoch)
+    part = tmp_path / "part"
+    torch.manual_seed(4)
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(part), *base, "--clustering.epochs=1"])
+    assert (part / ("cache_epoch_0_" + name)).is_file() and (part / "shard-000000.pkl").is_file()
+    first = _ckpt(part / ("cache_epoch_0_" + name))              # one epoch (the resumed run rewrites this file)
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(part), *base, "--clustering.epochs=2",
+               "--clustering.cached_epoch=0", "--clustering.resume_training=True"])
+    # the reference's loop is range(pre_epochs, epochs + pre_epochs) with pre_epochs = cached_epoch (:164): it re-runs
+    # epoch 0's number, so two resumed epochs are numbered 0 and 1
+    got = _ckpt(part / ("cache_epoch_1_" + name))
+    for m in want:
+        for layer in want[m]:
+            assert got[m][layer]["count"] == want[m][layer]["count"]
+            assert np.array_equal(got[m][layer]["centers"], want[m][layer]["centers"]), (m, layer)
+    assert sorted(p.name for p in part.glob("epoch_0_shard-*.pkl")) == ["epoch_0_shard-00000%d.pkl" % i for i in range(3)]
+
+    # cached_epoch without resume_training: no training (checkpoint untouched), assignment only, existing shards skipped
+    stamp = (part / ("cache_epoch_1_" + name)).stat().st_mtime_ns
+    (part / "epoch_1_shard-000001.pkl").write_bytes(b"sentinel")
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(part), *base, "--clustering.epochs=5",
+               "--clustering.cached_epoch=1"])
+    assert (part / ("cache_epoch_1_" + name)).stat().st_mtime_ns == stamp
+    assert not (part / ("cache_epoch_2_" + name)).exists()
+    assert (part / "epoch_1_shard-000001.pkl").read_bytes() == b"sentinel"          # :248-250 skip
+    rows = pickle.load(open(part / "epoch_1_shard-000000.pkl", "rb"))
+    rows_full = pickle.load(open(full / "shard-000000.pkl", "rb"))
+    assert [r["filename"] for r in rows] == [r["filename"] for r in rows_full]
+    same = sum(int(a["audio_assignments"][0]["array"]["layer_4"] == b["audio_assignments"][0]["array"]["layer_4"])
+               for a, b in zip(rows, rows_full))
+    assert same == len(rows)                                     # same centers -> same labels
+
+    # a checkpoint trained on shards 0..1 serves a run over shards 0..2 (load_cache_from_shard_subset, default True)
+    sub = tmp_path / "sub"
+    torch.manual_seed(4)
+    ccli.main(["cluster", "--feature_path=" + str(feat_dir / "shard-{000000..000001}.pkl"), "--out_path=" + str(sub),
+               *base, "--clustering.epochs=1"])
+    before = _ckpt(sub / "cache_epoch_0_shard-{000000..000001}.pkl")
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(sub), *base, "--clustering.cached_epoch=0"])
+    assert not (sub / ("cache_epoch_0_" + name)).exists()        # loaded the subset checkpoint, trained nothing
+    assert (sub / "epoch_0_shard-000002.pkl").is_file()
+    after = _ckpt(sub / "cache_epoch_0_shard-{000000..000001}.pkl")
+    assert np.array_equal(before["layer_vggish"]["layer_0"]["centers"], after["layer_vggish"]["layer_0"]["centers"])
+
+    # the reference's default layout (objects under sgd_clustering.KMeans): written with save_scheme_ver2=False,
+    # resumed from like ours
+    v1 = tmp_path / "v1"
+    torch.manual_seed(4)
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(v1), *base, "--clustering.epochs=1",
+               "--clustering.save_scheme_ver2=False"])
+    from acav100m_b200.clustering import checkpoint
+    tree = checkpoint.load_tree(v1 / ("cache_epoch_0_" + name))
+    assert np.array_equal(tree["layer_slow_fast"]["layer_2"]["centers"], first["layer_slow_fast"]["layer_2"]["centers"])
+    ccli.main(["cluster", "--feature_path=" + glob, "--out_path=" + str(v1), *base, "--clustering.epochs=2",
+               "--clustering.cached_epoch=0", "--clustering.resume_training=True", "--clustering.save_scheme_ver2=False"])
+    got = checkpoint.load_tree(v1 / ("cache_epoch_1_" + name))
+    for m in want:
+        for layer in want[m]:
+            assert np.array_equal(got[m][layer]["centers"], want[m][layer]["centers"]), (m, layer)
