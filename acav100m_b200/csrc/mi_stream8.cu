@@ -453,87 +453,52 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
             for (int r = 0; r < DEPTH; ++r)
                 stage[r] = wb_lo + (uint32_t)r < wb_hi ? s8_ld_stream(src4 + (size_t)r * kWarp, stream_pol)
                                                        : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            // 16 gathers from the current gain row
-            auto gather16 = [&](const uint4 &q, float (&g)[16]) {
+            for (uint32_t blk0 = wb_lo; blk0 < wb_hi; blk0 += DEPTH) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    g[j] = s8_gather(q.x, j, grow_b);
-                    g[4 + j] = s8_gather(q.y, j, grow_b);
-                    g[8 + j] = s8_gather(q.z, j, grow_b);
-                    g[12 + j] = s8_gather(q.w, j, grow_b);
-                }
-            };
-            auto max16 = [](const float (&g)[16]) {
-                const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-                return fmaxf(m, fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])),
-                                      fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
-            };
-            // the rare part: a vector whose maximum reaches the thread's best -- take the maximum that came first in the
-            // candidate list and make it the new best, or park it as a tie of a later sub-row
-            auto consider = [&](const uint4 &q, const float (&g)[16], float m, uint32_t blk) {
-                const uint32_t e0 = blk * kS8Blk + lane * 16u;
-                if (!(m > -INFINITY && (m > B.bs || (m == B.bs && B.bi != 0xFFFFFFFFu && e0 >= B.bend)))) return;
-                uint32_t bj = 0, bp = 0xFFFFFFFFu;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (g[j] == m) {
-                        const uint32_t pj = __ldg(P.pos_s + e0 + j);
-                        if (pj < bp) { bp = pj; bj = (uint32_t)j; }
-                    }
-                }
-                if (m > B.bs) {
-                    const uint32_t wsel = bj < 4 ? q.x : bj < 8 ? q.y : bj < 12 ? q.z : q.w;
-                    B.bs = m; B.bi = e0 + bj; B.bend = rend_blk * kS8Blk; B.ntie = 0;
-                    B.bpos = bp; B.brow = rb + crow; B.bbyte = (wsel >> (8 * (bj & 3u))) & 0xFFu; B.meta = true;
-                } else {
-                    s8_tie(B, e0 + bj, rend_blk * kS8Blk, P.pos_s);
-                }
-            };
-            uint32_t blk0 = wb_lo;
-            while (blk0 < wb_hi) {
-                while (blk0 >= rend_blk) {                       // next non-empty sub-row (uniform per warp)
-                    ++crow;
-                    rend_blk = rs_loc[crow + 1] / kS8Blk;
-                    grow_b = gain_b + (uint32_t)crow * (kS8GainStride * 4u);
-                }
-                const uint32_t lim = min(wb_hi, rend_blk);       // my blocks of this sub-row end here
-                // fast path: groups of DEPTH whole blocks of one sub-row.  Slot r of the unrolled loop is refilled with
-                // block (blk + DEPTH) as soon as block blk has been taken out of it (the refill may run up to DEPTH
-                // blocks past the span: another warp's blocks or the allocation's slack -- loaded, never scored).  The
-                // loop only keeps the group's maximum; the thread's best is looked at ONCE per group, and only a group
-                // that can change it is walked again, block by block (its vectors come back from L2).
-                for (; blk0 + DEPTH <= lim; blk0 += DEPTH) {
-                    float gm = -INFINITY;
-#pragma unroll
-                    for (int r = 0; r < DEPTH; ++r) {
+                for (int r = 0; r < DEPTH; ++r) {
+                    const uint32_t blk = blk0 + (uint32_t)r;
+                    if (blk < wb_hi) {
                         const uint4 q = stage[r];
-                        stage[r] = s8_ld_stream(src4 + (size_t)(blk0 - wb_lo + (uint32_t)r + DEPTH) * kWarp, stream_pol);
+                        if (blk + DEPTH < wb_hi)
+                            stage[r] = s8_ld_stream(src4 + (size_t)(blk - wb_lo + DEPTH) * kWarp, stream_pol);
+                        while (blk >= rend_blk) {                // next non-empty sub-row (uniform per warp)
+                            ++crow;
+                            rend_blk = rs_loc[crow + 1] / kS8Blk;
+                            grow_b = gain_b + (uint32_t)crow * (kS8GainStride * 4u);
+                        }
                         float g[16];
-                        gather16(q, g);
-                        gm = fmaxf(gm, max16(g));
-                    }
-                    // all blocks of the group lie in one sub-row, so "later than the best's sub-row" holds for all or none
-                    if (gm > B.bs || (gm == B.bs && gm > -INFINITY && B.bi != 0xFFFFFFFFu && blk0 * kS8Blk >= B.bend)) {
-#pragma unroll 1
-                        for (uint32_t r = 0; r < (uint32_t)DEPTH; ++r) {
-                            const uint4 q = s8_ld_stream(src4 + (size_t)(blk0 - wb_lo + r) * kWarp, stream_pol);
-                            float g[16];
-                            gather16(q, g);
-                            consider(q, g, max16(g), blk0 + r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            g[j] = s8_gather(q.x, j, grow_b);
+                            g[4 + j] = s8_gather(q.y, j, grow_b);
+                            g[8 + j] = s8_gather(q.z, j, grow_b);
+                            g[12 + j] = s8_gather(q.w, j, grow_b);
+                        }
+                        float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                        m = fmaxf(m, fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])),
+                                           fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
+                        if (m >= B.bs) {                         // rare once the thread has seen a good candidate
+                            const uint32_t e0 = blk * kS8Blk + lane * 16u;
+                            if (m > -INFINITY && (m > B.bs || (B.bi != 0xFFFFFFFFu && e0 >= B.bend))) {
+                                // of the maxima in this vector take the one that came first in the candidate list
+                                uint32_t bj = 0, bp = 0xFFFFFFFFu;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    if (g[j] == m) {
+                                        const uint32_t pj = __ldg(P.pos_s + e0 + j);
+                                        if (pj < bp) { bp = pj; bj = (uint32_t)j; }
+                                    }
+                                }
+                                if (m > B.bs) {
+                                    const uint32_t wsel = bj < 4 ? q.x : bj < 8 ? q.y : bj < 12 ? q.z : q.w;
+                                    B.bs = m; B.bi = e0 + bj; B.bend = rend_blk * kS8Blk; B.ntie = 0;
+                                    B.bpos = bp; B.brow = rb + crow; B.bbyte = (wsel >> (8 * (bj & 3u))) & 0xFFu; B.meta = true;
+                                } else {
+                                    s8_tie(B, e0 + bj, rend_blk * kS8Blk, P.pos_s);
+                                }
+                            }
                         }
                     }
-                }
-                // the last (< DEPTH) blocks of this sub-row: one at a time, the staged vectors shift down one slot
-#pragma unroll 1
-                for (; blk0 < lim; ++blk0) {
-                    const uint4 q = stage[0];
-#pragma unroll
-                    for (int r = 0; r + 1 < DEPTH; ++r) stage[r] = stage[r + 1];
-                    stage[DEPTH - 1] = s8_ld_stream(src4 + (size_t)(blk0 - wb_lo + DEPTH) * kWarp, stream_pol);
-                    float g[16];
-                    gather16(q, g);
-                    const float m = max16(g);
-                    if (m >= B.bs) consider(q, g, m, blk0);
                 }
             }
         }
@@ -734,7 +699,7 @@ int mi_s8_k_rows(int32_t k_a, int32_t k_v) { return s8_geom(k_a, k_v).k_rows; }
 int mi_s8_block() { return kS8Blk; }
 int mi_s8_tiles(int64_t w) { return (int)ceil_div(w > 0 ? w : 1, kS8Tile); }
 int64_t mi_s8_stream_capacity(int64_t w, int32_t k_a, int32_t k_v) {
-    return w + (int64_t)kS8Blk * s8_geom(k_a, k_v).k_rows + kS8Blk + 16 * kS8Blk;     // + slack for the scan's read-ahead
+    return w + (int64_t)kS8Blk * s8_geom(k_a, k_v).k_rows + kS8Blk;
 }
 
 int mi_s8_rows_that_fit(int32_t k_a, int32_t k_v) {
