@@ -31,11 +31,17 @@ def zipf_pairs(v, k, seed, s=1.1, p_corr=0.5):
     return np.stack([ca, cv], axis=1).astype(np.int64)
 
 
-def gaussian_mixture_torch(n, d, k_true, seed, device, spread=3.0, chunk=1 << 18, out=None):
-    """fp32 [n, d] on `device`, generated in chunks so the transient stays small."""
+def gaussian_mixture_torch(n, d, k_true, seed, device, spread=3.0, chunk=1 << 18, out=None, means_seed=None):
+    """fp32 [n, d] on `device`, generated in chunks so the transient stays small.  `means_seed`: draw the component
+    means from their own stream (ranks of a sharded run share the mixture and differ in the rows they hold)."""
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    means = torch.randn(k_true, d, generator=g, device=device) * spread
+    if means_seed is not None:
+        g.manual_seed(means_seed)
+        means = torch.randn(k_true, d, generator=g, device=device) * spread
+        g.manual_seed(seed)
+    else:
+        g.manual_seed(seed)
+        means = torch.randn(k_true, d, generator=g, device=device) * spread
     x = out if out is not None else torch.empty(n, d, dtype=torch.float32, device=device)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
