@@ -68,6 +68,7 @@ SIGNATURES = {
     "acav_mi_dense_destroy": (ctypes.c_int, [c_vp]),
     "acav_mi_dense_add": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "acav_mi_dense_score": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "acav_mi_dense_score_exact": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "acav_mi_dense_score_ami": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "acav_mi_debug_timers": (ctypes.c_int, [c_vp, c_vp]),
     "acav_mi_comm_handle_bytes": (ctypes.c_int, []),

@@ -966,6 +966,17 @@ int acav_mi_dense_score(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, fl
     return launch_mi_dense_score(h->s, cells, nb, pp, scores, (cudaStream_t)stream);
 }
 
+int acav_mi_dense_score_exact(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, const float *logs, int64_t n_logs,
+                              const float *consts, float *scores, float *per_pair, void *stream) {
+    if (!h || nb < 0 || (nb > 0 && (!cells || !scores)) || !logs || !consts) return ACAV_E_INVALID;
+    if (nb >= 65536ll * 32768ll) return ACAV_E_UNSUPPORTED;
+    (void)n_logs;                                  // the caller guarantees logs[k] for k <= samples in the tables + 1
+    float *pp = nullptr;
+    int rc = dense_per_pair(h, nb, per_pair, &pp, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_mi_dense_score_exact(h->s, cells, nb, logs, consts, pp, scores, (cudaStream_t)stream);
+}
+
 int acav_mi_dense_score_ami(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, int32_t average_method,
                             float *scores, float *per_pair, void *stream) {
     if (!h || nb < 0 || (nb > 0 && (!cells || !scores)) || average_method < 0 || average_method > 2) return ACAV_E_INVALID;

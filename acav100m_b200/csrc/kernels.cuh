@@ -169,6 +169,8 @@ int launch_mi_dense_reset(const MiDense &s, cudaStream_t st);
 int launch_mi_dense_add(const MiDense &s, const int64_t *cells, int64_t m, cudaStream_t st);
 int launch_mi_dense_score(const MiDense &s, const int64_t *cells, int64_t nb, float *per_pair, float *scores,
                           cudaStream_t st);
+int launch_mi_dense_score_exact(const MiDense &s, const int64_t *cells, int64_t nb, const float *logs,
+                                const float *consts_host, float *per_pair, float *scores, cudaStream_t st);
 // scratch: 4*P*C + P doubles (row / column sums of the EMI terms, plain and with the marginal bumped, and their total)
 int launch_mi_dense_score_ami(const MiDense &s, const int64_t *cells, int64_t nb, double *scratch, int32_t average_method,
                               float *per_pair, float *scores, cudaStream_t st);

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "mi_ami_math.h"
+#include "mi_dense_exact_math.h"
+#include "mi_pairs_math.h"
 
 namespace acav {
 
@@ -189,6 +191,67 @@ int launch_mi_dense_reset(const MiDense &s, cudaStream_t st) {
 int launch_mi_dense_add(const MiDense &s, const int64_t *cells, int64_t m, cudaStream_t st) {
     if (m == 0) return 0;
     mi_dense_add_kernel<<<(unsigned)ceil_div(s.p, 64), 64, 0, st>>>(s, cells, m);
+    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- bit-exact dense MI (mi_dense_exact_math.h): one warp per (candidate, pair) ---------------------------------------
+// Lane k*L + l owns accumulator stream (k, l) of ATen's cascade sum over the C*C cells of the candidate's table and walks
+// 32 consecutive cells per step with the rest of the warp; the 4 x L partials are folded with shuffles in ATen's order.
+__global__ void __launch_bounds__(32)
+mi_dense_exact_kernel(MiDense s, const int64_t *__restrict__ cells, const float *__restrict__ logs,
+                      DenseExactConsts k, float *__restrict__ per_pair) {
+    const int64_t bi = blockIdx.x;
+    const int p = blockIdx.y;
+    const int lane = threadIdx.x;
+    const int64_t cc = (int64_t)s.c * s.c;
+    DenseExactView v;
+    v.N = s.n_cells + (int64_t)p * cc; v.a = s.a_cols + (int64_t)p * s.c; v.b = s.b_rows + (int64_t)p * s.c; v.C = s.c;
+    v.c1 = (int32_t)cells[(bi * s.p + p) * 2]; v.c2 = (int32_t)cells[(bi * s.p + p) * 2 + 1];
+    const uint32_t n1 = s.n[p] + 1u;
+    v.nf = (float)n1; v.ln = logs[n1];
+    auto elem = [&](int64_t e) { return dense_exact_elem(v, k, logs, e); };
+    const DenseExactShape sh = dense_exact_shape(cc);
+    const int kk = lane / sh.L, l = lane % sh.L;
+    float part = lane < 4 * sh.L ? dense_exact_stream(sh, kk, l, elem) : 0.f;
+    if (lane < sh.L) part = dense_exact_leftover(sh, l, part, elem);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {                                // partial[0] += partial[q], lanes 0 .. L-1
+        const float other = __shfl_sync(0xffffffffu, part, (q * sh.L + l) & 31);
+        if (lane < sh.L) part = part + other;
+    }
+    float out = part;                                            // L == 1: the row sum is lane 0's partial
+    if (sh.L == 8) {
+        float acc = 0.f;
+        if (lane == 0)
+            for (int64_t e = sh.V * sh.L; e < cc; ++e) acc = acc + elem(e);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float pq = __shfl_sync(0xffffffffu, part, q);
+            acc = acc + pq;
+        }
+        out = acc;
+    }
+    if (lane == 0) per_pair[bi * s.p + p] = out;
+}
+
+// scores.mean(dim=-1) in torch's CPU summation order (pairs_mean, mi_pairs_math.h)
+__global__ void mi_dense_exact_mean_kernel(const float *__restrict__ per_pair, int64_t nb, int32_t p,
+                                           float *__restrict__ scores) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const float *row = per_pair + b * p;
+    scores[b] = pairs_mean(p, [&](int j) { return row[j]; });
+}
+
+int launch_mi_dense_score_exact(const MiDense &s, const int64_t *cells, int64_t nb, const float *logs,
+                                const float *consts_host, float *per_pair, float *scores, cudaStream_t st) {
+    if (nb == 0) return 0;
+    if (s.p > 65535 || s.p > kPairsMax) return ACAV_E_UNSUPPORTED;
+    DenseExactConsts k{consts_host[0], consts_host[1], consts_host[2], consts_host[3], consts_host[4], consts_host[5]};
+    mi_dense_exact_kernel<<<dim3((unsigned)nb, (unsigned)s.p), 32, 0, st>>>(s, cells, logs, k, per_pair);
+    ACAV_LAUNCH_CHECK();
+    mi_dense_exact_mean_kernel<<<(unsigned)ceil_div(nb, 128), 128, 0, st>>>(per_pair, nb, s.p, scores);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

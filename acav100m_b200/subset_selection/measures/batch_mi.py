@@ -8,14 +8,15 @@ dense MI of (table + one-hot), keeps the top k = 4 and re-appends the losers in 
 What runs where: the candidate bookkeeping (randperm, slicing, ``unique``) stays on torch CPU tensors
 exactly as in the reference -- the shuffle must consume the same generator stream to pick the same
 batches, and it, not the scoring, sets the pace (38 ms per iteration at 1 M candidates, SURVEY section
-3.5).  The scoring and the table update run in ``libacav_b200.so`` (``acav_mi_dense_*``): O(B*P) per
-iteration from running sums instead of the reference's 4*B*P*C*C logs.
+3.5).  The scoring and the table update run in ``libacav_b200.so`` (``acav_mi_dense_*``).
 
-Parity: scores agree with the reference's fp32 dense sum to ~1e-6 relative.  Which of several
-mathematically tied candidates ``topk`` returns in the reference is decided by the summation noise of
-that dense sum (its CPU and CUDA paths already disagree), so selected indices are identical only
-while no such tie decides a pick; ``tests/test_batch_mi_gpu.py`` checks scores and top-k sets
-iteration by iteration against the oracle.
+Parity: which of several near-equal candidates ``topk`` returns in the reference is decided by the fp32 rounding of
+its dense sum, so with ``exact=True`` (default) the B candidates are scored by ``acav_mi_dense_score_exact``: the
+reference's own dense evaluation, five fp32 roundings per cell, summed in the order of torch's CPU reduction kernel
+and averaged over the pairs in that kernel's order -- the same bits, hence the same top-k and, with the same seed,
+the same S as the reference's CPU run (``tests/test_batch_mi_gpu.py`` asserts it on goldens written by the
+unmodified reference).  ``exact=False`` scores in O(B*P) from fp64 running sums (~1e-6 relative agreement, picks
+identical while no near-tie decides one).
 """
 import math
 import time
@@ -25,11 +26,13 @@ import torch
 
 from ... import _lib
 from . import tables
+from .dense_mi import score_exact
 
 
 class EfficientBatchMI:
     def __init__(self, assignments, measure_type='mutual_info', average_method='arithmetic',
-                 ncentroids=20, batch_size=1, selection_size=1, device='cpu', keep_unselected=False, **kwargs):
+                 ncentroids=20, batch_size=1, selection_size=1, device='cpu', keep_unselected=False, exact=True,
+                 **kwargs):
         self.average_method = average_method.lower()
         self.ncentroids = int(ncentroids)
         self.assignments = torch.from_numpy(np.asarray(assignments)).to(torch.long)      # V x D (mi.py:24)
@@ -38,10 +41,13 @@ class EfficientBatchMI:
         self.k = selection_size
         self.keep_unselected = keep_unselected
         self.device = _lib.require_cuda(device if device not in (None, 'cpu', 'cuda') else None)
+        self.exact = exact
         self._engine = None
+        self._n_added = 0
 
     def init(self, clustering_combinations, candidates):
         """mi.py:27-30 with batch.py:20-27."""
+        self._n_added = 0
         self.combinations = [tuple(p) for p in clustering_combinations]
         self._pair_ids = torch.as_tensor(self.combinations, dtype=torch.long)            # P x 2
         self.candidate_ids = torch.as_tensor(np.asarray(candidates, dtype=np.int64))     # batch.py:20-22
@@ -77,6 +83,7 @@ class EfficientBatchMI:
         """batch.py:190-193 -- count clips into the tables."""
         ids = torch.as_tensor(ids, dtype=torch.long)
         cells = self._cells(ids)
+        self._n_added += int(cells.shape[0])
         with torch.cuda.device(self.device):
             _lib.call("acav_mi_dense_add", self._engine, _lib.ptr(cells), cells.shape[0], _lib.stream_ptr(self.device))
 
@@ -86,8 +93,11 @@ class EfficientBatchMI:
         cells = self._cells(batch_ids)
         scores = torch.empty(cells.shape[0], dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.call("acav_mi_dense_score", self._engine, _lib.ptr(cells), cells.shape[0], _lib.ptr(scores), None,
-                      _lib.stream_ptr(self.device))
+            if self.exact:
+                score_exact(self, cells, cells.shape[0], scores)
+            else:
+                _lib.call("acav_mi_dense_score", self._engine, _lib.ptr(cells), cells.shape[0], _lib.ptr(scores), None,
+                          _lib.stream_ptr(self.device))
         return scores.cpu()
 
     # -- host bookkeeping, as in the reference -----------------------------------------------------

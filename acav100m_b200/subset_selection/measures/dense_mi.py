@@ -8,11 +8,12 @@ the first maximum (:76-80).  Here the candidates' cells stay on the device and e
 ``acav_mi_dense_score`` call over all remaining candidates -- O(W*P) from the running sums of the table
 instead of O(W*P*C*C) logs -- plus one ``acav_mi_dense_add`` for the winner.
 
-Parity: scores agree with the reference's fp32 dense sum to ~1e-6 relative.  Many candidates tie exactly in
-exact arithmetic (same cell); the reference's dense sum gives tied candidates identical bits too (same table,
-same reduction), so the first index wins there and here; where two DIFFERENT cells are closer than the noise
-of the dense sum the pick can differ (the reference's own ``mi`` and ``mem_mi`` disagree in such places,
-SURVEY 8c).  ``tests/test_dense_mi_gpu.py`` replays the golden run teacher-forced and checks every iteration.
+Parity: with ``exact=True`` (default) every candidate is scored by ``acav_mi_dense_score_exact`` -- the reference's
+own O(W*P*C*C) dense evaluation with its five fp32 roundings per cell, summed in the order of torch's CPU reduction
+kernel -- so the scores carry the reference's bits and a free run selects the reference's indices
+(``tests/test_dense_mi_gpu.py``).  ``exact=False`` scores in O(W*P) from fp64 running sums (``acav_mi_dense_score``):
+~1e-6 relative agreement, picks identical except where two different cells are closer than the noise of the
+reference's dense sum.
 """
 import time
 
@@ -23,18 +24,30 @@ from ... import _lib
 from . import tables
 
 
+def score_exact(measure, cells, w, scores):
+    """``acav_mi_dense_score_exact`` for a measure object holding ``_engine``, ``_n_added``, ``ncentroids``, ``device``:
+    the log table must cover every count the tables can hold plus the candidate's sample."""
+    logs = tables.log_table_device(measure._n_added + 4, measure.device)
+    consts = tables.dense_exact_constants(measure.ncentroids)
+    _lib.call("acav_mi_dense_score_exact", measure._engine, _lib.ptr(cells), w, _lib.ptr(logs), logs.numel(),
+              consts.ctypes.data_as(_lib.c_vp), _lib.ptr(scores), None, _lib.stream_ptr(measure.device))
+
+
 class EfficientMI:
     def __init__(self, assignments, measure_type='mutual_info', average_method='arithmetic',
-                 ncentroids=20, device=None, **kwargs):
+                 ncentroids=20, device=None, exact=True, **kwargs):
         self.average_method = average_method.lower()
         self.ncentroids = int(ncentroids)
         self.assignments = torch.from_numpy(np.asarray(assignments)).to(torch.long)      # V x D (mi.py:24)
         self.eps = tables.EPS
         self.device = _lib.require_cuda(device if device not in (None, 'cpu', 'cuda') else None)
+        self.exact = exact
         self._engine = None
+        self._n_added = 0
 
     def init(self, clustering_combinations, candidates):
         """mi.py:27-30."""
+        self._n_added = 0
         self.combinations = [tuple(p) for p in clustering_combinations]
         self._pair_ids = torch.as_tensor(self.combinations, dtype=torch.long)            # P x 2
         self._release()
@@ -74,6 +87,7 @@ class EfficientMI:
         self._add_cells(cells)
 
     def _add_cells(self, cells):
+        self._n_added += int(cells.shape[0])
         with torch.cuda.device(self.device):
             _lib.call("acav_mi_dense_add", self._engine, _lib.ptr(cells), cells.shape[0], _lib.stream_ptr(self.device))
 
@@ -86,8 +100,11 @@ class EfficientMI:
         return scores
 
     def _score(self, cells, w, scores):
-        _lib.call("acav_mi_dense_score", self._engine, _lib.ptr(cells), w, _lib.ptr(scores), None,
-                  _lib.stream_ptr(self.device))
+        if self.exact:
+            score_exact(self, cells, w, scores)
+        else:
+            _lib.call("acav_mi_dense_score", self._engine, _lib.ptr(cells), w, _lib.ptr(scores), None,
+                      _lib.stream_ptr(self.device))
 
     def calc_measure(self):
         """mi.py:108-114."""

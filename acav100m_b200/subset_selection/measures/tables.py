@@ -64,3 +64,18 @@ def pair_table_constants(P, C):
     row = [xlogx(N[0, 0, 0]), xlogx(a[0, 0]), n[0], xlogx(N).sum([-1, -2])[0], xlogx(a).sum(-1)[0], xlogx(b).sum(-1)[0]]
     assert float(N[0, 0, 0] + 1) == 1.0 and float(a[0, 0] + 1) == 1.0 and float(n[0] + 1) == 1.0
     return np.tile(np.array([float(c) for c in row], dtype=np.float32), (P, 1))
+
+
+def dense_exact_constants(C):
+    """fp32 {eps, a0, b0, log eps, log a0, log b0}: an empty cell, an empty column marginal (``N.sum(dim=1)``) and an empty
+    row marginal (``N.sum(dim=2)``) of ``init_cache`` (measures/mi.py:32-39) and their torch-CPU logs, for the bit-exact
+    dense scorer (acav_mi_dense_score_exact).  Computed on a [2, C, C] tensor: with two or more outputs torch sums every
+    output serially, so the values do not depend on the number of pairs."""
+    N = torch.full((2, C, C), EPS)
+    a = N.sum(dim=1)
+    b = N.sum(dim=2)
+    vals = torch.stack([N[0, 0, 0], a[0, 0], b[0, 0]])
+    assert bool((a == a[0, 0]).all()) and bool((b == b[0, 0]).all())
+    assert float(vals[0] + 1) == 1.0 and float(vals[1] + 1) == 1.0 and float(vals[2] + 1) == 1.0
+    assert float(a.sum(dim=-1)[0] + 1) == 1.0                      # n0 = C*C*eps is absorbed by the first sample
+    return np.concatenate([vals.numpy(), vals.log().numpy()]).astype(np.float32)

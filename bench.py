@@ -347,7 +347,7 @@ def run_kmeans(args, dist, rank, world, epochs=None, report_pass=True):
     import types
     dev = torch.device("cuda", torch.cuda.current_device())
     n, d, k, b = args.km_rows, args.km_d, args.k, args.km_batch
-    x = synth.gaussian_mixture_torch(n, d, k, 1003 + rank, dev, means_seed=1003)
+    x = synth.gaussian_mixture_torch(n, d, k, 2003 + rank, dev, means_seed=1003)     # shared mixture, per-rank rows
     kargs = types.SimpleNamespace(computation=types.SimpleNamespace(device="cuda", num_gpus=world))
     torch.manual_seed(1003)
     km = KMeans(kargs, d, k, assign_mode=args.km_mode, warmup_rng="cuda",

@@ -341,6 +341,17 @@ int acav_mi_dense_add(acav_mi_dense_t *h, const int64_t *cells, int64_t m, void 
 int acav_mi_dense_score(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, float *scores, float *per_pair,
                         void *stream);
 
+/* The same scores BIT FOR BIT as the reference's CPU path computes them: every cell of
+ *   (N / n * (N.log() + n.log() - (a.log() + b.log()))).sum([2, 3])          (mi.py:90)
+ * with its five fp32 roundings, summed over the C*C cells in the order of torch's CPU reduction kernel (ATen
+ * cascade_sum: 8 lanes x 4 interleaved accumulators, cascade levels), then averaged over the pairs in the same
+ * kernel's order -- so a seeded run selects the very indices the reference selects (torch.topk / max see the same
+ * bits).  logs / n_logs as in acav_mi_set_tables (logs[k] for every count the tables can reach + 1); consts: HOST
+ * fp32[6] = { eps, a0, b0, log eps, log a0, log b0 }, the empty cell / column marginal / row marginal of init_cache
+ * (mi.py:32-39) and torch's logs of them.  Cost O(nb * P * C * C), like the reference; P <= 256. */
+int acav_mi_dense_score_exact(acav_mi_dense_t *h, const int64_t *cells, int64_t nb, const float *logs, int64_t n_logs,
+                              const float *consts, float *scores, float *per_pair, void *stream);
+
 /* The same for the adjusted-MI measure `ami` (EfficientAMI, mi.py:212-262): scores[i] = mean over pairs of
  * (MI - EMI) / max(generalized_mean(H_a, H_b) - EMI, eps) of (table_p + one-hot(candidate i)), with the reference's
  * single-term EMI (calc_EMI :217-231), evaluated in fp64.  average_method: 0 arithmetic, 1 max, 2 min

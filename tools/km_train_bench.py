@@ -30,7 +30,7 @@ p.add_argument("--profile", action="store_true", help="mark 3 graph-replayed ste
 a = p.parse_args()
 
 dev = torch.device("cuda", 0)
-x = synth.gaussian_mixture_torch(a.rows, a.d, a.k, 1003, dev)
+x = synth.gaussian_mixture_torch(a.rows, a.d, a.k, 2003, dev, means_seed=1003)          # bench.py's rank-0 shard
 nb = a.rows // a.b
 kargs = types.SimpleNamespace(computation=types.SimpleNamespace(device="cuda", num_gpus=1))
 
