@@ -138,20 +138,82 @@ def load_clusterings(args, model_names):
     return init_clusterings(args, model_names), False
 
 
-def _train_batch(args, features, clusterings):
-    """process_batch.py:6-17."""
+class _Stager:
+    """Double-buffered device copies of the collated batches: one non-blocking H2D per (model, layer) on a copy stream
+    into slot i % 2, so that batch i+1 is on its way while the KMeans objects (each on its own stream) work on batch i.
+    The slots have fixed addresses, which is what lets ``KMeans.add`` replay its step from a CUDA graph."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.copy = torch.cuda.Stream(self.device)
+        self.slots, self.done, self.i = [{}, {}], [[], []], 0
+
+    def _put(self, slot, key, t):
+        buf = self.slots[slot].get(key)
+        if buf is None or buf.shape != t.shape:
+            buf = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+            self.slots[slot][key] = buf
+        buf.copy_(t, non_blocking=True)
+        return buf
+
+    def upload(self, feats):
+        """feats: {model: {layer: CPU tensor} | CPU tensor} -> (same tree on the device, ready event, slot)."""
+        slot = self.i % 2
+        self.i += 1
+        with torch.cuda.stream(self.copy):
+            for ev in self.done[slot]:                     # the steps that read this slot two batches ago
+                self.copy.wait_event(ev)
+            self.done[slot] = []
+            out = {}
+            for name, f in feats.items():
+                if isinstance(f, dict):
+                    out[name] = {layer: self._put(slot, (name, layer), t) for layer, t in f.items()}
+                else:
+                    out[name] = self._put(slot, (name, None), f)
+            ready = torch.cuda.Event()
+            ready.record(self.copy)
+        return out, ready, slot
+
+    def consumed(self, slot, stream):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self.done[slot].append(ev)
+
+
+def _train_batch(args, features, clusterings, streams=None, ready=None, stager=None, slot=0, name=None):
+    """process_batch.py:6-17 -- every (model, layer) KMeans takes its step; with `streams` each on its own CUDA stream."""
     # the reference collects the mean distances and drops them (:171-175); skipping them saves a pass
     # over the batch and the host sync of `.item()`
-    if isinstance(features, dict):
-        for key, km in clusterings.items():
-            km.add(features[key], sync=False, distance=False)
-    else:
-        clusterings['model'].add(features, sync=False, distance=False)
+    items = clusterings.items() if isinstance(features, dict) else [('model', clusterings['model'])]
+    for key, km in items:
+        x = features[key] if isinstance(features, dict) else features
+        if streams is None:
+            km.add(x, sync=False, distance=False)
+            continue
+        s = streams.get((name, key))
+        if s is None:
+            s = streams[(name, key)] = torch.cuda.Stream(x.device)
+        s.wait_event(ready)
+        with torch.cuda.stream(s):
+            km.add(x, sync=False, distance=False)
+        stager.consumed(slot, s)
     return None
 
 
+def _loader_workers(args, n_shards):
+    """Worker processes of the shard loader: the reference's ``--computation.num_workers`` (default 40,
+    data/clustering.py:128-136), capped by the shards and the cores of this host."""
+    import os
+    want = args.computation.num_workers
+    want = 4 if want is None else int(want)
+    return max(0, min(want, n_shards, (os.cpu_count() or 2) - 1))
+
+
 def train_clusters(args, model_names):
-    """run_clustering.py:132-177."""
+    """run_clustering.py:132-177.  Shards are unpickled and collated by worker processes into page-locked shared memory
+    (clustering/loader.py), copied to the device one batch ahead on a copy stream, and the per-(model, layer) KMeans
+    objects step on their own streams."""
+    from .loader import ShardLoader
     clusterings, loaded = load_clusterings(args, model_names)
     if loaded and not args.clustering.resume_training:
         return clusterings
@@ -160,15 +222,28 @@ def train_clusters(args, model_names):
     shard_paths = D.expand_shards(args.data.path)
     pre_epochs = copy.deepcopy(args.clustering.cached_epoch) if loaded else 0
     epochs = math.ceil(args.clustering.epochs / max(args.computation.num_gpus or 1, 1))      # :146
+    on_gpu = str(args.computation.device).startswith('cuda')
+    stager = _Stager(torch.device('cuda', torch.cuda.current_device())) if on_gpu else None
+    streams = {} if on_gpu else None
     print("training sgd kmeans for models: {}".format(model_names))
     for epoch in range(pre_epochs, epochs + pre_epochs):
         for per_model in clusterings.values():
             for km in per_model.values():
                 km.lr = 0.1 ** (2 + epoch // 5)                                              # :168
-        for batch in D.batches(shard_paths, args.data.batch_size, drop_last=True):
+        loader = ShardLoader(shard_paths, args.data.batch_size, drop_last=True,
+                             workers=_loader_workers(args, len(shard_paths)), pin=on_gpu)
+        for batch in loader:
             batch = D.rank_slice(batch, rank, world)
+            feats = {name: batch[keys[name]] for name in model_names}
+            if stager is None:
+                for name in model_names:
+                    _train_batch(args, feats[name], clusterings[name])
+                continue
+            dev, ready, slot = stager.upload(feats)
             for name in model_names:
-                _train_batch(args, batch[keys[name]], clusterings[name])
+                _train_batch(args, dev[name], clusterings[name], streams, ready, stager, slot, name)
+        if on_gpu:
+            torch.cuda.synchronize()
         if rank == 0:
             save_clusterings(args, epoch, clusterings)
     return clusterings
@@ -186,6 +261,7 @@ def _extract_batch(features, clusterings):
 
 def assign_clusters(args, model_names, clusterings):
     """run_clustering.py:180-272 -- rank r labels shards r::world, one output shard per input shard."""
+    from .loader import ShardLoader
     rank, world = _world(args)
     keys = model_key_map(model_names)
     shard_paths = D.expand_shards(args.data.path)[rank::world]
@@ -199,7 +275,7 @@ def assign_clusters(args, model_names, clusterings):
             continue
         ids = defaultdict(list)
         shards = {name: defaultdict(dict) for name in model_names}
-        for batch in D.batches([shard_path], batch_size, drop_last=False):
+        for batch in ShardLoader([shard_path], batch_size, drop_last=False, workers=0):
             per_model = {name: _extract_batch(batch[keys[name]], clusterings[name]) for name in model_names}
             for j, idx in enumerate(batch['idx']):
                 shard_name = batch['shard_name'][j]

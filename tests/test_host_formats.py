@@ -371,3 +371,43 @@ def test_shard_subset_cache_lookup(tmp_path):
     assert rc.get_shard_subset_cache(args, tmp_path, 3, "shard-{000000..000009}.pkl") is None
     got2 = rc.get_shard_subset_cache(args, tmp_path, 2, "shard-{000000..000009}.pkl")
     assert got2.name == "cache_epoch_2_shard-{000000..000001}.pkl"
+
+
+# ---- parallel shard loader (clustering/loader.py): same batches as the in-process reader ------------------------------
+
+@pytest.mark.parametrize("workers,batch_size,drop_last", [(0, 7, False), (2, 7, False), (3, 64, True), (2, 100, False),
+                                                          (2, 23, True)])
+def test_parallel_loader_yields_the_in_process_batch_sequence(tmp_path, workers, batch_size, drop_last):
+    """Worker processes unpickle + collate whole shards into shared memory; the parent must cut exactly the batches of
+    data.batches (shard order, row order, batches straddling shards, ragged tail, drop_last)."""
+    import torch
+    from acav100m_b200.clustering import data as cdata, loader
+    from tests.shard_fixtures import write_feature_shards
+    feat_dir, _ = write_feature_shards(tmp_path / "d", n_shards=5, clips_per_shard=30, seed=2)
+    paths = cdata.expand_shards(str(feat_dir / "shard-{000000..000004}.pkl"))
+    want = list(cdata.batches(paths, batch_size, drop_last))
+    got = list(loader.ShardLoader(paths, batch_size, drop_last, workers=workers, hold=10))
+    assert len(got) == len(want) > 0
+    for g, w in zip(got, want):
+        assert g.keys() == w.keys()
+        for k, v in w.items():
+            if isinstance(v, dict):
+                for layer, t in v.items():
+                    assert torch.equal(g[k][layer], t), (k, layer)
+            elif torch.is_tensor(v):
+                assert torch.equal(g[k], v)
+            else:
+                assert g[k] == v, k
+
+
+def test_parallel_loader_skips_unreadable_shards_and_cleans_up(tmp_path):
+    from acav100m_b200.clustering import data as cdata, loader
+    from tests.shard_fixtures import write_feature_shards
+    feat_dir, _ = write_feature_shards(tmp_path / "d", n_shards=3, clips_per_shard=10, seed=5)
+    (feat_dir / "shard-000001.pkl").write_bytes(b"not a pickle")
+    paths = cdata.expand_shards(str(feat_dir / "shard-{000000..000002}.pkl"))
+    before = set(os.listdir("/dev/shm")) if os.path.isdir("/dev/shm") else set()
+    n = sum(len(b["idx"]) for b in loader.ShardLoader(paths, 8, False, workers=2))
+    assert n == 20
+    if os.path.isdir("/dev/shm"):
+        assert set(os.listdir("/dev/shm")) <= before, "shared-memory blocks must be unlinked"
