@@ -85,23 +85,32 @@ class EfficientMemMI:
             raise ValueError("cluster ids must lie in [0, ncentroids)")
         self._cells = cells
 
-    def init_from_cells(self, clustering_combinations, cells, w_global=None, lo=0, max_picks=None):
-        """Fast setup for big lists: `cells` is this rank's int64 [w, 2] tensor of (c1, c2) in list
-        order (pinned host or device memory), covering positions [lo, lo + w) of a candidate list of
-        `w_global` entries whose ids are their positions.  Skips the per-candidate python objects of
-        ``init`` (run_greedy.py:33 builds ``list(range(V))``)."""
+    def init_from_cells(self, clustering_combinations, cells, w_global=None, lo=0, max_picks=None, id_offset=0,
+                        all_columns=False):
+        """Fast setup for big lists, skipping the per-candidate python objects of ``init`` (run_greedy.py:33 builds
+        ``list(range(V))``).  One pair: `cells` is this rank's int64 [w, 2] tensor of (c1, c2) in list order -- or, with
+        `all_columns`, the [w, D] tensor of all clustering ids, from which the pair's two columns are taken.  Several
+        pairs: `cells` is the int64 [w, D] tensor of ALL clustering ids per candidate (the columns the pairs index).
+        Pinned host or device memory; covers positions [lo, lo + w) of a candidate list of `w_global` entries whose
+        clip ids are ``position + id_offset``."""
         self.combinations = [tuple(p) for p in clustering_combinations]
-        if len(self.combinations) != 1:
-            raise NotImplementedError("the CUDA engine handles one clustering pair (P = 1)")
+        if not self.combinations or any(len(p) != 2 for p in self.combinations):
+            raise ValueError("every clustering combination must name two columns, got %r" % (self.combinations,))
         w = cells.shape[0]
         self._W = int(w_global) if w_global is not None else w
         self._range = (int(lo), int(lo) + w)
         self.candidate_ids = None
+        self._id_offset = int(id_offset)
         self._dist = None
         if self.shard is not None:
             import torch.distributed as dist
             self._dist = dist
-        self._cells = cells.to(self.device, non_blocking=True).contiguous()
+        if len(self.combinations) > 1:
+            self._cells, self._rows = None, cells
+        else:
+            if all_columns:
+                cells = cells[:, list(self.combinations[0])]
+            self._cells = cells.to(self.device, non_blocking=True).contiguous()
         self.init_cache(max_picks=max_picks if max_picks is not None else min(self._W + 8, (1 << 24) - 8))
 
     def launches_per_iteration(self):
@@ -302,7 +311,7 @@ class EfficientMemMI:
         pos = pos.cpu()
         gains = gain.cpu().tolist()
         elapsed = time.time() - t0
-        S.extend((pos if self.candidate_ids is None else self.candidate_ids[pos]).tolist())
+        S.extend((pos + getattr(self, "_id_offset", 0) if self.candidate_ids is None else self.candidate_ids[pos]).tolist())
         GAIN = [float(g) for g in gains]
         timelapse = [elapsed / n_picks] * n_picks if n_picks else []
         LOOKUPS = [0] * n_picks

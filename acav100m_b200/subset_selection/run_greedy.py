@@ -23,13 +23,19 @@ def _run_greedy(args, assignments, clustering_types, subset_size, subset_ratio,
                                         device=args.computation.device,
                                         keep_unselected=args.batch.keep_unselected)
 
-    candidates = list(range(dataset_size))
-    if shuffle_candidates:
-        print("shuffling candidates")
-        random.shuffle(candidates)                                  # :37-40 (caller seeds `random`)
-    start_indices = [candidates[0]]                                 # :43-44
-    candidates = candidates[1:]
-    measure.init(clustering_combinations, candidates)
+    if not shuffle_candidates and hasattr(measure, 'init_from_cells'):
+        # list order: candidates are clips 1 .. V-1 and the start clip is 0 (:33,43-44) -- no per-clip python objects
+        start_indices = [0]
+        measure.init_from_cells(clustering_combinations, measure.assignments[1:], w_global=dataset_size - 1, id_offset=1,
+                                all_columns=True)
+    else:
+        candidates = list(range(dataset_size))
+        if shuffle_candidates:
+            print("shuffling candidates")
+            random.shuffle(candidates)                              # :37-40 (caller seeds `random`)
+        start_indices = [candidates[0]]                             # :43-44
+        candidates = candidates[1:]
+        measure.init(clustering_combinations, candidates)
     S, GAIN, timelapse, LOOKUPS = measure.run_greedy(
         subset_size, start_indices, None, verbose=verbose, log_every=args.log_every,
         log_times=args.log_times, node_rank=args.node_rank, pid=args.parent_pid)

@@ -191,3 +191,26 @@ def test_limits_are_reported():
     with pytest.raises(_lib.AcavError) as e:
         _lib.call("acav_mi_pairs_create", _lib.ctypes.byref(h), 10, 3, 4, 1, bad.ctypes.data_as(_lib.c_vp), 8, 0)
     assert e.value.status == -1
+
+
+def test_init_from_cells_with_several_pairs_equals_init():
+    """The big-list setup (no list(range(V)), no per-candidate python objects) for P > 1: same picks and scores as
+    init(pairs, candidates), and the unshuffled driver takes it."""
+    import types
+    from acav100m_b200.subset_selection import get_measure
+    from acav100m_b200.subset_selection.run_greedy import _run_greedy
+    rng = np.random.RandomState(11)
+    V, D, C, picks = 20_001, 5, 16, 120
+    a = rng.randint(0, C, size=(V, D)).astype(np.int64)
+    pairs = mo.cluster_pairing([("m%d" % i, "l") for i in range(D)], "combination")          # P = 10
+    want_pos, want_gain = mo.greedy_mem_mi_pairs_c(a[1:], C, pairs, picks)
+    m = get_measure("mem_mi")(a, ncentroids=C, device="cuda")
+    m.init_from_cells(pairs, torch.from_numpy(a[1:]), w_global=V - 1, id_offset=1)
+    pos, gain = m.select(picks)
+    assert np.array_equal(pos.cpu().numpy(), want_pos) and np.array_equal(gain.cpu().numpy(), want_gain)
+    args = types.SimpleNamespace(batch=types.SimpleNamespace(batch_size=20, selection_size=4, keep_unselected=True),
+                                 computation=types.SimpleNamespace(device="cuda"), log_every=1, log_times=None,
+                                 node_rank=None, parent_pid=None)
+    keys = [("m%d" % i, "l") for i in range(D)]
+    S, GAIN, _ = _run_greedy(args, a, keys, picks + 2, None, measure_name="mem_mi", shuffle_candidates=False)
+    assert S == [0] + (want_pos + 1).tolist() and np.array_equal(np.array(GAIN, dtype=np.float32), want_gain)
