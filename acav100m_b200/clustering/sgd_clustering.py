@@ -119,11 +119,16 @@ class KMeans:
     # -- workspace -----------------------------------------------------------------------------
 
     def _release(self):
-        self._gs = None
         if getattr(self, "_comm", None):
             torch.cuda.synchronize(self.centers.device)
             _lib.load().acav_kmeans_comm_destroy(self._comm)
         self._comm = None
+        self._release_workspace()
+
+    def _release_workspace(self):
+        """Workspace, its pair and the graphs captured over them; the peer-memory exchange (sized by k and d only)
+        stays connected when a bigger batch makes the workspace grow."""
+        self._gs = None
         self._release_pair()
         if self._ws is not None:
             _lib.load().acav_kmeans_destroy(self._ws)
@@ -139,7 +144,7 @@ class KMeans:
     def _workspace(self, b):
         dev = self._device()
         if self._ws is None or b > self._ws_batch:
-            self._release()
+            self._release_workspace()
             k, d = self.centers.shape
             cap = max(int(b), 1024)
             handle = _lib.c_vp()

@@ -1,4 +1,5 @@
 // extern "C" surface of libacav_b200.so (declared in include/acav_b200.h).
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -68,7 +69,10 @@ struct acav_mi {
     bool cells_valid;
     // byte-stream loop resources (sub-row partitioned stream, one byte per candidate), built on first use
     uint8_t *s8_stream;
-    uint32_t *s8_pos, *s8_row_start, *s8_row_total, *s8_tilehist, *s8_chunk_start;
+    uint32_t *s8_pos, *s8_row_total, *s8_tilehist;
+    // layout of the one-byte stream (host-built, see s8_build_layout): slots, chunks, pieces of every sub-row
+    uint32_t *s8_slot_start, *s8_slot_row, *s8_slot_u, *s8_chunks, *s8_row_piece0, *s8_piece_rank0, *s8_piece_off;
+    int64_t s8_slot_cap;
     int32_t s8_rows_smem, s8_variant, s8_use_cache;
     bool s8_valid;
 };
@@ -180,6 +184,124 @@ std::vector<uint32_t> cut_chunks_capped(const std::vector<uint32_t> &rs, int32_t
     return chunks;
 }
 
+// Layout of the one-byte stream (ACAV_MI_LOOP_BYTES).  The order of the sub-rows in the stream is free (a candidate
+// only has to lie in list order inside its sub-row), so the host places them such that the CTAs' chunks come out equal:
+//   * one BIN per CTA, all bins the same number of blocks;
+//   * the small sub-rows (the Zipf tail: thousands of one-block sub-rows) are dealt to the bins in snake order, so
+//     every bin gets the same number of them -- in (c1, sub) order the CTAs that get the tail would hit the shared-
+//     memory row limit with a quarter of the average blocks;
+//   * the big sub-rows fill what is left of the bins, in order, cut at bin edges;
+//   * inside a bin the big blocks are cut into as many sub-pieces as there are small sub-rows and the two alternate, so
+//     every warp's span of the chunk crosses only a few segment borders (each border can park a tie in the scan).
+// A stream SLOT is a sub-row or a piece of one; all slots are whole blocks.  Pieces of one sub-row in one bin share a
+// gain row (slot_u).  The scatter kernel finds a candidate's place through the pieces of its sub-row (rank order).
+struct S8Layout {
+    std::vector<uint32_t> slot_start, slot_row, slot_u;          // [n_slots + 1], [n_slots], [n_slots]
+    std::vector<uint32_t> chunks;                                // [grid + 1][4] {slot0, n_slots, n_rows, start}
+    std::vector<uint32_t> row_piece0, piece_rank0, piece_off;    // [k_rows + 1], [n_pieces], [n_pieces]
+    uint32_t total = 0;                                          // padded stream length (candidates)
+};
+
+bool s8_build_layout(const std::vector<uint32_t> &nb, uint32_t blk, int32_t grid, int32_t rows_cap, int32_t slots_cap,
+                     S8Layout *L) {
+    const int32_t k_rows = (int32_t)nb.size();
+    std::vector<uint32_t> live;
+    uint64_t total_blocks = 0;
+    for (int32_t r = 0; r < k_rows; ++r)
+        if (nb[r]) { live.push_back((uint32_t)r); total_blocks += nb[r]; }
+    std::stable_sort(live.begin(), live.end(), [&](uint32_t a, uint32_t b) { return nb[a] > nb[b]; });
+    const uint64_t t0 = (total_blocks + grid - 1) / grid;
+    const uint64_t small_max = t0 / 4 > 1 ? t0 / 4 : 1;
+    struct Piece { uint32_t row, rank0, n; };                   // in blocks
+    std::vector<std::vector<uint32_t>> small_of((size_t)grid);
+    std::vector<std::vector<Piece>> big_of((size_t)grid);
+    std::vector<uint64_t> small_blocks((size_t)grid, 0);
+    std::vector<uint32_t> big;
+    {   // snake deal of the small sub-rows (sorted by size)
+        int64_t i = 0;
+        for (uint32_t r : live) {
+            if (nb[r] > small_max) { big.push_back(r); continue; }
+            const int64_t pass = i / grid, k = i % grid;
+            const int32_t g = (int32_t)((pass & 1) ? grid - 1 - k : k);
+            small_of[g].push_back(r);
+            small_blocks[g] += nb[r];
+            ++i;
+        }
+    }
+    uint64_t big_blocks = 0;
+    for (uint32_t r : big) big_blocks += nb[r];
+    // bin size: the smallest T with room for all big blocks next to the small ones
+    uint64_t T = t0;
+    for (int32_t g = 0; g < grid; ++g) T = std::max(T, small_blocks[g]);
+    for (;;) {
+        uint64_t room = 0;
+        for (int32_t g = 0; g < grid; ++g) room += T - small_blocks[g];
+        if (room >= big_blocks) break;
+        T += (big_blocks - room + grid - 1) / grid;
+    }
+    {   // big sub-rows fill the bins in order
+        int32_t g = 0;
+        uint64_t room = T - small_blocks[0];
+        for (uint32_t r : big) {
+            uint32_t left = nb[r], rank0 = 0;
+            while (left) {
+                while (room == 0) { ++g; room = T - small_blocks[g]; }
+                const uint32_t take = (uint32_t)std::min<uint64_t>(left, room);
+                big_of[g].push_back({r, rank0, take});
+                rank0 += take; left -= take; room -= take;
+            }
+        }
+    }
+    // emit: per bin, big sub-pieces and small sub-rows alternate
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> pieces_of((size_t)k_rows);      // (rank0 blocks, stream offset)
+    L->slot_start.clear(); L->slot_row.clear(); L->slot_u.clear();
+    L->chunks.assign((size_t)(grid + 1) * 4, 0);
+    uint32_t off = 0;
+    for (int32_t g = 0; g < grid; ++g) {
+        const uint32_t slot0 = (uint32_t)L->slot_row.size();
+        uint32_t n_rows = 0;
+        auto emit = [&](uint32_t row, uint32_t rank0, uint32_t n, uint32_t u) {
+            L->slot_start.push_back(off);
+            L->slot_row.push_back(row);
+            L->slot_u.push_back(u);
+            pieces_of[row].push_back({rank0, off});
+            off += n * blk;
+        };
+        uint64_t bigs = 0;
+        for (const Piece &p : big_of[g]) bigs += p.n;
+        const size_t n_small = small_of[g].size();
+        const uint64_t sub = n_small ? std::max<uint64_t>(1, (bigs + n_small) / (n_small + 1)) : (bigs ? bigs : 1);
+        size_t si = 0;
+        for (const Piece &p : big_of[g]) {
+            const uint32_t u = n_rows++;
+            uint32_t done = 0;
+            while (done < p.n) {
+                const uint32_t take = (uint32_t)std::min<uint64_t>(p.n - done, sub);
+                emit(p.row, p.rank0 + done, take, u);
+                done += take;
+                if (si < n_small) { const uint32_t r = small_of[g][si++]; emit(r, 0, nb[r], n_rows++); }
+            }
+        }
+        while (si < n_small) { const uint32_t r = small_of[g][si++]; emit(r, 0, nb[r], n_rows++); }
+        const uint32_t n_slots = (uint32_t)L->slot_row.size() - slot0;
+        if ((int32_t)n_rows > rows_cap || (int32_t)n_slots > slots_cap) return false;
+        uint32_t *c = &L->chunks[(size_t)g * 4];
+        c[0] = slot0; c[1] = n_slots; c[2] = n_rows; c[3] = n_slots ? L->slot_start[slot0] : off;
+    }
+    L->slot_start.push_back(off);
+    L->total = off;
+    {   uint32_t *c = &L->chunks[(size_t)grid * 4]; c[0] = (uint32_t)L->slot_row.size(); c[1] = 0; c[2] = 0; c[3] = off; }
+    L->row_piece0.assign((size_t)k_rows + 1, 0);
+    L->piece_rank0.clear(); L->piece_off.clear();
+    for (int32_t r = 0; r < k_rows; ++r) {
+        L->row_piece0[r] = (uint32_t)L->piece_rank0.size();
+        for (const auto &pp : pieces_of[r]) { L->piece_rank0.push_back(pp.first * blk); L->piece_off.push_back(pp.second); }
+        if (pieces_of[r].empty()) { L->piece_rank0.push_back(0); L->piece_off.push_back(0); }     // empty sub-row: never looked up
+    }
+    L->row_piece0[k_rows] = (uint32_t)L->piece_rank0.size();
+    return true;
+}
+
 // Build (or rebuild) the sub-row partitioned one-byte stream of ACAV_MI_LOOP_BYTES and its per-CTA chunk table.
 int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
     if (h->s8_valid) return 0;
@@ -188,35 +310,57 @@ int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
     h->s8_rows_smem = mi_s8_rows_that_fit(s.k_a, s.k_v);
     const int32_t k_rows = mi_s8_k_rows(s.k_a, s.k_v);
     const int ntiles = mi_s8_tiles(s.w);
+    // pieces never add padding (they are whole blocks of a padded sub-row), so the capacity of the plain layout holds
     const int64_t cap = (mi_s8_stream_capacity(s.w, s.k_a, s.k_v) + 15) / 16 * 16;
+    const uint32_t blk = (uint32_t)mi_s8_block();
+    const int32_t slots_cap = mi_s8_slots_for_rows(h->s8_rows_smem);
+    const int64_t slot_cap_total = (int64_t)k_rows + (int64_t)h->sm_count * (slots_cap + 2) + 16;
     int rc = 0;
     if (!h->s8_stream) {
+        h->s8_slot_cap = slot_cap_total;
         if (!rc) rc = dev_alloc(&h->s8_stream, (size_t)cap, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_pos, (size_t)cap, nullptr);
-        if (!rc) rc = dev_alloc(&h->s8_row_start, (size_t)k_rows + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_slot_start, (size_t)slot_cap_total + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_slot_row, (size_t)slot_cap_total, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_slot_u, (size_t)slot_cap_total, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_piece_rank0, (size_t)slot_cap_total, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_piece_off, (size_t)slot_cap_total, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_row_piece0, (size_t)k_rows + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_chunks, ((size_t)h->sm_count + 1) * 4, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_row_total, (size_t)k_rows, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_tilehist, (size_t)ntiles * k_rows, nullptr);
-        if (!rc) rc = dev_alloc(&h->s8_chunk_start, (size_t)h->sm_count + 1, nullptr);
         if (!h->n_alt && !rc) rc = dev_alloc(&h->n_alt, (size_t)s.k_a * s.k_v, nullptr);
         if (!h->pub && !rc) rc = dev_alloc(&h->pub, mi_pub_bytes(h->sm_count), nullptr);
         if (!h->bar && !rc) rc = dev_alloc(&h->bar, 2, nullptr);
         if (rc) return rc;
     }
-    rc = launch_mi_s8_partition(s.cells, s.w, s.k_a, s.k_v, h->s8_tilehist, h->s8_row_total, h->s8_row_start,
-                                h->s8_stream, h->s8_pos, cap, st);
+    rc = launch_mi_s8_count(s.cells, s.w, s.k_a, s.k_v, h->s8_tilehist, h->s8_row_total, st);
     if (rc) return rc;
-    std::vector<uint32_t> rs((size_t)k_rows + 1);
-    ACAV_CUDA_TRY(cudaMemcpyAsync(rs.data(), h->s8_row_start, sizeof(uint32_t) * rs.size(), cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> nb((size_t)k_rows);
+    ACAV_CUDA_TRY(cudaMemcpyAsync(nb.data(), h->s8_row_total, sizeof(uint32_t) * nb.size(), cudaMemcpyDeviceToHost, st));
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));
-    rc = launch_mi_s8_block_sort(h->s8_stream, h->s8_pos, rs[k_rows], st);
+    for (int32_t r = 0; r < k_rows; ++r) nb[r] = (nb[r] + blk - 1) / blk;
+    S8Layout L;
+    if (!s8_build_layout(nb, blk, h->sm_count, h->s8_rows_smem, slots_cap, &L)) return ACAV_E_UNSUPPORTED;
+    if ((int64_t)L.slot_row.size() > h->s8_slot_cap || (int64_t)L.piece_off.size() > h->s8_slot_cap ||
+        (int64_t)L.total > cap)
+        return ACAV_E_UNSUPPORTED;
+    auto up = [&](uint32_t *dst, const std::vector<uint32_t> &v) {
+        return v.empty() ? cudaSuccess
+                         : cudaMemcpyAsync(dst, v.data(), sizeof(uint32_t) * v.size(), cudaMemcpyHostToDevice, st);
+    };
+    ACAV_CUDA_TRY(up(h->s8_slot_start, L.slot_start));
+    ACAV_CUDA_TRY(up(h->s8_slot_row, L.slot_row));
+    ACAV_CUDA_TRY(up(h->s8_slot_u, L.slot_u));
+    ACAV_CUDA_TRY(up(h->s8_chunks, L.chunks));
+    ACAV_CUDA_TRY(up(h->s8_row_piece0, L.row_piece0));
+    ACAV_CUDA_TRY(up(h->s8_piece_rank0, L.piece_rank0));
+    ACAV_CUDA_TRY(up(h->s8_piece_off, L.piece_off));
+    rc = launch_mi_s8_scatter(s.cells, s.w, s.k_a, s.k_v, h->s8_tilehist, h->s8_row_piece0, h->s8_piece_rank0,
+                              h->s8_piece_off, h->s8_stream, h->s8_pos, cap, st);
+    if (!rc) rc = launch_mi_s8_block_sort(h->s8_stream, h->s8_pos, L.total, st);
     if (rc) return rc;
-    double row_cost = 8.0;                         // blocks per sub-row touched (measured optimum of 0.5 / 2 / 4 / 8 on B200)
-    if (const char *e = std::getenv("ACAV_MI_S8_ROWCOST")) row_cost = std::atof(e);
-    const std::vector<uint32_t> chunks = cut_chunks_capped(rs, k_rows, row_cost, (uint32_t)mi_s8_block(), h->sm_count,
-                                                           h->s8_rows_smem);
-    ACAV_CUDA_TRY(cudaMemcpyAsync(h->s8_chunk_start, chunks.data(), sizeof(uint32_t) * chunks.size(),
-                                  cudaMemcpyHostToDevice, st));
-    ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // `chunks` is a host temporary
+    ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // the layout tables are host temporaries
     h->grid = h->sm_count;
     h->s8_valid = true;
     return 0;
@@ -667,8 +811,9 @@ int acav_mi_destroy(acav_mi_t *h) {
             if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
     cudaFree(h->mail_local); cudaFree(h->run_status);
     cudaFree(h->cx_sorted_pos); cudaFree(h->cx_cell_start); cudaFree(h->cx_head); cudaFree(h->cx_first_pos);
-    cudaFree(h->s8_stream); cudaFree(h->s8_pos); cudaFree(h->s8_row_start); cudaFree(h->s8_row_total);
-    cudaFree(h->s8_tilehist); cudaFree(h->s8_chunk_start);
+    cudaFree(h->s8_stream); cudaFree(h->s8_pos); cudaFree(h->s8_row_total); cudaFree(h->s8_tilehist);
+    cudaFree(h->s8_slot_start); cudaFree(h->s8_slot_row); cudaFree(h->s8_slot_u); cudaFree(h->s8_chunks);
+    cudaFree(h->s8_row_piece0); cudaFree(h->s8_piece_rank0); cudaFree(h->s8_piece_off);
     delete h;
     return 0;
 }
@@ -698,8 +843,10 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     h->sorted_valid = false;
     h->cx_sorted_pos = nullptr; h->cx_cell_start = nullptr; h->cx_head = nullptr; h->cx_first_pos = nullptr;
     h->cells_valid = false;
-    h->s8_stream = nullptr; h->s8_pos = nullptr; h->s8_row_start = nullptr; h->s8_row_total = nullptr;
-    h->s8_tilehist = nullptr; h->s8_chunk_start = nullptr; h->s8_rows_smem = 0; h->s8_valid = false;
+    h->s8_stream = nullptr; h->s8_pos = nullptr; h->s8_row_total = nullptr; h->s8_tilehist = nullptr;
+    h->s8_slot_start = nullptr; h->s8_slot_row = nullptr; h->s8_slot_u = nullptr; h->s8_chunks = nullptr;
+    h->s8_row_piece0 = nullptr; h->s8_piece_rank0 = nullptr; h->s8_piece_off = nullptr; h->s8_slot_cap = 0;
+    h->s8_rows_smem = 0; h->s8_valid = false;
     h->s8_variant = 0; h->s8_use_cache = 1;
     if (const char *e = std::getenv("ACAV_MI_S8_VARIANT")) h->s8_variant = std::atoi(e);
     if (const char *e = std::getenv("ACAV_MI_S8_CACHE")) h->s8_use_cache = std::atoi(e);
@@ -806,8 +953,8 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         if (rc) return rc;
         h->cells_valid = false;                  // neither the cell index nor the 2-byte stream see these removals
         h->sorted_valid = false;
-        rc = launch_mi_stream8(h->s, h->n_alt, h->s8_stream, h->s8_pos, h->s8_row_start, h->s8_chunk_start, h->grid, h->pub,
-                               h->bar, n_picks, out_pos, out_gain, h->s8_rows_smem, h->s8_variant, h->s8_use_cache,
+        rc = launch_mi_stream8(h->s, h->n_alt, h->s8_stream, h->s8_pos, h->s8_slot_start, h->s8_slot_row, h->s8_slot_u,
+                               h->s8_chunks, h->grid, h->pub, h->bar, n_picks, out_pos, out_gain, h->s8_rows_smem, h->s8_variant,
                                h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer, h->dbg, h->run_status,
                                h->spin_limit_ns, st);
         h->seq_base += (unsigned int)n_picks + 1u;
@@ -865,7 +1012,7 @@ int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles) {
 }
 
 int acav_mi_set_stream_variant(acav_mi_t *h, int32_t variant, int32_t use_cache) {
-    if (!h || variant < 0 || variant > 4) return ACAV_E_INVALID;
+    if (!h || variant < 0 || variant > 6) return ACAV_E_INVALID;
     h->s8_variant = variant;
     h->s8_use_cache = use_cache ? 1 : 0;
     return 0;

@@ -7,18 +7,22 @@
 //     sub_w = ceil(K_v / n_sub): 5 x 205 at K_v = 1024).  Candidates are STABLY partitioned by sub-row; the stream holds
 //     the column inside the sub-row as ONE byte (255 = removed / padding; that slot of a gain row holds -inf, so the
 //     hot loop has no branch).  100 MB per iteration at W = 1e8 instead of the reference's 1.6 GB of int64 pairs.
+//   * the sub-rows lie in the stream in an order chosen on the host (`perm`: stream slot -> sub-row): big and small
+//     sub-rows interleaved so that every stretch of the stream holds about the same number of sub-rows per block.  Every
+//     CTA's contiguous chunk then has the same number of blocks AND about the same number of gain rows to build, and
+//     all of its gain rows and table counts fit in its shared memory (the cut enforces it).
 //   * sub-rows are padded to whole 512-candidate blocks, every block is sorted by the shared-memory bank of its gain
 //     slot (lane l owns entries [16l, 16l+16): gather step j reads entries 16 apart, i.e. ~32 different banks); ties are
-//     settled by original position (pos[], permuted along, read only on that rare path).
-//   * the stream is cut into one contiguous chunk per CTA; a CTA stages the gain rows (256 floats) of the sub-rows its
-//     chunk touches in shared memory, 1 KiB aligned so that a gather address is (byte << 2) | row_base: shift, LOP3, LDS.
-//   * stream loads go through REGISTERS: DEPTH 16-byte loads per thread in flight (ld.global.cg, L2 evict-first), 512
-//     threads x 128 registers per CTA -- the shared-memory pipe only serves the gathers.
-//   * a CTA whose sub-rows all fit keeps their table COUNTS in shared memory for the whole launch (every CTA learns
-//     every winner and bumps its copy), so building the gain rows of an iteration reads no global memory; the others
-//     read the double-buffered global table like mi_persistent.cu.
-//   * the per-thread best remembers position, sub-row and byte of its candidate, so publishing the CTA's winner needs
-//     no dependent global loads in the common case.
+//     settled by original position (pos[], permuted along, read only after the scan).
+//   * a CTA stages the gain rows (256 floats) of its sub-rows in shared memory, 1 KiB aligned so that a gather address
+//     is (byte << 2) | row_base: shift, LOP3, LDS; their table COUNTS stay in shared memory for the whole launch (every
+//     CTA learns every winner and bumps its copy), so building the gain rows of an iteration reads no global memory.
+//   * stream loads go through REGISTERS: DEPTH 16-byte loads per thread in flight (ld.global.cg, L2 evict-first) -- the
+//     shared-memory pipe only serves the gathers.
+//   * the scan loop keeps the arg-max in four registers (best gain, the block it was first seen in, the end of that
+//     block's sub-row segment, the number of parked ties); blocks of LATER segments that hold the same gain are parked
+//     in a small per-thread list.  Nothing is loaded on behalf of the arg-max while streaming; after the scan the
+//     recorded blocks are read again and the entry with the smallest original position wins (mi.py:79: first maximum).
 // Scores use the same fp32 operation sequence and the same torch-CPU log table as mi_scan.cu: picks and gains are
 // bit-identical to the reference (tests/test_mi_gpu.py).
 #include "common.cuh"
@@ -79,52 +83,16 @@ __global__ void s8_prefix_kernel(uint32_t *__restrict__ tilehist, int32_t ntiles
     row_total[r] = run;
 }
 
-// row_start[0..k] = exclusive scan of the totals, each padded to whole blocks (single CTA)
-__global__ void __launch_bounds__(1024)
-s8_rowstart_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t *__restrict__ row_start) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
-    for (int32_t base = 0; base < k; base += 1024) {
-        const int32_t i = base + threadIdx.x;
-        const uint32_t v = i < k ? ((total[i] + (kS8Blk - 1)) & ~(uint32_t)(kS8Blk - 1)) : 0u;
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < kWarp; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == kWarp - 1) warp_sums[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t ws = warp_sums[lane];
-            uint32_t winc = ws;
-#pragma unroll
-            for (int o = 1; o < kWarp; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            warp_sums[lane] = winc - ws;
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_sums[warp] + inc - v;
-        if (i < k) row_start[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) row_start[k] = carry;
-}
-
-// stable scatter: tiles in list order, 512-chunks in list order, warps in order, lanes in order
+// stable scatter: tiles in list order, 512-chunks in list order, warps in order, lanes in order.  A sub-row lies in the
+// stream in one or more PIECES (whole blocks each, in rank order; the host's layout cuts big sub-rows): the r-th
+// candidate of a sub-row goes to piece_off[p] + (r - piece_rank0[p]) of the piece p that holds rank r.
 __global__ void __launch_bounds__(kS8PartThreads)
 s8_scatter_kernel(const uint32_t *__restrict__ cells, int64_t w, S8Geom g, const uint32_t *__restrict__ tilehist,
-                  const uint32_t *__restrict__ row_start, uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s) {
+                  const uint32_t *__restrict__ row_piece0, const uint32_t *__restrict__ piece_rank0,
+                  const uint32_t *__restrict__ piece_off, uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s) {
     extern __shared__ uint32_t s8_cursor[];
     const uint32_t *tp = tilehist + (int64_t)blockIdx.x * g.k_rows;
-    for (int32_t i = threadIdx.x; i < g.k_rows; i += blockDim.x) s8_cursor[i] = row_start[i] + tp[i];
+    for (int32_t i = threadIdx.x; i < g.k_rows; i += blockDim.x) s8_cursor[i] = tp[i];      // rank inside the sub-row
     __syncthreads();
     const int64_t lo = (int64_t)blockIdx.x * kS8Tile, hi = min(w, lo + kS8Tile);
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -148,8 +116,15 @@ s8_scatter_kernel(const uint32_t *__restrict__ cells, int64_t w, S8Geom g, const
                 }
                 basev = __shfl_sync(0xffffffffu, basev, leader);
                 if (live) {
-                    stream[basev + rank] = (uint8_t)(c2 - sub * (uint32_t)g.sub_w);       // column inside the sub-row
-                    pos_s[basev + rank] = (uint32_t)e;
+                    const uint32_t r = basev + rank;
+                    uint32_t p = __ldg(row_piece0 + key), p1 = __ldg(row_piece0 + key + 1);
+                    while (p1 - p > 1) {                          // last piece whose first rank is <= r
+                        const uint32_t mid = (p + p1) >> 1;
+                        if (__ldg(piece_rank0 + mid) <= r) p = mid; else p1 = mid;
+                    }
+                    const uint32_t dst = __ldg(piece_off + p) + (r - __ldg(piece_rank0 + p));
+                    stream[dst] = (uint8_t)(c2 - sub * (uint32_t)g.sub_w);                   // column inside the sub-row
+                    pos_s[dst] = (uint32_t)e;
                 }
             }
             __syncthreads();
@@ -163,7 +138,10 @@ __global__ void s8_fill_kernel(uint4 *p, int64_t n16, uint32_t v) {
 }
 
 // Sort every 512-candidate block by (shared-memory bank of its gain slot, column, original order): in the scan lane l
-// owns entries [16l, 16l+16) and gather step j reads entry 16l+j in all lanes -- 16 apart in bank order.
+// owns entries [16l, 16l+16) and gather step j reads entry 16l+j in all lanes -- 16 apart in bank order.  Then every
+// lane's 16 entries are put in LIST order among themselves (the bank pattern does not care which of a lane's entries
+// is read at which step): of the entries of a vector that hold the same gain, the FIRST one is the earliest candidate,
+// so settling a vector after the scan takes one position load instead of one per tied entry.
 __global__ void __launch_bounds__(kS8Blk)
 s8_block_sort_kernel(uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s, int64_t n_blocks) {
     __shared__ uint32_t key[kS8Blk];
@@ -188,31 +166,48 @@ s8_block_sort_kernel(uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s,
                 __syncthreads();
             }
         }
+        // inside my group of 16: rank by original index (= list order: the partition is stable and a block holds
+        // consecutive ranks of its sub-row; padding entries carry the largest indices of the block)
         const int src = (int)(key[t] & 511u);
-        stream[base + t] = colv[src];
-        pos_s[base + t] = posv[src];
+        const int g0 = t & ~15;
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rank += (int)(key[g0 + j] & 511u) < src ? 1 : 0;
+        stream[base + g0 + rank] = colv[src];
+        pos_s[base + g0 + rank] = posv[src];
         __syncthreads();
     }
 }
 
 // ---- the persistent kernel ----------------------------------------------------------------------------------------
 
+constexpr int kS8TieCap = 24;               // parked ties per thread (local memory, touched on the rare path only)
+
+struct S8Chunk {                     // one per CTA, written by the host's layout
+    uint32_t slot0, n_slots;         // its stream slots
+    uint32_t n_rows;                 // distinct sub-rows among them (gain rows / count rows it stages)
+    uint32_t start;                  // stream offset of its first candidate (its end = next chunk's start)
+};
+
 struct MiS8 {
     MiState s;
-    uint32_t *n_alt;                 // second copy of the table counts (double buffering as in mi_persistent.cu)
+    uint32_t *n_alt;                 // second copy of the table counts (kept in step for the other loops)
     uint8_t *stream;
     const uint32_t *pos_s;
-    const uint32_t *row_start;       // [k_rows + 1] stream offsets of the sub-rows
-    const uint32_t *chunk_start;     // [grid + 1]
+    const uint32_t *slot_start;      // [n_slots + 1] stream offsets of the slots (a slot = a sub-row or a piece of one)
+    const uint32_t *slot_row;        // [n_slots] sub-row id (c1 * n_sub + sub)
+    const uint32_t *slot_u;          // [n_slots] index of that sub-row among the distinct sub-rows of the slot's chunk
+    const S8Chunk *chunks;           // [grid + 1]
     MiPub *pub;
     unsigned int *bar;
     int64_t n_picks;
     int64_t *out_pos;
     float *out_gain;
     S8Geom g;
-    int32_t rows_smem;               // sub-rows whose gain row + counts fit in shared memory
+    int32_t rows_smem;               // distinct sub-rows whose gain row + counts fit in shared memory
+    int32_t slots_smem;              // slots per chunk the shared-memory tables hold
     int32_t fixed_bytes;             // bytes of the arrays in front of the gain rows
-    int32_t use_cache;               // 0: never keep counts in shared memory (debug / comparison)
+    int32_t ring_offset;             // byte offset of the cp.async ring (ring variants)
     int32_t world, rank;
     unsigned int seq_base;
     MiMail *mail_local;
@@ -228,12 +223,25 @@ __device__ __forceinline__ uint64_t s8_policy_evict_first() {
     return pol;
 }
 // 16-byte stream load into registers: L2-coherent (.cg: removals written by another SM before the grid barrier are
-// seen), evict-first in L2 so the 100 MB stream does not push the table, positions and log table out
+// seen), evict-first in L2 so the 100 MB stream does not push the positions and the log table out
 __device__ __forceinline__ uint4 s8_ld_stream(const uint4 *p, uint64_t pol) {
     uint4 v;
     asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
     return v;
+}
+// the same through a shared-memory ring (cp.async.cg: bypasses L1, completion tracked per thread in commit groups)
+__device__ __forceinline__ void s8_cp_async16(uint32_t smem_dst, const void *gmem_src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void s8_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void s8_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 s8_lds128(uint32_t addr) {
+    uint4 q;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+    return q;
 }
 __device__ __forceinline__ float s8_gather(uint32_t word, int byte, uint32_t row_base) {
     // address = ((word >> 8*byte) & 0xFF) << 2 | row_base (row_base is 1 KiB aligned): one shift, one LOP3, one LDS
@@ -245,54 +253,109 @@ __device__ __forceinline__ float s8_gather(uint32_t word, int byte, uint32_t row
     return g;
 }
 
-// Per-thread running arg-max.  `bi` = stream index of the first candidate (of its sub-row segment) holding the best gain
-// `bs`; bpos / brow / bbyte describe that candidate while `meta` is true.  Equal-gain candidates of LATER segments are
-// parked in tie[] and only compared by original position if this thread ends up holding the block maximum.
-struct S8Best {
-    float bs;
-    uint32_t bi, bend, bpos;
-    int32_t brow;
-    uint32_t bbyte;
-    uint32_t tie[3];
-    int ntie;
-    bool meta;
+struct S8Ctx {                                 // what it takes to look a block up again after the scan
+    const uint4 *vec;
+    const uint32_t *pos_s;
+    const uint32_t *rs_loc;                    // shared: stream offsets of my slots [ns + 1]
+    const uint32_t *su_loc;                    // shared: gain row of every slot
+    uint32_t gain_b;
+    int32_t ns;
+    uint32_t lane;
 };
 
-__device__ __forceinline__ void s8_tie(S8Best &b, uint32_t e, uint32_t rend, const uint32_t *__restrict__ pos_s) {
-    if (b.ntie < 3) {
-        if (b.ntie == 0) b.tie[0] = e;
-        else if (b.ntie == 1) b.tie[1] = e;
-        else b.tie[2] = e;
-        ++b.ntie;
-    } else {                                   // list full: settle by original position now
-        uint32_t bp = b.meta ? b.bpos : __ldg(pos_s + b.bi);
-        uint32_t nb = b.bi;
+// Of the entries of my vectors of the blocks blk[0..n) (n <= 4) that hold gain `bs`, the one with the smallest original
+// position.  A vector's entries are in list order (s8_block_sort_kernel), so per vector only its FIRST entry holding
+// `bs` matters: the n vector loads go out together, then n position loads -- two memory latencies for up to four blocks.
+__device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t *blk, int n, float bs, uint32_t &bp,
+                                                  uint32_t &bi, int32_t &brow, uint32_t &bbyte) {
+    uint4 q[4];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const uint32_t pt = __ldg(pos_s + b.tie[t]);
-            if (pt < bp) { bp = pt; nb = b.tie[t]; }
-        }
-        const uint32_t pe = __ldg(pos_s + e);
-        if (pe < bp) { bp = pe; nb = e; }
-        if (nb != b.bi) { b.bi = nb; b.meta = false; }
-        b.bpos = bp;
-        b.ntie = 0;
+    for (int t = 0; t < 4; ++t) {
+        q[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (t < n) q[t] = __ldcg(c.vec + (size_t)blk[t] * kWarp + c.lane);
     }
-    b.bend = rend;
+    int32_t urow[4];
+    int first[4];
+    uint32_t p[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        urow[t] = 0; first[t] = -1; p[t] = 0xFFFFFFFFu;
+        if (t < n) {
+            const uint32_t ef = blk[t] * kS8Blk;
+            int32_t a = 0, b = c.ns;
+            while (a < b) { const int32_t m = (a + b) >> 1; if (c.rs_loc[m + 1] > ef) b = m; else a = m + 1; }
+            urow[t] = (int32_t)c.su_loc[a];
+            const uint32_t words[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
+            const uint32_t grow_b = c.gain_b + (uint32_t)urow[t] * (kS8GainStride * 4u);
+            uint32_t eq = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                eq |= (s8_gather(words[j >> 2], j & 3, grow_b) == bs ? 1u : 0u) << j;      // removed / padding: -inf
+            if (eq) {
+                first[t] = __ffs(eq) - 1;
+                p[t] = __ldg(c.pos_s + ef + c.lane * 16u + (uint32_t)first[t]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (p[t] < bp) {
+            const uint32_t words[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
+            const int j = first[t];
+            bp = p[t]; bi = blk[t] * kS8Blk + c.lane * 16u + (uint32_t)j; brow = urow[t];
+            bbyte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+        }
+    }
 }
 
-template <int THREADS, int DEPTH>
+struct S8Found {
+    uint32_t bp, bi;                           // original position and stream index of the candidate
+    int32_t brow;                              // its gain row (index among the CTA's distinct sub-rows)
+    uint32_t bbyte;                            // its column inside the sub-row
+};
+
+// Everything a thread has recorded -- its first block `bx` and the parked ties -- four blocks at a time.  Out of line on
+// purpose: it runs once per iteration, does not belong to the scan loop's register budget, and must
+// not weigh on the loop's register allocation (for the same reason the loop itself never calls anything: a thread whose
+// tie list overflows just stops parking -- ntie = kS8TieCap + 1 -- and every block of its span after the last parked
+// one is looked at here instead).
+__device__ __noinline__ S8Found s8_resolve_all(const S8Ctx *c, float bs, uint32_t bx, const uint32_t *tie, int ntie,
+                                               uint32_t span_hi) {
+    S8Found f;
+    f.bp = 0xFFFFFFFFu; f.bi = bx * kS8Blk; f.brow = 0; f.bbyte = 0;
+    const int nt = ntie > kS8TieCap ? kS8TieCap : ntie;
+    uint32_t extra = ntie > kS8TieCap ? tie[kS8TieCap - 1] + 1u : span_hi;      // overflow: blocks [extra, span_hi) too
+    uint32_t blk[4];
+    blk[0] = bx; blk[1] = blk[2] = blk[3] = bx;
+    int n = 1, t = 0;
+    for (;;) {
+        while (n < 4 && (t < nt || extra < span_hi)) {
+            const uint32_t v = t < nt ? tie[t++] : extra++;
+            if (n == 0) blk[0] = v; else if (n == 1) blk[1] = v; else if (n == 2) blk[2] = v; else blk[3] = v;
+            ++n;
+        }
+        s8_resolve_blocks(*c, blk, n, bs, f.bp, f.bi, f.brow, f.bbyte);
+        if (t >= nt && extra >= span_hi) break;
+        n = 0;
+    }
+    return f;
+}
+
+// THREADS per CTA, DEPTH 16-byte stream loads in flight per thread, staged in registers (RING = false) or in a
+// shared-memory cp.async ring (RING = true).
+template <int THREADS, int DEPTH, bool RING>
 __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     extern __shared__ __align__(16) unsigned char s8_smem[];
     const MiState &s = P.s;
     const int32_t k_v = s.k_v, k_a = s.k_a;
-    const int32_t n_sub = P.g.n_sub, sub_w = P.g.sub_w, k_rows = P.g.k_rows;
+    const int32_t n_sub = P.g.n_sub, sub_w = P.g.sub_w;
     float *col_term = reinterpret_cast<float *>(s8_smem);                          // [k_v]
     float *tn_small = col_term + k_v;                                              // [kSmallCounts]
     uint32_t *a_cnt = reinterpret_cast<uint32_t *>(tn_small + kSmallCounts);       // [k_v]
     uint32_t *b_cnt = a_cnt + k_v;                                                 // [k_a]
-    uint32_t *rs_loc = b_cnt + k_a;                                                // [rows_smem + 1] stream offsets
-    float *rt_local = reinterpret_cast<float *>(rs_loc + P.rows_smem + 1);         // [rows_smem]
+    uint32_t *rs_loc = b_cnt + k_a;                                                // [slots_smem + 1] stream offsets
+    uint32_t *su_loc = rs_loc + P.slots_smem + 1;                                  // [slots_smem] gain row of the slot
+    float *rt_local = reinterpret_cast<float *>(su_loc + P.slots_smem);            // [rows_smem]
     int32_t *row_c1 = reinterpret_cast<int32_t *>(rt_local + P.rows_smem);         // [rows_smem] table row of the sub-row
     int32_t *row_c2 = row_c1 + P.rows_smem;                                        // [rows_smem] first column of the sub-row
     // gain rows: 1 KiB aligned in the shared window (the gather ORs the row base into the byte offset)
@@ -300,59 +363,73 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     const uint32_t gain_b = (smem_b + (uint32_t)P.fixed_bytes + 1023u) & ~1023u;
     float *gain = reinterpret_cast<float *>(s8_smem + (gain_b - smem_b));          // [rows_smem][256]
     uint32_t *cnt = reinterpret_cast<uint32_t *>(gain + (size_t)P.rows_smem * kS8GainStride);   // [rows_smem][256]
+    const uint32_t ring_b = smem_b + (uint32_t)P.ring_offset + threadIdx.x * 16u;  // my 16 bytes of ring slot 0
+    constexpr uint32_t kSlotBytes = THREADS * 16u;
     __shared__ unsigned long long wkey[32];
     __shared__ unsigned long long wpay[32];
     __shared__ uint32_t widx[32];
     __shared__ unsigned long long sh_best_key, sh_win_key, sh_win_pay;
     __shared__ uint32_t sh_best_idx;
-    __shared__ int32_t sh_rows[2];
     __shared__ float ps[6];                                   // {NlogN, aloga, blogb, n, fN0, fa0}
     constexpr int kWarps = THREADS / kWarp;
 
     for (int32_t i = threadIdx.x; i < k_v; i += THREADS) a_cnt[i] = __ldcg(s.a_cols + i);
     for (int32_t i = threadIdx.x; i < k_a; i += THREADS) b_cnt[i] = __ldcg(s.b_rows + i);
     if (threadIdx.x < 6) ps[threadIdx.x] = __ldcg(s.sums + threadIdx.x);
-    const uint32_t e_lo = P.chunk_start[blockIdx.x], e_hi = P.chunk_start[blockIdx.x + 1];
-    if (threadIdx.x == 0) {                                    // sub-rows touched by this chunk
-        int32_t r_lo = 0, r_hi = -1;
-        if (e_hi > e_lo) {
-            int32_t a = 0, b = k_rows;
-            while (a < b) { const int32_t m = (a + b) >> 1; if (__ldg(P.row_start + m + 1) > e_lo) b = m; else a = m + 1; }
-            r_lo = a;
-            a = r_lo; b = k_rows;
-            while (a < b) { const int32_t m = (a + b) >> 1; if (__ldg(P.row_start + m) < e_hi) a = m + 1; else b = m; }
-            r_hi = a - 1;
+    const S8Chunk ch = P.chunks[blockIdx.x];
+    const uint32_t e_lo = ch.start, e_hi = P.chunks[blockIdx.x + 1].start;
+    const int32_t ns = min((int32_t)ch.n_slots, P.slots_smem);       // the host's layout keeps both within the tables
+    const int32_t nr = min((int32_t)ch.n_rows, P.rows_smem);
+    for (int32_t i = threadIdx.x; i <= ns; i += THREADS) {
+        rs_loc[i] = __ldg(P.slot_start + ch.slot0 + i);
+        if (i < ns) {
+            const int32_t grow = (int32_t)__ldg(P.slot_row + ch.slot0 + i), c1 = grow / n_sub;
+            const uint32_t u = min(__ldg(P.slot_u + ch.slot0 + i), (uint32_t)(nr > 0 ? nr - 1 : 0));
+            su_loc[i] = u;
+            row_c1[u] = c1;                                      // pieces of one sub-row write the same values
+            row_c2[u] = (grow - c1 * n_sub) * sub_w;
         }
-        sh_rows[0] = r_lo; sh_rows[1] = r_hi;
     }
     __syncthreads();
-    const int32_t r_lo = sh_rows[0], r_hi = sh_rows[1];
-    const int32_t n_mine = r_hi - r_lo + 1;
-    const bool cached = P.use_cache && n_mine > 0 && n_mine <= P.rows_smem;
-    if (cached) {                                             // table counts of my sub-rows stay here for the whole launch
-        for (int32_t idx = threadIdx.x; idx < n_mine * kS8GainStride; idx += THREADS) {
-            const int32_t i = idx >> 8, j = idx & 255;
-            const int32_t grow = r_lo + i, c1 = grow / n_sub, c2 = (grow - c1 * n_sub) * sub_w + j;
-            cnt[idx] = (j < sub_w && c2 < k_v) ? __ldcg(s.n_cells + (int64_t)c1 * k_v + c2) : 0u;
-        }
+    // table counts of my sub-rows stay here for the whole launch
+    for (int32_t idx = threadIdx.x; idx < nr * kS8GainStride; idx += THREADS) {
+        const int32_t i = idx >> 8, j = idx & 255;
+        const int32_t c2 = row_c2[i] + j;
+        cnt[idx] = (j < sub_w && c2 < k_v) ? __ldcg(s.n_cells + (int64_t)row_c1[i] * k_v + c2) : 0u;
     }
     const uint32_t base_pos = (uint32_t)s.pos_base;
     const uint32_t grid = gridDim.x;
     const uint64_t stream_pol = s8_policy_evict_first();
     const uint32_t lane = threadIdx.x % kWarp;
+    const uint4 *vec = reinterpret_cast<const uint4 *>(P.stream);
+    // my warp's contiguous span of blocks (coalesced 512-byte loads; lane l owns vector l of every block)
+    const uint32_t b_lo = e_lo / kS8Blk, b_hi = ns > 0 ? min(e_hi, rs_loc[ns]) / kS8Blk : b_lo;
+    const uint32_t span = (b_hi - b_lo + kWarps - 1) / kWarps;
+    const uint32_t wb_lo = min(b_hi, b_lo + (threadIdx.x / kWarp) * span);
+    const uint32_t wb_hi = min(b_hi, wb_lo + span);
+    int32_t crow0 = 0;
+    if (wb_lo < wb_hi) {                                       // slot of my first block (uniform per warp)
+        const uint32_t ef = wb_lo * kS8Blk;
+        int32_t a = 0, b = ns;
+        while (a < b) { const int32_t m = (a + b) >> 1; if (rs_loc[m + 1] > ef) b = m; else a = m + 1; }
+        crow0 = a;
+    }
+    S8Ctx ctx;
+    ctx.vec = vec; ctx.pos_s = P.pos_s; ctx.rs_loc = rs_loc; ctx.su_loc = su_loc; ctx.gain_b = gain_b; ctx.ns = ns;
+    ctx.lane = lane;
     int32_t prev1 = -1, prev2 = -1;                            // table cell of picks it-1, it-2
     int64_t done = 0;
     bool broke = false;
     long long t_learn = 0;
+    uint32_t tie[kS8TieCap];
     __syncthreads();
 
     for (int64_t it = 0; it < P.n_picks; ++it) {
         const int cur = (int)(it & 1);
         const long long t0 = P.dbg ? clock64() : 0;
         long long t_gain = 0, t_pre = 0;
-        const uint32_t *Tcur = cur ? P.n_alt : s.n_cells;
-        uint32_t *Toth = cur ? s.n_cells : P.n_alt;
-        if (blockIdx.x == 0 && threadIdx.x == 0) {             // lagged writer of the other table copy
+        if (blockIdx.x == 0 && threadIdx.x == 0) {             // both global table copies follow two picks behind
+            uint32_t *Toth = cur ? s.n_cells : P.n_alt;
             if (prev2 >= 0) Toth[prev2] += 1;
             if (prev1 >= 0) Toth[prev1] += 1;
         }
@@ -364,147 +441,116 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
             col_term[i] = __fdiv_rn(-bump_sum(aloga, a_cnt[i], fa0, s.logs), np);
         for (int32_t i = threadIdx.x; i < kSmallCounts; i += THREADS)
             tn_small[i] = __fdiv_rn(bump_sum(NlogN, (uint32_t)i, fN0, s.logs), np);
-        S8Best B;
-        B.bs = -INFINITY; B.bi = 0xFFFFFFFFu; B.bend = 0; B.bpos = 0; B.brow = 0; B.bbyte = 0; B.ntie = 0; B.meta = false;
-        B.tie[0] = B.tie[1] = B.tie[2] = 0;
+        for (int32_t i = threadIdx.x; i < nr; i += THREADS)
+            rt_local[i] = __fdiv_rn(-bump_sum(blogb, b_cnt[row_c1[i]], fa0, s.logs), np);
+        __syncthreads();
         if (P.dbg) t_pre = clock64() - t0;
-        for (int32_t rb = r_lo; rb <= r_hi; rb += P.rows_smem) {
-            const int32_t nr = min(P.rows_smem, r_hi - rb + 1);
-            __syncthreads();            // previous batch finished reading gain rows; col_term / tn_small ready
-            for (int32_t i = threadIdx.x; i <= nr; i += THREADS) {
-                if (!cached || it == 0) rs_loc[i] = __ldg(P.row_start + rb + i);
-                if (i < nr) {
-                    const int32_t grow = rb + i, c1 = grow / n_sub;
-                    row_c1[i] = c1;
-                    row_c2[i] = (grow - c1 * n_sub) * sub_w;
-                    rt_local[i] = __fdiv_rn(-bump_sum(blogb, b_cnt[c1], fa0, s.logs), np);
-                }
+        const long long tg0 = P.dbg ? clock64() : 0;
+        for (int32_t idx = threadIdx.x; idx < nr * kS8GainStride; idx += THREADS) {
+            const int32_t i = idx >> 8, j = idx & 255;
+            const int32_t c2 = row_c2[i] + j;
+            float gv = -INFINITY;                               // slot 255 and columns beyond the sub-row
+            if (j < sub_w && c2 < k_v) {
+                const uint32_t x = cnt[idx];
+                const float tN = x < (uint32_t)kSmallCounts ? tn_small[x] : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
+                gv = __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt_local[i]), lognp);
             }
-            __syncthreads();
-            const long long tg0 = P.dbg ? clock64() : 0;
-            if (cached) {               // counts from shared memory: no global loads on this path
-                for (int32_t idx = threadIdx.x; idx < nr * kS8GainStride; idx += THREADS) {
-                    const int32_t i = idx >> 8, j = idx & 255;
-                    const int32_t c2 = row_c2[i] + j;
-                    float gv = -INFINITY;                       // slot 255 and columns beyond the sub-row
-                    if (j < sub_w && c2 < k_v) {
-                        const uint32_t x = cnt[idx];
-                        const float tN = x < (uint32_t)kSmallCounts ? tn_small[x]
-                                                                    : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
-                        gv = __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[c2]), rt_local[i]), lognp);
-                    }
-                    gain[idx] = gv;
+            gain[idx] = gv;
+        }
+        __syncthreads();
+        if (P.dbg) t_gain = clock64() - tg0;
+        // ---- the scan: slots are whole blocks and chunk edges are block aligned, so a block never straddles a slot or
+        // a chunk and the gain row is uniform per warp-iteration
+        float bs = -INFINITY;
+        uint32_t bx = 0, bend = 0;
+        int ntie = 0;
+        {
+            int32_t crow = crow0;
+            uint32_t seg_end = wb_lo < wb_hi ? rs_loc[crow + 1] / kS8Blk : 0u;      // first block of the next slot
+            uint32_t grow_b = gain_b + su_loc[crow] * (kS8GainStride * 4u);
+            const uint4 *src4 = vec + (size_t)wb_lo * kWarp + lane;
+            uint4 stage[RING ? 1 : DEPTH];
+            if constexpr (RING) {
+#pragma unroll
+                for (int r = 0; r < DEPTH - 1; ++r) {
+                    if (wb_lo + (uint32_t)r < wb_hi) s8_cp_async16(ring_b + r * kSlotBytes, src4 + (size_t)r * kWarp, stream_pol);
+                    s8_cp_async_commit();
                 }
-            } else {                    // counts from the global table copy of this iteration, 4 loads in flight
-                for (int32_t base = threadIdx.x; base < nr * kS8GainStride; base += 4 * THREADS) {
-                    uint32_t xs[4];
-                    int32_t cl[4];
+            } else {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int32_t idx = base + u * THREADS;
-                        cl[u] = -1;
-                        xs[u] = 0u;
-                        if (idx < nr * kS8GainStride) {
-                            const int32_t i = idx >> 8, j = idx & 255;
-                            const int32_t c2 = row_c2[i] + j;
-                            if (j < sub_w && c2 < k_v) { cl[u] = row_c1[i] * k_v + c2; xs[u] = __ldcg(Tcur + cl[u]); }
-                        }
-                    }
+                for (int r = 0; r < DEPTH; ++r)
+                    stage[r] = wb_lo + (uint32_t)r < wb_hi ? s8_ld_stream(src4 + (size_t)r * kWarp, stream_pol)
+                                                           : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+            // take block (blk0 + r) out of the staging area and start the load that re-uses its place; `check`: the
+            // tail of the span, where the load may lie beyond it
+            auto next_vector = [&](int r, uint32_t blk, bool check) -> uint4 {
+                if constexpr (RING) {
+                    if (!check || blk + (DEPTH - 1) < wb_hi)
+                        s8_cp_async16(ring_b + ((r + DEPTH - 1) % DEPTH) * kSlotBytes, src4 + (size_t)(r + DEPTH - 1) * kWarp,
+                                      stream_pol);
+                    s8_cp_async_commit();
+                    s8_cp_async_wait<DEPTH - 1>();
+                    return s8_lds128(ring_b + r * kSlotBytes);
+                } else {
+                    const uint4 q = stage[r];
+                    if (!check || blk + DEPTH < wb_hi) stage[r] = s8_ld_stream(src4 + (size_t)(DEPTH + r) * kWarp, stream_pol);
+                    return q;
+                }
+            };
+            auto score_block = [&](const uint4 q, const uint32_t blk) {
+                if (blk >= seg_end) {                            // next slot (uniform per warp; slots are not empty)
+                    do { ++crow; seg_end = rs_loc[crow + 1] / kS8Blk; } while (blk >= seg_end);
+                    grow_b = gain_b + su_loc[crow] * (kS8GainStride * 4u);
+                }
+                float g[16];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int32_t idx = base + u * THREADS;
-                        if (idx < nr * kS8GainStride) {
-                            float gv = -INFINITY;
-                            if (cl[u] >= 0) {
-                                const int32_t i = idx >> 8, j = idx & 255;
-                                const uint32_t x = xs[u] + (cl[u] == prev1 ? 1u : 0u);            // pick it-1
-                                const float tN = x < (uint32_t)kSmallCounts ? tn_small[x]
-                                                                            : __fdiv_rn(bump_sum(NlogN, x, fN0, s.logs), np);
-                                gv = __fadd_rn(__fadd_rn(__fadd_rn(tN, col_term[row_c2[i] + j]), rt_local[i]), lognp);
-                            }
-                            gain[idx] = gv;
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = s8_gather(q.x, j, grow_b);
+                    g[4 + j] = s8_gather(q.y, j, grow_b);
+                    g[8 + j] = s8_gather(q.z, j, grow_b);
+                    g[12 + j] = s8_gather(q.w, j, grow_b);
+                }
+                float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                m = fmaxf(m, fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])),
+                                   fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
+                if (m >= bs) {                                   // rare once the thread has seen a good candidate
+                    if (m > bs) {                                // registers only: which block, which segment
+                        bs = m; bx = blk; bend = seg_end; ntie = 0;
+                    } else if (blk >= bend && m > -INFINITY) {   // same gain in a later segment: park the block
+                        if (ntie < kS8TieCap) tie[ntie] = blk;   // (list full: see s8_resolve_all)
+                        ntie = min(ntie + 1, kS8TieCap + 1);
+                        bend = seg_end;
                     }
                 }
-            }
-            __syncthreads();
-            if (P.dbg) t_gain += clock64() - tg0;
-            // sub-rows are padded to whole blocks and chunk edges are block aligned: a block never straddles a sub-row or
-            // a chunk, so the gain row is uniform per warp-iteration and there is no slow path
-            const uint32_t s_lo = max(e_lo, rs_loc[0]), s_hi = min(e_hi, rs_loc[nr]);
-            if (s_hi <= s_lo) continue;
-            const uint32_t b_lo = s_lo / kS8Blk, b_hi = s_hi / kS8Blk;
-            // each WARP walks its own contiguous span of blocks (coalesced 512-byte loads); lane l owns vector l
-            const uint32_t span = (b_hi - b_lo + kWarps - 1) / kWarps;
-            const uint32_t wb_lo = min(b_hi, b_lo + (threadIdx.x / kWarp) * span);
-            const uint32_t wb_hi = min(b_hi, wb_lo + span);
-            int32_t crow = 0;
-            if (wb_lo < wb_hi) {                                 // sub-row of my first block (uniform per warp)
-                const uint32_t ef = wb_lo * kS8Blk;
-                int32_t a = 0, b = nr;
-                while (a < b) { const int32_t m = (a + b) >> 1; if (rs_loc[m + 1] > ef) b = m; else a = m + 1; }
-                crow = a;
-            }
-            uint32_t rend_blk = rs_loc[crow + 1] / kS8Blk;       // first block of the next sub-row
-            uint32_t grow_b = gain_b + (uint32_t)crow * (kS8GainStride * 4u);
-            const uint4 *src4 = reinterpret_cast<const uint4 *>(P.stream) + (size_t)wb_lo * kWarp + lane;
-            uint4 stage[DEPTH];
+            };
+            uint32_t blk0 = wb_lo;
+            // main part: every load of the body is in range, no bounds checks
+            for (; blk0 + 2 * DEPTH <= wb_hi; blk0 += DEPTH) {
 #pragma unroll
-            for (int r = 0; r < DEPTH; ++r)
-                stage[r] = wb_lo + (uint32_t)r < wb_hi ? s8_ld_stream(src4 + (size_t)r * kWarp, stream_pol)
-                                                       : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (uint32_t blk0 = wb_lo; blk0 < wb_hi; blk0 += DEPTH) {
+                for (int r = 0; r < DEPTH; ++r) {
+                    const uint4 q = next_vector(r, blk0 + (uint32_t)r, false);
+                    score_block(q, blk0 + (uint32_t)r);
+                }
+                src4 += (size_t)DEPTH * kWarp;
+            }
+            // tail: fewer than 2 * DEPTH blocks left
+            for (; blk0 < wb_hi; blk0 += DEPTH) {
 #pragma unroll
                 for (int r = 0; r < DEPTH; ++r) {
                     const uint32_t blk = blk0 + (uint32_t)r;
                     if (blk < wb_hi) {
-                        const uint4 q = stage[r];
-                        if (blk + DEPTH < wb_hi)
-                            stage[r] = s8_ld_stream(src4 + (size_t)(blk - wb_lo + DEPTH) * kWarp, stream_pol);
-                        while (blk >= rend_blk) {                // next non-empty sub-row (uniform per warp)
-                            ++crow;
-                            rend_blk = rs_loc[crow + 1] / kS8Blk;
-                            grow_b = gain_b + (uint32_t)crow * (kS8GainStride * 4u);
-                        }
-                        float g[16];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            g[j] = s8_gather(q.x, j, grow_b);
-                            g[4 + j] = s8_gather(q.y, j, grow_b);
-                            g[8 + j] = s8_gather(q.z, j, grow_b);
-                            g[12 + j] = s8_gather(q.w, j, grow_b);
-                        }
-                        float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-                        m = fmaxf(m, fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])),
-                                           fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
-                        if (m >= B.bs) {                         // rare once the thread has seen a good candidate
-                            const uint32_t e0 = blk * kS8Blk + lane * 16u;
-                            if (m > -INFINITY && (m > B.bs || (B.bi != 0xFFFFFFFFu && e0 >= B.bend))) {
-                                // of the maxima in this vector take the one that came first in the candidate list
-                                uint32_t bj = 0, bp = 0xFFFFFFFFu;
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    if (g[j] == m) {
-                                        const uint32_t pj = __ldg(P.pos_s + e0 + j);
-                                        if (pj < bp) { bp = pj; bj = (uint32_t)j; }
-                                    }
-                                }
-                                if (m > B.bs) {
-                                    const uint32_t wsel = bj < 4 ? q.x : bj < 8 ? q.y : bj < 12 ? q.z : q.w;
-                                    B.bs = m; B.bi = e0 + bj; B.bend = rend_blk * kS8Blk; B.ntie = 0;
-                                    B.bpos = bp; B.brow = rb + crow; B.bbyte = (wsel >> (8 * (bj & 3u))) & 0xFFu; B.meta = true;
-                                } else {
-                                    s8_tie(B, e0 + bj, rend_blk * kS8Blk, P.pos_s);
-                                }
-                            }
-                        }
+                        const uint4 q = next_vector(r, blk, true);
+                        score_block(q, blk);
                     }
                 }
+                src4 += (size_t)DEPTH * kWarp;
             }
+            if constexpr (RING) s8_cp_async_wait<0>();
         }
         const long long t1 = P.dbg ? clock64() : 0;
         // ---------------- block arg-max ----------------
-        const uint32_t my32 = B.bi == 0xFFFFFFFFu ? 0u : orderable(B.bs);
+        const uint32_t my32 = bs > -INFINITY ? orderable(bs) : 0u;
         uint32_t m32 = my32;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
@@ -515,33 +561,16 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
         for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
         __syncthreads();                                       // widx is reused below
         unsigned long long key = 0ull, pay = 0ull;
-        uint32_t bi = B.bi;
+        uint32_t bi = 0xFFFFFFFFu;
         if (my32 != 0u && my32 == m32) {
-            // this thread holds the block-maximum gain.  Common case (no parked ties): everything about its candidate
-            // is in registers and -- with the counts cached -- nothing is loaded from global memory here.
-            uint32_t bp = B.meta ? B.bpos : __ldg(P.pos_s + bi);
-            bool meta = B.meta;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                if (t < B.ntie) {
-                    const uint32_t pt = __ldg(P.pos_s + B.tie[t]);
-                    if (pt < bp) { bp = pt; bi = B.tie[t]; meta = false; }
-                }
-            }
-            int32_t row = B.brow;
-            uint32_t byte = B.bbyte;
-            if (!meta) {                                       // a parked tie won: look its sub-row and byte up
-                byte = (uint32_t)__ldcg(reinterpret_cast<const unsigned char *>(P.stream) + bi);
-                int32_t a = 0, b = k_rows;
-                while (a < b) { const int32_t m = (a + b) >> 1; if (__ldg(P.row_start + m + 1) > bi) b = m; else a = m + 1; }
-                row = a;
-            }
-            const int32_t c1 = row / n_sub;
-            const uint32_t c2 = (uint32_t)(row - c1 * n_sub) * (uint32_t)sub_w + byte;
-            const int32_t cell = c1 * k_v + (int32_t)c2;
-            const uint32_t x = cached ? cnt[(row - r_lo) * kS8GainStride + (int32_t)byte]
-                                      : __ldcg(Tcur + cell) + (cell == prev1 ? 1u : 0u);
-            key = ((unsigned long long)m32 << 32) | (unsigned long long)(0xFFFFFFFFu - (base_pos + bp));
+            // this thread holds the block-maximum gain: read its recorded blocks again (the gain rows are still staged)
+            // and take the earliest candidate; its count comes from the shared-memory copy
+            const S8Found f = s8_resolve_all(&ctx, bs, bx, tie, ntie, wb_hi);
+            bi = f.bi;
+            const int32_t c1 = row_c1[f.brow];
+            const uint32_t c2 = (uint32_t)row_c2[f.brow] + f.bbyte;
+            const uint32_t x = cnt[f.brow * kS8GainStride + (int32_t)f.bbyte];
+            key = ((unsigned long long)m32 << 32) | (unsigned long long)(0xFFFFFFFFu - (base_pos + f.bp));
             pay = ((unsigned long long)c1 << 48) | ((unsigned long long)c2 << 32) | x;
         }
         {   // block arg-max of (key, payload, stream index); thread 0 publishes the CTA's candidate
@@ -578,8 +607,10 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
         const long long t3 = P.dbg ? clock64() : 0;
         if (P.dbg && threadIdx.x == 0) {
             long long *d = P.dbg + 8 * blockIdx.x;
-            d[0] = t_gain; d[1] = t1 - t0 - t_gain; d[2] = t2 - t1; d[3] = clock64() - t2;
-            d[4] = (long long)(e_hi - e_lo) / kS8Blk; d[5] = n_mine; d[6] = t_pre; d[7] = t_learn;
+            d[0] = t_gain; d[1] = t1 - t0 - t_gain - t_pre; d[2] = t2 - t1; d[3] = clock64() - t2;
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            d[4] = (long long)(e_hi - e_lo) / kS8Blk; d[5] = nr | ((long long)smid << 16); d[6] = t_pre; d[7] = t_learn;
         }
         // ---------------- everyone learns the winner ----------------
         {
@@ -645,21 +676,23 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
         const unsigned long long win = sh_win_key, wpayload = sh_win_pay;
         if (win == 0ull) { broke = true; break; }              // nothing left on any rank
         const int32_t c1 = (int32_t)(wpayload >> 48), c2w = (int32_t)((wpayload >> 32) & 0xFFFFu);
+        const uint32_t xw = (uint32_t)(wpayload & 0xFFFFFFFFull);
+        {   // my copy of the cell's count, if the cell lies in one of my sub-rows (at most one thread matches)
+            const int32_t sub_c2 = (c2w / sub_w) * sub_w;
+            for (int32_t i = threadIdx.x; i < nr; i += THREADS)
+                if (row_c1[i] == c1 && row_c2[i] == sub_c2) cnt[i * kS8GainStride + (c2w - sub_c2)] = xw + 1;
+        }
         if (threadIdx.x == 0) {
             if (sh_best_key == win) {                          // keys are unique: exactly one owner CTA
                 P.stream[sh_best_idx] = (uint8_t)kS8Removed;   // remove_idx_all mi.py:104-106 (the -inf slot)
                 s.cells[(int64_t)key_pos(win) - s.pos_base] = 0xFFFFFFFFu;     // list-order view stays in sync
             }
-            const uint32_t x = (uint32_t)(wpayload & 0xFFFFFFFFull), y = a_cnt[c2w], z = b_cnt[c1];
-            ps[0] = bump_sum(ps[0], x, ps[4], s.logs);         // update_cache mi.py:383-389
+            const uint32_t y = a_cnt[c2w], z = b_cnt[c1];
+            ps[0] = bump_sum(ps[0], xw, ps[4], s.logs);        // update_cache mi.py:383-389
             ps[1] = bump_sum(ps[1], y, ps[5], s.logs);
             ps[2] = bump_sum(ps[2], z, ps[5], s.logs);
             ps[3] = __fadd_rn(ps[3], 1.0f);                    // update_mats :401-406
             a_cnt[c2w] = y + 1; b_cnt[c1] = z + 1;
-            if (cached) {                                      // my copy of the cell's count, if the cell is mine
-                const int32_t sub = c2w / sub_w, wrow = c1 * n_sub + sub;
-                if (wrow >= r_lo && wrow <= r_hi) cnt[(wrow - r_lo) * kS8GainStride + (c2w - sub * sub_w)] = x + 1;
-            }
             if (blockIdx.x == 0) {
                 P.out_pos[it] = (int64_t)key_pos(win);
                 P.out_gain[it] = key_score(win);
@@ -688,9 +721,16 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     }
 }
 
+constexpr size_t kS8RingBytesMax = 64 * 1024;           // 1024 threads x 16 bytes x 4 slots (every ring variant)
+
+int s8_slots_for_rows(int32_t rows) { return 2 * rows + 8; }
 size_t s8_fixed_bytes(int32_t k_a, int32_t k_v, int32_t rows) {
-    const size_t words = 2 * (size_t)k_v + kSmallCounts + (size_t)k_a + ((size_t)rows + 1) + 3 * (size_t)rows;
+    const size_t slots = (size_t)s8_slots_for_rows(rows);
+    const size_t words = 2 * (size_t)k_v + kSmallCounts + (size_t)k_a + (slots + 1) + slots + 3 * (size_t)rows;
     return words * 4;
+}
+size_t s8_table_bytes(int32_t k_a, int32_t k_v, int32_t rows) {         // everything in front of the ring
+    return ((s8_fixed_bytes(k_a, k_v, rows) + 1024 + (size_t)rows * kS8GainStride * 8) + 15) & ~(size_t)15;
 }
 
 }  // namespace
@@ -701,44 +741,58 @@ int mi_s8_tiles(int64_t w) { return (int)ceil_div(w > 0 ? w : 1, kS8Tile); }
 int64_t mi_s8_stream_capacity(int64_t w, int32_t k_a, int32_t k_v) {
     return w + (int64_t)kS8Blk * s8_geom(k_a, k_v).k_rows + kS8Blk;
 }
+int mi_s8_slots_for_rows(int32_t rows) { return s8_slots_for_rows(rows); }
 
+// distinct sub-rows a CTA can stage (gain row + count row each), leaving room for the 64 KiB ring of the ring variants
 int mi_s8_rows_that_fit(int32_t k_a, int32_t k_v) {
     int32_t rows = 0;
-    while (rows < 4096 &&
-           s8_fixed_bytes(k_a, k_v, rows + 1) + 1024 + (size_t)(rows + 1) * kS8GainStride * 8 <= kS8SmemBudget)
-        ++rows;
+    while (rows < 4096 && s8_table_bytes(k_a, k_v, rows + 1) + kS8RingBytesMax <= kS8SmemBudget) ++rows;
     return rows;
 }
 
+// shape test (the layout of a concrete list can still fail when its sub-rows do not fit: mi_prepare_stream8)
 bool mi_s8_supported(int32_t k_a, int32_t k_v) {
     const S8Geom g = s8_geom(k_a, k_v);
-    return g.k_rows <= 24000 && mi_s8_rows_that_fit(k_a, k_v) >= 1 && (int64_t)k_a * k_v < (1ll << 31);   // partition histogram: 96 KB of shared memory
+    return g.k_rows <= 24000 && mi_s8_rows_that_fit(k_a, k_v) >= 4 && (int64_t)k_a * k_v < (1ll << 31);   // partition histogram: 96 KB of shared memory
 }
 
-int launch_mi_s8_partition(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_v, uint32_t *tilehist,
-                           uint32_t *row_total, uint32_t *row_start, uint8_t *stream, uint32_t *pos_s,
-                           int64_t stream_capacity, cudaStream_t st) {
+// first half of the partition: per-tile histograms, their prefix over tiles and the sub-row totals
+int launch_mi_s8_count(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_v, uint32_t *tilehist,
+                       uint32_t *row_total, cudaStream_t st) {
     const S8Geom g = s8_geom(k_a, k_v);
     const int ntiles = mi_s8_tiles(w);
     const size_t smem = (size_t)g.k_rows * sizeof(uint32_t);
     if (smem > 96 * 1024) return ACAV_E_UNSUPPORTED;
-    static size_t done_count[kMaxDevices], done_scatter[kMaxDevices];
+    static size_t done_count[kMaxDevices];
     if (smem > 48 * 1024) {
         int rc = ensure_dynamic_smem(s8_count_kernel, (size_t)96 * 1024, done_count);
-        if (!rc) rc = ensure_dynamic_smem(s8_scatter_kernel, (size_t)96 * 1024, done_scatter);
         if (rc) return rc;
     }
     s8_count_kernel<<<ntiles, kS8PartThreads, smem, st>>>(cells, w, g, tilehist);
     ACAV_LAUNCH_CHECK();
     s8_prefix_kernel<<<(unsigned)ceil_div(g.k_rows, 256), 256, 0, st>>>(tilehist, ntiles, g.k_rows, row_total);
     ACAV_LAUNCH_CHECK();
-    s8_rowstart_kernel<<<1, 1024, 0, st>>>(row_total, g.k_rows, row_start);
-    ACAV_LAUNCH_CHECK();
+    return 0;
+}
+
+// second half, once the host has laid the sub-rows out (pieces of every sub-row: row_piece0 / piece_rank0 / piece_off)
+int launch_mi_s8_scatter(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_v, const uint32_t *tilehist,
+                         const uint32_t *row_piece0, const uint32_t *piece_rank0, const uint32_t *piece_off,
+                         uint8_t *stream, uint32_t *pos_s, int64_t stream_capacity, cudaStream_t st) {
+    const S8Geom g = s8_geom(k_a, k_v);
+    const int ntiles = mi_s8_tiles(w);
+    const size_t smem = (size_t)g.k_rows * sizeof(uint32_t);
+    static size_t done_scatter[kMaxDevices];
+    if (smem > 48 * 1024) {
+        int rc = ensure_dynamic_smem(s8_scatter_kernel, (size_t)96 * 1024, done_scatter);
+        if (rc) return rc;
+    }
     // padding entries of every sub-row: the "removed" byte (stream_capacity is a multiple of 16)
     const int64_t n16 = stream_capacity / 16;
     s8_fill_kernel<<<(unsigned)ceil_div(n16, 256), 256, 0, st>>>(reinterpret_cast<uint4 *>(stream), n16, 0xFFFFFFFFu);
     ACAV_LAUNCH_CHECK();
-    s8_scatter_kernel<<<ntiles, kS8PartThreads, smem, st>>>(cells, w, g, tilehist, row_start, stream, pos_s);
+    s8_scatter_kernel<<<ntiles, kS8PartThreads, smem, st>>>(cells, w, g, tilehist, row_piece0, piece_rank0, piece_off,
+                                                            stream, pos_s);
     ACAV_LAUNCH_CHECK();
     return 0;
 }
@@ -752,45 +806,50 @@ int launch_mi_s8_block_sort(uint8_t *stream, uint32_t *pos_s, int64_t w_padded, 
     return 0;
 }
 
-template <int THREADS, int DEPTH>
-static int launch_s8_variant(const MiS8 &P, size_t smem, int32_t grid, cudaStream_t st) {
+template <int THREADS, int DEPTH, bool RING>
+static int launch_s8_variant(MiS8 &P, size_t table_bytes, int32_t grid, cudaStream_t st) {
     static size_t attr_done[kMaxDevices];
-    { int rc = ensure_dynamic_smem(mi_stream8_kernel<THREADS, DEPTH>, smem, attr_done); if (rc) return rc; }
-    MiS8 Pc = P;
-    void *args[] = {&Pc};
-    ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_stream8_kernel<THREADS, DEPTH>, dim3(grid), dim3(THREADS), args,
-                                              smem, st));
+    const size_t smem = table_bytes + (RING ? (size_t)DEPTH * THREADS * 16 : 0);
+    P.ring_offset = (int32_t)table_bytes;
+    { int rc = ensure_dynamic_smem(mi_stream8_kernel<THREADS, DEPTH, RING>, smem, attr_done); if (rc) return rc; }
+    void *args[] = {&P};
+    ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_stream8_kernel<THREADS, DEPTH, RING>, dim3(grid), dim3(THREADS),
+                                              args, smem, st));
     return 0;
 }
 
 int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const uint32_t *pos_s,
-                      const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
-                      unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
-                      int32_t variant, int32_t use_cache, int32_t world, int32_t rank, unsigned int seq_base,
+                      const uint32_t *slot_start, const uint32_t *slot_row, const uint32_t *slot_u, const void *chunks,
+                      int32_t grid, void *pub, unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain,
+                      int32_t rows_smem, int32_t variant, int32_t world, int32_t rank, unsigned int seq_base,
                       void *mail_local, void *const *mail_peer, long long *dbg, int *status,
                       unsigned long long spin_limit_ns, cudaStream_t st) {
     MiS8 P;
-    P.s = s; P.n_alt = n_alt; P.stream = stream; P.pos_s = pos_s; P.row_start = row_start; P.chunk_start = chunk_start;
+    P.s = s; P.n_alt = n_alt; P.stream = stream; P.pos_s = pos_s; P.slot_start = slot_start; P.slot_row = slot_row;
+    P.slot_u = slot_u; P.chunks = reinterpret_cast<const S8Chunk *>(chunks);
     P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks; P.out_pos = out_pos; P.out_gain = out_gain;
-    P.g = s8_geom(s.k_a, s.k_v); P.rows_smem = rows_smem; P.use_cache = use_cache;
+    P.g = s8_geom(s.k_a, s.k_v); P.rows_smem = rows_smem; P.slots_smem = s8_slots_for_rows(rows_smem);
     P.fixed_bytes = (int32_t)s8_fixed_bytes(s.k_a, s.k_v, rows_smem);
+    P.ring_offset = 0;
     P.world = world; P.rank = rank; P.seq_base = seq_base;
     P.mail_local = reinterpret_cast<MiMail *>(mail_local);
     for (int r = 0; r < kMaxWorld; ++r)
         P.mail_peer[r] = (world > 1 && r < world) ? reinterpret_cast<MiMail *>(mail_peer[r]) : nullptr;
     P.dbg = dbg; P.status = status; P.spin_limit_ns = spin_limit_ns;
-    const size_t smem = (size_t)P.fixed_bytes + 1024 + (size_t)rows_smem * kS8GainStride * 8;
+    const size_t table_bytes = s8_table_bytes(s.k_a, s.k_v, rows_smem);
     // both table copies start equal; the barrier words start at zero
     ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
     ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     switch (variant) {
-        case 1: return launch_s8_variant<512, 8>(P, smem, grid, st);
-        case 2: return launch_s8_variant<768, 4>(P, smem, grid, st);
-        case 3: return launch_s8_variant<1024, 2>(P, smem, grid, st);
-        case 4: return launch_s8_variant<512, 4>(P, smem, grid, st);
-        default: return launch_s8_variant<512, 6>(P, smem, grid, st);
+        case 1: return launch_s8_variant<512, 8, false>(P, table_bytes, grid, st);
+        case 2: return launch_s8_variant<768, 4, false>(P, table_bytes, grid, st);
+        case 3: return launch_s8_variant<1024, 2, false>(P, table_bytes, grid, st);
+        case 4: return launch_s8_variant<512, 4, false>(P, table_bytes, grid, st);
+        case 5: return launch_s8_variant<1024, 3, true>(P, table_bytes, grid, st);
+        case 6: return launch_s8_variant<768, 3, false>(P, table_bytes, grid, st);
+        default: return launch_s8_variant<1024, 4, true>(P, table_bytes, grid, st);
     }
 }
 

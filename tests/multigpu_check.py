@@ -71,10 +71,10 @@ for mode, comm, resident in (("exact", "p2p", False), ("tensor", "nccl", False),
     ok = (torch.equal(km.counts.cpu(), st.counts) and km.count == st.count and km.fallback == st.fallback
           and rel < 1e-5) or int(total_flips) > 0
     bit_exact = torch.equal(centers, st.centers)
+    n_graphs = len(km._gs["graphs"]) if km._gs else 0      # before calc_best: a bigger batch re-creates the workspace
     best, _ = km.calc_best(x[:2048])
     want, _ = ko.assign(st, x[:2048])
     agree = (best.cpu() == want).float().mean().item()
-    n_graphs = len(km._gs["graphs"]) if km._gs else 0
     print(f"[rank {rank}] kmeans {mode}/{km.comm_name()}{'/resident' if resident else ''}: ok={ok} bit-exact={bit_exact} "
           f"max rel |dcenter| {rel:.2e} ids agree {agree:.4f} near-tie flips {int(total_flips)} graphs {n_graphs}", flush=True)
     assert ok and agree > 0.999

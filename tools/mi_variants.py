@@ -21,10 +21,10 @@ sm = torch.cuda.get_device_properties(0).multi_processor_count
 ref = None
 
 CONFIGS = [("persistent", None, None, None), ("cells", None, None, None)]
-for variant in (0, 1, 4, 2, 3):
+for variant in (0, 1, 2, 3, 4, 5, 6):
     CONFIGS.append(("bytes", variant, 1, None))
-# row cost of the chunk cut, in 512-candidate blocks per sub-row touched (default 2)
-CONFIGS += [("bytes", 0, 0, None), ("bytes", 0, 1, 0.5), ("bytes", 0, 1, 4), ("bytes", 0, 1, 8), ("bytes", 2, 1, 4)]
+# row cost of the chunk cut, in 512-candidate blocks per sub-row touched (default 3)
+CONFIGS += [("bytes", 4, 1, 1), ("bytes", 4, 1, 8), ("bytes", 1, 1, 1), ("bytes", 1, 1, 8)]
 
 
 def timers(m, names=("gain rows", "scan", "reduce+publish", "barrier wait")):
