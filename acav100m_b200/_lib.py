@@ -83,6 +83,7 @@ SIGNATURES = {
 ASSIGN_EXACT, ASSIGN_TENSOR = 0, 1
 TILE_AUTO, TILE_SINGLE, TILE_PAIR_256, TILE_PAIR_512 = 0, 1, 2, 3
 MI_LOOP_KERNELS, MI_LOOP_PERSISTENT, MI_LOOP_CELLS, MI_LOOP_BYTES = 0, 1, 2, 3
+E_INVALID, E_UNSUPPORTED, E_STATE, E_NO_DEVICE = -1, -2, -3, -4         # ACAV_E_* of include/acav_b200.h
 PERSISTENT_READY = True         # persistent greedy-MI kernel validated against the C oracle on a B200
 TENSOR_PATH_READY = True        # tcgen05 assignment validated against the exact kernel on a B200
 

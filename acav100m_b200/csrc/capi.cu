@@ -70,8 +70,11 @@ struct acav_mi {
     // byte-stream loop resources (sub-row partitioned stream, one byte per candidate), built on first use
     uint8_t *s8_stream;
     uint32_t *s8_pos, *s8_row_total, *s8_tilehist;
+    unsigned long long *s8_vrank;
     // layout of the one-byte stream (host-built, see s8_build_layout): slots, chunks, pieces of every sub-row
-    uint32_t *s8_slot_start, *s8_slot_row, *s8_slot_u, *s8_chunks, *s8_row_piece0, *s8_piece_rank0, *s8_piece_off;
+    uint32_t *s8_slot_start, *s8_slot_row, *s8_slot_u, *s8_chunks, *s8_row_start, *s8_blk_src;
+    uint8_t *s8_stage_stream;            // staging layout the scatter writes ((c1, sub) order), read by the block sort
+    uint32_t *s8_stage_pos;
     int64_t s8_slot_cap;
     int32_t s8_rows_smem, s8_variant, s8_use_cache;
     bool s8_valid;
@@ -194,11 +197,13 @@ std::vector<uint32_t> cut_chunks_capped(const std::vector<uint32_t> &rs, int32_t
 //   * inside a bin the big blocks are cut into as many sub-pieces as there are small sub-rows and the two alternate, so
 //     every warp's span of the chunk crosses only a few segment borders (each border can park a tie in the scan).
 // A stream SLOT is a sub-row or a piece of one; all slots are whole blocks.  Pieces of one sub-row in one bin share a
-// gain row (slot_u).  The scatter kernel finds a candidate's place through the pieces of its sub-row (rank order).
+// gain row (slot_u).  The scatter kernel writes a plain staging layout (sub-rows in id order); blk_src tells the block
+// sort where every block of the stream comes from.
 struct S8Layout {
     std::vector<uint32_t> slot_start, slot_row, slot_u;          // [n_slots + 1], [n_slots], [n_slots]
     std::vector<uint32_t> chunks;                                // [grid + 1][4] {slot0, n_slots, n_rows, start}
-    std::vector<uint32_t> row_piece0, piece_rank0, piece_off;    // [k_rows + 1], [n_pieces], [n_pieces]
+    std::vector<uint32_t> row_start;                             // [k_rows + 1] staging layout: sub-rows in id order
+    std::vector<uint32_t> blk_src;                               // [blocks] stream block -> staging block
     uint32_t total = 0;                                          // padded stream length (candidates)
 };
 
@@ -252,9 +257,11 @@ bool s8_build_layout(const std::vector<uint32_t> &nb, uint32_t blk, int32_t grid
             }
         }
     }
+    // staging layout: sub-rows in id order
+    L->row_start.assign((size_t)k_rows + 1, 0);
+    for (int32_t r = 0; r < k_rows; ++r) L->row_start[r + 1] = L->row_start[r] + nb[r] * blk;
     // emit: per bin, big sub-pieces and small sub-rows alternate
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> pieces_of((size_t)k_rows);      // (rank0 blocks, stream offset)
-    L->slot_start.clear(); L->slot_row.clear(); L->slot_u.clear();
+    L->slot_start.clear(); L->slot_row.clear(); L->slot_u.clear(); L->blk_src.clear();
     L->chunks.assign((size_t)(grid + 1) * 4, 0);
     uint32_t off = 0;
     for (int32_t g = 0; g < grid; ++g) {
@@ -264,7 +271,8 @@ bool s8_build_layout(const std::vector<uint32_t> &nb, uint32_t blk, int32_t grid
             L->slot_start.push_back(off);
             L->slot_row.push_back(row);
             L->slot_u.push_back(u);
-            pieces_of[row].push_back({rank0, off});
+            const uint32_t src0 = L->row_start[row] / blk + rank0;
+            for (uint32_t i = 0; i < n; ++i) L->blk_src.push_back(src0 + i);
             off += n * blk;
         };
         uint64_t bigs = 0;
@@ -291,14 +299,6 @@ bool s8_build_layout(const std::vector<uint32_t> &nb, uint32_t blk, int32_t grid
     L->slot_start.push_back(off);
     L->total = off;
     {   uint32_t *c = &L->chunks[(size_t)grid * 4]; c[0] = (uint32_t)L->slot_row.size(); c[1] = 0; c[2] = 0; c[3] = off; }
-    L->row_piece0.assign((size_t)k_rows + 1, 0);
-    L->piece_rank0.clear(); L->piece_off.clear();
-    for (int32_t r = 0; r < k_rows; ++r) {
-        L->row_piece0[r] = (uint32_t)L->piece_rank0.size();
-        for (const auto &pp : pieces_of[r]) { L->piece_rank0.push_back(pp.first * blk); L->piece_off.push_back(pp.second); }
-        if (pieces_of[r].empty()) { L->piece_rank0.push_back(0); L->piece_off.push_back(0); }     // empty sub-row: never looked up
-    }
-    L->row_piece0[k_rows] = (uint32_t)L->piece_rank0.size();
     return true;
 }
 
@@ -320,12 +320,14 @@ int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
         h->s8_slot_cap = slot_cap_total;
         if (!rc) rc = dev_alloc(&h->s8_stream, (size_t)cap, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_pos, (size_t)cap, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_vrank, (size_t)cap / 16 + 1, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_slot_start, (size_t)slot_cap_total + 1, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_slot_row, (size_t)slot_cap_total, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_slot_u, (size_t)slot_cap_total, nullptr);
-        if (!rc) rc = dev_alloc(&h->s8_piece_rank0, (size_t)slot_cap_total, nullptr);
-        if (!rc) rc = dev_alloc(&h->s8_piece_off, (size_t)slot_cap_total, nullptr);
-        if (!rc) rc = dev_alloc(&h->s8_row_piece0, (size_t)k_rows + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_stage_stream, (size_t)cap, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_stage_pos, (size_t)cap, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_row_start, (size_t)k_rows + 1, nullptr);
+        if (!rc) rc = dev_alloc(&h->s8_blk_src, (size_t)cap / blk + 1, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_chunks, ((size_t)h->sm_count + 1) * 4, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_row_total, (size_t)k_rows, nullptr);
         if (!rc) rc = dev_alloc(&h->s8_tilehist, (size_t)ntiles * k_rows, nullptr);
@@ -342,9 +344,7 @@ int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
     for (int32_t r = 0; r < k_rows; ++r) nb[r] = (nb[r] + blk - 1) / blk;
     S8Layout L;
     if (!s8_build_layout(nb, blk, h->sm_count, h->s8_rows_smem, slots_cap, &L)) return ACAV_E_UNSUPPORTED;
-    if ((int64_t)L.slot_row.size() > h->s8_slot_cap || (int64_t)L.piece_off.size() > h->s8_slot_cap ||
-        (int64_t)L.total > cap)
-        return ACAV_E_UNSUPPORTED;
+    if ((int64_t)L.slot_row.size() > h->s8_slot_cap || (int64_t)L.total > cap) return ACAV_E_UNSUPPORTED;
     auto up = [&](uint32_t *dst, const std::vector<uint32_t> &v) {
         return v.empty() ? cudaSuccess
                          : cudaMemcpyAsync(dst, v.data(), sizeof(uint32_t) * v.size(), cudaMemcpyHostToDevice, st);
@@ -353,12 +353,12 @@ int mi_prepare_stream8(acav_mi *h, cudaStream_t st) {
     ACAV_CUDA_TRY(up(h->s8_slot_row, L.slot_row));
     ACAV_CUDA_TRY(up(h->s8_slot_u, L.slot_u));
     ACAV_CUDA_TRY(up(h->s8_chunks, L.chunks));
-    ACAV_CUDA_TRY(up(h->s8_row_piece0, L.row_piece0));
-    ACAV_CUDA_TRY(up(h->s8_piece_rank0, L.piece_rank0));
-    ACAV_CUDA_TRY(up(h->s8_piece_off, L.piece_off));
-    rc = launch_mi_s8_scatter(s.cells, s.w, s.k_a, s.k_v, h->s8_tilehist, h->s8_row_piece0, h->s8_piece_rank0,
-                              h->s8_piece_off, h->s8_stream, h->s8_pos, cap, st);
-    if (!rc) rc = launch_mi_s8_block_sort(h->s8_stream, h->s8_pos, L.total, st);
+    ACAV_CUDA_TRY(up(h->s8_row_start, L.row_start));
+    ACAV_CUDA_TRY(up(h->s8_blk_src, L.blk_src));
+    rc = launch_mi_s8_scatter(s.cells, s.w, s.k_a, s.k_v, h->s8_tilehist, h->s8_row_start, h->s8_stage_stream,
+                              h->s8_stage_pos, cap, st);
+    if (!rc) rc = launch_mi_s8_block_arrange(h->s8_stage_stream, h->s8_stage_pos, h->s8_blk_src, h->s8_stream, h->s8_pos,
+                                             h->s8_vrank, L.total, st);
     if (rc) return rc;
     ACAV_CUDA_TRY(cudaStreamSynchronize(st));      // the layout tables are host temporaries
     h->grid = h->sm_count;
@@ -811,9 +811,9 @@ int acav_mi_destroy(acav_mi_t *h) {
             if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
     cudaFree(h->mail_local); cudaFree(h->run_status);
     cudaFree(h->cx_sorted_pos); cudaFree(h->cx_cell_start); cudaFree(h->cx_head); cudaFree(h->cx_first_pos);
-    cudaFree(h->s8_stream); cudaFree(h->s8_pos); cudaFree(h->s8_row_total); cudaFree(h->s8_tilehist);
+    cudaFree(h->s8_stream); cudaFree(h->s8_pos); cudaFree(h->s8_vrank); cudaFree(h->s8_row_total); cudaFree(h->s8_tilehist);
     cudaFree(h->s8_slot_start); cudaFree(h->s8_slot_row); cudaFree(h->s8_slot_u); cudaFree(h->s8_chunks);
-    cudaFree(h->s8_row_piece0); cudaFree(h->s8_piece_rank0); cudaFree(h->s8_piece_off);
+    cudaFree(h->s8_row_start); cudaFree(h->s8_blk_src); cudaFree(h->s8_stage_stream); cudaFree(h->s8_stage_pos);
     delete h;
     return 0;
 }
@@ -843,9 +843,10 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     h->sorted_valid = false;
     h->cx_sorted_pos = nullptr; h->cx_cell_start = nullptr; h->cx_head = nullptr; h->cx_first_pos = nullptr;
     h->cells_valid = false;
-    h->s8_stream = nullptr; h->s8_pos = nullptr; h->s8_row_total = nullptr; h->s8_tilehist = nullptr;
+    h->s8_stream = nullptr; h->s8_pos = nullptr; h->s8_vrank = nullptr; h->s8_row_total = nullptr; h->s8_tilehist = nullptr;
     h->s8_slot_start = nullptr; h->s8_slot_row = nullptr; h->s8_slot_u = nullptr; h->s8_chunks = nullptr;
-    h->s8_row_piece0 = nullptr; h->s8_piece_rank0 = nullptr; h->s8_piece_off = nullptr; h->s8_slot_cap = 0;
+    h->s8_row_start = nullptr; h->s8_blk_src = nullptr; h->s8_stage_stream = nullptr; h->s8_stage_pos = nullptr;
+    h->s8_slot_cap = 0;
     h->s8_rows_smem = 0; h->s8_valid = false;
     h->s8_variant = 0; h->s8_use_cache = 1;
     if (const char *e = std::getenv("ACAV_MI_S8_VARIANT")) h->s8_variant = std::atoi(e);
@@ -953,7 +954,7 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         if (rc) return rc;
         h->cells_valid = false;                  // neither the cell index nor the 2-byte stream see these removals
         h->sorted_valid = false;
-        rc = launch_mi_stream8(h->s, h->n_alt, h->s8_stream, h->s8_pos, h->s8_slot_start, h->s8_slot_row, h->s8_slot_u,
+        rc = launch_mi_stream8(h->s, h->n_alt, h->s8_stream, h->s8_pos, h->s8_vrank, h->s8_slot_start, h->s8_slot_row, h->s8_slot_u,
                                h->s8_chunks, h->grid, h->pub, h->bar, n_picks, out_pos, out_gain, h->s8_rows_smem, h->s8_variant,
                                h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer, h->dbg, h->run_status,
                                h->spin_limit_ns, st);
@@ -1012,7 +1013,7 @@ int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles) {
 }
 
 int acav_mi_set_stream_variant(acav_mi_t *h, int32_t variant, int32_t use_cache) {
-    if (!h || variant < 0 || variant > 6) return ACAV_E_INVALID;
+    if (!h || variant < 0 || variant > 5) return ACAV_E_INVALID;
     h->s8_variant = variant;
     h->s8_use_cache = use_cache ? 1 : 0;
     return 0;

@@ -137,12 +137,14 @@ int mi_s8_slots_for_rows(int32_t rows);
 int launch_mi_s8_count(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_v, uint32_t *tilehist,
                        uint32_t *row_total, cudaStream_t st);
 int launch_mi_s8_scatter(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_v, const uint32_t *tilehist,
-                         const uint32_t *row_piece0, const uint32_t *piece_rank0, const uint32_t *piece_off,
-                         uint8_t *stream, uint32_t *pos_s, int64_t stream_capacity, cudaStream_t st);
-int launch_mi_s8_block_sort(uint8_t *stream, uint32_t *pos_s, int64_t w_padded, cudaStream_t st);
+                         const uint32_t *row_start, uint8_t *stage_stream, uint32_t *stage_pos, int64_t stream_capacity,
+                         cudaStream_t st);
+int launch_mi_s8_block_arrange(const uint8_t *stage_stream, const uint32_t *stage_pos, const uint32_t *blk_src,
+                               uint8_t *stream, uint32_t *pos_s, unsigned long long *vrank, int64_t w_padded,
+                               cudaStream_t st);
 // chunks: [grid + 1] records of four uint32 {first slot, slots, distinct sub-rows, stream offset} (S8Chunk)
 int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const uint32_t *pos_s,
-                      const uint32_t *slot_start, const uint32_t *slot_row, const uint32_t *slot_u, const void *chunks,
+                      const unsigned long long *vrank, const uint32_t *slot_start, const uint32_t *slot_row, const uint32_t *slot_u, const void *chunks,
                       int32_t grid, void *pub, unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain,
                       int32_t rows_smem, int32_t variant, int32_t world, int32_t rank, unsigned int seq_base,
                       void *mail_local, void *const *mail_peer, long long *dbg, int *status,

@@ -13,7 +13,7 @@
 //     all of its gain rows and table counts fit in its shared memory (the cut enforces it).
 //   * sub-rows are padded to whole 512-candidate blocks, every block is sorted by the shared-memory bank of its gain
 //     slot (lane l owns entries [16l, 16l+16): gather step j reads entries 16 apart, i.e. ~32 different banks); ties are
-//     settled by original position (pos[], permuted along, read only after the scan).
+//     settled by original position (pos[] and the per-vector rank words, permuted along, read only after the scan).
 //   * a CTA stages the gain rows (256 floats) of its sub-rows in shared memory, 1 KiB aligned so that a gather address
 //     is (byte << 2) | row_base: shift, LOP3, LDS; their table COUNTS stay in shared memory for the whole launch (every
 //     CTA learns every winner and bumps its copy), so building the gain rows of an iteration reads no global memory.
@@ -83,16 +83,15 @@ __global__ void s8_prefix_kernel(uint32_t *__restrict__ tilehist, int32_t ntiles
     row_total[r] = run;
 }
 
-// stable scatter: tiles in list order, 512-chunks in list order, warps in order, lanes in order.  A sub-row lies in the
-// stream in one or more PIECES (whole blocks each, in rank order; the host's layout cuts big sub-rows): the r-th
-// candidate of a sub-row goes to piece_off[p] + (r - piece_rank0[p]) of the piece p that holds rank r.
+// stable scatter into the STAGING layout (sub-rows in (c1, sub) order, each padded to whole blocks): tiles in list
+// order, 512-chunks in list order, warps in order, lanes in order.  The block sort then moves every block to its place
+// in the stream the host laid out (s8_build_layout).
 __global__ void __launch_bounds__(kS8PartThreads)
 s8_scatter_kernel(const uint32_t *__restrict__ cells, int64_t w, S8Geom g, const uint32_t *__restrict__ tilehist,
-                  const uint32_t *__restrict__ row_piece0, const uint32_t *__restrict__ piece_rank0,
-                  const uint32_t *__restrict__ piece_off, uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s) {
+                  const uint32_t *__restrict__ row_start, uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s) {
     extern __shared__ uint32_t s8_cursor[];
     const uint32_t *tp = tilehist + (int64_t)blockIdx.x * g.k_rows;
-    for (int32_t i = threadIdx.x; i < g.k_rows; i += blockDim.x) s8_cursor[i] = tp[i];      // rank inside the sub-row
+    for (int32_t i = threadIdx.x; i < g.k_rows; i += blockDim.x) s8_cursor[i] = row_start[i] + tp[i];
     __syncthreads();
     const int64_t lo = (int64_t)blockIdx.x * kS8Tile, hi = min(w, lo + kS8Tile);
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -116,15 +115,8 @@ s8_scatter_kernel(const uint32_t *__restrict__ cells, int64_t w, S8Geom g, const
                 }
                 basev = __shfl_sync(0xffffffffu, basev, leader);
                 if (live) {
-                    const uint32_t r = basev + rank;
-                    uint32_t p = __ldg(row_piece0 + key), p1 = __ldg(row_piece0 + key + 1);
-                    while (p1 - p > 1) {                          // last piece whose first rank is <= r
-                        const uint32_t mid = (p + p1) >> 1;
-                        if (__ldg(piece_rank0 + mid) <= r) p = mid; else p1 = mid;
-                    }
-                    const uint32_t dst = __ldg(piece_off + p) + (r - __ldg(piece_rank0 + p));
-                    stream[dst] = (uint8_t)(c2 - sub * (uint32_t)g.sub_w);                   // column inside the sub-row
-                    pos_s[dst] = (uint32_t)e;
+                    stream[basev + rank] = (uint8_t)(c2 - sub * (uint32_t)g.sub_w);       // column inside the sub-row
+                    pos_s[basev + rank] = (uint32_t)e;
                 }
             }
             __syncthreads();
@@ -137,22 +129,34 @@ __global__ void s8_fill_kernel(uint4 *p, int64_t n16, uint32_t v) {
     if (i < n16) p[i] = make_uint4(v, v, v, v);
 }
 
-// Sort every 512-candidate block by (shared-memory bank of its gain slot, column, original order): in the scan lane l
-// owns entries [16l, 16l+16) and gather step j reads entry 16l+j in all lanes -- 16 apart in bank order.  Then every
-// lane's 16 entries are put in LIST order among themselves (the bank pattern does not care which of a lane's entries
-// is read at which step): of the entries of a vector that hold the same gain, the FIRST one is the earliest candidate,
-// so settling a vector after the scan takes one position load instead of one per tied entry.
+// Arrange every 512-candidate block for the scan's gathers.  In the scan lane l owns the 16 bytes [16l, 16l+16) of a
+// block and gather step j reads byte 16l+j in all lanes; a step is one shared-memory wavefront iff, bank by bank, the
+// lanes that hit the bank read the SAME gain slot (one address: broadcast).  So the block is sorted by (bank, slot) and
+// its RUNS (entries of one slot) are dealt to the 16 steps: a run goes, whole, to the step with the most room among
+// those where its bank is still free (or already serves the same slot); what does not fit goes on to the next such
+// step.  A 205-column sub-row has 6-7 slots per bank, so a conflict-free schedule nearly always exists -- where the
+// plain "sort by bank, 16 consecutive entries per lane" layout puts two slots of a bank in one step whenever a bank
+// holds more than 16 entries of the block (every other bank of a flat sub-row: 1.5-2 wavefronts per step).
+// Order inside a block is not list order any more; vrank holds, per vector, every entry's rank in list order (16 x 4
+// bits) so that settling a vector after the scan takes one position load.
+constexpr int kS8Steps = 16;
+constexpr int kS8ArrangeWarps = 8;
+
+// step 1: sort the block by (bank, slot, original order) -- one CTA per block; block b of the stream is read from
+// block blk_src[b] of the staging layout
 __global__ void __launch_bounds__(kS8Blk)
-s8_block_sort_kernel(uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s, int64_t n_blocks) {
+s8_block_sort_kernel(const uint8_t *__restrict__ stage_stream, const uint32_t *__restrict__ stage_pos,
+                     const uint32_t *__restrict__ blk_src, uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s,
+                     int64_t n_blocks) {
     __shared__ uint32_t key[kS8Blk];
     __shared__ uint8_t colv[kS8Blk];
     __shared__ uint32_t posv[kS8Blk];
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t base = blk * kS8Blk;
+        const int64_t base = blk * kS8Blk, sbase = (int64_t)blk_src[blk] * kS8Blk;
         const int t = threadIdx.x;
-        const uint32_t c = stream[base + t];
+        const uint32_t c = stage_stream[sbase + t];
         colv[t] = (uint8_t)c;
-        posv[t] = pos_s[base + t];
+        posv[t] = stage_pos[sbase + t];
         key[t] = ((c & 31u) << 20) | (c << 9) | (uint32_t)t;        // c < 2^8, t < 2^9
         __syncthreads();
         for (int size = 2; size <= kS8Blk; size <<= 1) {
@@ -166,16 +170,105 @@ s8_block_sort_kernel(uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s,
                 __syncthreads();
             }
         }
-        // inside my group of 16: rank by original index (= list order: the partition is stable and a block holds
-        // consecutive ranks of its sub-row; padding entries carry the largest indices of the block)
         const int src = (int)(key[t] & 511u);
-        const int g0 = t & ~15;
-        int rank = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) rank += (int)(key[g0 + j] & 511u) < src ? 1 : 0;
-        stream[base + g0 + rank] = colv[src];
-        pos_s[base + g0 + rank] = posv[src];
+        stream[base + t] = colv[src];
+        pos_s[base + t] = posv[src];
         __syncthreads();
+    }
+}
+
+// step 2: deal the runs of the sorted block to the 16 gather steps -- one WARP per block (the dealing is a sequential
+// greedy over ~200 runs; 40 warps per SM keep it off the critical path of the build)
+__global__ void __launch_bounds__(kS8ArrangeWarps *kWarp)
+s8_block_arrange_kernel(uint8_t *__restrict__ stream, uint32_t *__restrict__ pos_s, unsigned long long *__restrict__ vrank,
+                        int64_t n_blocks) {
+    __shared__ uint32_t posv_s[kS8ArrangeWarps][kS8Blk];
+    __shared__ uint8_t colv_s[kS8ArrangeWarps][kS8Blk];
+    __shared__ uint16_t dest_s[kS8ArrangeWarps][kS8Blk];        // sorted index -> byte of the block (lane * 16 + step)
+    // run starts [514] + per (step, bank) the slot served (0xFE = none yet) [512 bytes]; after the dealing the same
+    // memory holds the inverse map, byte of the block -> sorted index [512]
+    __shared__ uint16_t scratch_s[kS8ArrangeWarps][kS8Blk + 2 + kS8Steps * 16];
+    const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+    uint32_t *posv = posv_s[warp];
+    uint8_t *colv = colv_s[warp];
+    uint16_t *dest = dest_s[warp], *inv = scratch_s[warp], *run_start = scratch_s[warp];
+    uint8_t *bank_slot = reinterpret_cast<uint8_t *>(scratch_s[warp] + kS8Blk + 2);
+    const int64_t warps_total = (int64_t)gridDim.x * kS8ArrangeWarps;
+    for (int64_t blk = (int64_t)blockIdx.x * kS8ArrangeWarps + warp; blk < n_blocks; blk += warps_total) {
+        const int64_t base = blk * kS8Blk;
+        // load the sorted block (16 bytes of slots and 16 positions per lane), find the runs of equal slot
+        {
+            const uint4 q = *reinterpret_cast<const uint4 *>(stream + base + lane * 16);
+            *reinterpret_cast<uint4 *>(colv + lane * 16) = q;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4 *>(posv + lane * 16 + j * 4) =
+                    *reinterpret_cast<const uint4 *>(pos_s + base + lane * 16 + j * 4);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bank_slot[lane * 16 + j] = 0xFE;
+        }
+        __syncwarp();
+        int n_runs = 0;
+        for (int i0 = 0; i0 < kS8Blk; i0 += kWarp) {
+            const int i = i0 + lane;
+            const bool is_start = i == 0 || colv[i] != colv[i - 1];
+            const unsigned bal = __ballot_sync(0xffffffffu, is_start);
+            if (is_start) run_start[n_runs + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+            n_runs += __popc(bal);
+        }
+        if (lane == 0) run_start[n_runs] = (uint16_t)kS8Blk;
+        __syncwarp();
+        // lanes 0..15 each keep one step (its fill count); all lanes place the entries of a run piece
+        int fill = 0;
+        for (int r = 0; r < n_runs; ++r) {
+            int s0 = run_start[r];
+            int left = (int)run_start[r + 1] - s0;
+            const uint32_t rv = colv[s0], rb = rv & 31u;
+            while (left > 0) {
+                // my step's offer: its room, preferred if the bank is free there (or serves this slot already)
+                uint32_t offer = 0;
+                if (lane < kS8Steps && fill < 32) {
+                    const uint8_t cur = bank_slot[lane * 32 + rb];
+                    const bool clean = cur == 0xFE || cur == (uint8_t)rv;
+                    offer = ((clean ? 64u : 0u) + (uint32_t)(32 - fill)) << 8 | (uint32_t)(31 - lane);
+                }
+                const uint32_t top = __reduce_max_sync(0xffffffffu, offer);
+                const int who = 31 - (int)(top & 0xFFu);
+                const int wroom = (int)((top >> 8) & 63u);     // room is 1..32; the clean flag is bit 6
+                const int wfill = 32 - wroom;
+                const int take = left < wroom ? left : wroom;
+                if (lane < take) dest[s0 + lane] = (uint16_t)((wfill + lane) * 16 + who);
+                if (lane == who) { fill += take; bank_slot[who * 32 + rb] = (uint8_t)rv; }
+                __syncwarp();
+                s0 += take;
+                left -= take;
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < kS8Blk; i += kWarp) inv[dest[i]] = (uint16_t)i;
+        __syncwarp();
+        {   // my vector = bytes [16 lane, 16 lane + 16) of the arranged block; ranks of its entries in list order
+            uint32_t sl[16], ps[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const int i = inv[lane * 16 + j]; sl[j] = colv[i]; ps[j] = posv[i]; }
+            unsigned long long word = 0ull;
+            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                int rank = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) rank += (ps[k] < ps[j] || (ps[k] == ps[j] && k < j)) ? 1 : 0;   // padding: arbitrary
+                word |= (unsigned long long)rank << (4 * j);
+                w4[j >> 2] |= sl[j] << (8 * (j & 3));
+            }
+            *reinterpret_cast<uint4 *>(stream + base + lane * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4 *>(pos_s + base + lane * 16 + j * 4) =
+                    make_uint4(ps[4 * j], ps[4 * j + 1], ps[4 * j + 2], ps[4 * j + 3]);
+            vrank[blk * kWarp + lane] = word;
+        }
+        __syncwarp();
     }
 }
 
@@ -194,6 +287,7 @@ struct MiS8 {
     uint32_t *n_alt;                 // second copy of the table counts (kept in step for the other loops)
     uint8_t *stream;
     const uint32_t *pos_s;
+    const unsigned long long *vrank; // [stream bytes / 16] list-order ranks inside every vector
     const uint32_t *slot_start;      // [n_slots + 1] stream offsets of the slots (a slot = a sub-row or a piece of one)
     const uint32_t *slot_row;        // [n_slots] sub-row id (c1 * n_sub + sub)
     const uint32_t *slot_u;          // [n_slots] index of that sub-row among the distinct sub-rows of the slot's chunk
@@ -207,7 +301,6 @@ struct MiS8 {
     int32_t rows_smem;               // distinct sub-rows whose gain row + counts fit in shared memory
     int32_t slots_smem;              // slots per chunk the shared-memory tables hold
     int32_t fixed_bytes;             // bytes of the arrays in front of the gain rows
-    int32_t ring_offset;             // byte offset of the cp.async ring (ring variants)
     int32_t world, rank;
     unsigned int seq_base;
     MiMail *mail_local;
@@ -230,24 +323,16 @@ __device__ __forceinline__ uint4 s8_ld_stream(const uint4 *p, uint64_t pol) {
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
     return v;
 }
-// the same through a shared-memory ring (cp.async.cg: bypasses L1, completion tracked per thread in commit groups)
-__device__ __forceinline__ void s8_cp_async16(uint32_t smem_dst, const void *gmem_src, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void s8_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void s8_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint4 s8_lds128(uint32_t addr) {
-    uint4 q;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-    return q;
-}
 __device__ __forceinline__ float s8_gather(uint32_t word, int byte, uint32_t row_base) {
-    // address = ((word >> 8*byte) & 0xFF) << 2 | row_base (row_base is 1 KiB aligned): one shift, one LOP3, one LDS
-    const uint32_t sh = byte == 0 ? (word << 2) : (word >> (8 * byte - 2));
-    uint32_t addr;
-    asm("lop3.b32 %0, %1, 0x3FC, %2, 0xEA;" : "=r"(addr) : "r"(sh), "r"(row_base));      // (a & b) | c
+    // address = row_base + 4 * byte `byte` of `word`: one PRMT (integer pipe) and one IMAD (FMA pipe), then the LDS.
+    // (shift + LOP3 -- both on the integer pipe, which issues a warp instruction every other cycle -- made that pipe the
+    // co-limiter of the scan next to the issue slots: ncu math_pipe_throttle 1.3 per issued instruction.)
+    uint32_t v, addr;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(word), "n"(0x4440));
+    if (byte == 1) asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(word), "n"(0x4441));
+    if (byte == 2) asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(word), "n"(0x4442));
+    if (byte == 3) asm("prmt.b32 %0, %1, 0, %2;" : "=r"(v) : "r"(word), "n"(0x4443));
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(v), "r"(row_base));
     float g;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(addr));
     return g;
@@ -255,6 +340,7 @@ __device__ __forceinline__ float s8_gather(uint32_t word, int byte, uint32_t row
 
 struct S8Ctx {                                 // what it takes to look a block up again after the scan
     const uint4 *vec;
+    const unsigned long long *vrank;           // per vector: list-order rank of each of its 16 entries (4 bits each)
     const uint32_t *pos_s;
     const uint32_t *rs_loc;                    // shared: stream offsets of my slots [ns + 1]
     const uint32_t *su_loc;                    // shared: gain row of every slot
@@ -264,15 +350,21 @@ struct S8Ctx {                                 // what it takes to look a block 
 };
 
 // Of the entries of my vectors of the blocks blk[0..n) (n <= 4) that hold gain `bs`, the one with the smallest original
-// position.  A vector's entries are in list order (s8_block_sort_kernel), so per vector only its FIRST entry holding
-// `bs` matters: the n vector loads go out together, then n position loads -- two memory latencies for up to four blocks.
+// position.  vrank gives every entry's list-order rank inside its vector, so per vector only the lowest-ranked entry
+// holding `bs` matters: the n vector (and rank word) loads go out together, then n position loads -- two memory
+// latencies for up to four blocks.
 __device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t *blk, int n, float bs, uint32_t &bp,
                                                   uint32_t &bi, int32_t &brow, uint32_t &bbyte) {
     uint4 q[4];
+    unsigned long long rk[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         q[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        if (t < n) q[t] = __ldcg(c.vec + (size_t)blk[t] * kWarp + c.lane);
+        rk[t] = 0ull;
+        if (t < n) {
+            q[t] = __ldcg(c.vec + (size_t)blk[t] * kWarp + c.lane);
+            rk[t] = __ldg(c.vrank + (size_t)blk[t] * kWarp + c.lane);
+        }
     }
     int32_t urow[4];
     int first[4];
@@ -287,14 +379,13 @@ __device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t
             urow[t] = (int32_t)c.su_loc[a];
             const uint32_t words[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
             const uint32_t grow_b = c.gain_b + (uint32_t)urow[t] * (kS8GainStride * 4u);
-            uint32_t eq = 0;
+            uint32_t best_rank = 16u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                eq |= (s8_gather(words[j >> 2], j & 3, grow_b) == bs ? 1u : 0u) << j;      // removed / padding: -inf
-            if (eq) {
-                first[t] = __ffs(eq) - 1;
-                p[t] = __ldg(c.pos_s + ef + c.lane * 16u + (uint32_t)first[t]);
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t r = (uint32_t)(rk[t] >> (4 * j)) & 15u;
+                if (s8_gather(words[j >> 2], j & 3, grow_b) == bs && r < best_rank) { best_rank = r; first[t] = j; }   // removed / padding: -inf
             }
+            if (first[t] >= 0) p[t] = __ldg(c.pos_s + ef + c.lane * 16u + (uint32_t)first[t]);
         }
     }
 #pragma unroll
@@ -341,9 +432,9 @@ __device__ __noinline__ S8Found s8_resolve_all(const S8Ctx *c, float bs, uint32_
     return f;
 }
 
-// THREADS per CTA, DEPTH 16-byte stream loads in flight per thread, staged in registers (RING = false) or in a
-// shared-memory cp.async ring (RING = true).
-template <int THREADS, int DEPTH, bool RING>
+// THREADS per CTA, DEPTH 16-byte stream loads in flight per thread, staged in registers.  (A shared-memory cp.async ring
+// as in mi_persistent.cu was measured too: 8 more shared-memory wavefronts and 5 more instructions per block, 10 % slower.)
+template <int THREADS, int DEPTH>
 __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     extern __shared__ __align__(16) unsigned char s8_smem[];
     const MiState &s = P.s;
@@ -363,8 +454,6 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     const uint32_t gain_b = (smem_b + (uint32_t)P.fixed_bytes + 1023u) & ~1023u;
     float *gain = reinterpret_cast<float *>(s8_smem + (gain_b - smem_b));          // [rows_smem][256]
     uint32_t *cnt = reinterpret_cast<uint32_t *>(gain + (size_t)P.rows_smem * kS8GainStride);   // [rows_smem][256]
-    const uint32_t ring_b = smem_b + (uint32_t)P.ring_offset + threadIdx.x * 16u;  // my 16 bytes of ring slot 0
-    constexpr uint32_t kSlotBytes = THREADS * 16u;
     __shared__ unsigned long long wkey[32];
     __shared__ unsigned long long wpay[32];
     __shared__ uint32_t widx[32];
@@ -415,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
         crow0 = a;
     }
     S8Ctx ctx;
-    ctx.vec = vec; ctx.pos_s = P.pos_s; ctx.rs_loc = rs_loc; ctx.su_loc = su_loc; ctx.gain_b = gain_b; ctx.ns = ns;
+    ctx.vec = vec; ctx.vrank = P.vrank; ctx.pos_s = P.pos_s; ctx.rs_loc = rs_loc; ctx.su_loc = su_loc; ctx.gain_b = gain_b; ctx.ns = ns;
     ctx.lane = lane;
     int32_t prev1 = -1, prev2 = -1;                            // table cell of picks it-1, it-2
     int64_t done = 0;
@@ -464,63 +553,59 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
         float bs = -INFINITY;
         uint32_t bx = 0, bend = 0;
         int ntie = 0;
+        unsigned long long seen = 0ull;                        // gain rows that hold `bs` so far
         {
             int32_t crow = crow0;
             uint32_t seg_end = wb_lo < wb_hi ? rs_loc[crow + 1] / kS8Blk : 0u;      // first block of the next slot
-            uint32_t grow_b = gain_b + su_loc[crow] * (kS8GainStride * 4u);
+            uint32_t cur_u = su_loc[crow];                                          // gain row of the slot (< 64)
+            uint32_t grow_b = gain_b + cur_u * (kS8GainStride * 4u);
             const uint4 *src4 = vec + (size_t)wb_lo * kWarp + lane;
-            uint4 stage[RING ? 1 : DEPTH];
-            if constexpr (RING) {
+            uint4 stage[DEPTH];
 #pragma unroll
-                for (int r = 0; r < DEPTH - 1; ++r) {
-                    if (wb_lo + (uint32_t)r < wb_hi) s8_cp_async16(ring_b + r * kSlotBytes, src4 + (size_t)r * kWarp, stream_pol);
-                    s8_cp_async_commit();
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < DEPTH; ++r)
-                    stage[r] = wb_lo + (uint32_t)r < wb_hi ? s8_ld_stream(src4 + (size_t)r * kWarp, stream_pol)
-                                                           : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            }
-            // take block (blk0 + r) out of the staging area and start the load that re-uses its place; `check`: the
-            // tail of the span, where the load may lie beyond it
+            for (int r = 0; r < DEPTH; ++r)
+                stage[r] = wb_lo + (uint32_t)r < wb_hi ? s8_ld_stream(src4 + (size_t)r * kWarp, stream_pol)
+                                                       : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            // take block (blk0 + r) out of the staging registers and start the load that re-uses its place; `check`:
+            // the tail of the span, where that load may lie beyond it
             auto next_vector = [&](int r, uint32_t blk, bool check) -> uint4 {
-                if constexpr (RING) {
-                    if (!check || blk + (DEPTH - 1) < wb_hi)
-                        s8_cp_async16(ring_b + ((r + DEPTH - 1) % DEPTH) * kSlotBytes, src4 + (size_t)(r + DEPTH - 1) * kWarp,
-                                      stream_pol);
-                    s8_cp_async_commit();
-                    s8_cp_async_wait<DEPTH - 1>();
-                    return s8_lds128(ring_b + r * kSlotBytes);
-                } else {
-                    const uint4 q = stage[r];
-                    if (!check || blk + DEPTH < wb_hi) stage[r] = s8_ld_stream(src4 + (size_t)(DEPTH + r) * kWarp, stream_pol);
-                    return q;
-                }
+                const uint4 q = stage[r];
+                if (!check || blk + DEPTH < wb_hi) stage[r] = s8_ld_stream(src4 + (size_t)(DEPTH + r) * kWarp, stream_pol);
+                return q;
             };
             auto score_block = [&](const uint4 q, const uint32_t blk) {
                 if (blk >= seg_end) {                            // next slot (uniform per warp; slots are not empty)
                     do { ++crow; seg_end = rs_loc[crow + 1] / kS8Blk; } while (blk >= seg_end);
-                    grow_b = gain_b + su_loc[crow] * (kS8GainStride * 4u);
+                    cur_u = su_loc[crow];
+                    grow_b = gain_b + cur_u * (kS8GainStride * 4u);
                 }
-                float g[16];
+                // two halves of eight gathers (the eight results of a half are folded before the next half's addresses are
+                // formed: 16 fewer live registers than sixteen gathers at once, which is what lets DEPTH grow)
+                float m;
+                {
+                    float g[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    g[j] = s8_gather(q.x, j, grow_b);
-                    g[4 + j] = s8_gather(q.y, j, grow_b);
-                    g[8 + j] = s8_gather(q.z, j, grow_b);
-                    g[12 + j] = s8_gather(q.w, j, grow_b);
+                    for (int j = 0; j < 4; ++j) { g[j] = s8_gather(q.x, j, grow_b); g[4 + j] = s8_gather(q.y, j, grow_b); }
+                    m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
                 }
-                float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-                m = fmaxf(m, fmaxf(fmaxf(fmaxf(g[8], g[9]), fmaxf(g[10], g[11])),
-                                   fmaxf(fmaxf(g[12], g[13]), fmaxf(g[14], g[15]))));
+                {
+                    float g[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { g[j] = s8_gather(q.z, j, grow_b); g[4 + j] = s8_gather(q.w, j, grow_b); }
+                    m = fmaxf(m, fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]))));
+                }
                 if (m >= bs) {                                   // rare once the thread has seen a good candidate
                     if (m > bs) {                                // registers only: which block, which segment
-                        bs = m; bx = blk; bend = seg_end; ntie = 0;
-                    } else if (blk >= bend && m > -INFINITY) {   // same gain in a later segment: park the block
-                        if (ntie < kS8TieCap) tie[ntie] = blk;   // (list full: see s8_resolve_all)
-                        ntie = min(ntie + 1, kS8TieCap + 1);
+                        bs = m; bx = blk; bend = seg_end; ntie = 0; seen = 1ull << cur_u;
+                    } else if (blk >= bend && m > -INFINITY) {   // same gain in a later segment
+                        const uint32_t u = cur_u;
                         bend = seg_end;
+                        // a later PIECE of a sub-row that already holds this gain cannot win: its candidates all come
+                        // after those of the earlier piece in the list.  Another sub-row: park the block.
+                        if (!((seen >> u) & 1ull)) {
+                            seen |= 1ull << u;
+                            if (ntie < kS8TieCap) tie[ntie] = blk;   // (list full: see s8_resolve_all)
+                            ntie = min(ntie + 1, kS8TieCap + 1);
+                        }
                     }
                 }
             };
@@ -546,24 +631,19 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                 }
                 src4 += (size_t)DEPTH * kWarp;
             }
-            if constexpr (RING) s8_cp_async_wait<0>();
         }
         const long long t1 = P.dbg ? clock64() : 0;
-        // ---------------- block arg-max ----------------
+        // ---------------- warp arg-max, then block arg-max ----------------
+        // Every warp settles its own best as soon as its span is done (the two memory latencies of that overlap with
+        // the warps still streaming); the block then only compares 32 finished keys.
         const uint32_t my32 = bs > -INFINITY ? orderable(bs) : 0u;
         uint32_t m32 = my32;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
-        if (lane == 0) widx[threadIdx.x / kWarp] = m32;
-        __syncthreads();
-        m32 = lane < kWarps ? widx[lane] : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m32 = max(m32, __shfl_xor_sync(0xffffffffu, m32, o));
-        __syncthreads();                                       // widx is reused below
         unsigned long long key = 0ull, pay = 0ull;
         uint32_t bi = 0xFFFFFFFFu;
         if (my32 != 0u && my32 == m32) {
-            // this thread holds the block-maximum gain: read its recorded blocks again (the gain rows are still staged)
+            // this thread holds the warp's best gain: read its recorded blocks again (the gain rows are still staged)
             // and take the earliest candidate; its count comes from the shared-memory copy
             const S8Found f = s8_resolve_all(&ctx, bs, bx, tie, ntie, wb_hi);
             bi = f.bi;
@@ -721,15 +801,13 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     }
 }
 
-constexpr size_t kS8RingBytesMax = 64 * 1024;           // 1024 threads x 16 bytes x 4 slots (every ring variant)
-
 int s8_slots_for_rows(int32_t rows) { return 2 * rows + 8; }
 size_t s8_fixed_bytes(int32_t k_a, int32_t k_v, int32_t rows) {
     const size_t slots = (size_t)s8_slots_for_rows(rows);
     const size_t words = 2 * (size_t)k_v + kSmallCounts + (size_t)k_a + (slots + 1) + slots + 3 * (size_t)rows;
     return words * 4;
 }
-size_t s8_table_bytes(int32_t k_a, int32_t k_v, int32_t rows) {         // everything in front of the ring
+size_t s8_table_bytes(int32_t k_a, int32_t k_v, int32_t rows) {         // dynamic shared memory of the kernel
     return ((s8_fixed_bytes(k_a, k_v, rows) + 1024 + (size_t)rows * kS8GainStride * 8) + 15) & ~(size_t)15;
 }
 
@@ -743,11 +821,11 @@ int64_t mi_s8_stream_capacity(int64_t w, int32_t k_a, int32_t k_v) {
 }
 int mi_s8_slots_for_rows(int32_t rows) { return s8_slots_for_rows(rows); }
 
-// distinct sub-rows a CTA can stage (gain row + count row each), leaving room for the 64 KiB ring of the ring variants
+// distinct sub-rows a CTA can stage (gain row + count row each)
 int mi_s8_rows_that_fit(int32_t k_a, int32_t k_v) {
     int32_t rows = 0;
-    while (rows < 4096 && s8_table_bytes(k_a, k_v, rows + 1) + kS8RingBytesMax <= kS8SmemBudget) ++rows;
-    return rows;
+    while (rows < 64 && s8_table_bytes(k_a, k_v, rows + 1) <= kS8SmemBudget) ++rows;
+    return rows;                                              // <= 64: the scan keeps a 64-bit set of gain rows
 }
 
 // shape test (the layout of a concrete list can still fail when its sub-rows do not fit: mi_prepare_stream8)
@@ -775,10 +853,10 @@ int launch_mi_s8_count(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_
     return 0;
 }
 
-// second half, once the host has laid the sub-rows out (pieces of every sub-row: row_piece0 / piece_rank0 / piece_off)
+// second half: scatter into the staging layout (row_start: offset of every sub-row there, by sub-row id)
 int launch_mi_s8_scatter(const uint32_t *cells, int64_t w, int32_t k_a, int32_t k_v, const uint32_t *tilehist,
-                         const uint32_t *row_piece0, const uint32_t *piece_rank0, const uint32_t *piece_off,
-                         uint8_t *stream, uint32_t *pos_s, int64_t stream_capacity, cudaStream_t st) {
+                         const uint32_t *row_start, uint8_t *stage_stream, uint32_t *stage_pos, int64_t stream_capacity,
+                         cudaStream_t st) {
     const S8Geom g = s8_geom(k_a, k_v);
     const int ntiles = mi_s8_tiles(w);
     const size_t smem = (size_t)g.k_rows * sizeof(uint32_t);
@@ -789,48 +867,51 @@ int launch_mi_s8_scatter(const uint32_t *cells, int64_t w, int32_t k_a, int32_t 
     }
     // padding entries of every sub-row: the "removed" byte (stream_capacity is a multiple of 16)
     const int64_t n16 = stream_capacity / 16;
-    s8_fill_kernel<<<(unsigned)ceil_div(n16, 256), 256, 0, st>>>(reinterpret_cast<uint4 *>(stream), n16, 0xFFFFFFFFu);
+    s8_fill_kernel<<<(unsigned)ceil_div(n16, 256), 256, 0, st>>>(reinterpret_cast<uint4 *>(stage_stream), n16, 0xFFFFFFFFu);
     ACAV_LAUNCH_CHECK();
-    s8_scatter_kernel<<<ntiles, kS8PartThreads, smem, st>>>(cells, w, g, tilehist, row_piece0, piece_rank0, piece_off,
-                                                            stream, pos_s);
+    s8_scatter_kernel<<<ntiles, kS8PartThreads, smem, st>>>(cells, w, g, tilehist, row_start, stage_stream, stage_pos);
     ACAV_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_mi_s8_block_sort(uint8_t *stream, uint32_t *pos_s, int64_t w_padded, cudaStream_t st) {
+// third step: every block of the stream is fetched from its place in the staging layout, sorted, and arranged
+int launch_mi_s8_block_arrange(const uint8_t *stage_stream, const uint32_t *stage_pos, const uint32_t *blk_src,
+                               uint8_t *stream, uint32_t *pos_s, unsigned long long *vrank, int64_t w_padded,
+                               cudaStream_t st) {
     const int64_t n_blocks = w_padded / kS8Blk;
     if (n_blocks == 0) return 0;
     const unsigned grid = (unsigned)(n_blocks < 65535 * 16 ? n_blocks : 65535 * 16);
-    s8_block_sort_kernel<<<grid, kS8Blk, 0, st>>>(stream, pos_s, n_blocks);
+    s8_block_sort_kernel<<<grid, kS8Blk, 0, st>>>(stage_stream, stage_pos, blk_src, stream, pos_s, n_blocks);
+    ACAV_LAUNCH_CHECK();
+    const int64_t ctas = ceil_div(n_blocks, (int64_t)kS8ArrangeWarps);
+    s8_block_arrange_kernel<<<(unsigned)(ctas < 148 * 40 ? ctas : 148 * 40), kS8ArrangeWarps * kWarp, 0, st>>>(
+        stream, pos_s, vrank, n_blocks);
     ACAV_LAUNCH_CHECK();
     return 0;
 }
 
-template <int THREADS, int DEPTH, bool RING>
-static int launch_s8_variant(MiS8 &P, size_t table_bytes, int32_t grid, cudaStream_t st) {
+template <int THREADS, int DEPTH>
+static int launch_s8_variant(MiS8 &P, size_t smem, int32_t grid, cudaStream_t st) {
     static size_t attr_done[kMaxDevices];
-    const size_t smem = table_bytes + (RING ? (size_t)DEPTH * THREADS * 16 : 0);
-    P.ring_offset = (int32_t)table_bytes;
-    { int rc = ensure_dynamic_smem(mi_stream8_kernel<THREADS, DEPTH, RING>, smem, attr_done); if (rc) return rc; }
+    { int rc = ensure_dynamic_smem(mi_stream8_kernel<THREADS, DEPTH>, smem, attr_done); if (rc) return rc; }
     void *args[] = {&P};
-    ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_stream8_kernel<THREADS, DEPTH, RING>, dim3(grid), dim3(THREADS),
-                                              args, smem, st));
+    ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_stream8_kernel<THREADS, DEPTH>, dim3(grid), dim3(THREADS), args,
+                                              smem, st));
     return 0;
 }
 
 int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const uint32_t *pos_s,
-                      const uint32_t *slot_start, const uint32_t *slot_row, const uint32_t *slot_u, const void *chunks,
+                      const unsigned long long *vrank, const uint32_t *slot_start, const uint32_t *slot_row, const uint32_t *slot_u, const void *chunks,
                       int32_t grid, void *pub, unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain,
                       int32_t rows_smem, int32_t variant, int32_t world, int32_t rank, unsigned int seq_base,
                       void *mail_local, void *const *mail_peer, long long *dbg, int *status,
                       unsigned long long spin_limit_ns, cudaStream_t st) {
     MiS8 P;
-    P.s = s; P.n_alt = n_alt; P.stream = stream; P.pos_s = pos_s; P.slot_start = slot_start; P.slot_row = slot_row;
+    P.s = s; P.n_alt = n_alt; P.stream = stream; P.pos_s = pos_s; P.vrank = vrank; P.slot_start = slot_start; P.slot_row = slot_row;
     P.slot_u = slot_u; P.chunks = reinterpret_cast<const S8Chunk *>(chunks);
     P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks; P.out_pos = out_pos; P.out_gain = out_gain;
     P.g = s8_geom(s.k_a, s.k_v); P.rows_smem = rows_smem; P.slots_smem = s8_slots_for_rows(rows_smem);
     P.fixed_bytes = (int32_t)s8_fixed_bytes(s.k_a, s.k_v, rows_smem);
-    P.ring_offset = 0;
     P.world = world; P.rank = rank; P.seq_base = seq_base;
     P.mail_local = reinterpret_cast<MiMail *>(mail_local);
     for (int r = 0; r < kMaxWorld; ++r)
@@ -842,14 +923,13 @@ int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const 
     ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
     ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
-    switch (variant) {
-        case 1: return launch_s8_variant<512, 8, false>(P, table_bytes, grid, st);
-        case 2: return launch_s8_variant<768, 4, false>(P, table_bytes, grid, st);
-        case 3: return launch_s8_variant<1024, 2, false>(P, table_bytes, grid, st);
-        case 4: return launch_s8_variant<512, 4, false>(P, table_bytes, grid, st);
-        case 5: return launch_s8_variant<1024, 3, true>(P, table_bytes, grid, st);
-        case 6: return launch_s8_variant<768, 3, false>(P, table_bytes, grid, st);
-        default: return launch_s8_variant<1024, 4, true>(P, table_bytes, grid, st);
+    switch (variant) {                             // measured at W = 1e8, K = 1024: 32.7 / 37.9 / 33.9 / 33.0 / 38.2 / 33.0 us
+        case 1: return launch_s8_variant<512, 8>(P, table_bytes, grid, st);
+        case 2: return launch_s8_variant<768, 4>(P, table_bytes, grid, st);
+        case 3: return launch_s8_variant<1024, 2>(P, table_bytes, grid, st);
+        case 4: return launch_s8_variant<512, 4>(P, table_bytes, grid, st);
+        case 5: return launch_s8_variant<1024, 4>(P, table_bytes, grid, st);
+        default: return launch_s8_variant<1024, 3>(P, table_bytes, grid, st);
     }
 }
 

@@ -233,13 +233,24 @@ class EfficientMemMI:
             return _lib.MI_LOOP_CELLS
         if self.loop in ('bytes', _lib.MI_LOOP_BYTES):
             return _lib.MI_LOOP_BYTES
-        # "auto": the persistent row-partitioned kernel whenever one of its gain rows fits in shared memory
-        # (K <= 8140 for a square table), else the cell index (K <= 16384), else three kernels per iteration
+        # "auto": the cheapest exact loop for this shape, by the measured cost per iteration on B200
+        #   cell index    ~ 8.5 us * (K / 1024)^2       (scans the K_a x K_v cells)
+        #   byte stream   ~ 12 us + 0.21 ns * W_local   (one byte per remaining candidate)
+        #   2-byte stream ~ 12 us + 0.34 ns * W_local
+        # then whatever else the shape supports; a layout that cannot be built for the concrete list (ACAV_E_UNSUPPORTED
+        # from acav_mi_prepare) moves on to the next one (select()).
+        return self._auto_order()[getattr(self, "_auto_skip", 0)]
+
+    def _auto_order(self):
         C = self.ncentroids
-        for mode in (_lib.MI_LOOP_PERSISTENT, _lib.MI_LOOP_CELLS):
-            if _lib.load().acav_mi_loop_supported(C, C, mode):
-                return mode
-        return _lib.MI_LOOP_KERNELS
+        world = self.shard[1] if self.shard is not None else 1
+        w_local = max(self._W // world, 1)
+        cost = {_lib.MI_LOOP_CELLS: 8.5 * (C / 1024.0) ** 2,
+                _lib.MI_LOOP_BYTES: 12.0 + 0.21e-3 * w_local,
+                _lib.MI_LOOP_PERSISTENT: 12.0 + 0.34e-3 * w_local}
+        lib = _lib.load()
+        order = [m for m in sorted(cost, key=cost.get) if lib.acav_mi_loop_supported(C, C, m)]
+        return order + [_lib.MI_LOOP_KERNELS]
 
     def check_status(self):
         """Raise if the last persistent launch gave up waiting for a peer GPU (synchronises the stream)."""
@@ -272,9 +283,28 @@ class EfficientMemMI:
                         err = None
                     except _lib.AcavError as e:
                         err = e
-                    if not self._all_ranks_ok(err is None):
-                        raise RuntimeError("greedy-MI setup failed on %s rank: %s"
-                                           % ("this" if err else "another", err))
+                    while not self._all_ranks_ok(err is None):
+                        # "auto": every rank moves on to the next loop together; a named loop fails loudly
+                        if self.loop != 'auto' or self._loop_mode() == _lib.MI_LOOP_KERNELS:
+                            raise RuntimeError("greedy-MI setup failed on %s rank: %s"
+                                               % ("this" if err else "another", err))
+                        self._auto_skip = getattr(self, "_auto_skip", 0) + 1
+                        try:
+                            _lib.call("acav_mi_prepare", self._engine, self._loop_mode(), st)
+                            err = None
+                        except _lib.AcavError as e:
+                            err = e
+                    self._ready_mode = self._loop_mode()
+                if self._dist is None and self.loop == 'auto' and getattr(self, "_ready_mode", None) is None:
+                    # one GPU: build the layout of the chosen loop now; if this list does not fit it, take the next loop
+                    while True:
+                        try:
+                            _lib.call("acav_mi_prepare", self._engine, self._loop_mode(), st)
+                            break
+                        except _lib.AcavError as e:
+                            if e.status != _lib.E_UNSUPPORTED or self._loop_mode() == _lib.MI_LOOP_KERNELS:
+                                raise
+                            self._auto_skip = getattr(self, "_auto_skip", 0) + 1
                     self._ready_mode = self._loop_mode()
                 _lib.call("acav_mi_run", self._engine, n_picks, _lib.ptr(pos), _lib.ptr(gain),
                           self._loop_mode(), st)

@@ -264,10 +264,9 @@ int acav_mi_comm_connect(acav_mi_t *h, const void *handles);
  * {per-iteration prologue, winner hand-over of the previous iteration}.  NULL switches it off (default). */
 int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles);
 
-/* Tuning of ACAV_MI_LOOP_BYTES (benchmarking): variant 0..6 = (threads per CTA, 16-byte loads in flight per thread)
- * (1024,4 ring) (512,8) (768,4) (1024,2) (512,4) (1024,3 ring) (768,3) -- `ring`: staged through a shared-memory
- * cp.async ring instead of registers; use_cache is ignored (the table counts of a CTA's
- * sub-rows always live in its shared memory).  Also settable through the environment (ACAV_MI_S8_VARIANT) before
+/* Tuning of ACAV_MI_LOOP_BYTES (benchmarking): variant 0..5 = (threads per CTA, 16-byte loads in flight per thread)
+ * (1024,3) (512,8) (768,4) (1024,2) (512,4) (1024,4); use_cache is ignored (the table counts of a CTA's sub-rows
+ * always live in its shared memory).  Also settable through the environment (ACAV_MI_S8_VARIANT) before
  * acav_mi_create. */
 int acav_mi_set_stream_variant(acav_mi_t *h, int32_t variant, int32_t use_cache);
 

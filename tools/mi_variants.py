@@ -21,10 +21,9 @@ sm = torch.cuda.get_device_properties(0).multi_processor_count
 ref = None
 
 CONFIGS = [("persistent", None, None, None), ("cells", None, None, None)]
-for variant in (0, 1, 2, 3, 4, 5, 6):
+for variant in (0, 1, 2, 3, 4, 5):
     CONFIGS.append(("bytes", variant, 1, None))
-# row cost of the chunk cut, in 512-candidate blocks per sub-row touched (default 3)
-CONFIGS += [("bytes", 4, 1, 1), ("bytes", 4, 1, 8), ("bytes", 1, 1, 1), ("bytes", 1, 1, 8)]
+
 
 
 def timers(m, names=("gain rows", "scan", "reduce+publish", "barrier wait")):
