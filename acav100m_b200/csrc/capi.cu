@@ -31,6 +31,9 @@ struct acav_kmeans {
     float *lr_eff;
     bool partition_valid;
     int64_t partition_rows;
+    // side stream for the independent kernels of a step (ACAV_KM_NOFORK=1: everything on the caller's stream)
+    KmFork fork;
+    bool fork_ok;
 };
 
 struct acav_kmeans_comm {
@@ -481,6 +484,9 @@ int acav_kmeans_destroy(acav_kmeans_t *h) {
     cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
     cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial);
     cudaFree(h->cand_rows); cudaFree(h->cand_ids); cudaFree(h->full_rows); cudaFree(h->counters);
+    if (h->fork.side) cudaStreamDestroy(h->fork.side);
+    if (h->fork.ev_fork) cudaEventDestroy(h->fork.ev_fork);
+    if (h->fork.ev_join) cudaEventDestroy(h->fork.ev_join);
     delete h;
     return 0;
 }
@@ -493,6 +499,14 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!h) return (int)cudaErrorMemoryAllocation;
     h->k = k; h->d = d; h->max_batch = max_batch; h->bytes = 0;
     h->partition_valid = false; h->partition_rows = 0;
+    h->fork.side = nullptr; h->fork.ev_fork = nullptr; h->fork.ev_join = nullptr; h->fork_ok = false;
+    {
+        const char *e = std::getenv("ACAV_KM_NOFORK");
+        if (!(e && e[0] == '1') && cudaStreamCreateWithFlags(&h->fork.side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->fork.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->fork.ev_join, cudaEventDisableTiming) == cudaSuccess)
+            h->fork_ok = true;
+    }
     int rc = query_sm_count(&h->sm_count);
     const int64_t nblk = ceil_div(max_batch, 512);
     if (!rc) rc = dev_alloc(&h->xn, (size_t)max_batch, &h->bytes);
@@ -563,8 +577,17 @@ int acav_kmeans_assign(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
         return rc;
     }
     if (mode != ACAV_ASSIGN_TENSOR) return ACAV_E_INVALID;
-    int rc = acav_kmeans_prepare_centers(h, centers, counts, underused_threshold, reinit_r, stream);
-    if (!rc) rc = acav_kmeans_prepare_batch(h, x, b, ldx, stream);
+    // the bf16 copy of the batch and the preparation of the centroids do not depend on each other
+    int rc = 0;
+    if (h->fork_ok) {
+        rc = km_fork(&h->fork, st);
+        if (!rc) rc = acav_kmeans_prepare_batch(h, x, b, ldx, h->fork.side);
+        if (!rc) rc = acav_kmeans_prepare_centers(h, centers, counts, underused_threshold, reinit_r, stream);
+        if (!rc) rc = km_join(&h->fork, st);
+    } else {
+        rc = acav_kmeans_prepare_centers(h, centers, counts, underused_threshold, reinit_r, stream);
+        if (!rc) rc = acav_kmeans_prepare_batch(h, x, b, ldx, stream);
+    }
     if (!rc) rc = acav_kmeans_assign_prepared(h, x, b, ldx, centers, counts, underused_threshold, reinit_r, best,
                                               min_dist, mean_dist, n_refined, stream);
     return rc;
@@ -606,10 +629,15 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
     float *mind = min_dist ? min_dist : h->mind;
     if (!rc) rc = launch_merge_classify(h->partial, (int32_t)b, n_split, h->xn, h->cparams, h->cn, h->k, best, mind, h->cand_rows,
                                         h->cand_ids, h->full_rows, h->counters, st);
+    // rows with a short candidate list and rows that need all K centroids are disjoint: both re-checks side by side
+    const bool fk = h->fork_ok && !rc;
+    if (fk) rc = km_fork(&h->fork, st);
     if (!rc) rc = launch_candidate_refine(x, ldx, h->d, centers, h->xn, h->cn, counts, underused_threshold, reinit_r,
-                                          h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind, st);
+                                          h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind,
+                                          fk ? h->fork.side : st);
     if (!rc) rc = launch_assign_exact(x, ldx, h->full_rows, b, h->counters + 1, centers, h->k, h->d, h->xn, h->cn,
                                       counts, underused_threshold, reinit_r, best, mind, h->packed, h->sm_count, st);
+    if (fk && !rc) rc = km_join(&h->fork, st);
     // exact distance to the assigned centroid, only when the caller wants distances back
     if (!rc && (min_dist || mean_dist))
         rc = launch_exact_min_dist(x, b, h->d, ldx, centers, best, h->xn, h->cn, counts, underused_threshold,
@@ -646,7 +674,7 @@ static int update_common(acav_kmeans_t *h, const float *x, int64_t b, int64_t ld
     if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
     int rc = launch_effective_lr(counts_b, h->k, lr, h->lr_eff, fallback, st);
     if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, counts_b, h->lr_eff, centers,
-                                counts, deltas, nullptr, false, st);
+                                counts, deltas, nullptr, false, st, h->fork_ok ? &h->fork : nullptr);
     h->partition_valid = false;
     return rc;
 }
@@ -786,7 +814,7 @@ int acav_kmeans_update_p2p(acav_kmeans_t *h, acav_kmeans_comm_t *comm, const flo
     int rc = launch_km_hist_exchange(comm->c, counts_b_local, lr, comm->counts_global, comm->lr_eff, fallback, counts, st);
     const KmPush push = km_comm_push_target(comm->c);
     if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, comm->counts_global, comm->lr_eff,
-                                centers, counts, nullptr, &push, false, st);
+                                centers, counts, nullptr, &push, false, st, h->fork_ok ? &h->fork : nullptr);
     if (!rc) rc = launch_km_reduce_broadcast(comm->c, comm->counts_global, comm->lr_eff, centers, st);
     h->partition_valid = false;
     return rc;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace acav {
 
 // kmeans_exact.cu
@@ -58,9 +60,25 @@ struct KmPush {                  // where the deltas of a multi-GPU step go: rec
         return red[o] + ((int64_t)rank * k_own + (c - o * k_own)) * d;
     }
 };
+// Side stream of a workspace: independent kernels of a step run next to each other (fork = the side stream waits for
+// an event of the main stream, join = the other way round; both are capturable into a CUDA graph).
+struct KmFork {
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
+};
+inline int km_fork(const KmFork *f, cudaStream_t st) {
+    ACAV_CUDA_TRY(cudaEventRecord(f->ev_fork, st));
+    ACAV_CUDA_TRY(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+    return 0;
+}
+inline int km_join(const KmFork *f, cudaStream_t st) {
+    ACAV_CUDA_TRY(cudaEventRecord(f->ev_join, f->side));
+    ACAV_CUDA_TRY(cudaStreamWaitEvent(st, f->ev_join, 0));
+    return 0;
+}
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st);
+                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st, const KmFork *fork = nullptr);
 int launch_sequential_lr(double lr, float *lr_eff, cudaStream_t st);
 
 // kmeans_comm.cu: the multi-GPU step over NVLink peer memory (no NCCL): histogram exchange + lr decision, and the

@@ -546,7 +546,8 @@ int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_e
 
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st) {
+                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st,
+                  const KmFork *fork) {
     const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     if (push && !vec4) return ACAV_E_UNSUPPORTED;
@@ -569,6 +570,7 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
         return 0;
     }
     KmPush pz = push ? *push : KmPush();
+    bool forked = false;
     if (vec4) {
         // heavy centroids (>= kUpdHeavyRows rows of this batch): cp.async ring kernel; its blocks for light
         // centroids exit at once, and km_update_kernel below skips the heavy ones
@@ -589,16 +591,20 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
             { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdSplit>, bsmem, bdone[1]); if (rc) return rc; }
             { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdPush>, bsmem, bdone[2]); if (rc) return rc; }
             dim3 bgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kBulkCols));     // loops over the heavy list
+            // heavy and light centroids are disjoint rows of centers / counts / deltas: the two kernels run side by side
+            cudaStream_t bst = st;
+            if (fork) { int rc = km_fork(fork, st); if (rc) return rc; bst = fork->side; }
             if (push)
-                km_update_bulk_kernel<kUpdPush><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                km_update_bulk_kernel<kUpdPush><<<bgrid, kBulkThreads, bsmem, bst>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                          centers, counts, nullptr, pz);
             else if (deltas)
-                km_update_bulk_kernel<kUpdSplit><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                km_update_bulk_kernel<kUpdSplit><<<bgrid, kBulkThreads, bsmem, bst>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                           centers, counts, deltas, pz);
             else
-                km_update_bulk_kernel<kUpdFused><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
+                km_update_bulk_kernel<kUpdFused><<<bgrid, kBulkThreads, bsmem, bst>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
                                                                           centers, counts, nullptr, pz);
             ACAV_LAUNCH_CHECK();
+            forked = fork != nullptr;
         }
         dim3 sgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kUpdThreads * 4));   // loops over the heavy list
         if (!use_ring) {
@@ -628,6 +634,7 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
             km_update_kernel<1, kUpdFused><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
     }
     ACAV_LAUNCH_CHECK();
+    if (forked) return km_join(fork, st);
     return 0;
 }
 

@@ -21,12 +21,50 @@ struct MiPub {                       // one per CTA and iteration parity: the CT
     unsigned long long payload;      // (c1 << 48) | (c2 << 32) | table count x of that cell
 };
 
-struct MiMail {                      // one per (parity, source rank), written by peers over NVLink
-    unsigned long long key;
-    unsigned long long payload;
-    unsigned int seq;                // iteration tag, stored last with release semantics
-    unsigned int pad[3];
+// One per (parity, source rank), written by peers over NVLink.  The 128 bits of (key, payload) travel in three 64-bit
+// words that each carry the low 16 bits of the iteration tag on top: a word is valid when its tag is the expected one
+// (8-byte accesses are single-copy atomic), so the sender needs NO release fence -- three plain stores, one NVLink
+// one-way latency -- and the receiver no acquire.  (Round 1 stored key, payload and then a flag with st.release.sys: the
+// fence waits for the two payload stores to be acknowledged across the link before the flag may leave, ~2 us per
+// iteration.)  A slot is rewritten every second iteration, so a stale word is two tags behind, never 65536.
+struct MiMail {
+    unsigned long long w[3];
+    unsigned long long pad;
 };
+
+__device__ __forceinline__ void mail_store(MiMail *m, unsigned long long key, unsigned long long pay, unsigned int tag) {
+    const unsigned long long t = (unsigned long long)(tag & 0xFFFFu) << 48;
+    const unsigned long long w0 = t | (key & 0xFFFFFFFFFFFFull);
+    const unsigned long long w1 = t | (key >> 48) | ((pay & 0xFFFFFFFFull) << 16);
+    const unsigned long long w2 = t | (pay >> 32);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&m->w[0]), "l"(w0) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&m->w[1]), "l"(w1) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(&m->w[2]), "l"(w2) : "memory");
+}
+
+// Bounded wait for a peer's entry of this iteration (see wait_peer_tag in common.cuh for why bounded).
+__device__ __forceinline__ bool mail_wait(const MiMail *m, unsigned int tag, unsigned long long limit_ns,
+                                          unsigned long long &key, unsigned long long &pay) {
+    const unsigned long long want = (unsigned long long)(tag & 0xFFFFu);
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        unsigned long long w0, w1, w2;
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w0) : "l"(&m->w[0]) : "memory");
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w1) : "l"(&m->w[1]) : "memory");
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w2) : "l"(&m->w[2]) : "memory");
+        if ((w0 >> 48) == want && (w1 >> 48) == want && (w2 >> 48) == want) {
+            key = (w0 & 0xFFFFFFFFFFFFull) | ((w1 & 0xFFFFull) << 48);
+            pay = ((w1 >> 16) & 0xFFFFFFFFull) | ((w2 & 0xFFFFFFFFull) << 32);
+            return true;
+        }
+        if ((++spins & 1023u) == 0u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > limit_ns) return false;
+        }
+    }
+}
 
 constexpr int kMaxWorld = 16;
 

@@ -570,17 +570,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) mi_persistent_kernel(MiPer
                     k2 = __shfl_sync(0xffffffffu, k2, 0);
                     p2 = __shfl_sync(0xffffffffu, p2, 0);
                     if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
-                        MiMail *m = P.mail_peer[threadIdx.x] + (size_t)cur * P.world + P.rank;
-                        m->key = k2; m->payload = p2;
-                        st_release_sys(&m->seq, tag);
+                        mail_store(P.mail_peer[threadIdx.x] + (size_t)cur * P.world + P.rank, k2, p2, tag);
                     }
                     unsigned long long gk = 0ull, gp = 0ull;
                     bool timed_out = false;
                     if ((int)threadIdx.x < P.world) {
-                        const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
-                        timed_out = !wait_peer_tag(&m->seq, tag, P.spin_limit_ns);
-                        gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
-                        gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
+                        timed_out = !mail_wait(P.mail_local + (size_t)cur * P.world + threadIdx.x, tag, P.spin_limit_ns, gk, gp);
                     }
                     if (__any_sync(0xffffffffu, timed_out)) {      // a peer never delivered: stop here, say why
                         gk = 0ull; gp = 0ull;

@@ -258,7 +258,7 @@ s8_block_arrange_kernel(uint8_t *__restrict__ stream, uint32_t *__restrict__ pos
                 int rank = 0;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) rank += (ps[k] < ps[j] || (ps[k] == ps[j] && k < j)) ? 1 : 0;   // padding: arbitrary
-                word |= (unsigned long long)rank << (4 * j);
+                word |= (unsigned long long)j << (4 * rank);           // entry index by list-order rank
                 w4[j >> 2] |= sl[j] << (8 * (j & 3));
             }
             *reinterpret_cast<uint4 *>(stream + base + lane * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
@@ -349,11 +349,14 @@ struct S8Ctx {                                 // what it takes to look a block 
     uint32_t lane;
 };
 
-// Of the entries of my vectors of the blocks blk[0..n) (n <= 4) that hold gain `bs`, the one with the smallest original
-// position.  vrank gives every entry's list-order rank inside its vector, so per vector only the lowest-ranked entry
-// holding `bs` matters: the n vector (and rank word) loads go out together, then n position loads -- two memory
+// A recorded block: block index in the low 26 bits, its gain row (sub-row of the CTA, < 64) above.
+constexpr uint32_t kS8BlkMask = (1u << 26) - 1u;
+
+// Of the entries of my vectors of the recorded blocks rec[0..n) (n <= 4) that hold gain `bs`, the one with the smallest
+// original position.  vrank lists the entries of a vector in list order (16 x 4-bit indices), so per vector only the first
+// listed entry holding `bs` matters: the n vector (and rank word) loads go out together, then n position loads -- two memory
 // latencies for up to four blocks.
-__device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t *blk, int n, float bs, uint32_t &bp,
+__device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t *rec, int n, float bs, uint32_t &bp,
                                                   uint32_t &bi, int32_t &brow, uint32_t &bbyte) {
     uint4 q[4];
     unsigned long long rk[4];
@@ -362,30 +365,34 @@ __device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t
         q[t] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         rk[t] = 0ull;
         if (t < n) {
-            q[t] = __ldcg(c.vec + (size_t)blk[t] * kWarp + c.lane);
-            rk[t] = __ldg(c.vrank + (size_t)blk[t] * kWarp + c.lane);
+            const size_t vi = (size_t)(rec[t] & kS8BlkMask) * kWarp + c.lane;
+            q[t] = __ldcg(c.vec + vi);
+            rk[t] = __ldg(c.vrank + vi);
         }
     }
-    int32_t urow[4];
     int first[4];
     uint32_t p[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        urow[t] = 0; first[t] = -1; p[t] = 0xFFFFFFFFu;
+        first[t] = -1; p[t] = 0xFFFFFFFFu;
         if (t < n) {
-            const uint32_t ef = blk[t] * kS8Blk;
-            int32_t a = 0, b = c.ns;
-            while (a < b) { const int32_t m = (a + b) >> 1; if (c.rs_loc[m + 1] > ef) b = m; else a = m + 1; }
-            urow[t] = (int32_t)c.su_loc[a];
             const uint32_t words[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
-            const uint32_t grow_b = c.gain_b + (uint32_t)urow[t] * (kS8GainStride * 4u);
-            uint32_t best_rank = 16u;
+            const uint32_t grow_b = c.gain_b + (rec[t] >> 26) * (kS8GainStride * 4u);
+            uint32_t eq = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t r = (uint32_t)(rk[t] >> (4 * j)) & 15u;
-                if (s8_gather(words[j >> 2], j & 3, grow_b) == bs && r < best_rank) { best_rank = r; first[t] = j; }   // removed / padding: -inf
+            for (int j = 0; j < 16; ++j)
+                eq |= (s8_gather(words[j >> 2], j & 3, grow_b) == bs ? 1u : 0u) << j;      // removed / padding: -inf
+            if (eq) {
+                first[t] = __ffs(eq) - 1;
+                if (eq & (eq - 1u)) {                          // several entries hold it: the first one in list order
+                    unsigned long long w = rk[t];                 // entry indices by list-order rank, 4 bits each
+                    for (int r = 0; r < 16; ++r, w >>= 4) {
+                        const int j = (int)(w & 15ull);
+                        if ((eq >> j) & 1u) { first[t] = j; break; }
+                    }
+                }
+                p[t] = __ldg(c.pos_s + (size_t)(rec[t] & kS8BlkMask) * kS8Blk + c.lane * 16u + (uint32_t)first[t]);
             }
-            if (first[t] >= 0) p[t] = __ldg(c.pos_s + ef + c.lane * 16u + (uint32_t)first[t]);
         }
     }
 #pragma unroll
@@ -393,7 +400,7 @@ __device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t
         if (p[t] < bp) {
             const uint32_t words[4] = {q[t].x, q[t].y, q[t].z, q[t].w};
             const int j = first[t];
-            bp = p[t]; bi = blk[t] * kS8Blk + c.lane * 16u + (uint32_t)j; brow = urow[t];
+            bp = p[t]; bi = (rec[t] & kS8BlkMask) * kS8Blk + c.lane * 16u + (uint32_t)j; brow = (int32_t)(rec[t] >> 26);
             bbyte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
         }
     }
@@ -413,19 +420,26 @@ struct S8Found {
 __device__ __noinline__ S8Found s8_resolve_all(const S8Ctx *c, float bs, uint32_t bx, const uint32_t *tie, int ntie,
                                                uint32_t span_hi) {
     S8Found f;
-    f.bp = 0xFFFFFFFFu; f.bi = bx * kS8Blk; f.brow = 0; f.bbyte = 0;
+    f.bp = 0xFFFFFFFFu; f.bi = (bx & kS8BlkMask) * kS8Blk; f.brow = 0; f.bbyte = 0;
     const int nt = ntie > kS8TieCap ? kS8TieCap : ntie;
-    uint32_t extra = ntie > kS8TieCap ? tie[kS8TieCap - 1] + 1u : span_hi;      // overflow: blocks [extra, span_hi) too
-    uint32_t blk[4];
-    blk[0] = bx; blk[1] = blk[2] = blk[3] = bx;
+    uint32_t extra = ntie > kS8TieCap ? (tie[kS8TieCap - 1] & kS8BlkMask) + 1u : span_hi;   // overflow: blocks [extra, span_hi) too
+    uint32_t rec[4];
+    rec[0] = bx; rec[1] = rec[2] = rec[3] = bx;
     int n = 1, t = 0;
     for (;;) {
         while (n < 4 && (t < nt || extra < span_hi)) {
-            const uint32_t v = t < nt ? tie[t++] : extra++;
-            if (n == 0) blk[0] = v; else if (n == 1) blk[1] = v; else if (n == 2) blk[2] = v; else blk[3] = v;
+            uint32_t v;
+            if (t < nt) v = tie[t++];
+            else {                                             // a block nobody recorded: look its gain row up
+                const uint32_t ef = extra * kS8Blk;
+                int32_t a = 0, b = c->ns;
+                while (a < b) { const int32_t m = (a + b) >> 1; if (c->rs_loc[m + 1] > ef) b = m; else a = m + 1; }
+                v = extra++ | (c->su_loc[a] << 26);
+            }
+            if (n == 0) rec[0] = v; else if (n == 1) rec[1] = v; else if (n == 2) rec[2] = v; else rec[3] = v;
             ++n;
         }
-        s8_resolve_blocks(*c, blk, n, bs, f.bp, f.bi, f.brow, f.bbyte);
+        s8_resolve_blocks(*c, rec, n, bs, f.bp, f.bi, f.brow, f.bbyte);
         if (t >= nt && extra >= span_hi) break;
         n = 0;
     }
@@ -594,8 +608,8 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                     m = fmaxf(m, fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7]))));
                 }
                 if (m >= bs) {                                   // rare once the thread has seen a good candidate
-                    if (m > bs) {                                // registers only: which block, which segment
-                        bs = m; bx = blk; bend = seg_end; ntie = 0; seen = 1ull << cur_u;
+                    if (m > bs) {                                // registers only: which block (and its gain row)
+                        bs = m; bx = blk | (cur_u << 26); bend = seg_end; ntie = 0; seen = 1ull << cur_u;
                     } else if (blk >= bend && m > -INFINITY) {   // same gain in a later segment
                         const uint32_t u = cur_u;
                         bend = seg_end;
@@ -603,9 +617,9 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                         // after those of the earlier piece in the list.  Another sub-row: park the block.
                         if (!((seen >> u) & 1ull)) {
                             seen |= 1ull << u;
-                            if (ntie < kS8TieCap) tie[ntie] = blk;   // (list full: see s8_resolve_all)
+                            if (ntie < kS8TieCap) tie[ntie] = blk | (u << 26);   // (list full: see s8_resolve_all)
                             ntie = min(ntie + 1, kS8TieCap + 1);
-                        }
+                            }
                     }
                 }
             };
@@ -633,6 +647,7 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
             }
         }
         const long long t1 = P.dbg ? clock64() : 0;
+        if (P.dbg && lane == 0) P.dbg[8 * (long long)grid + 64 * blockIdx.x + threadIdx.x / kWarp] = t1 - t0;   // my warp's scan end
         // ---------------- warp arg-max, then block arg-max ----------------
         // Every warp settles its own best as soon as its span is done (the two memory latencies of that overlap with
         // the warps still streaming); the block then only compares 32 finished keys.
@@ -664,6 +679,7 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                 if (ok > k2) { k2 = ok; p2 = op; i2 = oi; }
             }
             if (lane == 0) { wkey[threadIdx.x / kWarp] = k2; wpay[threadIdx.x / kWarp] = p2; widx[threadIdx.x / kWarp] = i2; }
+            if (P.dbg && lane == 0) P.dbg[8 * (long long)grid + 64 * blockIdx.x + 32 + threadIdx.x / kWarp] = clock64() - t0;   // settled
             __syncthreads();
             if (threadIdx.x < kWarp) {
                 const bool live = (int)threadIdx.x < kWarps;
@@ -725,17 +741,12 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                     k2 = __shfl_sync(0xffffffffu, k2, 0);
                     p2 = __shfl_sync(0xffffffffu, p2, 0);
                     if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
-                        MiMail *m = P.mail_peer[threadIdx.x] + (size_t)cur * P.world + P.rank;
-                        m->key = k2; m->payload = p2;
-                        st_release_sys(&m->seq, tag);
+                        mail_store(P.mail_peer[threadIdx.x] + (size_t)cur * P.world + P.rank, k2, p2, tag);
                     }
                     unsigned long long gk = 0ull, gp = 0ull;
                     bool timed_out = false;
                     if ((int)threadIdx.x < P.world) {
-                        const MiMail *m = P.mail_local + (size_t)cur * P.world + threadIdx.x;
-                        timed_out = !wait_peer_tag(&m->seq, tag, P.spin_limit_ns);
-                        gk = *reinterpret_cast<const volatile unsigned long long *>(&m->key);
-                        gp = *reinterpret_cast<const volatile unsigned long long *>(&m->payload);
+                        timed_out = !mail_wait(P.mail_local + (size_t)cur * P.world + threadIdx.x, tag, P.spin_limit_ns, gk, gp);
                     }
                     if (__any_sync(0xffffffffu, timed_out)) {      // a peer never delivered: stop here, say why
                         gk = 0ull; gp = 0ull;

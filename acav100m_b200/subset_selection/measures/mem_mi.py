@@ -234,9 +234,9 @@ class EfficientMemMI:
         if self.loop in ('bytes', _lib.MI_LOOP_BYTES):
             return _lib.MI_LOOP_BYTES
         # "auto": the cheapest exact loop for this shape, by the measured cost per iteration on B200
-        #   cell index    ~ 8.5 us * (K / 1024)^2       (scans the K_a x K_v cells)
-        #   byte stream   ~ 12 us + 0.21 ns * W_local   (one byte per remaining candidate)
-        #   2-byte stream ~ 12 us + 0.34 ns * W_local
+        #   cell index    ~ 8.8 us * (K / 1024)^2         (scans the K_a x K_v cells)
+        #   byte stream   ~ 14.5 us + 0.18 ns * W_local   (one byte per remaining candidate)
+        #   2-byte stream ~ 14.5 us + 0.43 ns * W_local   (both measured 4000 picks into a run, W_local = 1.25e7 and 1e8)
         # then whatever else the shape supports; a layout that cannot be built for the concrete list (ACAV_E_UNSUPPORTED
         # from acav_mi_prepare) moves on to the next one (select()).
         return self._auto_order()[getattr(self, "_auto_skip", 0)]
@@ -245,9 +245,9 @@ class EfficientMemMI:
         C = self.ncentroids
         world = self.shard[1] if self.shard is not None else 1
         w_local = max(self._W // world, 1)
-        cost = {_lib.MI_LOOP_CELLS: 8.5 * (C / 1024.0) ** 2,
-                _lib.MI_LOOP_BYTES: 12.0 + 0.21e-3 * w_local,
-                _lib.MI_LOOP_PERSISTENT: 12.0 + 0.34e-3 * w_local}
+        cost = {_lib.MI_LOOP_CELLS: 8.8 * (C / 1024.0) ** 2,
+                _lib.MI_LOOP_BYTES: 14.5 + 0.18e-3 * w_local,
+                _lib.MI_LOOP_PERSISTENT: 14.5 + 0.43e-3 * w_local}
         lib = _lib.load()
         order = [m for m in sorted(cost, key=cost.get) if lib.acav_mi_loop_supported(C, C, m)]
         return order + [_lib.MI_LOOP_KERNELS]

@@ -51,6 +51,7 @@ def parse_args():
     p.add_argument("--workload", default="default", choices=["default", "c2", "c3", "c4"])
     p.add_argument("--k", type=int, default=1024)
     p.add_argument("--mi-candidates", type=int, default=100_000_000, help="per GPU")
+    p.add_argument("--later-picks", type=int, default=2000, help="untimed picks before the `later_iterations` measurement (0 = skip)")
     p.add_argument("--mi-loop", default="bytes", help="headline loop: bytes (1-byte candidate stream) / persistent (2-byte stream) / cells / auto")
     p.add_argument("--km-rows", type=int, default=1_250_000, help="per GPU, resident")
     p.add_argument("--km-d", type=int, default=2048)
@@ -270,6 +271,17 @@ def run_mi(args, dist, rank, world):
                     "table cell, each iteration scans the K_a x K_v cells instead of the candidates (identical picks)"}
         res["launches"] += 2
         del mc
+    # the same loop later in the run: the timed iterations above are picks warmup .. warmup+steps of an EMPTY table, where
+    # thousands of cells tie for the best gain; a selection of 1e7 clips spends its life past that
+    res["later_iterations"] = None
+    if args.later_picks > 0:
+        ms_l, _ = timed(dist, lambda: m.select(args.later_picks), lambda: m.select(args.steps))
+        m.check_status()
+        res["later_iterations"] = {"after_picks": args.warmup + args.steps + args.later_picks,
+                                   "us_per_iteration": ms_l * 1e3 / args.steps,
+                                   "what": "the same engine, %d more picks on (untimed), then %d timed iterations"
+                                           % (args.later_picks, args.steps)}
+        res["launches"] += 2
     # the other candidate-stream loop beside it (2 bytes per candidate: round 1's headline kernel)
     res["two_byte_stream_loop"] = None
     if not args.skip_cells and not name.startswith("persistent"):
@@ -799,6 +811,7 @@ def main():
             "mi_loop": mi["loop"], "gpu_launches": mi["launches"] + (km["gpu_launches"] if km else 0),
             "e2e": e2e, "roofline": roofline,
             "parity_n": (mi["parity_n"] or {}).get("result"), "parity": mi["parity_n"],
+            "later_iterations": mi.get("later_iterations"),
             "cell_index_loop": mi.get("cell_index_loop"), "two_byte_stream_loop": mi.get("two_byte_stream_loop"),
             "c4": mi.get("c4"),
             "cpu_baseline": cpu, "cpu_model": cpu_model(), "kmeans": km, "clocks": clocks,

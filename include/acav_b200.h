@@ -258,10 +258,12 @@ int acav_mi_comm_handle_bytes(void);
 int acav_mi_comm_export(acav_mi_t *h, int32_t world, int32_t rank, void *handle_out);
 int acav_mi_comm_connect(acav_mi_t *h, const void *handles);
 
-/* Profiling aid: when `cycles` (device int64 [8 * #SMs]) is non-NULL the persistent loop records, per
+/* Profiling aid: when `cycles` (device int64 [72 * #SMs]) is non-NULL the persistent loop records, per
  * CTA and for the last iteration it ran, SM cycles spent in {gain rows, candidate scan, block reduce +
  * publish, grid-barrier wait}, then {stream blocks, table rows} of the CTA's chunk and the cycles of
- * {per-iteration prologue, winner hand-over of the previous iteration}.  NULL switches it off (default). */
+ * {per-iteration prologue, winner hand-over of the previous iteration} (the first 8 * #SMs words); the byte-stream
+ * loop adds, from word 8 * #SMs on, 64 words per CTA: when each of its warps finished its span and when it had settled
+ * its best candidate (cycles since the iteration began).  NULL switches it off (default). */
 int acav_mi_debug_timers(acav_mi_t *h, int64_t *cycles);
 
 /* Tuning of ACAV_MI_LOOP_BYTES (benchmarking): variant 0..5 = (threads per CTA, 16-byte loads in flight per thread)

@@ -13,11 +13,11 @@ m = get_measure("mem_mi")(cells, ncentroids=k, device="cuda", loop="persistent")
 m.init_from_cells([(0, 1)], cells)
 m.select(warm)
 sm = torch.cuda.get_device_properties(0).multi_processor_count
-buf = torch.zeros(8 * sm, dtype=torch.int64, device="cuda")
+buf = torch.zeros(72 * sm, dtype=torch.int64, device="cuda")
 _lib.call("acav_mi_debug_timers", m._engine, _lib.ptr(buf))
 m.select(8)
 torch.cuda.synchronize()
-raw = buf.cpu().numpy().reshape(sm, 8).astype(np.float64)
+raw = buf.cpu().numpy()[:8 * sm].reshape(sm, 8).astype(np.float64)
 t = raw[:, :4] / 1.965e3        # us at 1965 MHz
 names = ["gain rows", "scan", "reduce+publish", "barrier wait"]
 for j, n in enumerate(names):

@@ -27,12 +27,12 @@ for variant in (0, 1, 2, 3, 4, 5):
 
 
 def timers(m, names=("gain rows", "scan", "reduce+publish", "barrier wait")):
-    buf = torch.zeros(8 * sm, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(72 * sm, dtype=torch.int64, device="cuda")
     _lib.call("acav_mi_debug_timers", m._engine, _lib.ptr(buf))
     m.select(8)
     torch.cuda.synchronize()
     _lib.call("acav_mi_debug_timers", m._engine, None)
-    raw = buf.cpu().numpy().reshape(sm, 8).astype(np.float64)
+    raw = buf.cpu().numpy()[:8 * sm].reshape(sm, 8).astype(np.float64)
     t = raw[:, :4] / 1.965e3
     out = {n: {"min": round(float(t[:, j].min()), 1), "mean": round(float(t[:, j].mean()), 1), "max": round(float(t[:, j].max()), 1)}
            for j, n in enumerate(names)}
