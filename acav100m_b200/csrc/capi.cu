@@ -16,7 +16,8 @@ struct acav_kmeans {
     int64_t bytes;
     // assignment scratch
     float *xn, *cn, *mind;
-    unsigned long long *packed;      // exact kernel: per-row (distance, index) keys merged across centroid groups
+    unsigned long long *packed;      // exact kernel: per-row (distance, index) keys merged across centroid groups (idle: ~0)
+    unsigned int *tickets;           // exact kernel, single-launch variant: finished centroid groups per 64-row block (idle: 0)
     // tensor-core path: bf16 copies, epilogue parameters, screening results, TMA descriptors
     int32_t dp;
     void *xb, *cb, *cparams, *partial;
@@ -479,7 +480,7 @@ int acav_device_info(int *sm_count, int *cc_major, int *cc_minor) {
 
 int acav_kmeans_destroy(acav_kmeans_t *h) {
     if (!h) return 0;
-    cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind); cudaFree(h->packed);
+    cudaFree(h->xn); cudaFree(h->cn); cudaFree(h->mind); cudaFree(h->packed); cudaFree(h->tickets);
     cudaFree(h->blockhist); cudaFree(h->lrank); cudaFree(h->total); cudaFree(h->seg_start);
     cudaFree(h->sorted_rows); cudaFree(h->lr_eff);
     cudaFree(h->xb); cudaFree(h->cb); cudaFree(h->cparams); cudaFree(h->partial);
@@ -513,6 +514,9 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) rc = dev_alloc(&h->cn, (size_t)k, &h->bytes);
     if (!rc) rc = dev_alloc(&h->mind, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->packed, (size_t)max_batch, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->tickets, (size_t)max_batch / 64 + 2, &h->bytes);
+    if (!rc && cudaMemset(h->packed, 0xFF, sizeof(unsigned long long) * (size_t)(max_batch ? max_batch : 1)) != cudaSuccess) rc = ACAV_E_STATE;
+    if (!rc && cudaMemset(h->tickets, 0, sizeof(unsigned int) * ((size_t)max_batch / 64 + 2)) != cudaSuccess) rc = ACAV_E_STATE;
     if (!rc) rc = dev_alloc(&h->blockhist, (size_t)(nblk * k), &h->bytes);
     if (!rc) rc = dev_alloc(&h->lrank, (size_t)max_batch, &h->bytes);
     if (!rc) rc = dev_alloc(&h->total, (size_t)k, &h->bytes);
@@ -636,7 +640,8 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
                                           h->cand_rows, h->cand_ids, h->counters, (int32_t)b, best, mind,
                                           fk ? h->fork.side : st);
     if (!rc) rc = launch_assign_exact(x, ldx, h->full_rows, b, h->counters + 1, centers, h->k, h->d, h->xn, h->cn,
-                                      counts, underused_threshold, reinit_r, best, mind, h->packed, h->sm_count, st);
+                                      counts, underused_threshold, reinit_r, best, mind, h->packed, h->sm_count, st,
+                                      h->tickets);
     if (fk && !rc) rc = km_join(&h->fork, st);
     // exact distance to the assigned centroid, only when the caller wants distances back
     if (!rc && (min_dist || mean_dist))

@@ -13,7 +13,7 @@ int launch_row_norm2(const float *x, int64_t rows, int32_t d, int64_t ldx, const
 int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int64_t nrows,
                         const int32_t *nrows_dev, const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
                         const float *counts, float thr, float r, int64_t *best, float *mind,
-                        unsigned long long *packed, int32_t sm_count, cudaStream_t st);
+                        unsigned long long *packed, int32_t sm_count, cudaStream_t st, unsigned int *tickets = nullptr);
 int launch_assign_noise(const float *noise, int32_t k, int64_t b, int64_t *best, float *mind,
                         cudaStream_t st);
 int launch_mean(const float *v, int64_t n, float *out, cudaStream_t st);

@@ -54,7 +54,8 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
                     const float *__restrict__ centers, int32_t k, int32_t d,
                     const float *__restrict__ xn, const float *__restrict__ cn,
                     const float *__restrict__ counts, float thr, float r,
-                    unsigned long long *__restrict__ packed) {
+                    unsigned long long *__restrict__ packed, unsigned int *__restrict__ tickets,
+                    int64_t *__restrict__ best, float *__restrict__ mind) {
     // tiles are widened to fp64 once, on the way into shared memory (F2F.F64 is a slow pipe: doing it
     // per FMA operand made the kernel conversion-bound)
     __shared__ __align__(16) double Xs[kKC][kPad];
@@ -152,6 +153,28 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
             atomicMin(packed + rr, key);
         }
     }
+    if (tickets) {
+        // one launch instead of init + main + finish: the LAST centroid group to finish a row block writes its rows out
+        // and leaves packed[] / the ticket in their idle state (~0 / 0) for the next launch
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last = atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            for (int r2 = tid; r2 < kTR; r2 += 256) {
+                const int64_t rr = row0 + r2;
+                if (rr >= nrows) break;
+                const unsigned long long key = __ldcg(packed + rr);
+                packed[rr] = ~0ull;
+                const int64_t dst = rowlist ? (int64_t)rowlist[rr] : rr;
+                best[dst] = (int64_t)(key & 0xFFFFFFFFull);
+                if (mind) mind[dst] = from_orderable((uint32_t)(key >> 32));
+            }
+            if (tid == 0) tickets[blockIdx.x] = 0u;
+        }
+    }
 }
 
 __global__ void assign_exact_init_kernel(unsigned long long *__restrict__ packed, int64_t n) {
@@ -159,7 +182,7 @@ __global__ void assign_exact_init_kernel(unsigned long long *__restrict__ packed
     if (i < n) packed[i] = ~0ull;
 }
 
-__global__ void assign_exact_finish_kernel(const unsigned long long *__restrict__ packed,
+__global__ void assign_exact_finish_kernel(unsigned long long *__restrict__ packed,
                                            const int32_t *__restrict__ rowlist, int64_t nrows,
                                            const int32_t *__restrict__ nrows_dev,
                                            int64_t *__restrict__ best, float *__restrict__ mind) {
@@ -167,6 +190,7 @@ __global__ void assign_exact_finish_kernel(const unsigned long long *__restrict_
     if (nrows_dev) nrows = min(nrows, (int64_t)*nrows_dev);
     if (i >= nrows) return;
     const unsigned long long key = packed[i];
+    packed[i] = ~0ull;                                   // idle state for the single-launch variant (tickets != null)
     const int64_t dst = rowlist ? (int64_t)rowlist[i] : i;
     best[dst] = (int64_t)(key & 0xFFFFFFFFull);
     if (mind) mind[dst] = from_orderable((uint32_t)(key >> 32));
@@ -216,17 +240,23 @@ int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int
                         const int32_t *nrows_dev,
                         const float *centers, int32_t k, int32_t d, const float *xn, const float *cn,
                         const float *counts, float thr, float r, int64_t *best, float *mind,
-                        unsigned long long *packed, int32_t sm_count, cudaStream_t st) {
+                        unsigned long long *packed, int32_t sm_count, cudaStream_t st, unsigned int *tickets) {
     if (nrows == 0) return 0;
     const unsigned row_blocks = (unsigned)ceil_div(nrows, kTR);
     const int32_t tiles = (int32_t)ceil_div(k, kTC);
     int32_t split = 1;                                   // aim for >= 4 CTAs per SM
     while (split < tiles && (int64_t)row_blocks * split < 4ll * sm_count) split *= 2;
     if (split > tiles) split = tiles;
+    if (tickets) {                                       // packed[] idles at ~0, tickets at 0 (acav_kmeans_create)
+        assign_exact_kernel<<<dim3(row_blocks, (unsigned)split), 256, 0, st>>>(
+            x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, packed, tickets, best, mind);
+        ACAV_LAUNCH_CHECK();
+        return 0;
+    }
     assign_exact_init_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(packed, nrows);
     ACAV_LAUNCH_CHECK();
     assign_exact_kernel<<<dim3(row_blocks, (unsigned)split), 256, 0, st>>>(
-        x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, packed);
+        x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, packed, nullptr, nullptr, nullptr);
     ACAV_LAUNCH_CHECK();
     assign_exact_finish_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(packed, rowlist, nrows, nrows_dev,
                                                                               best, mind);

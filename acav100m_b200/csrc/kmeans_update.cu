@@ -69,8 +69,12 @@ constexpr uint32_t kUpdHeavyRows = 128;              // centroids with at least 
 
 // seg_start[0..k] = exclusive scan of total[0..k) (single block, chunks of 1024 with carry); also the list of
 // "heavy" centroids (>= kUpdHeavyRows rows of this batch): seg_start[k+1] = their number, seg_start[k+2..] = ids.
+// With `blockhist` given (small batches: nblk <= kFusedPrefixBlocks) the kernel also does km_block_prefix_kernel's work for
+// its centroid first -- one launch less on the training step's chain.
+constexpr int32_t kFusedPrefixBlocks = 64;
 __global__ void __launch_bounds__(1024)
-km_segment_start_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t *__restrict__ seg_start) {
+km_segment_start_kernel(uint32_t *__restrict__ total, int32_t k, uint32_t *__restrict__ seg_start,
+                        uint32_t *__restrict__ blockhist, int32_t nblk, float *__restrict__ counts_b) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     __shared__ uint32_t n_heavy;
@@ -79,7 +83,22 @@ km_segment_start_kernel(const uint32_t *__restrict__ total, int32_t k, uint32_t 
     const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
     for (int32_t base = 0; base < k; base += 1024) {
         int32_t i = base + threadIdx.x;
-        uint32_t v = i < k ? total[i] : 0u;
+        uint32_t v = 0u;
+        if (i < k) {
+            if (blockhist) {                       // exclusive prefix over blocks (in place) + batch histogram (:113)
+                uint32_t run = 0;
+                for (int32_t blk = 0; blk < nblk; ++blk) {
+                    const uint32_t t = blockhist[(int64_t)blk * k + i];
+                    blockhist[(int64_t)blk * k + i] = run;
+                    run += t;
+                }
+                total[i] = run;
+                counts_b[i] = (float)run;
+                v = run;
+            } else {
+                v = total[i];
+            }
+        }
         uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < kWarp; o <<= 1) {
@@ -513,10 +532,15 @@ int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockh
         km_block_rank_kernel<<<nblk, kRankRows, smem, st>>>(best, b, k, blockhist, lrank);
         ACAV_LAUNCH_CHECK();
     }
-    km_block_prefix_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(blockhist, nblk, k, total, counts_b);
-    ACAV_LAUNCH_CHECK();
-    km_segment_start_kernel<<<1, 1024, 0, st>>>(total, k, seg_start);
-    ACAV_LAUNCH_CHECK();
+    if (nblk <= kFusedPrefixBlocks) {
+        km_segment_start_kernel<<<1, 1024, 0, st>>>(total, k, seg_start, blockhist, nblk, counts_b);
+        ACAV_LAUNCH_CHECK();
+    } else {
+        km_block_prefix_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(blockhist, nblk, k, total, counts_b);
+        ACAV_LAUNCH_CHECK();
+        km_segment_start_kernel<<<1, 1024, 0, st>>>(total, k, seg_start, nullptr, 0, nullptr);
+        ACAV_LAUNCH_CHECK();
+    }
     if (nblk > 0) {
         km_scatter_rows_kernel<<<nblk, kRankRows, 0, st>>>(best, b, k, blockhist, lrank, seg_start, sorted_rows);
         ACAV_LAUNCH_CHECK();

@@ -534,7 +534,7 @@ def run_config4(args, dist, rank, world):
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    m = mi_engine(cells, args.k, rank, world, "cells", w_rank * world, w_rank * rank, max_picks=picks + 16)
+    m = mi_engine(cells, args.k, rank, world, "auto", w_rank * world, w_rank * rank, max_picks=picks + 16)   # auto -> cell index at K = 1024
     chunk, done, pos_all, gain_all = 1_000_000, 0, [], []
     marks = []
     while done < picks:
