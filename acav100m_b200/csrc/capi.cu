@@ -1,6 +1,9 @@
 // extern "C" surface of libacav_b200.so (declared in include/acav_b200.h).
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <new>
 #include <vector>
 
@@ -86,14 +89,81 @@ struct acav_mi {
 
 namespace {
 
+// Device buffers of at least 1 MiB are kept by the library when an engine is destroyed and handed to the next engine
+// that asks for exactly that size (per device, at most kCacheMaxBytes in total): cudaMalloc / cudaFree of the ~1.5 GB a
+// greedy-MI engine needs at W = 1e8 cost 15-70 ms (page-table work, device synchronisation) -- as much as copying the
+// candidate list to the device.  Buffers shared with other processes (CUDA IPC) are small and never come through here.
+// ACAV_NO_BUFFER_CACHE=1 switches the cache off.
+constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+constexpr size_t kCacheMaxBytes = (size_t)24 << 30;
+struct BufCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> idle;                   // size -> buffer
+    std::unordered_map<void *, size_t> sizes;             // every live or idle buffer handed out by dev_alloc
+    size_t idle_bytes = 0;
+};
+BufCache g_buf_cache[kMaxDevices];
+bool buf_cache_on() {
+    static int on = -1;
+    if (on < 0) { const char *e = std::getenv("ACAV_NO_BUFFER_CACHE"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
+}
+BufCache *buf_cache() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_buf_cache[dev];
+}
+
 template <typename T>
 int dev_alloc(T **p, size_t n, int64_t *bytes) {
     *p = nullptr;
     size_t sz = sizeof(T) * (n ? n : 1);
+    BufCache *c = (sz >= kCacheMinBytes && buf_cache_on()) ? buf_cache() : nullptr;
+    if (c) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        auto it = c->idle.find(sz);
+        if (it != c->idle.end()) {
+            *p = reinterpret_cast<T *>(it->second);
+            c->idle.erase(it);
+            c->idle_bytes -= sz;
+            if (bytes) *bytes += (int64_t)sz;
+            return 0;
+        }
+    }
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), sz);
+    if (e != cudaSuccess && c) {                          // out of memory with idle buffers around: give them back, retry
+        {
+            std::lock_guard<std::mutex> lock(c->mu);
+            for (auto &kv : c->idle) { c->sizes.erase(kv.second); cudaFree(kv.second); }
+            c->idle.clear();
+            c->idle_bytes = 0;
+        }
+        cudaGetLastError();
+        e = cudaMalloc(reinterpret_cast<void **>(p), sz);
+    }
     if (e != cudaSuccess) return (int)e;
+    if (c) { std::lock_guard<std::mutex> lock(c->mu); c->sizes[*p] = sz; }
     if (bytes) *bytes += (int64_t)sz;
     return 0;
+}
+
+// counterpart of dev_alloc for buffers that may be big; the caller has synchronised with every stream that used it
+void dev_free(void *p) {
+    if (!p) return;
+    BufCache *c = buf_cache_on() ? buf_cache() : nullptr;
+    if (c) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        auto it = c->sizes.find(p);
+        if (it != c->sizes.end()) {
+            if (c->idle_bytes + it->second <= kCacheMaxBytes) {
+                c->idle.emplace(it->second, p);
+                c->idle_bytes += it->second;
+                return;
+            }
+            c->sizes.erase(it);
+        }
+    }
+    cudaFree(p);
 }
 
 int query_sm_count(int32_t *out) {
@@ -441,7 +511,8 @@ int mi_prepare_cells(acav_mi *h, cudaStream_t st) {
     if (!rc) rc = launch_mi_cells_build(s, tilehist, total, start, tmp_cells, tmp_pos, sorted_cells, h->cx_sorted_pos,
                                         h->cx_cell_start, h->cx_head, h->cx_first_pos, &n_live, st);
     if (!rc) rc = (int)cudaStreamSynchronize(st);
-    cudaFree(tilehist); cudaFree(total); cudaFree(start); cudaFree(tmp_cells); cudaFree(tmp_pos); cudaFree(sorted_cells);
+    if (rc) cudaStreamSynchronize(st);               // the scratch goes back to the buffer cache: no kernel may still use it
+    dev_free(tilehist); dev_free(total); dev_free(start); dev_free(tmp_cells); dev_free(tmp_pos); dev_free(sorted_cells);
     if (rc) return rc;
     h->cells_valid = true;
     return 0;
@@ -835,18 +906,19 @@ int acav_kmeans_underused_flags(const float *counts, int32_t k, const float *thr
 int acav_mi_destroy(acav_mi_t *h) {
     if (!h) return 0;
     MiState &s = h->s;
-    cudaFree(s.cells); cudaFree(s.n_cells); cudaFree(s.a_cols); cudaFree(s.b_rows); cudaFree(s.gain);
-    cudaFree(s.col_term); cudaFree(s.row_term); cudaFree(s.sums); cudaFree(s.key); cudaFree(h->consts_dev);
-    cudaFree(h->c2s); cudaFree(h->pos_s); cudaFree(h->row_start); cudaFree(h->row_total); cudaFree(h->tilehist);
-    cudaFree(h->chunk_start); cudaFree(h->n_alt); cudaFree(h->pub); cudaFree(h->bar);
+    cudaDeviceSynchronize();                 // the buffers go back to the library's cache, not through cudaFree
+    dev_free(s.cells); dev_free(s.n_cells); dev_free(s.a_cols); dev_free(s.b_rows); dev_free(s.gain);
+    dev_free(s.col_term); dev_free(s.row_term); dev_free(s.sums); dev_free(s.key); dev_free(h->consts_dev);
+    dev_free(h->c2s); dev_free(h->pos_s); dev_free(h->row_start); dev_free(h->row_total); dev_free(h->tilehist);
+    dev_free(h->chunk_start); dev_free(h->n_alt); dev_free(h->pub); dev_free(h->bar);
     if (h->comm_connected)
         for (int r = 0; r < h->world; ++r)
             if (r != h->rank && h->mail_peer[r]) cudaIpcCloseMemHandle(h->mail_peer[r]);
-    cudaFree(h->mail_local); cudaFree(h->run_status);
-    cudaFree(h->cx_sorted_pos); cudaFree(h->cx_cell_start); cudaFree(h->cx_head); cudaFree(h->cx_first_pos);
-    cudaFree(h->s8_stream); cudaFree(h->s8_pos); cudaFree(h->s8_vrank); cudaFree(h->s8_row_total); cudaFree(h->s8_tilehist);
-    cudaFree(h->s8_slot_start); cudaFree(h->s8_slot_row); cudaFree(h->s8_slot_u); cudaFree(h->s8_chunks);
-    cudaFree(h->s8_row_start); cudaFree(h->s8_blk_src); cudaFree(h->s8_stage_stream); cudaFree(h->s8_stage_pos);
+    cudaFree(h->mail_local); dev_free(h->run_status);
+    dev_free(h->cx_sorted_pos); dev_free(h->cx_cell_start); dev_free(h->cx_head); dev_free(h->cx_first_pos);
+    dev_free(h->s8_stream); dev_free(h->s8_pos); dev_free(h->s8_vrank); dev_free(h->s8_row_total); dev_free(h->s8_tilehist);
+    dev_free(h->s8_slot_start); dev_free(h->s8_slot_row); dev_free(h->s8_slot_u); dev_free(h->s8_chunks);
+    dev_free(h->s8_row_start); dev_free(h->s8_blk_src); dev_free(h->s8_stage_stream); dev_free(h->s8_stage_pos);
     delete h;
     return 0;
 }
