@@ -325,10 +325,13 @@ def run_mi(args, dist, rank, world):
             dist.barrier()
         t0 = time.perf_counter()
         m2 = mi_engine(host, args.k, rank, world, args.mi_loop, W * world, W * rank)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
         pos, gain = m2.select(args.steps)
         pos_h, gain_h = pos.cpu(), gain.cpu()
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        t2 = time.perf_counter()
+        dt = torch.tensor([t2 - t0], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         scored2 = sum(w_global - i for i in range(args.steps))
@@ -336,6 +339,8 @@ def run_mi(args, dist, rank, world):
                "h2d_bytes_per_step": host.numel() * 8 / args.steps,
                "d2h_bytes_per_step": (pos_h.numel() * 8 + gain_h.numel() * 4) / args.steps,
                "seconds": float(dt.item()),
+               "phases_ms_rank0": {"h2d_pack_tables": round(1e3 * (t1 - t0), 2),
+                                   "layout_build_plus_iterations_plus_d2h": round(1e3 * (t2 - t1), 2)},
                "what": "EfficientMemMI built from a pinned host int64 [W,2] tensor + %d greedy iterations + "
                        "D2H of (S, GAIN)" % args.steps}
         res["launches"] += 2
@@ -709,8 +714,12 @@ def config_dict(args, world):
                         "C3 per-GPU shard (1.25M x 2048 fp32, K=1024, batch 8192/GPU) for k-means",
             "mi_candidates_per_gpu": args.mi_candidates, "k": args.k, "km_rows_per_gpu": args.km_rows,
             "km_d": args.km_d, "km_batch_per_gpu": args.km_batch, "parallelism": "shard%d" % world,
-            "l2": "candidate stream %.0f MB/GPU > 126 MB L2; k-means walks %.1f GB/GPU of resident rows"
-                  % (args.mi_candidates * 2 / 1e6, args.km_rows * args.km_d * 4 / 1e9)}
+            "l2": ("greedy MI: every iteration streams the whole candidate list of the GPU -- %.0f MB in the one-byte layout "
+                   "(--mi-loop bytes, loaded with an L2 evict-first policy: ncu counts 104 MB of DRAM reads per iteration at "
+                   "1e8 candidates, L2 hit rate 13 %%, profiles/r02_mi_bytes_final.ncu.txt and roofline.traffic -- nothing is "
+                   "served from the 126 MB L2), %.0f MB > L2 in the 2-byte layout (two_byte_stream_loop); k-means walks "
+                   "%.1f GB/GPU of resident rows"
+                   % (args.mi_candidates / 1e6, args.mi_candidates * 2 / 1e6, args.km_rows * args.km_d * 4 / 1e9))}
 
 
 def main_reference(args):

@@ -235,3 +235,43 @@ def test_byte_stream_variants_match_c_oracle(W, C, picks, seed, variant, cache):
     want_N = np.zeros((C, C), dtype=np.int64)
     np.add.at(want_N, (a[pos_want, 0], a[pos_want, 1]), 1)
     assert np.array_equal(N.numpy(), want_N)
+
+
+@pytest.mark.parametrize("W,C,picks,want_loop", [(30_000, 64, 300, "cells"), (60_000, 4096, 60, None)])
+def test_auto_loop_picks_a_supported_loop_and_matches_c_oracle(W, C, picks, want_loop):
+    """loop='auto' (the CLI default) orders the exact loops by their measured cost for the shape and takes the first
+    one whose layout can be built for this list: the cell index wherever K^2 << W; at K = 4096 neither the one-byte
+    stream (69632 sub-rows) nor the cell index fits the cost model's first place, whatever runs must give the oracle's picks."""
+    from acav100m_b200 import _lib
+    a = synth.zipf_pairs(W, C, 41)
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C, loop="auto")
+    m.init([(0, 1)], list(range(W)))
+    order = m._auto_order()
+    assert order[-1] == _lib.MI_LOOP_KERNELS and all(_lib.load().acav_mi_loop_supported(C, C, x) for x in order)
+    pos, gain = m.select(picks)
+    assert np.array_equal(pos.cpu().numpy(), pos_want) and np.array_equal(gain.cpu().numpy(), gain_want)
+    if want_loop is not None:
+        assert m.loop_name() == want_loop
+
+
+def test_auto_loop_moves_on_when_a_layout_cannot_be_built(monkeypatch):
+    """acav_mi_prepare returning ACAV_E_UNSUPPORTED for the first choice (here: forced) makes select() take the next loop."""
+    from acav100m_b200 import _lib
+    W, C, picks = 20_000, 32, 120
+    a = synth.zipf_pairs(W, C, 43)
+    pos_want, gain_want = mo.greedy_mem_mi_c(a[:, 0], a[:, 1], C, picks, bucketed=True)
+    m = gpu_measure(a, C, loop="auto")
+    m.init([(0, 1)], list(range(W)))
+    first = m._auto_order()[0]
+    real_call = _lib.call
+
+    def flaky(name, *args):
+        if name == "acav_mi_prepare" and args[1] == first:
+            raise _lib.AcavError(name, _lib.E_UNSUPPORTED, "forced by the test")
+        return real_call(name, *args)
+
+    monkeypatch.setattr(_lib, "call", flaky)
+    pos, gain = m.select(picks)
+    assert m._loop_mode() == m._auto_order()[1]
+    assert np.array_equal(pos.cpu().numpy(), pos_want) and np.array_equal(gain.cpu().numpy(), gain_want)
