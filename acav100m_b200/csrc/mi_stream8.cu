@@ -579,12 +579,11 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
             for (int r = 0; r < DEPTH; ++r)
                 stage[r] = wb_lo + (uint32_t)r < wb_hi ? s8_ld_stream(src4 + (size_t)r * kWarp, stream_pol)
                                                        : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            // take block (blk0 + r) out of the staging registers and start the load that re-uses its place; `check`:
-            // the tail of the span, where that load may lie beyond it
-            auto next_vector = [&](int r, uint32_t blk, bool check) -> uint4 {
-                const uint4 q = stage[r];
+            // the load that re-uses the staging registers of block (blk0 + r) is issued AFTER that block is scored: its
+            // registers are dead by then (issued before, the compiler copies the four of them aside: 8 moves per block);
+            // `check`: the tail of the span, where that load may lie beyond it
+            auto refill = [&](int r, uint32_t blk, bool check) {
                 if (!check || blk + DEPTH < wb_hi) stage[r] = s8_ld_stream(src4 + (size_t)(DEPTH + r) * kWarp, stream_pol);
-                return q;
             };
             auto score_block = [&](const uint4 q, const uint32_t blk) {
                 if (blk >= seg_end) {                            // next slot (uniform per warp; slots are not empty)
@@ -628,8 +627,8 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
             for (; blk0 + 2 * DEPTH <= wb_hi; blk0 += DEPTH) {
 #pragma unroll
                 for (int r = 0; r < DEPTH; ++r) {
-                    const uint4 q = next_vector(r, blk0 + (uint32_t)r, false);
-                    score_block(q, blk0 + (uint32_t)r);
+                    score_block(stage[r], blk0 + (uint32_t)r);
+                    refill(r, blk0 + (uint32_t)r, false);
                 }
                 src4 += (size_t)DEPTH * kWarp;
             }
@@ -639,8 +638,8 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                 for (int r = 0; r < DEPTH; ++r) {
                     const uint32_t blk = blk0 + (uint32_t)r;
                     if (blk < wb_hi) {
-                        const uint4 q = next_vector(r, blk, true);
-                        score_block(q, blk);
+                        score_block(stage[r], blk);
+                        refill(r, blk, true);
                     }
                 }
                 src4 += (size_t)DEPTH * kWarp;
