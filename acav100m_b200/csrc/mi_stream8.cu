@@ -25,6 +25,8 @@
 //     recorded blocks are read again and the entry with the smallest original position wins (mi.py:79: first maximum).
 // Scores use the same fp32 operation sequence and the same torch-CPU log table as mi_scan.cu: picks and gains are
 // bit-identical to the reference (tests/test_mi_gpu.py).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "mi_loop.cuh"
@@ -301,6 +303,7 @@ struct MiS8 {
     int32_t rows_smem;               // distinct sub-rows whose gain row + counts fit in shared memory
     int32_t slots_smem;              // slots per chunk the shared-memory tables hold
     int32_t fixed_bytes;             // bytes of the arrays in front of the gain rows
+    int32_t prefetch;                // ask what settling will read into L2 when a block is recorded
     int32_t world, rank;
     unsigned int seq_base;
     MiMail *mail_local;
@@ -404,6 +407,17 @@ __device__ __forceinline__ void s8_resolve_blocks(const S8Ctx &c, const uint32_t
             bbyte = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
         }
     }
+}
+
+// What settling a recorded block will read -- my vector, its order word, my 16 positions -- is asked into L2 when the
+// block is recorded (fire and forget): the stream itself is loaded evict-first, so by the end of the span the vector
+// would come from HBM again, and the position after it.
+__device__ __forceinline__ void s8_prefetch_settle(const uint4 *vec, const unsigned long long *vrank, const uint32_t *pos_s,
+                                                   uint32_t blk, uint32_t lane) {
+    const size_t vi = (size_t)blk * kWarp + lane;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(vec + vi));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(vrank + vi));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pos_s + vi * 16));
 }
 
 struct S8Found {
@@ -609,6 +623,7 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                 if (m >= bs) {                                   // rare once the thread has seen a good candidate
                     if (m > bs) {                                // registers only: which block (and its gain row)
                         bs = m; bx = blk | (cur_u << 26); bend = seg_end; ntie = 0; seen = 1ull << cur_u;
+                        if (P.prefetch) s8_prefetch_settle(vec, P.vrank, P.pos_s, blk, lane);
                     } else if (blk >= bend && m > -INFINITY) {   // same gain in a later segment
                         const uint32_t u = cur_u;
                         bend = seg_end;
@@ -617,6 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
                         if (!((seen >> u) & 1ull)) {
                             seen |= 1ull << u;
                             if (ntie < kS8TieCap) tie[ntie] = blk | (u << 26);   // (list full: see s8_resolve_all)
+                            if (P.prefetch) s8_prefetch_settle(vec, P.vrank, P.pos_s, blk, lane);
                             ntie = min(ntie + 1, kS8TieCap + 1);
                             }
                     }
@@ -922,6 +938,8 @@ int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const 
     P.pub = reinterpret_cast<MiPub *>(pub); P.bar = bar; P.n_picks = n_picks; P.out_pos = out_pos; P.out_gain = out_gain;
     P.g = s8_geom(s.k_a, s.k_v); P.rows_smem = rows_smem; P.slots_smem = s8_slots_for_rows(rows_smem);
     P.fixed_bytes = (int32_t)s8_fixed_bytes(s.k_a, s.k_v, rows_smem);
+    P.prefetch = 1;
+    if (const char *e = std::getenv("ACAV_MI_S8_PREFETCH")) P.prefetch = std::atoi(e);
     P.world = world; P.rank = rank; P.seq_base = seq_base;
     P.mail_local = reinterpret_cast<MiMail *>(mail_local);
     for (int r = 0; r < kMaxWorld; ++r)
