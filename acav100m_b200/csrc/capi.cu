@@ -12,6 +12,17 @@
 
 using namespace acav;
 
+namespace acav {
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = std::getenv("ACAV_NO_PDL");
+        on = (e && e[0] == '1') ? 0 : 1;
+    }
+    return on == 1;
+}
+}  // namespace acav
+
 struct acav_kmeans {
     int32_t k, d;
     int64_t max_batch;
@@ -35,6 +46,7 @@ struct acav_kmeans {
     float *lr_eff;
     bool partition_valid;
     int64_t partition_rows;
+    const float *hist_max_of;        // the counts_b buffer whose maximum lr_eff[2] holds (nullptr: none)
     // side stream for the independent kernels of a step (ACAV_KM_NOFORK=1: everything on the caller's stream)
     KmFork fork;
     bool fork_ok;
@@ -570,7 +582,7 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     acav_kmeans *h = new (std::nothrow) acav_kmeans();
     if (!h) return (int)cudaErrorMemoryAllocation;
     h->k = k; h->d = d; h->max_batch = max_batch; h->bytes = 0;
-    h->partition_valid = false; h->partition_rows = 0;
+    h->partition_valid = false; h->partition_rows = 0; h->hist_max_of = nullptr;
     h->fork.side = nullptr; h->fork.ev_fork = nullptr; h->fork.ev_join = nullptr; h->fork_ok = false;
     {
         const char *e = std::getenv("ACAV_KM_NOFORK");
@@ -593,7 +605,7 @@ int acav_kmeans_create(acav_kmeans_t **out, int32_t k, int32_t d, int64_t max_ba
     if (!rc) rc = dev_alloc(&h->total, (size_t)k, &h->bytes);
     if (!rc) rc = dev_alloc(&h->seg_start, (size_t)2 * k + 2, &h->bytes);     // offsets [k+1] + heavy-centroid list
     if (!rc) rc = dev_alloc(&h->sorted_rows, (size_t)max_batch, &h->bytes);
-    if (!rc) rc = dev_alloc(&h->lr_eff, 2, &h->bytes);
+    if (!rc) rc = dev_alloc(&h->lr_eff, 4, &h->bytes);              // [0] lr, [1] 1 - lr (sequential), [2] max of the batch histogram
     // tensor-core path (bf16 operands padded to a multiple of 64 columns)
     h->dp = (int32_t)ceil_div(d, 64) * 64;
     h->tensor_ready = false;
@@ -696,6 +708,7 @@ int acav_kmeans_assign_prepared(acav_kmeans_t *h, const float *x, int64_t b, int
     // tcgen05 distance GEMM + top-4 screen; merge / classify; exact re-check of near-ties
     int32_t n_split = 1;                       // partial top-4 lists per row
     const int32_t variant = resolve_tile_variant(h);
+    ACAV_CUDA_TRY(cudaMemsetAsync(h->counters, 0, 2 * sizeof(int32_t), st));     // for launch_merge_classify
     int rc = variant == ACAV_TILE_SINGLE
                  ? launch_assign_umma(h->tmap_x, h->tmap_c, h->xn, h->cparams, (int32_t)b, h->k, h->dp, h->sm_count,
                                       h->partial, &n_split, st)
@@ -736,8 +749,12 @@ int acav_kmeans_assign_noise(const float *noise, int32_t k, int64_t b,
 
 int acav_kmeans_histogram(acav_kmeans_t *h, const int64_t *best, int64_t b, float *counts_b, void *stream) {
     if (!h || !best || !counts_b || b < 0 || b > h->max_batch) return ACAV_E_INVALID;
+    // lr_eff[2] <- the histogram's maximum (small batches: the single-block prefix kernel has it anyway), so that the
+    // update kernels of acav_kmeans_update_fused can take the learning-rate decision themselves
+    bool max_written = false;
     int rc = launch_partition(best, b, h->k, h->blockhist, h->lrank, h->total, h->seg_start, h->sorted_rows,
-                              counts_b, (cudaStream_t)stream);
+                              counts_b, (cudaStream_t)stream, h->lr_eff + 2, &max_written);
+    h->hist_max_of = (rc == 0 && max_written && b > 0) ? counts_b : nullptr;
     h->partition_valid = (rc == 0);
     h->partition_rows = b;
     return rc;
@@ -748,10 +765,16 @@ static int update_common(acav_kmeans_t *h, const float *x, int64_t b, int64_t ld
                          cudaStream_t st) {
     if (!h || !x || !counts_b || !centers || !counts || ldx < h->d) return ACAV_E_INVALID;
     if (!h->partition_valid || h->partition_rows != b) return ACAV_E_STATE;
-    int rc = launch_effective_lr(counts_b, h->k, lr, h->lr_eff, fallback, st);
+    // One process (no deltas to exchange) and counts_b is the very buffer acav_kmeans_histogram filled: the update
+    // kernels decide the step's lr from the maximum left in lr_eff[2] (same arithmetic, one launch less on the chain).
+    // Otherwise (all-reduced counts, another buffer, batches beyond the single-block prefix) km_effective_lr_kernel does.
+    const bool fold = !deltas && h->hist_max_of == counts_b && counts_b != nullptr && !km_heavy_ring();
+    int rc = fold ? 0 : launch_effective_lr(counts_b, h->k, lr, h->lr_eff, fallback, st);
     if (!rc) rc = launch_update(x, ldx, h->k, h->d, h->seg_start, h->sorted_rows, counts_b, h->lr_eff, centers,
-                                counts, deltas, nullptr, false, st, h->fork_ok ? &h->fork : nullptr);
+                                counts, deltas, nullptr, false, st, h->fork_ok ? &h->fork : nullptr,
+                                fold ? lr : -1.0, fold ? fallback : nullptr);
     h->partition_valid = false;
+    h->hist_max_of = nullptr;
     return rc;
 }
 

@@ -38,6 +38,29 @@ inline int ensure_dynamic_smem(F *func, size_t bytes, size_t (&done)[kMaxDevices
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (the k-means step's chain of small kernels) ----
+// A kernel launched with launch_pdl() may be scheduled while its predecessor in the stream is still draining; it
+// must not touch memory before pdl_begin(), which (a) lets ITS successor be scheduled early in turn and (b) waits until
+// the predecessor grid has completed and its writes are visible.  Launched the ordinary way, pdl_begin() is a no-op.
+// Works in streams and under stream capture (the graph gets programmatic edges).  ACAV_NO_PDL=1 launches plainly.
+__device__ __forceinline__ void pdl_begin() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();                                    // capi.cu (reads ACAV_NO_PDL once)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // fp32 -> uint32 whose unsigned order equals the float order (-0 canonicalised to +0).
 __device__ __forceinline__ uint32_t orderable(float s) {
     if (s == 0.0f) s = 0.0f;

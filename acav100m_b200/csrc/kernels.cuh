@@ -48,7 +48,7 @@ int launch_exact_min_dist(const float *x, int64_t b, int32_t d, int64_t ldx, con
 // kmeans_update.cu
 int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockhist, uint32_t *lrank,
                      uint32_t *total, uint32_t *seg_start, uint32_t *sorted_rows, float *counts_b,
-                     cudaStream_t st);
+                     cudaStream_t st, float *hist_max = nullptr, bool *hist_max_written = nullptr);
 int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_eff, int32_t *fallback,
                         cudaStream_t st);
 constexpr int kKmMaxWorld = 16;
@@ -78,7 +78,9 @@ inline int km_join(const KmFork *f, cudaStream_t st) {
 }
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
-                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st, const KmFork *fork = nullptr);
+                  float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st, const KmFork *fork = nullptr,
+                  double lr_in = -1.0, int32_t *fallback = nullptr);   // lr_in >= 0: the kernels decide the step's lr from lr_eff[2]
+bool km_heavy_ring();
 int launch_sequential_lr(double lr, float *lr_eff, cudaStream_t st);
 
 // kmeans_comm.cu: the multi-GPU step over NVLink peer memory (no NCCL): histogram exchange + lr decision, and the

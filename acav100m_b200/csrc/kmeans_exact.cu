@@ -56,6 +56,7 @@ assign_exact_kernel(const float *__restrict__ x, int64_t ldx, const int32_t *__r
                     const float *__restrict__ counts, float thr, float r,
                     unsigned long long *__restrict__ packed, unsigned int *__restrict__ tickets,
                     int64_t *__restrict__ best, float *__restrict__ mind) {
+    pdl_begin();
     // tiles are widened to fp64 once, on the way into shared memory (F2F.F64 is a slow pipe: doing it
     // per FMA operand made the kernel conversion-bound)
     __shared__ __align__(16) double Xs[kKC][kPad];
@@ -248,9 +249,8 @@ int launch_assign_exact(const float *x, int64_t ldx, const int32_t *rowlist, int
     while (split < tiles && (int64_t)row_blocks * split < 4ll * sm_count) split *= 2;
     if (split > tiles) split = tiles;
     if (tickets) {                                       // packed[] idles at ~0, tickets at 0 (acav_kmeans_create)
-        assign_exact_kernel<<<dim3(row_blocks, (unsigned)split), 256, 0, st>>>(
-            x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, packed, tickets, best, mind);
-        ACAV_LAUNCH_CHECK();
+        ACAV_CUDA_TRY(launch_pdl(assign_exact_kernel, dim3(row_blocks, (unsigned)split), dim3(256), 0, st,
+                                 x, ldx, rowlist, nrows, nrows_dev, centers, k, d, xn, cn, counts, thr, r, packed, tickets, best, mind));
         return 0;
     }
     assign_exact_init_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(packed, nrows);

@@ -26,6 +26,7 @@ namespace acav {
 // fp32 [rows, d] -> bf16 [rows, dp] (zero padded) + |row|^2 as the reference computes it (norm ** 2).
 __global__ void km_prep_rows_kernel(const float *__restrict__ x, int64_t rows, int32_t d, int64_t ldx,
                                     int32_t dp, __nv_bfloat16 *__restrict__ xb, float *__restrict__ xn) {
+    pdl_begin();
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
     const int lane = threadIdx.x % kWarp;
     if (r >= rows) return;
@@ -225,6 +226,7 @@ __global__ void km_merge_classify_kernel(const Top4 *__restrict__ partial, int32
                                          int64_t *__restrict__ best, float *__restrict__ mind,
                                          int32_t *__restrict__ cand_rows, int32_t *__restrict__ cand_ids,
                                          int32_t *__restrict__ full_rows, int32_t *__restrict__ counters) {
+    pdl_begin();
     const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= b) return;
     float d0 = INFINITY, d5min = INFINITY;
@@ -417,9 +419,8 @@ int launch_prep_rows(const float *x, int64_t rows, int32_t d, int64_t ldx, int32
                      cudaStream_t st) {
     if (rows == 0) return 0;
     const int wpb = 8;
-    km_prep_rows_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * kWarp, 0, st>>>(
-        x, rows, d, ldx, dp, reinterpret_cast<__nv_bfloat16 *>(xb), xn);
-    ACAV_LAUNCH_CHECK();
+    ACAV_CUDA_TRY(launch_pdl(km_prep_rows_kernel, dim3((unsigned)ceil_div(rows, wpb)), dim3(wpb * kWarp), 0, st,
+                             x, rows, d, ldx, dp, reinterpret_cast<__nv_bfloat16 *>(xb), xn));
     return 0;
 }
 
@@ -457,12 +458,13 @@ int launch_assign_umma(const void *tmap_x, const void *tmap_c, const float *xn, 
 int launch_merge_classify(const void *partial, int32_t b, int32_t n_split, const float *xn, const void *cparams,
                           const float *cn, int32_t k, int64_t *best, float *mind, int32_t *cand_rows, int32_t *cand_ids, int32_t *full_rows,
                           int32_t *counters, cudaStream_t st) {
-    ACAV_CUDA_TRY(cudaMemsetAsync(counters, 0, 2 * sizeof(int32_t), st));
+    // counters[0..1] were zeroed by the caller BEFORE the distance kernel (a memset between the two kernels would
+    // make this launch an ordinary one)
     if (b == 0) return 0;
-    km_merge_classify_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, st>>>(
-        reinterpret_cast<const Top4 *>(partial), b, n_split, xn, reinterpret_cast<const CentroidParam *>(cparams), cn, k,
-        best, mind, cand_rows, cand_ids, full_rows, counters);
-    ACAV_LAUNCH_CHECK();
+    ACAV_CUDA_TRY(launch_pdl(km_merge_classify_kernel, dim3((unsigned)ceil_div(b, 256)), dim3(256), 0, st,
+                             reinterpret_cast<const Top4 *>(partial), b, n_split, xn,
+                             reinterpret_cast<const CentroidParam *>(cparams), cn, k, best, mind, cand_rows, cand_ids,
+                             full_rows, counters));
     return 0;
 }
 

@@ -21,6 +21,7 @@ constexpr int kRankRows = 512;   // rows per block in the rank / scatter kernels
 __global__ void __launch_bounds__(kRankRows)
 km_block_rank_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
                      uint32_t *__restrict__ blockhist, uint32_t *__restrict__ lrank) {
+    pdl_begin();
     extern __shared__ uint32_t hist[];
     for (int32_t i = threadIdx.x; i < k; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -53,6 +54,7 @@ km_block_rank_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
 // Per centroid: exclusive prefix over blocks (in place) and the batch histogram (fp32, :113).
 __global__ void km_block_prefix_kernel(uint32_t *__restrict__ blockhist, int32_t nblk, int32_t k,
                                        uint32_t *__restrict__ total, float *__restrict__ counts_b) {
+    pdl_begin();
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     uint32_t run = 0;
@@ -74,13 +76,17 @@ constexpr uint32_t kUpdHeavyRows = 128;              // centroids with at least 
 constexpr int32_t kFusedPrefixBlocks = 64;
 __global__ void __launch_bounds__(1024)
 km_segment_start_kernel(uint32_t *__restrict__ total, int32_t k, uint32_t *__restrict__ seg_start,
-                        uint32_t *__restrict__ blockhist, int32_t nblk, float *__restrict__ counts_b) {
+                        uint32_t *__restrict__ blockhist, int32_t nblk, float *__restrict__ counts_b,
+                        float *__restrict__ hist_max) {
     __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t warp_max[32];
     __shared__ uint32_t carry;
+    pdl_begin();
     __shared__ uint32_t n_heavy;
     if (threadIdx.x == 0) { carry = 0; n_heavy = 0; }
     __syncthreads();
     const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp;
+    uint32_t vmax = 0u;                            // this thread's largest count (for the learning-rate decision, :116)
     for (int32_t base = 0; base < k; base += 1024) {
         int32_t i = base + threadIdx.x;
         uint32_t v = 0u;
@@ -99,6 +105,7 @@ km_segment_start_kernel(uint32_t *__restrict__ total, int32_t k, uint32_t *__res
                 v = total[i];
             }
         }
+        vmax = max(vmax, v);
         uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < kWarp; o <<= 1) {
@@ -126,12 +133,22 @@ km_segment_start_kernel(uint32_t *__restrict__ total, int32_t k, uint32_t *__res
         __syncthreads();
     }
     if (threadIdx.x == 0) { seg_start[k] = carry; seg_start[k + 1] = n_heavy; }
+    if (hist_max) {                                // max_c counts_b[c] as fp32: what km_effective_lr_kernel would reduce
+        vmax = __reduce_max_sync(0xffffffffu, vmax);
+        if (lane == 0) warp_max[warp] = vmax;
+        __syncthreads();
+        if (warp == 0) {
+            vmax = __reduce_max_sync(0xffffffffu, warp_max[lane]);
+            if (lane == 0) *hist_max = (float)vmax;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kRankRows)
 km_scatter_rows_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
                        const uint32_t *__restrict__ blockhist, const uint32_t *__restrict__ lrank,
                        const uint32_t *__restrict__ seg_start, uint32_t *__restrict__ sorted_rows) {
+    pdl_begin();
     const int64_t row = (int64_t)blockIdx.x * kRankRows + threadIdx.x;
     if (row >= b) return;
     int64_t key = best[row];
@@ -147,6 +164,7 @@ km_scatter_rows_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
 __global__ void __launch_bounds__(1024)
 km_effective_lr_kernel(const float *__restrict__ counts_b, int32_t k, double lr,
                        float *__restrict__ lr_eff, int32_t *__restrict__ fallback) {
+    pdl_begin();
     __shared__ float wmax[32];
     float m = 0.f;
     for (int32_t i = threadIdx.x; i < k; i += blockDim.x) m = fmaxf(m, counts_b[i]);
@@ -166,6 +184,18 @@ km_effective_lr_kernel(const float *__restrict__ counts_b, int32_t k, double lr,
     }
 }
 
+// The step's learning rate: decided by an earlier kernel (lr_in < 0: *lr_eff_p), or -- one launch less on the step's
+// chain -- here, from the batch histogram's maximum that km_segment_start_kernel left in lr_eff_p[2], with the arithmetic
+// of km_effective_lr_kernel (:116-119).
+__device__ __forceinline__ float step_lr(const float *__restrict__ lr_eff_p, double lr_in, bool *fell_back) {
+    *fell_back = false;
+    if (lr_in < 0.0) return *lr_eff_p;
+    const float mm = lr_eff_p[2];
+    double eff = lr_in;
+    if ((double)mm * lr_in >= 1.0) { eff = 0.5 / (double)mm; *fell_back = true; }
+    return (float)eff;
+}
+
 // Where a (centroid, columns) delta goes:
 //   kUpdFused : centers = centers*decay + delta (:121,:127), one process;
 //   kUpdSplit : centers *= decay and the local delta is written out for an all-reduce (:125-126);
@@ -183,18 +213,25 @@ enum { kUpdFused = 0, kUpdSplit = 1, kUpdPush = 2, kUpdSeq = 3 };
 // row loads are kept in flight per thread, so a heavily skewed batch is bound by the 4-cycle add chain
 // rather than by memory latency.
 template <int VEC, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, VEC == 4 ? 8 : 4)
 km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
                  const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                  const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
-                 float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push) {
-    constexpr int kChunk = 256, kGroup = 32 / VEC;          // rows per register buffer
+                 float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push,
+                 double lr_in, int32_t *__restrict__ fallback) {
+    pdl_begin();
+    // rows per register buffer: 2 x 4 x 16 bytes in flight per thread and <= 64 registers, so that eight blocks share
+    // an SM -- the batch's average centroid owns b / K = 8 rows, and what bounds the kernel then is how many blocks'
+    // dependent chains (segment -> row ids -> rows -> centroid) run side by side, not the depth of one chain
+    constexpr int kChunk = 256, kGroup = VEC == 4 ? 4 : 32;
     __shared__ uint32_t sidx[kChunk];
     const int32_t c = blockIdx.x;
+    bool fell_back;
+    const float lr = step_lr(lr_eff_p, lr_in, &fell_back);
+    if (fell_back && fallback && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *fallback += 1;
     if (VEC == 4 && seg_start[c + 1] - seg_start[c] >= kUpdHeavyRows) return;   // heavy centroid: km_update_stream_kernel's
     const int32_t col = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
     const bool active = col < d;
-    const float lr = *lr_eff_p;
     const float cb = counts_b[c];
     if (MODE != kUpdPush && blockIdx.y == 0 && threadIdx.x == 0) counts[c] = __fadd_rn(counts[c], cb);          // :120
     const uint32_t lo = seg_start[c], hi = seg_start[c + 1];
@@ -207,6 +244,17 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
         if (active) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = centers[(int64_t)c * d + col + v];
+        }
+    }
+    float cold[VEC];                                        // the centroid's old values: asked for before the rows
+    if constexpr (MODE == kUpdFused || MODE == kUpdSplit) {
+        if (active) {
+            if constexpr (VEC == 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(centers + (int64_t)c * d + col);
+                cold[0] = t.x; cold[1] = t.y; cold[2] = t.z; cold[3] = t.w;
+            } else {
+                cold[0] = centers[(int64_t)c * d + col];
+            }
         }
     }
     const float *xcol = x + col;
@@ -263,15 +311,19 @@ km_update_kernel(const float *__restrict__ x, int64_t ldx, int32_t d,
     }
     const float decay = __fsub_rn(1.f, __fmul_rn(cb, lr));                                    // :121
     float *cp = centers + (int64_t)c * d + col;
+    float out[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-        float scaled = __fmul_rn(cp[v], decay);
-        if (MODE == kUpdFused) {
-            cp[v] = __fadd_rn(scaled, acc[v]);                                                 // :127
-        } else {
-            cp[v] = scaled;
-            deltas[(int64_t)c * d + col + v] = acc[v];
-        }
+        const float scaled = __fmul_rn(cold[v], decay);
+        out[v] = MODE == kUpdFused ? __fadd_rn(scaled, acc[v]) : scaled;                       // :127
+    }
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(cp) = make_float4(out[0], out[1], out[2], out[3]);
+        if (MODE != kUpdFused)
+            *reinterpret_cast<float4 *>(deltas + (int64_t)c * d + col) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+        cp[0] = out[0];
+        if (MODE != kUpdFused) deltas[(int64_t)c * d + col] = acc[0];
     }
 }
 
@@ -404,7 +456,8 @@ __global__ void __launch_bounds__(kBulkThreads)
 km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32_t d,
                       const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ sorted_rows,
                       const float *__restrict__ counts_b, const float *__restrict__ lr_eff_p,
-                      float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push) {
+                      float *__restrict__ centers, float *__restrict__ counts, float *__restrict__ deltas, KmPush push,
+                      double lr_in) {
     extern __shared__ __align__(128) unsigned char bsmem[];
     float *ring = reinterpret_cast<float *>(bsmem);                                     // [stages][rows][64]
     uint64_t *full = reinterpret_cast<uint64_t *>(bsmem + (size_t)kBulkStages * kBulkRows * kBulkCols * 4);
@@ -412,7 +465,8 @@ km_update_bulk_kernel(const float *__restrict__ x, int64_t ldx, int32_t k, int32
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int32_t col0 = blockIdx.y * kBulkCols;
     const uint32_t row_bytes = (uint32_t)min(kBulkCols, d - col0) * 4u;                 // multiple of 16 (d % 4 == 0)
-    const float lr = *lr_eff_p;
+    bool fell_back;
+    const float lr = step_lr(lr_eff_p, lr_in, &fell_back);
     const uint32_t n_heavy = seg_start[k + 1];
     if (threadIdx.x == 0) {
         for (int s = 0; s < kBulkStages; ++s) { ptx::mbar_init(&full[s], kBulkProducers); ptx::mbar_init(&empty[s], 1); }
@@ -520,7 +574,7 @@ __global__ void km_apply_deltas_kernel(float *__restrict__ centers, const float 
 
 int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockhist, uint32_t *lrank,
                      uint32_t *total, uint32_t *seg_start, uint32_t *sorted_rows, float *counts_b,
-                     cudaStream_t st) {
+                     cudaStream_t st, float *hist_max, bool *hist_max_written) {
     const int32_t nblk = (int32_t)ceil_div(b, kRankRows);
     const size_t smem = (size_t)k * sizeof(uint32_t);
     if (smem > 48 * 1024) {
@@ -529,21 +583,18 @@ int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockh
                                            (int)smem));
     }
     if (nblk > 0) {
-        km_block_rank_kernel<<<nblk, kRankRows, smem, st>>>(best, b, k, blockhist, lrank);
-        ACAV_LAUNCH_CHECK();
+        ACAV_CUDA_TRY(launch_pdl(km_block_rank_kernel, dim3(nblk), dim3(kRankRows), smem, st, best, b, k, blockhist, lrank));
     }
     if (nblk <= kFusedPrefixBlocks) {
-        km_segment_start_kernel<<<1, 1024, 0, st>>>(total, k, seg_start, blockhist, nblk, counts_b);
-        ACAV_LAUNCH_CHECK();
+        ACAV_CUDA_TRY(launch_pdl(km_segment_start_kernel, dim3(1), dim3(1024), 0, st, total, k, seg_start, blockhist, nblk, counts_b, hist_max));
+        if (hist_max_written) *hist_max_written = hist_max != nullptr;
     } else {
-        km_block_prefix_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(blockhist, nblk, k, total, counts_b);
-        ACAV_LAUNCH_CHECK();
-        km_segment_start_kernel<<<1, 1024, 0, st>>>(total, k, seg_start, nullptr, 0, nullptr);
-        ACAV_LAUNCH_CHECK();
+        ACAV_CUDA_TRY(launch_pdl(km_block_prefix_kernel, dim3((unsigned)ceil_div(k, 256)), dim3(256), 0, st, blockhist, nblk, k, total, counts_b));
+        ACAV_CUDA_TRY(launch_pdl(km_segment_start_kernel, dim3(1), dim3(1024), 0, st, total, k, seg_start, nullptr, 0, nullptr, nullptr));
+        if (hist_max_written) *hist_max_written = false;
     }
     if (nblk > 0) {
-        km_scatter_rows_kernel<<<nblk, kRankRows, 0, st>>>(best, b, k, blockhist, lrank, seg_start, sorted_rows);
-        ACAV_LAUNCH_CHECK();
+        ACAV_CUDA_TRY(launch_pdl(km_scatter_rows_kernel, dim3(nblk), dim3(kRankRows), 0, st, best, b, k, blockhist, lrank, seg_start, sorted_rows));
     }
     return 0;
 }
@@ -563,16 +614,26 @@ int launch_sequential_lr(double lr, float *lr_eff, cudaStream_t st) {
 
 int launch_effective_lr(const float *counts_b, int32_t k, double lr, float *lr_eff, int32_t *fallback,
                         cudaStream_t st) {
-    km_effective_lr_kernel<<<1, 1024, 0, st>>>(counts_b, k, lr, lr_eff, fallback);
-    ACAV_LAUNCH_CHECK();
+    ACAV_CUDA_TRY(launch_pdl(km_effective_lr_kernel, dim3(1), dim3(1024), 0, st, counts_b, k, lr, lr_eff, fallback));
     return 0;
+}
+
+bool km_heavy_ring() {
+    static int use_ring = -1;
+    if (use_ring < 0) {
+        const char *e = std::getenv("ACAV_KM_HEAVY");
+        use_ring = (e && e[0] == 'r') ? 1 : 0;
+    }
+    return use_ring == 1;
 }
 
 int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint32_t *seg_start,
                   const uint32_t *sorted_rows, const float *counts_b, const float *lr_eff,
                   float *centers, float *counts, float *deltas, const KmPush *push, bool sequential, cudaStream_t st,
-                  const KmFork *fork) {
-    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+                  const KmFork *fork, double lr_in, int32_t *fallback) {
+    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) &&
+                      (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(centers) |
+                         reinterpret_cast<uintptr_t>(deltas)) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     if (push && !vec4) return ACAV_E_UNSUPPORTED;
     if (sequential) {                                  // :103-109: no histogram decay, no deltas
@@ -582,13 +643,13 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
             { int rc = ensure_dynamic_smem(km_update_bulk_kernel<kUpdSeq>, bsmem, sdone); if (rc) return rc; }
             dim3 bgrid((unsigned)(k < 96 ? k : 96), (unsigned)ceil_div(d, kBulkCols));
             km_update_bulk_kernel<kUpdSeq><<<bgrid, kBulkThreads, bsmem, st>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
-                                                                                centers, counts, nullptr, KmPush());
+                                                                                centers, counts, nullptr, KmPush(), -1.0);
             ACAV_LAUNCH_CHECK();
             dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128 * 4));
-            km_update_kernel<4, kUpdSeq><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, KmPush());
+            ACAV_CUDA_TRY(launch_pdl(km_update_kernel<4, kUpdSeq>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, KmPush(), -1.0, nullptr));
         } else {
             dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128));
-            km_update_kernel<1, kUpdSeq><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, KmPush());
+            ACAV_CUDA_TRY(launch_pdl(km_update_kernel<1, kUpdSeq>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, KmPush(), -1.0, nullptr));
         }
         ACAV_LAUNCH_CHECK();
         return 0;
@@ -603,11 +664,8 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
         { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdFused>, smem, done_fused); if (rc) return rc; }
         { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdSplit>, smem, done_split); if (rc) return rc; }
         { int rc = ensure_dynamic_smem(km_update_stream_kernel<kUpdPush>, smem, done_push); if (rc) return rc; }
-        static int use_ring = -1;
-        if (use_ring < 0) {
-            const char *e = std::getenv("ACAV_KM_HEAVY");
-            use_ring = (e && e[0] == 'r') ? 1 : 0;                                       // "ring": the cp.async kernel
-        }
+        const int use_ring = km_heavy_ring() ? 1 : 0;                                    // "ring": the cp.async kernel
+        if (use_ring && lr_in >= 0.0) return ACAV_E_STATE;                               // that kernel reads *lr_eff
         if (!use_ring) {
             const size_t bsmem = (size_t)kBulkStages * kBulkRows * kBulkCols * 4 + 2 * kBulkStages * sizeof(uint64_t);
             static size_t bdone[3][kMaxDevices];
@@ -620,13 +678,13 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
             if (fork) { int rc = km_fork(fork, st); if (rc) return rc; bst = fork->side; }
             if (push)
                 km_update_bulk_kernel<kUpdPush><<<bgrid, kBulkThreads, bsmem, bst>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
-                                                                         centers, counts, nullptr, pz);
+                                                                         centers, counts, nullptr, pz, -1.0);
             else if (deltas)
                 km_update_bulk_kernel<kUpdSplit><<<bgrid, kBulkThreads, bsmem, bst>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
-                                                                          centers, counts, deltas, pz);
+                                                                          centers, counts, deltas, pz, lr_in);
             else
                 km_update_bulk_kernel<kUpdFused><<<bgrid, kBulkThreads, bsmem, bst>>>(x, ldx, k, d, seg_start, sorted_rows, counts_b, lr_eff,
-                                                                          centers, counts, nullptr, pz);
+                                                                          centers, counts, nullptr, pz, lr_in);
             ACAV_LAUNCH_CHECK();
             forked = fork != nullptr;
         }
@@ -645,17 +703,17 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
     }
     dim3 grid((unsigned)k, (unsigned)ceil_div(d, 128 * vec));
     if (push) {
-        km_update_kernel<4, kUpdPush><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
+        ACAV_CUDA_TRY(launch_pdl(km_update_kernel<4, kUpdPush>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz, -1.0, nullptr));
     } else if (deltas) {
         if (vec4)
-            km_update_kernel<4, kUpdSplit><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas, pz);
+            ACAV_CUDA_TRY(launch_pdl(km_update_kernel<4, kUpdSplit>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas, pz, lr_in, fallback));
         else
-            km_update_kernel<1, kUpdSplit><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas, pz);
+            ACAV_CUDA_TRY(launch_pdl(km_update_kernel<1, kUpdSplit>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, deltas, pz, lr_in, fallback));
     } else {
         if (vec4)
-            km_update_kernel<4, kUpdFused><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
+            ACAV_CUDA_TRY(launch_pdl(km_update_kernel<4, kUpdFused>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz, lr_in, fallback));
         else
-            km_update_kernel<1, kUpdFused><<<grid, 128, 0, st>>>(x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz);
+            ACAV_CUDA_TRY(launch_pdl(km_update_kernel<1, kUpdFused>, grid, dim3(128), 0, st, x, ldx, d, seg_start, sorted_rows, counts_b, lr_eff, centers, counts, nullptr, pz, lr_in, fallback));
     }
     ACAV_LAUNCH_CHECK();
     if (forked) return km_join(fork, st);
@@ -667,13 +725,13 @@ int launch_update(const float *x, int64_t ldx, int32_t k, int32_t d, const uint3
 // (flags, 0.5f) to the assignment entry points in place of (counts, threshold): flags[i] < 0.5 <=> counts[i] < thr.
 __global__ void km_underused_flags_kernel(const float *__restrict__ counts, int32_t k, const float *__restrict__ thr,
                                           float *__restrict__ flags) {
+    pdl_begin();
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < k) flags[i] = counts[i] < *thr ? 0.f : 1.f;
 }
 
 int launch_underused_flags(const float *counts, int32_t k, const float *thr_dev, float *flags, cudaStream_t st) {
-    km_underused_flags_kernel<<<(unsigned)ceil_div(k, 256), 256, 0, st>>>(counts, k, thr_dev, flags);
-    ACAV_LAUNCH_CHECK();
+    ACAV_CUDA_TRY(launch_pdl(km_underused_flags_kernel, dim3((unsigned)ceil_div(k, 256)), dim3(256), 0, st, counts, k, thr_dev, flags));
     return 0;
 }
 
