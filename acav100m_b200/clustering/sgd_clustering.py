@@ -179,13 +179,16 @@ class KMeans:
     def launches_per_step(self):
         """CUDA kernels of this library launched by one add() past warm-up (bench.py gpu_launches)."""
         # tensor mode: centroid prep (2) + row prep + distance GEMM + classify + candidate re-check + exact kernel
-        # + exact distance of the winner + mean; then the stable partition (3 up to 16384 rows, else 4) and the update:
-        #   one GPU: effective lr + 2 update kernels; NCCL: + apply; peer memory: histogram exchange + 2 update
-        #   kernels + signal, reduce/broadcast, signal, gather
+        # + exact distance of the winner + mean; then the stable partition (3 kernels up to 32768 rows, else 4) and the
+        # update:
+        #   one GPU: 2 update kernels (they take the lr decision themselves; beyond 32768 rows + effective lr);
+        #   NCCL: effective lr + 2 update kernels + apply; peer memory: histogram exchange + 2 update kernels + signal,
+        #   reduce/broadcast, signal, gather
         assign = 4 if self._mode() == _lib.ASSIGN_EXACT else 9
         _, world = self._world()
-        tail = 3 if world == 1 else (7 if self._comm else 4)
-        part = 3 if 0 < self._ws_batch <= 16384 else 4
+        mid = 0 < self._ws_batch <= 32768
+        tail = (2 if mid else 3) if world == 1 else (7 if self._comm else 4)
+        part = 3 if mid else 4
         return assign + part + tail + (1 if self._gs is not None else 0)
 
     # -- operator ------------------------------------------------------------------------------

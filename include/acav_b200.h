@@ -147,7 +147,11 @@ int acav_kmeans_histogram(acav_kmeans_t *h, const int64_t *best, int64_t b,
  *   counts += counts_b ; centers *= (1 - counts_b*lr_eff)                              [:120-121]
  *   centers += sum_{j: best[j]=i} fl32(x_j*lr_eff), summed in row order j             [:122-127]
  * The row-ordered fp32 sum is what torch-scatter's CPU kernel computes, so the result is
- * bit-identical to the reference's CPU path.  fallback: int32[1] device counter or NULL. */
+ * bit-identical to the reference's CPU path.  fallback: int32[1] device counter or NULL.
+ * When counts_b is the very buffer the preceding acav_kmeans_histogram filled (up to 32768 rows), the
+ * update kernels take the lr decision themselves from the maximum that call left in the workspace --
+ * the buffer must then be unmodified; counts changed by the caller belong in another buffer (or in
+ * acav_kmeans_update_local, which always reduces counts_b again). */
 int acav_kmeans_update_fused(acav_kmeans_t *h, const float *x, int64_t b, int64_t ldx,
                              const float *counts_b, double lr,
                              float *centers, float *counts, int32_t *fallback, void *stream);

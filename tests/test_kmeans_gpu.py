@@ -123,7 +123,9 @@ def test_training_trajectory_matches_reference(golden_dir, name):
 # d % 4 != 0 control that must stay on the scalar kernel, and the skewed early-training shape b = 8192, k = 3
 @pytest.mark.parametrize("b,d,k", [(1, 8, 1), (63, 13, 5), (64, 64, 64), (65, 88, 17), (1000, 352, 33),
                                    (4096, 128, 300), (4096, 128, 8), (4099, 132, 8), (4096, 130, 8),
-                                   (5003, 256, 3), (8192, 2304, 3), (8192, 2048, 40)])
+                                   (5003, 256, 3), (8192, 2304, 3), (8192, 2048, 40),
+                                   # fused block prefix + lr decision inside the update kernels up to 32768 rows, four kernels + lr kernel beyond
+                                   (16384, 64, 700), (16385, 64, 700), (40000, 32, 50), (1025, 16, 2600)])
 def test_update_is_bit_exact_given_assignments(b, d, k):
     rng = np.random.RandomState(b + d + k)
     x = torch.from_numpy((rng.standard_normal((b, d)) * 10 ** rng.uniform(-2, 2, (b, 1))).astype(np.float32))
