@@ -17,21 +17,54 @@ namespace acav {
 constexpr int kRankRows = 512;   // rows per block in the rank / scatter kernels
 
 // Stable local rank of every row among the rows of the same centroid inside its 512-row block, and
-// the block's histogram.  Warps take turns in row order so ranks follow row order.
+// the block's histogram.
+// <false>: warps take turns in row order over one shared histogram (k counters of shared memory): sixteen
+// __match_any_sync in a row -- each keeps its scheduler's MIO queue busy for ~600 cycles when the 32 ids differ.
+// <true> (k up to kRankParMaxK): every warp matches its own 32 rows at once and leaves its counts in its own uint16
+// histogram; a row's rank is its rank inside the warp plus the earlier warps' counts of its centroid.
+constexpr int kRankParMaxK = 6144;                 // 16 warps x k x 2 bytes <= 192 KiB
+template <bool kPar>
 __global__ void __launch_bounds__(kRankRows)
 km_block_rank_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
                      uint32_t *__restrict__ blockhist, uint32_t *__restrict__ lrank) {
     pdl_begin();
-    extern __shared__ uint32_t hist[];
+    extern __shared__ __align__(16) uint32_t hist[];
+    const int64_t row = (int64_t)blockIdx.x * kRankRows + threadIdx.x;
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    uint32_t *dst = blockhist + (int64_t)blockIdx.x * k;
+    if constexpr (kPar) {
+        constexpr int kW = kRankRows / kWarp;
+        uint16_t *whist = reinterpret_cast<uint16_t *>(hist);          // [kW][k]
+        for (int32_t i = threadIdx.x; i < kW * k / 2; i += blockDim.x) hist[i] = 0u;
+        int64_t key = -1;
+        if (row < b) {
+            key = best[row];
+            if (key < 0 || key >= k) key = -1;      // out-of-range ids are ignored (never produced)
+        }
+        __syncthreads();
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        uint32_t rank = __popc(m & ((1u << lane) - 1u));
+        if (key >= 0 && rank == 0) whist[warp * k + key] = (uint16_t)__popc(m);
+        __syncthreads();
+        if (key >= 0) {
+            for (int w = 0; w < warp; ++w) rank += whist[w * k + key];
+            lrank[row] = rank;
+        }
+        for (int32_t i = threadIdx.x; i < k; i += blockDim.x) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kW; ++w) t += whist[w * k + i];
+            dst[i] = t;
+        }
+        return;
+    }
     for (int32_t i = threadIdx.x; i < k; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    const int64_t row = (int64_t)blockIdx.x * kRankRows + threadIdx.x;
     int64_t key = -1;
     if (row < b) {
         key = best[row];
         if (key < 0 || key >= k) key = -1;          // out-of-range ids are ignored (never produced)
     }
-    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     for (int w = 0; w < kRankRows / kWarp; ++w) {
         if (warp == w) {
             unsigned m = __match_any_sync(0xffffffffu, key);
@@ -47,7 +80,6 @@ km_block_rank_kernel(const int64_t *__restrict__ best, int64_t b, int32_t k,
         }
         __syncthreads();
     }
-    uint32_t *dst = blockhist + (int64_t)blockIdx.x * k;
     for (int32_t i = threadIdx.x; i < k; i += blockDim.x) dst[i] = hist[i];
 }
 
@@ -576,14 +608,16 @@ int launch_partition(const int64_t *best, int64_t b, int32_t k, uint32_t *blockh
                      uint32_t *total, uint32_t *seg_start, uint32_t *sorted_rows, float *counts_b,
                      cudaStream_t st, float *hist_max, bool *hist_max_written) {
     const int32_t nblk = (int32_t)ceil_div(b, kRankRows);
-    const size_t smem = (size_t)k * sizeof(uint32_t);
-    if (smem > 48 * 1024) {
-        if (smem > 200 * 1024) return ACAV_E_UNSUPPORTED;
-        ACAV_CUDA_TRY(cudaFuncSetAttribute(km_block_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-    }
-    if (nblk > 0) {
-        ACAV_CUDA_TRY(launch_pdl(km_block_rank_kernel, dim3(nblk), dim3(kRankRows), smem, st, best, b, k, blockhist, lrank));
+    const bool par = k <= kRankParMaxK;
+    const size_t smem = par ? (size_t)(kRankRows / kWarp) * k * sizeof(uint16_t) : (size_t)k * sizeof(uint32_t);
+    if (smem > 200 * 1024) return ACAV_E_UNSUPPORTED;
+    static size_t rdone[2][kMaxDevices];
+    if (nblk > 0 && par) {
+        { int rc = ensure_dynamic_smem(km_block_rank_kernel<true>, smem, rdone[1]); if (rc) return rc; }
+        ACAV_CUDA_TRY(launch_pdl(km_block_rank_kernel<true>, dim3(nblk), dim3(kRankRows), smem, st, best, b, k, blockhist, lrank));
+    } else if (nblk > 0) {
+        { int rc = ensure_dynamic_smem(km_block_rank_kernel<false>, smem, rdone[0]); if (rc) return rc; }
+        ACAV_CUDA_TRY(launch_pdl(km_block_rank_kernel<false>, dim3(nblk), dim3(kRankRows), smem, st, best, b, k, blockhist, lrank));
     }
     if (nblk <= kFusedPrefixBlocks) {
         ACAV_CUDA_TRY(launch_pdl(km_segment_start_kernel, dim3(1), dim3(1024), 0, st, total, k, seg_start, blockhist, nblk, counts_b, hist_max));

@@ -125,7 +125,7 @@ def test_training_trajectory_matches_reference(golden_dir, name):
                                    (4096, 128, 300), (4096, 128, 8), (4099, 132, 8), (4096, 130, 8),
                                    (5003, 256, 3), (8192, 2304, 3), (8192, 2048, 40),
                                    # fused block prefix + lr decision inside the update kernels up to 32768 rows, four kernels + lr kernel beyond
-                                   (16384, 64, 700), (16385, 64, 700), (40000, 32, 50), (1025, 16, 2600)])
+                                   (16384, 64, 700), (16385, 64, 700), (40000, 32, 50), (1025, 16, 2600), (600, 8, 6200)])
 def test_update_is_bit_exact_given_assignments(b, d, k):
     rng = np.random.RandomState(b + d + k)
     x = torch.from_numpy((rng.standard_normal((b, d)) * 10 ** rng.uniform(-2, 2, (b, 1))).astype(np.float32))
