@@ -81,6 +81,7 @@ struct acav_mi {
     void *mail_peer[kMiMaxWorld];
     bool comm_connected;
     int *run_status;             // device word written by the persistent loops (kMiRun*)
+    void *clean_pub; unsigned int *clean_bar;   // the pub / bar buffers mi_refresh_kernel zeroed after the last run
     unsigned long long spin_limit_ns;
     long long *dbg;              // optional per-CTA phase timers of the persistent loop
     // cell-index loop resources (candidates sorted by table cell), built on first use
@@ -959,10 +960,10 @@ int acav_mi_create(acav_mi_t **out, int64_t w, int32_t k_a, int32_t k_v, int64_t
     s.w = w; s.k_a = k_a; s.k_v = k_v; s.pos_base = pos_base; s.logs = nullptr; s.n_logs = 0;
     h->max_picks = max_picks; h->loaded = false; h->tabled = false; h->consts_dev = nullptr;
     h->c2s = nullptr; h->pos_s = nullptr; h->row_start = nullptr; h->row_total = nullptr; h->tilehist = nullptr;
-    h->chunk_start = nullptr; h->n_alt = nullptr; h->pub = nullptr; h->bar = nullptr; h->grid = 0; h->rows_smem = 0;
+    h->chunk_start = nullptr; h->n_alt = nullptr; h->pub = nullptr; h->bar = nullptr; h->clean_pub = nullptr; h->clean_bar = nullptr; h->grid = 0; h->rows_smem = 0;
     h->w_sorted = 0; h->world = 1; h->rank = 0; h->seq_base = 0; h->mail_local = nullptr; h->comm_connected = false;
     for (int r = 0; r < kMiMaxWorld; ++r) h->mail_peer[r] = nullptr;
-    h->dbg = nullptr; h->run_status = nullptr;
+    h->dbg = nullptr; h->run_status = nullptr; h->clean_pub = nullptr; h->clean_bar = nullptr;
     h->spin_limit_ns = 20ull * 1000000000ull;                             // 20 s; ACAV_MI_SPIN_TIMEOUT_MS overrides
     if (const char *e = std::getenv("ACAV_MI_SPIN_TIMEOUT_MS")) {
         const double ms = std::atof(e);
@@ -1046,6 +1047,17 @@ int acav_mi_apply(acav_mi_t *h, const uint64_t *key_cells, int32_t n, int64_t *o
                            (cudaStream_t)stream);
 }
 
+static bool mi_sync_clean(const acav_mi_t *h) {
+    return h->pub && h->bar && h->clean_pub == (void *)h->pub && h->clean_bar == h->bar;
+}
+// row / column terms from the state the loop wrote back; the loop's barrier words and records zeroed for the next run
+static int mi_refresh_after_run(acav_mi_t *h, cudaStream_t st) {
+    int rc = launch_mi_refresh_terms(h->s, st, h->pub, mi_pub_bytes(h->sm_count), h->bar);
+    h->clean_pub = rc ? nullptr : (void *)h->pub;
+    h->clean_bar = rc ? nullptr : h->bar;
+    return rc;
+}
+
 int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t mode, void *stream) {
     if (!h || n_picks < 0 || (n_picks > 0 && (!out_pos || !out_gain))) return ACAV_E_INVALID;
     if (!h->tabled || !h->loaded) return ACAV_E_STATE;
@@ -1060,9 +1072,10 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         h->s8_valid = false;
         rc = launch_mi_cells(h->s, h->cx_cell_start, h->cx_sorted_pos, h->cx_head, h->cx_first_pos, grid, h->pub, h->bar,
                              n_picks, out_pos, out_gain, h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer,
-                             h->run_status, h->spin_limit_ns, st);
+                             h->run_status, h->spin_limit_ns, st, mi_sync_clean(h));
+        h->clean_pub = nullptr;
         h->seq_base += (unsigned int)n_picks + 1u;
-        if (!rc) rc = launch_mi_refresh_terms(h->s, st);
+        if (!rc) rc = mi_refresh_after_run(h, st);
         return rc;
     }
     if (mode == ACAV_MI_LOOP_KERNELS) {
@@ -1085,9 +1098,10 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
         rc = launch_mi_stream8(h->s, h->n_alt, h->s8_stream, h->s8_pos, h->s8_vrank, h->s8_slot_start, h->s8_slot_row, h->s8_slot_u,
                                h->s8_chunks, h->grid, h->pub, h->bar, n_picks, out_pos, out_gain, h->s8_rows_smem, h->s8_variant,
                                h->world, h->rank, h->seq_base, h->mail_local, h->mail_peer, h->dbg, h->run_status,
-                               h->spin_limit_ns, st);
+                               h->spin_limit_ns, st, mi_sync_clean(h));
+        h->clean_pub = nullptr;
         h->seq_base += (unsigned int)n_picks + 1u;
-        if (!rc) rc = launch_mi_refresh_terms(h->s, st);
+        if (!rc) rc = mi_refresh_after_run(h, st);
         return rc;
     }
     if (mode != ACAV_MI_LOOP_PERSISTENT) return ACAV_E_INVALID;
@@ -1099,9 +1113,10 @@ int acav_mi_run(acav_mi_t *h, int64_t n_picks, int64_t *out_pos, float *out_gain
     h->s8_valid = false;
     rc = launch_mi_persistent(h->s, h->n_alt, h->c2s, h->pos_s, h->row_start, h->chunk_start, h->grid, h->pub, h->bar,
                               n_picks, out_pos, out_gain, h->rows_smem, h->world, h->rank, h->seq_base, h->mail_local,
-                              h->mail_peer, h->dbg, h->run_status, h->spin_limit_ns, st);
+                              h->mail_peer, h->dbg, h->run_status, h->spin_limit_ns, st, mi_sync_clean(h));
+    h->clean_pub = nullptr;
     h->seq_base += (unsigned int)n_picks + 1u;          // mailbox tags never repeat across runs
-    if (!rc) rc = launch_mi_refresh_terms(h->s, st);
+    if (!rc) rc = mi_refresh_after_run(h, st);
     return rc;
 }
 

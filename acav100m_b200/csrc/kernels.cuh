@@ -121,7 +121,8 @@ struct MiState {                 // device-resident table + running sums of one 
 int launch_mi_pack(const int64_t *cells, int64_t w, uint32_t *packed, cudaStream_t st);
 int launch_mi_reset(const MiState &s, const float *consts_dev, cudaStream_t st);
 int launch_mi_add_sample(const MiState &s, int32_t c1, int32_t c2, cudaStream_t st);
-int launch_mi_refresh_terms(const MiState &s, cudaStream_t st);
+int launch_mi_refresh_terms(const MiState &s, cudaStream_t st, void *pub = nullptr, size_t pub_bytes = 0,
+                            unsigned int *bar = nullptr);   // pub/bar given: zeroed for the next run of a persistent loop
 int launch_mi_gain_table(const MiState &s, cudaStream_t st);
 int launch_mi_scan(const MiState &s, int sm_count, cudaStream_t st);
 int launch_mi_emit(const MiState &s, unsigned long long *out, cudaStream_t st);
@@ -144,7 +145,7 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
                          unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
-                         long long *dbg, int *status, unsigned long long spin_limit_ns, cudaStream_t st);
+                         long long *dbg, int *status, unsigned long long spin_limit_ns, cudaStream_t st, bool sync_clean = false);
 
 // mi_stream8.cu (one-byte candidate stream, register-staged)
 int mi_s8_k_rows(int32_t k_a, int32_t k_v);
@@ -168,7 +169,7 @@ int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const 
                       int32_t grid, void *pub, unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain,
                       int32_t rows_smem, int32_t variant, int32_t world, int32_t rank, unsigned int seq_base,
                       void *mail_local, void *const *mail_peer, long long *dbg, int *status,
-                      unsigned long long spin_limit_ns, cudaStream_t st);
+                      unsigned long long spin_limit_ns, cudaStream_t st, bool sync_clean = false);
 
 // mi_cells.cu (cell-index loop)
 int mi_cells_tiles(int64_t w);
@@ -180,7 +181,7 @@ int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t
                     uint32_t *first_pos, int32_t grid, void *pub, unsigned int *bar, int64_t n_picks,
                     int64_t *out_pos, float *out_gain, int32_t world, int32_t rank, unsigned int seq_base,
                     void *mail_local, void *const *mail_peer, int *status, unsigned long long spin_limit_ns,
-                    cudaStream_t st);
+                    cudaStream_t st, bool sync_clean = false);
 
 // mi_dense.cu
 struct MiDense {

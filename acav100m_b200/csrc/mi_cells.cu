@@ -426,7 +426,7 @@ int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t
                     uint32_t *first_pos, int32_t grid, void *pub, unsigned int *bar, int64_t n_picks,
                     int64_t *out_pos, float *out_gain, int32_t world, int32_t rank, unsigned int seq_base,
                     void *mail_local, void *const *mail_peer, int *status, unsigned long long spin_limit_ns,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool sync_clean) {
     MiCells P;
     P.status = status; P.spin_limit_ns = spin_limit_ns;
     P.s = s; P.cell_start = cell_start; P.sorted_pos = sorted_pos; P.head = head; P.first_pos = first_pos;
@@ -443,9 +443,13 @@ int launch_mi_cells(const MiState &s, const uint32_t *cell_start, const uint32_t
     if (P.cache_rows) smem += cache;
     static size_t attr_done[kMaxDevices];
     if (smem > 48 * 1024) { int rc = ensure_dynamic_smem(mi_cells_kernel, smem, attr_done); if (rc) return rc; }
-    ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
+    // the barrier words and the records start at zero: mi_refresh_kernel leaves them so after every run (sync_clean);
+    // the status word can only be set by a peer timeout
+    if (!sync_clean) {
+        ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
+        ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
+    }
+    if (world > 1 || !sync_clean) ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     void *args[] = {&P};
     ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_cells_kernel, dim3(grid), dim3(kCellThreads), args, smem, st));
     return 0;

@@ -702,7 +702,7 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
                          const uint32_t *row_start, const uint32_t *chunk_start, int32_t grid, void *pub,
                          unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain, int32_t rows_smem,
                          int32_t world, int32_t rank, unsigned int seq_base, void *mail_local, void *const *mail_peer,
-                         long long *dbg, int *status, unsigned long long spin_limit_ns, cudaStream_t st) {
+                         long long *dbg, int *status, unsigned long long spin_limit_ns, cudaStream_t st, bool sync_clean) {
     MiPersist P;
     P.dbg = dbg; P.status = status; P.spin_limit_ns = spin_limit_ns;
     P.s = s; P.n_alt = n_alt; P.c2s_ro = c2s; P.c2s = c2s; P.pos_s = pos_s; P.row_start = row_start;
@@ -718,9 +718,13 @@ int launch_mi_persistent(const MiState &s, uint32_t *n_alt, uint16_t *c2s, const
     { int rc = ensure_dynamic_smem(mi_persistent_kernel, smem, attr_done); if (rc) return rc; }
     // both table copies start equal; the barrier words start at zero
     ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
+    // the barrier words and the records start at zero: mi_refresh_kernel leaves them so after every run (sync_clean);
+    // the status word can only be set by a peer timeout
+    if (!sync_clean) {
+        ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
+        ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
+    }
+    if (world > 1 || !sync_clean) ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     void *args[] = {&P};
     ACAV_CUDA_TRY(cudaLaunchCooperativeKernel((void *)mi_persistent_kernel, dim3(grid), dim3(kPersistThreads), args,
                                               smem, st));

@@ -73,8 +73,12 @@ __global__ void __launch_bounds__(1024) mi_add_sample_kernel(MiState s, int32_t 
 
 // recompute the row / column terms from the current marginals and sums (after the persistent kernel
 // wrote its replicated state back)
-__global__ void __launch_bounds__(1024) mi_refresh_kernel(MiState s) {
+__global__ void __launch_bounds__(1024) mi_refresh_kernel(MiState s, uint32_t *pub, uint32_t pub_words, unsigned int *bar) {
     if (threadIdx.x == 0) { s.key[0] = 0ull; s.key[1] = 0ull; }
+    // the grid-barrier words and the per-CTA records of the persistent loops: zero for the next run (saves that run
+    // two memsets in front of its launch)
+    for (uint32_t i = threadIdx.x; i < pub_words; i += blockDim.x) pub[i] = 0u;
+    if (bar && threadIdx.x < 2) bar[threadIdx.x] = 0u;
     mi_terms(s);
 }
 
@@ -192,8 +196,8 @@ int launch_mi_add_sample(const MiState &s, int32_t c1, int32_t c2, cudaStream_t 
     return 0;
 }
 
-int launch_mi_refresh_terms(const MiState &s, cudaStream_t st) {
-    mi_refresh_kernel<<<1, 1024, 0, st>>>(s);
+int launch_mi_refresh_terms(const MiState &s, cudaStream_t st, void *pub, size_t pub_bytes, unsigned int *bar) {
+    mi_refresh_kernel<<<1, 1024, 0, st>>>(s, reinterpret_cast<uint32_t *>(pub), pub ? (uint32_t)(pub_bytes / 4) : 0u, bar);
     ACAV_LAUNCH_CHECK();
     return 0;
 }

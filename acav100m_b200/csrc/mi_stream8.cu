@@ -931,7 +931,7 @@ int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const 
                       int32_t grid, void *pub, unsigned int *bar, int64_t n_picks, int64_t *out_pos, float *out_gain,
                       int32_t rows_smem, int32_t variant, int32_t world, int32_t rank, unsigned int seq_base,
                       void *mail_local, void *const *mail_peer, long long *dbg, int *status,
-                      unsigned long long spin_limit_ns, cudaStream_t st) {
+                      unsigned long long spin_limit_ns, cudaStream_t st, bool sync_clean) {
     MiS8 P;
     P.s = s; P.n_alt = n_alt; P.stream = stream; P.pos_s = pos_s; P.vrank = vrank; P.slot_start = slot_start; P.slot_row = slot_row;
     P.slot_u = slot_u; P.chunks = reinterpret_cast<const S8Chunk *>(chunks);
@@ -948,9 +948,13 @@ int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const 
     const size_t table_bytes = s8_table_bytes(s.k_a, s.k_v, rows_smem);
     // both table copies start equal; the barrier words start at zero
     ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
-    ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
+    // the barrier words and the records start at zero: mi_refresh_kernel leaves them so after every run (sync_clean);
+    // the status word can only be set by a peer timeout
+    if (!sync_clean) {
+        ACAV_CUDA_TRY(cudaMemsetAsync(pub, 0, mi_pub_bytes(grid), st));
+        ACAV_CUDA_TRY(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), st));
+    }
+    if (world > 1 || !sync_clean) ACAV_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), st));
     switch (variant) {                             // measured at W = 1e8, K = 1024: 32.7 / 37.9 / 33.9 / 33.0 / 38.2 / 33.0 us
         case 1: return launch_s8_variant<512, 8>(P, table_bytes, grid, st);
         case 2: return launch_s8_variant<768, 4>(P, table_bytes, grid, st);

@@ -13,6 +13,7 @@ added in torch's CPU summation order so that scores stay bit-identical.
 New (not in the reference): ``shard=(rank, world)`` splits the candidate list into contiguous ranges
 across ranks with one small all-gather per iteration; every rank returns the same S and GAIN.
 """
+import contextlib
 import time
 
 import numpy as np
@@ -263,6 +264,26 @@ class EfficientMemMI:
             raise RuntimeError("greedy-MI persistent loop stopped: a peer GPU's winner did not arrive within the "
                                "spin limit (a rank failed or ran a different number of iterations)")
 
+    def _result_views(self, n):
+        """(positions int64[n], gains fp32[n]) carved out of a block allocated 64 K picks at a time: two allocator calls
+        less in front of every launch of a persistent loop (a select(20) is ~0.7 ms of GPU time)."""
+        blk = getattr(self, "_res_blk", None)
+        if blk is None or blk[2] + n > blk[0].numel():
+            cap = max(int(n), 65536)
+            blk = [torch.empty(cap, dtype=torch.int64, device=self.device),
+                   torch.empty(cap, dtype=torch.float32, device=self.device), 0]
+            self._res_blk = blk
+        lo = blk[2]
+        blk[2] = lo + int(n)
+        return blk[0][lo:lo + n], blk[1][lo:lo + n]
+
+    def _device_guard(self):
+        """torch.cuda.device(self.device), or nothing when that device is current already."""
+        dev = torch.device(self.device)
+        if dev.type == "cuda" and (dev.index is None or dev.index == torch.cuda.current_device()):
+            return contextlib.nullcontext()
+        return torch.cuda.device(dev)
+
     def select(self, n_picks):
         """Run `n_picks` greedy iterations; returns (positions int64[n] in the candidate list,
         gains fp32[n]) as device tensors, without a host sync."""
@@ -271,9 +292,8 @@ class EfficientMemMI:
         if self._pairs is not None:
             self._picked += n_picks
             return self._pairs.select(n_picks)
-        pos = torch.empty(n_picks, dtype=torch.int64, device=self.device)
-        gain = torch.empty(n_picks, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        pos, gain = self._result_views(n_picks)
+        with self._device_guard():
             st = _lib.stream_ptr(self.device)
             if self._dist is None or self._nvlink:
                 if self._nvlink and getattr(self, "_ready_mode", None) != self._loop_mode():
