@@ -19,11 +19,13 @@ Workload (config.workload, DESIGN.md "Measurement"):
   * --workload c2 / c3 / c4 run BASELINE configs 2, 3 (one epoch + assignment pass) and 4 (1e8 -> 1e7 picks to
     completion) end to end instead and print their own line.
 Inputs are synthetic (acav100m_b200.synth) and resident in HBM when the timed region starts; "e2e"
-repeats the measurement through the public API starting from pinned HOST buffers.
+repeats the measurement through the public API starting from pinned HOST buffers (a whole job -- host list -> engine
+-> `steps` picks -> results on the host -- timed once, after one identical untimed job).
 `--impl reference` times the reference's CPU implementation (the oracle port; the reference is pure
 Python and does not travel to the GPU box) on the host cores for the same metric.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -320,17 +322,26 @@ def run_mi(args, dist, rank, world):
         host = torch.empty((W, 2), dtype=torch.int64, pin_memory=True)
         host.copy_(cells)
         del cells
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
-        m2 = mi_engine(host, args.k, rank, world, args.mi_loop, W * world, W * rank)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        pos, gain = m2.select(args.steps)
-        pos_h, gain_h = pos.cpu(), gain.cpu()
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
+        def job():
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            m2 = mi_engine(host, args.k, rank, world, args.mi_loop, W * world, W * rank)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            pos, gain = m2.select(args.steps)
+            pos_h, gain_h = pos.cpu(), gain.cpu()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            del m2
+            return t0, t1, t2, pos_h, gain_h
+
+        # one whole job untimed first (device buffers of the sizes this list needs come out of the library's cache
+        # afterwards, as for any user selecting from a second list), then the timed one
+        job()
+        gc.collect()
+        t0, t1, t2, pos_h, gain_h = job()
         dt = torch.tensor([t2 - t0], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -341,9 +352,10 @@ def run_mi(args, dist, rank, world):
                "seconds": float(dt.item()),
                "phases_ms_rank0": {"h2d_pack_tables": round(1e3 * (t1 - t0), 2),
                                    "layout_build_plus_iterations_plus_d2h": round(1e3 * (t2 - t1), 2)},
+               "warmup_jobs": 1,
                "what": "EfficientMemMI built from a pinned host int64 [W,2] tensor + %d greedy iterations + "
-                       "D2H of (S, GAIN)" % args.steps}
-        res["launches"] += 2
+                       "D2H of (S, GAIN); one identical job untimed before it" % args.steps}
+        res["launches"] += 4
     return res, e2e
 
 
