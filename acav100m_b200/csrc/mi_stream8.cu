@@ -286,7 +286,7 @@ struct S8Chunk {                     // one per CTA, written by the host's layou
 
 struct MiS8 {
     MiState s;
-    uint32_t *n_alt;                 // second copy of the table counts (kept in step for the other loops)
+    uint32_t *n_alt;                 // unused here (the 2-byte loop's second table image)
     uint8_t *stream;
     const uint32_t *pos_s;
     const unsigned long long *vrank; // [stream bytes / 16] list-order ranks inside every vector
@@ -534,7 +534,6 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     S8Ctx ctx;
     ctx.vec = vec; ctx.vrank = P.vrank; ctx.pos_s = P.pos_s; ctx.rs_loc = rs_loc; ctx.su_loc = su_loc; ctx.gain_b = gain_b; ctx.ns = ns;
     ctx.lane = lane;
-    int32_t prev1 = -1, prev2 = -1;                            // table cell of picks it-1, it-2
     int64_t done = 0;
     bool broke = false;
     long long t_learn = 0;
@@ -545,11 +544,6 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
         const int cur = (int)(it & 1);
         const long long t0 = P.dbg ? clock64() : 0;
         long long t_gain = 0, t_pre = 0;
-        if (blockIdx.x == 0 && threadIdx.x == 0) {             // both global table copies follow two picks behind
-            uint32_t *Toth = cur ? s.n_cells : P.n_alt;
-            if (prev2 >= 0) Toth[prev2] += 1;
-            if (prev1 >= 0) Toth[prev1] += 1;
-        }
         // ---------------- score my chunk ----------------
         const float NlogN = ps[0], aloga = ps[1], blogb = ps[2], fN0 = ps[4], fa0 = ps[5];
         const float np = __fadd_rn(ps[3], 1.0f);
@@ -802,10 +796,11 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
             if (blockIdx.x == 0) {
                 P.out_pos[it] = (int64_t)key_pos(win);
                 P.out_gain[it] = key_score(win);
+                // the global table: nobody reads it during the launch (every CTA keeps the counts of its sub-rows in
+                // shared memory), so it simply follows pick by pick -- a reduction that nothing waits for
+                atomicAdd(s.n_cells + (int64_t)c1 * k_v + c2w, 1u);
             }
         }
-        prev2 = prev1;
-        prev1 = c1 * k_v + c2w;
         done = it + 1;
         __syncthreads();
         if (P.dbg) t_learn = clock64() - t3;
@@ -814,12 +809,6 @@ __global__ void __launch_bounds__(THREADS, 1) mi_stream8_kernel(MiS8 P) {
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
             for (int64_t j = done; j < P.n_picks; ++j) { P.out_pos[j] = -1; P.out_gain[j] = nanf(""); }
-            // canonical copy 0 holds picks <= done-2 if `done` is even (it was the read copy of iteration `done`),
-            // <= done-3 if odd (an early exit at an odd `done` happened after CTA 0 had already completed copy 0)
-            if (!(broke && (done & 1))) {
-                if (prev1 >= 0) s.n_cells[prev1] += 1;
-                if ((done & 1) && prev2 >= 0) s.n_cells[prev2] += 1;
-            }
             for (int i = 0; i < 4; ++i) s.sums[i] = ps[i];
         }
         for (int32_t i = threadIdx.x; i < k_v; i += THREADS) s.a_cols[i] = a_cnt[i];
@@ -946,8 +935,6 @@ int launch_mi_stream8(const MiState &s, uint32_t *n_alt, uint8_t *stream, const 
         P.mail_peer[r] = (world > 1 && r < world) ? reinterpret_cast<MiMail *>(mail_peer[r]) : nullptr;
     P.dbg = dbg; P.status = status; P.spin_limit_ns = spin_limit_ns;
     const size_t table_bytes = s8_table_bytes(s.k_a, s.k_v, rows_smem);
-    // both table copies start equal; the barrier words start at zero
-    ACAV_CUDA_TRY(cudaMemcpyAsync(n_alt, s.n_cells, sizeof(uint32_t) * (size_t)s.k_a * s.k_v, cudaMemcpyDeviceToDevice, st));
     // the barrier words and the records start at zero: mi_refresh_kernel leaves them so after every run (sync_clean);
     // the status word can only be set by a peer timeout
     if (!sync_clean) {

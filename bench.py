@@ -330,18 +330,22 @@ def run_mi(args, dist, rank, world):
             m2 = mi_engine(host, args.k, rank, world, args.mi_loop, W * world, W * rank)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
+            from acav100m_b200 import _lib
+            _lib.call("acav_mi_prepare", m2._engine, m2._loop_mode(), _lib.stream_ptr(m2.device))
+            torch.cuda.synchronize()
+            t1b = time.perf_counter()
             pos, gain = m2.select(args.steps)
             pos_h, gain_h = pos.cpu(), gain.cpu()
             torch.cuda.synchronize()
             t2 = time.perf_counter()
             del m2
-            return t0, t1, t2, pos_h, gain_h
+            return t0, t1, t1b, t2, pos_h, gain_h
 
         # one whole job untimed first (device buffers of the sizes this list needs come out of the library's cache
         # afterwards, as for any user selecting from a second list), then the timed one
         job()
         gc.collect()
-        t0, t1, t2, pos_h, gain_h = job()
+        t0, t1, t1b, t2, pos_h, gain_h = job()
         dt = torch.tensor([t2 - t0], device="cuda", dtype=torch.float64)
         if dist:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -351,7 +355,8 @@ def run_mi(args, dist, rank, world):
                "d2h_bytes_per_step": (pos_h.numel() * 8 + gain_h.numel() * 4) / args.steps,
                "seconds": float(dt.item()),
                "phases_ms_rank0": {"h2d_pack_tables": round(1e3 * (t1 - t0), 2),
-                                   "layout_build_plus_iterations_plus_d2h": round(1e3 * (t2 - t1), 2)},
+                                   "layout_build": round(1e3 * (t1b - t1), 2),
+                                   "iterations_plus_d2h": round(1e3 * (t2 - t1b), 2)},
                "warmup_jobs": 1,
                "what": "EfficientMemMI built from a pinned host int64 [W,2] tensor + %d greedy iterations + "
                        "D2H of (S, GAIN); one identical job untimed before it" % args.steps}
