@@ -111,6 +111,11 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                  "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            # nvidia-smi's start-up (NVML initialisation over every GPU of the box) takes the driver's locks for a few
+            # hundred ms; a sub-millisecond timed region that falls into it pays for that.  Wait for the first sample.
+            t_end = time.time() + 5.0
+            while not self.lines and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
