@@ -21,7 +21,7 @@ run $SAN --tool racecheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "b
 # km_update_bulk_kernel is excluded from racecheck: its ring is written by cp.async.bulk (async proxy) and read by the
 # consumer warp under full/empty mbarriers, an ordering racecheck does not model -- it reports the bulk-copy write
 # against every consumer read (profiles/r02_sanitize_b.log keeps that report); memcheck and the bit-exact tests cover it.
-run $SAN --tool racecheck --kernel-name-exclude kernel_substring=km_update_bulk_kernel --error-exitcode 1 python -m pytest -q -x -m gpu -k "update_is_bit_exact and (4096-128-8 or 65-88-17 or 4096-130-8)" tests/test_kmeans_gpu.py
+run $SAN --tool racecheck --kernel-name-exclude kernel_substring=km_update_bulk_kernel --error-exitcode 1 python -m pytest -q -x -m gpu -k "update_is_bit_exact and (4096-128-8 or 65-88-17 or 4096-130-8 or 1025-16-2600)" tests/test_kmeans_gpu.py
 run $SAN --tool racecheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "reference_bits or one_pair or subset_of_columns" \
     tests/test_zz_mi_pairs_gpu.py tests/test_zz_ami_gpu.py
 run $SAN --tool synccheck --error-exitcode 1 python -m pytest -q -x -m gpu -k "uniform_ids or mixed" tests/test_mi_gpu.py
