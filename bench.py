@@ -336,7 +336,10 @@ def run_mi(args, dist, rank, world):
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             from acav100m_b200 import _lib
-            _lib.call("acav_mi_prepare", m2._engine, m2._loop_mode(), _lib.stream_ptr(m2.device))
+            try:                                               # the layout build on its own clock (select() would do it)
+                _lib.call("acav_mi_prepare", m2._engine, m2._loop_mode(), _lib.stream_ptr(m2.device))
+            except _lib.AcavError:
+                pass                                           # loop="auto": select() moves on to the next loop itself
             torch.cuda.synchronize()
             t1b = time.perf_counter()
             pos, gain = m2.select(args.steps)
